@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — CEM plans/sec & predicted frames/sec (BASELINE.json metric) for the visual-MPC hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision ...]
+
+One "step" = one CEM plan: `iterations` x [sample M action sequences -> roll the CDNA/conv-LSTM predictor
+S-1 cell steps -> pixel-distance cost of P predicted frames -> top-K elites -> refit].
+N=1 workload = BASELINE config c2 (M=200, S=15, 64x64x3, 3 iterations, K=10).  N>1: weak scaling, every
+rank keeps M=200 samples (global M = 200*N), one all-gather of M float64 scores per CEM iteration.
+
+value      : predicted frames/s, whole job, context already resident in HBM, timed with CUDA events on the
+             engine's stream, max over ranks (plans_per_sec is reported beside it).
+e2e        : same metric through the policy-facing backend.plan() with HOST buffers (context H2D, result
+             D2H inside the timed region).
+roofline   : conv-LSTM gate convolutions (dominant kernel class), CUDA-event time per launch from a
+             profiled plan, ALGORITHMIC flops, vs MEASURED_PEAKS.json bf16 (sustained: timed inside a long step).
+cpu_baseline: the oracle port (NumPy CEM + PyTorch-CPU predictor) on a bounded sample, rank 0, N=1 only.
+--impl reference: the same oracle port as its own arm (the TF1 reference cannot run: SURVEY.md 8c).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CFG = dict(M=200, S=15, C=2, H=64, W=64, iters=3, K=10, nactions=5, repeat=3, adim=4, sdim=4)
+METRIC = "CEM predicted frames/sec (M=200,H=15,64x64; plans/sec alongside)"
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def synth(spec, seed=0):
+    from visual_foresight_b200 import spec as S
+    from visual_foresight_b200.synthetic import synth_inputs
+    inp = synth_inputs(spec, seed)
+    w = [S.init_weights(spec, seed, v) for v in range(spec.ncam)]
+    return inp, w
+
+
+def plan_kwargs(spec, M):
+    from visual_foresight_b200.hparams import HParams
+    from visual_foresight_b200.samplers import GaussianCEMSampler, action_bounds, per_dim_variance
+    hp = HParams(**GaussianCEMSampler.get_default_hparams())
+    lo, hi = action_bounds(hp, spec.adim)
+    return dict(num_elites=CFG["K"], nactions=CFG["nactions"], repeat=CFG["repeat"], std=np.sqrt(per_dim_variance(hp, spec.adim)),
+                clip=(lo, hi), mean0=None, reduce_std_scale=1.0, finalweight=10.0, task_weights=None, seed=0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_port_plan_time(spec, inp, weights, sample_M, iters=1, threads=None):
+    """Oracle port (reference NumPy CEM restated + PyTorch-CPU predictor) on `sample_M` samples for `iters`
+    CEM iterations; returns seconds."""
+    import torch
+    import helpers as Hh
+    from oracle import cem as OC
+    if threads:
+        torch.set_num_threads(threads)
+    kw = plan_kwargs(spec, sample_M)
+    K = min(CFG["K"], sample_M)
+    noise = np.random.default_rng(0).standard_normal((iters, sample_M, 20)).astype(np.float32)
+
+    def evaluate(actions):
+        _, od, _ = Hh.oracle_rollout(spec, weights, inp, actions.astype(np.float32))
+        return OC.eval_pixel_cost(od, inp["goal"])
+    t0 = time.perf_counter()
+    OC.cem_plan(evaluate, num_samples=sample_M, iterations=iters, num_elites_k=K, nactions=CFG["nactions"], repeat=CFG["repeat"],
+                adim=spec.adim, std=kw["std"], noise=noise, clip=kw["clip"])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(spec, inp, weights, sample_M=8):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_port_plan_time(spec, inp, weights, 2, 1)                       # warm-up (thread pool, oneDNN primitives)
+    t = cpu_port_plan_time(spec, inp, weights, sample_M, 1)
+    plan_s = t * (CFG["M"] / sample_M) * CFG["iters"]
+    frames = CFG["iters"] * CFG["M"] * spec.n_pred * spec.ncam
+    return {"value": frames / plan_s, "unit": "frames/s", "plans_per_sec": 1.0 / plan_s, "cores": torch.get_num_threads(),
+            "kind": "port", "sample": "1 CEM iteration on %d of %d samples (S=%d, %dx%d), %.1f s, scaled x%.0f to 3 iterations x M=%d" %
+            (sample_M, CFG["M"], spec.seq_len, spec.height, spec.width, t, CFG["M"] / sample_M * CFG["iters"], CFG["M"])}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    from visual_foresight_b200 import spec as S
+    spec = S.spec_64(height=CFG["H"], width=CFG["W"], seq_len=CFG["S"], context_frames=CFG["C"], adim=CFG["adim"], sdim=CFG["sdim"])
+    inp, w = synth(spec)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_M = args.ref_samples
+    for _ in range(args.warmup):
+        cpu_port_plan_time(spec, inp, w, 2, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_plan_time(spec, inp, w, sample_M, 1)
+    dt = (time.perf_counter() - t0) / args.steps
+    plan_s = dt * (CFG["M"] / sample_M) * CFG["iters"]
+    frames = CFG["iters"] * CFG["M"] * spec.n_pred
+    v = frames / plan_s
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "plans_per_sec": 1.0 / plan_s, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": plan_s * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c2: M=200 S=15 64x64x3 3 CEM iters K=10 pixel-distance cost", "sample": "each step = 1 CEM iteration on %d samples, scaled to a full plan" % sample_M},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "1 CEM iteration on %d of 200 samples per step, scaled x%.0f" % (sample_M, CFG["M"] / sample_M * CFG["iters"])},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "TF1 reference cannot execute (tensorflow/video_prediction absent, SURVEY.md 8c): oracle port = reference NumPy CEM restated + PyTorch-CPU spec-P predictor"}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from visual_foresight_b200 import spec as S
+    from visual_foresight_b200.distributed import EngineShard, ShardedCEMPlanner, init_from_env
+    from visual_foresight_b200.predictor import EngineBackend
+    import __graft_entry__ as ge
+    if not os.path.exists(os.path.join(ROOT, "visual_foresight_b200", "libvfengine.so")):
+        ge.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    spec = S.spec_64(height=CFG["H"], width=CFG["W"], seq_len=CFG["S"], context_frames=CFG["C"], adim=CFG["adim"], sdim=CFG["sdim"])
+    inp, w = synth(spec)
+    M_local = CFG["M"] if not args.samples else args.samples
+    M_global = M_local * world
+    be = EngineBackend(spec, w, M_local, device=local_rank, precision=args.precision)
+    stream = torch.cuda.current_stream()
+    be.engine.set_stream(stream.cuda_stream)
+    ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"]}
+    desig = inp["desig"].astype(np.float32)
+    kw = plan_kwargs(spec, M_local)
+    goal = inp["goal"].astype(np.float32)
+    shard = EngineShard(be)
+    planner = ShardedCEMPlanner(shard, rank, world)
+    frames_per_plan = CFG["iters"] * M_global * spec.n_pred * spec.ncam
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_plan(plan_index):
+        """context resident; begin() (tiny param upload) outside the event bracket is still inside the step loop"""
+        planner.plan(M_global, CFG["iters"], goal=goal, plan_index=plan_index, **kw)
+
+    def e2e_plan(plan_index):
+        be.set_context(ctx)                                    # host frames/states/actions -> device
+        be.engine.set_desig(desig)                             # designated pixel -> one-hot distribution on device
+        return planner.plan(M_global, CFG["iters"], goal=goal, plan_index=plan_index, **kw)   # best actions + scores -> host
+
+    be.set_context(ctx)
+    be.engine.set_desig(desig)
+    for i in range(args.warmup):
+        device_plan(i)
+    # ---- value: device-resident ---------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = be.engine.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(args.steps):
+        device_plan(100 + i)
+    e1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = be.engine.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    # ---- e2e: host buffers in/out ----------------------------------------------------------------------------
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for i in range(args.steps):
+        res = e2e_plan(200 + i)
+    f1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_e2e = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    # ---- roofline: one profiled plan ---------------------------------------------------------------------------
+    be.engine.profile_enable(True)
+    device_plan(300)
+    prof = be.engine.profile_read()
+    be.engine.profile_enable(False)
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    fl = S.flops_per_sample_step(spec)
+    alg_lstm = fl["conv_lstm"] * spec.n_steps * M_local * CFG["iters"]          # algorithmic flops of the profiled plan's LSTM convs
+    lstm_ms = prof["lstm_conv"]["ms"]
+    ach = alg_lstm / (lstm_ms * 1e-3) / 1e12 if lstm_ms > 0 else 0.0
+    plan_ms_prof = None
+    roofline = {"bound": "tensor", "kernel": "conv-LSTM gate convolution (%s)" % args.precision,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": peak_src + " bf16 sustained",
+                "traffic": None, "launches": prof["lstm_conv"]["launches"], "ms_per_launch": lstm_ms / max(prof["lstm_conv"]["launches"], 1),
+                "share_of_step": lstm_ms / (ms / args.steps), "other_conv_ms": prof["other_conv"]["ms"],
+                "algorithmic_flops_per_launch": alg_lstm / max(prof["lstm_conv"]["launches"], 1),
+                "whole_plan_frac": (S.flops_per_plan(spec, M_local, CFG["iters"]) / (ms / args.steps * 1e-3) / 1e12) / peak_tf}
+    if rank == 0:
+        step_ms = ms / args.steps
+        value = frames_per_plan / (step_ms * 1e-3)
+        e2e_v = frames_per_plan / (ms_e2e / args.steps * 1e-3)
+        h2d = inp["frames"].nbytes + inp["states"].nbytes + inp["ctx_actions"].nbytes + desig.nbytes + goal.nbytes
+        d2h = res["best_actions"].nbytes + res["elite_idx"].nbytes + res["scores"].nbytes
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "plans_per_sec": 1e3 / step_ms, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32_simt": "f32", "f16x3": "f32 (fp16 hi/lo split x3 on tcgen05, fp32 accumulate)", "f16x1": "f16 (fp32 accumulate)"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": "c2: M=%d/GPU (global %d) S=15 C=2 64x64x3 3 CEM iters K=10 pixel-distance cost, random-init spec-P CDNA/conv-LSTM" % (M_local, M_global),
+                           "parallelism": "sample-parallel dp%d, 1 all-gather of M f64 scores per CEM iteration" % world,
+                           "l2": "per-step working set (~%d MB activations) exceeds the 126 MB L2; no flush" % int(M_local * 9.5),
+                           "precision": args.precision},
+                "e2e": {"value": e2e_v, "unit": "frames/s", "plans_per_sec": 1e3 / (ms_e2e / args.steps), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches), "wall_s": t_wall, "clocks": clocks, "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(spec, inp, w, args.cpu_samples)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("VF_PRECISION", "fp32_simt"), choices=["fp32_simt", "f16x3", "f16x1"])
+    ap.add_argument("--samples", type=int, default=0, help="override per-GPU M (debug)")
+    ap.add_argument("--cpu-samples", type=int, default=8)
+    ap.add_argument("--ref-samples", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_rank()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,302 @@
+"""-m gpu: the CUDA path through the C-ABI (ctypes -> libvfengine.so) against the oracle on seeded
+inputs and against the committed golden fixtures.
+
+Tolerances (stated here as the contract):
+  * integer / index work (top-K elite sets, one-hot, shard invariance)      : bit-exact
+  * predicted frames vs oracle (spec P, fp32), all precisions marked fp32-grade: max-abs <= 1e-4
+  * scores                                                                     : rel 1e-5
+Parity is vs the build's oracle (spec P); TF1 parity is unpinned."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as Hh
+from oracle import cem as OC
+from visual_foresight_b200 import spec as S
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FRAME_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng_small():
+    from visual_foresight_b200.engine import Engine
+    sp = S.spec_64(height=32, width=32, seq_len=5)
+    e = Engine(sp, 8)
+    yield e
+    e.close()
+
+
+# ---- kernels ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 16, 16, 8, 64, 5), (3, 8, 8, 64, 128, 5), (2, 32, 32, 6, 32, 5),
+                                               (2, 12, 16, 40, 32, 3), (1, 6, 8, 20, 64, 3), (2, 16, 16, 32, 3, 3),
+                                               (2, 16, 16, 53, 7, 3)])
+def test_conv_simt_vs_torch(eng_small, B, H, W, Cin, Cout, k):
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(B * 1000 + Cin)
+    x = rng.standard_normal((B, H, W, Cin)).astype(np.float32)
+    w = (rng.standard_normal((k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    y = eng_small.debug_conv2d(x, w, b)
+    ref = F.conv2d(torch.from_numpy(x).double().permute(0, 3, 1, 2), torch.from_numpy(w).double().permute(3, 2, 0, 1),
+                   torch.from_numpy(b).double(), padding=k // 2).permute(0, 2, 3, 1).numpy()
+    assert np.abs(y - ref).max() < 2e-5
+
+
+def test_topk_is_stable_argsort(eng_small):
+    rng = np.random.default_rng(0)
+    for n, k in [(5, 5), (200, 10), (600, 30), (4096, 205), (1000, 667)]:
+        s = rng.standard_normal(n)
+        s[rng.integers(0, n, n // 4)] = s[rng.integers(0, n, n // 4)]      # ties
+        if n > 100:
+            s[7] = np.nan
+        np.testing.assert_array_equal(eng_small.topk(s, k), np.argsort(s, kind="stable")[:k])
+    np.testing.assert_array_equal(eng_small.topk(np.zeros(37), 37), np.arange(37))
+
+
+def test_topk_on_reference_scores(eng_small, golden):
+    for t in (1, 2):
+        np.testing.assert_array_equal(eng_small.topk(golden["act_t%d_scores_itr2" % t], 5), golden["act_t%d_best_indices" % t])
+
+
+def test_refit_vs_reference(eng_small, golden):
+    mean, cov, fac = eng_small.refit(golden["gauss_fit_elites"], 5, 3)
+    np.testing.assert_allclose(mean, golden["gauss_fit_mean"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(cov, golden["gauss_fit_sigma"], rtol=1e-11, atol=1e-16)
+    np.testing.assert_allclose(fac @ fac.T, golden["gauss_fit_sigma"], rtol=1e-10, atol=1e-15)
+
+
+def test_pixel_cost_vs_reference_golden(golden):
+    """device cost kernel on the reference's own input -> the reference's own scores."""
+    from visual_foresight_b200.engine import Engine
+    gen = golden["cost_gen_distrib"]
+    e = Engine(S.spec_64(height=24, width=32, ndesig=2, seq_len=15), gen.shape[0])
+    for fw, key in ((10.0, "cost_scores_2desig"), (3.0, "cost_scores_2desig_fw3")):
+        sc = e.score_external(gen, golden["cost_goal_pix"], finalweight=fw)
+        np.testing.assert_allclose(sc, golden[key], rtol=1e-5)
+    # ragged / edge: a single plane, goal outside the image, one-hot distribution
+    one = np.zeros((1, 1, 1, 24, 32, 2), np.float32)
+    one[0, 0, 0, 3, 4, 0] = 1
+    one[0, 0, 0, 23, 31, 1] = 2
+    sc = e.score_external(one, np.array([[[40.0, -3.0], [0, 0]]]), finalweight=10.0)
+    want = 0.5 * (np.hypot(40 - 3, -3 - 4) + np.hypot(23, 31))
+    np.testing.assert_allclose(sc, [want], rtol=1e-6)
+    e.close()
+
+
+# ---- predictor ----------------------------------------------------------------------------------------
+def _engine_rollout(sp, weights, inp, acts, precision="fp32_simt"):
+    from visual_foresight_b200.engine import Engine
+    e = Engine(sp, acts.shape[0], precision=precision)
+    e.load_weights(weights)
+    e.set_context(inp["frames"], inp["states"] if sp.sdim else None, inp["ctx_actions"])
+    e.set_desig(inp["desig"])
+    out = e.predict(acts)
+    return e, out
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_rollout_vs_golden_fixture(case):
+    from make_predictor_golden import CASES
+    c = dict(CASES[case])
+    M = c.pop("M")
+    sp = S.spec_64(**c)
+    w = Hh.make_weights(sp, seed=3)
+    inp = Hh.synth_inputs(sp, seed=5)
+    acts = Hh.gaussian_actions(sp, M, sp.seq_len - sp.context_frames + 2, seed=7)
+    e, (gi, gd, gs) = _engine_rollout(sp, w, inp, acts)
+    g = np.load(os.path.join(GOLD, "oracle_predictor_golden.npz"))
+    assert np.abs(gi - g[case + "_frames"]).max() <= FRAME_TOL
+    assert np.abs(gd - g[case + "_distrib"]).max() <= 1e-5
+    np.testing.assert_allclose(gs, g[case + "_states"], atol=1e-5)
+    np.testing.assert_allclose(gd.sum(axis=(3, 4)), 1.0, atol=1e-5)        # renormalised distributions
+    e.close()
+
+
+def test_rollout_intermediates_vs_oracle():
+    """layer-by-layer parity at the last cell step (localises a mismatch to a kernel)."""
+    import torch
+    from oracle.predictor import OraclePredictor
+    sp = S.spec_64(height=32, width=32, seq_len=4)
+    w = Hh.make_weights(sp, seed=1)
+    inp = Hh.synth_inputs(sp, seed=2)
+    acts = Hh.gaussian_actions(sp, 2, 3, seed=3)
+    e, (gi, gd, gs) = _engine_rollout(sp, w, inp, acts)
+    dbg = {sp.seq_len - 2: {}}
+    o = OraclePredictor(sp, w[0], torch.float32)
+    onehot = OC.switch_on_pix(inp["desig"], 2, 1, 32, 32, 1)
+    oi, od, os_ = o.rollout(inp["frames"][:, 0].astype(np.float32) / 255, inp["states"], onehot[:, 0],
+                            Hh.step_actions(sp, inp["ctx_actions"], acts), debug_steps=dbg)
+    d = dbg[sp.seq_len - 2]
+    for name in ["enc0.conv", "enc0.lstm.h", "enc0.lstm.c", "enc1.conv", "enc1.lstm.h", "enc2.conv", "enc2.lstm.h",
+                 "dec0.conv", "dec0.lstm.h", "dec1.conv", "dec1.lstm.h", "dec2.conv", "scratch", "mask_logits"]:
+        ref = d[name].permute(0, 2, 3, 1).contiguous().numpy()
+        got = e.debug_fetch(name).reshape(ref.shape)
+        assert np.abs(got - ref).max() <= 2e-4, name
+    kref = d["cdna.kernels"].numpy().reshape(2, -1)
+    assert np.abs(e.debug_fetch("cdna.kernels").reshape(2, -1) - kref).max() <= 1e-5
+    assert np.abs(gi - oi[:, :, None]).max() <= FRAME_TOL
+    e.close()
+
+
+def test_rollout_c1_config_vs_oracle():
+    """BASELINE config c1 (M=8, S=5, 48x64) — frames within 1e-4 of the oracle, fp64 oracle as arbiter."""
+    import torch
+    sp = S.spec_64(height=48, width=64, seq_len=5)
+    w = Hh.make_weights(sp, seed=0)
+    inp = Hh.synth_inputs(sp, seed=0)
+    acts = Hh.gaussian_actions(sp, 8, 15, seed=0)
+    e, (gi, gd, gs) = _engine_rollout(sp, w, inp, acts)
+    oi, od, os_ = Hh.oracle_rollout(sp, w, inp, acts)
+    o64 = Hh.oracle_rollout(sp, w, inp, acts, dtype=torch.float64)[0]
+    assert np.abs(gi - oi).max() <= FRAME_TOL
+    assert np.abs(gi - o64).max() <= FRAME_TOL
+    assert np.abs(gd - od).max() <= 1e-5
+    sc = e.score(inp["goal"], M=8)
+    np.testing.assert_allclose(sc, OC.eval_pixel_cost(od, inp["goal"]), rtol=1e-5)
+    e.close()
+
+
+# ---- CEM ------------------------------------------------------------------------------------------------
+def _plan_kwargs(sp, M, K, iters, seed=0):
+    from visual_foresight_b200.samplers import GaussianCEMSampler, action_bounds, per_dim_variance
+    from visual_foresight_b200.hparams import HParams
+    hp = HParams(**GaussianCEMSampler.get_default_hparams())
+    lo, hi = action_bounds(hp, sp.adim)
+    return dict(num_samples=M, iterations=iters, num_elites=K, nactions=5, repeat=3,
+                std=np.sqrt(per_dim_variance(hp, sp.adim)), clip=(lo, hi), mean0=None, reduce_std_scale=1.0,
+                finalweight=10.0, task_weights=None, seed=seed, plan_index=0)
+
+
+def test_cem_plan_vs_oracle_explicit_noise():
+    """Whole perform_CEM on device with the SAME standard-normal noise as the oracle planner: sampled
+    actions equal, scores within tolerance, elite index sets bit-exact, best actions equal."""
+    from visual_foresight_b200.predictor import EngineBackend
+    sp = S.spec_64(height=32, width=32, seq_len=6)
+    w = Hh.make_weights(sp, seed=4)
+    inp = Hh.synth_inputs(sp, seed=4)
+    M, K, iters = 12, 4, 3
+    kw = _plan_kwargs(sp, M, K, iters)
+    noise = np.random.default_rng(9).standard_normal((iters, M, 20)).astype(np.float32)
+    be = EngineBackend(sp, w, M)
+    ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"],
+           "context_pixel_distributions": OC.switch_on_pix(inp["desig"], 2, 1, 32, 32, 1)}
+    res = be.plan(ctx, goal_pix=inp["goal"], noise=noise, **kw)
+
+    def evaluate(actions):
+        _, od, _ = Hh.oracle_rollout(sp, w, inp, actions.astype(np.float32))
+        return OC.eval_pixel_cost(od, inp["goal"])
+    best, idx, scores, all_actions = OC.cem_plan(evaluate, num_samples=M, iterations=iters, num_elites_k=K, nactions=5,
+                                                 repeat=3, adim=4, std=kw["std"], noise=noise, clip=kw["clip"])
+    np.testing.assert_allclose(res["scores"], scores, rtol=1e-5)
+    np.testing.assert_array_equal(res["elite_idx"], idx)
+    np.testing.assert_allclose(res["best_actions"], best, rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(be.engine.cem_actions(), all_actions[-1], rtol=1e-12, atol=1e-15)
+    be.engine.close()
+
+
+def test_philox_sampling_matches_restatement_and_shards_are_invariant():
+    """Device Philox normals == numpy restatement; a plan split into two shards (run back to back on one
+    GPU, scores exchanged through the host) gives bit-identical scores and elites to the unsharded plan."""
+    from visual_foresight_b200.predictor import EngineBackend, cem_params
+    sp = S.spec_64(height=32, width=32, seq_len=4)
+    w = Hh.make_weights(sp, seed=6)
+    inp = Hh.synth_inputs(sp, seed=6)
+    M, K, iters = 8, 3, 2
+    kw = _plan_kwargs(sp, M, K, iters, seed=1234567890123)
+    ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"],
+           "context_pixel_distributions": OC.switch_on_pix(inp["desig"], 2, 1, 32, 32, 1)}
+    full = EngineBackend(sp, w, M)
+    res = full.plan(ctx, goal_pix=inp["goal"], **kw)
+    # iteration-0 actions of the full plan vs the numpy Philox restatement
+    full.set_context(ctx)
+    p = cem_params(sp, n_ctx_actions=1, **{k: v for k, v in kw.items()})
+    full.engine.cem_begin(p, inp["goal"].astype(np.float32))
+    full.engine.cem_iter_rollout(0)
+    a0 = full.engine.cem_actions()
+    std = kw["std"]
+    for m in (0, 5):
+        for d in (0, 7, 19):
+            z = OC.philox_normal(kw["seed"], 0, 0, m, d)
+            want = np.clip(std[d % 4] * z, kw["clip"][0][d % 4], kw["clip"][1][d % 4])
+            np.testing.assert_allclose(a0[m, (d // 4) * 3, d % 4], want, rtol=1e-10, atol=1e-14)
+    # two shards
+    halves = [EngineBackend(sp, w, M // 2), EngineBackend(sp, w, M // 2)]
+    for r, b in enumerate(halves):
+        b.set_context(ctx)
+        pr = cem_params(sp, n_ctx_actions=1, global_samples=M, sample_offset=r * (M // 2),
+                        **dict(kw, num_samples=M // 2))
+        b.engine.cem_begin(pr, inp["goal"].astype(np.float32))
+    for it in range(iters):
+        seg = []
+        for r, b in enumerate(halves):
+            b.engine.cem_iter_rollout(it)
+            seg.append(b.engine.cem_scores_read(it, r * (M // 2), M // 2))
+        for r, b in enumerate(halves):
+            b.engine.cem_scores_write(it, (1 - r) * (M // 2), seg[1 - r])
+            b.engine.cem_iter_select(it)
+    outs = [b.engine.cem_finish() for b in halves]
+    for best, eidx, scores in outs:
+        np.testing.assert_array_equal(scores, res["scores"])
+        np.testing.assert_array_equal(eidx, res["elite_idx"])
+        np.testing.assert_array_equal(best, res["best_actions"])
+    for b in halves + [full]:
+        b.engine.close()
+
+
+# ---- policy surface -----------------------------------------------------------------------------------------
+def test_controller_with_foreign_predictor_matches_reference(golden):
+    """The reference's full act() golden, with the (foreign) BlobPredictor returning host arrays and the
+    DEVICE cost kernel scoring them: same sampled actions, scores, elites and chosen action."""
+    from fake_predictor import BlobPredictor
+    from visual_foresight_b200.cem_controller import PixelCostController
+    from visual_foresight_b200.policy import get_policy_args
+    ag = {"adim": 4, "sdim": 4, "image_height": 48, "image_width": 64, "gpu_id": 0}
+    pol = PixelCostController(ag, {"predictor_class": BlobPredictor, "rejection_sampling": False, "verbose": False,
+                                   "num_samples": 24, "minimum_selection": 5}, 0, 1)
+    pol.reset()
+    np.random.seed(42)
+    for t in range(3):
+        obs = {"images": golden["act_images"][:t + 1], "state": golden["act_state"][:t + 1]}
+        out = pol.act(**get_policy_args(pol, obs, t, 0, {"desig_pix": golden["act_desig"], "goal_pix": golden["act_goal"]}))
+        np.testing.assert_allclose(out["actions"], golden["act_t%d_action" % t], rtol=1e-9, atol=1e-12)
+        if t >= 1:
+            for i in range(3):
+                np.testing.assert_allclose(out["plan_stat"]["scores_itr%d" % i], golden["act_t%d_scores_itr%d" % (t, i)], rtol=1e-5)
+            np.testing.assert_array_equal(pol._best_indices, golden["act_t%d_best_indices" % t])
+
+
+def test_controller_device_path_end_to_end():
+    """Policy.act() on the engine (device CEM): contract of the returned dict, determinism, replan gate."""
+    from visual_foresight_b200.cem_controller import PixelCostController
+    from visual_foresight_b200.policy import get_policy_args
+    ag = {"adim": 4, "sdim": 4, "image_height": 32, "image_width": 32, "gpu_id": 0}
+    pp = {"rejection_sampling": False, "verbose": False, "num_samples": 16, "minimum_selection": 4,
+          "model_spec": {"seq_len": 6}, "replan_interval": 2, "cem_seed": 5}
+    rng = np.random.default_rng(0)
+    images = rng.integers(0, 256, (4, 1, 32, 32, 3), dtype=np.uint8)
+    state = rng.uniform(-.5, .5, (4, 4))
+    outs = []
+    for rep in range(2):
+        pol = PixelCostController(ag, dict(pp), 0, 1)
+        pol.reset()
+        acts = []
+        for t in range(4):
+            obs = {"images": images[:t + 1], "state": state[:t + 1]}
+            o = pol.act(**get_policy_args(pol, obs, t, 0, {"desig_pix": np.array([[8, 8]]), "goal_pix": np.array([[24, 20]])}))
+            assert o["actions"].shape == (4,)
+            acts.append(o["actions"].copy())
+            if t == 1:
+                assert sorted(o["plan_stat"]) == ["scores_itr0", "scores_itr1", "scores_itr2"]
+                assert o["plan_stat"]["scores_itr0"].shape == (16,) and np.all(np.isfinite(o["plan_stat"]["scores_itr2"]))
+                first_plan = pol._best_actions.copy()
+            if t == 2:      # replan_interval=2: step 2 replays the plan made at step 1
+                np.testing.assert_array_equal(o["actions"], first_plan[0, 1])
+        assert np.all(acts[0] == 0)
+        outs.append(np.stack(acts))
+        pol.predictor.backend.engine.close()
+    np.testing.assert_array_equal(outs[0], outs[1])

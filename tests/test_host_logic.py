@@ -1,0 +1,172 @@
+"""Host-side mirror of the reference plugin surface (HParams, Policy glue, samplers, CEM controller)
+against outputs of the UNMODIFIED reference code (tests/golden/ref_cem_golden.npz)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from fake_predictor import BlobPredictor
+from oracle.cem import OracleBackend
+from visual_foresight_b200 import samplers as S
+from visual_foresight_b200.cem_controller import PixelCostController
+from visual_foresight_b200.hparams import HParams
+from visual_foresight_b200.policy import NullPolicy, get_policy_args
+
+
+def ghp(**over):
+    d = S.GaussianCEMSampler.get_default_hparams()
+    d.update(replan_interval=0)
+    d.update(over)
+    return HParams(**d)
+
+
+def test_hparams_semantics():
+    hp = HParams(a=1, b=None)
+    with pytest.raises(ValueError):
+        hp.add_hparam("a", 2)
+    with pytest.raises(KeyError):
+        hp.set_hparam("zzz", 2)
+    hp.set_hparam("a", 5)
+    hp.b = [1, 2]
+    assert hp.a == 5 and hp.get("b") == [1, 2] and "a" in hp and "q" not in hp and hp.values() == {"a": 5, "b": [1, 2]}
+    with pytest.raises(AttributeError):
+        hp.nope
+
+
+def test_initial_covariance(golden):
+    for adim in (2, 3, 4, 5):
+        for t in (0, 3):
+            np.testing.assert_array_equal(S.initial_covariance(ghp(reduce_std_dev=0.5), adim, t), golden["sigma0_adim%d_t%d" % (adim, t)])
+    np.testing.assert_array_equal(S.initial_covariance(ghp(action_order=["x", "y", "z", "theta", "grasp"]), 5, 0), golden["sigma0_order"])
+
+
+def test_clip_band_discretize(golden):
+    np.testing.assert_array_equal(S.clip_actions(golden["trunc_in3"].copy(), ghp()), golden["trunc_out3"])
+    np.testing.assert_array_equal(S.clip_actions(golden["trunc_in2"].copy(), ghp()), golden["trunc_out2"])
+    np.testing.assert_array_equal(S.clip_actions(golden["trunc_in3"].copy(), ghp(action_order=["z", "x", "theta", "y"])), golden["trunc_out3_order"])
+    np.testing.assert_array_equal(S.band_mask_covariance(golden["blockdiag_in"], 5, 4), golden["blockdiag_out"])
+    np.testing.assert_array_equal(S.discretize_actions(golden["discretize_in"].copy(), [2, 3]), golden["discretize_out"])
+
+
+def test_shifted_covariance_runs():
+    cov = np.cov(np.random.RandomState(0).randn(40, 20), rowvar=False)
+    out = S.shifted_covariance(cov, 4, ghp(replan_interval=3, reuse_cov=0.25))
+    init = S.initial_covariance(ghp(), 4)
+    np.testing.assert_allclose(out[:-4, :-4], cov[4:, 4:] + 0.25 * init[:-4, :-4])
+    np.testing.assert_allclose(out[-4:, -4:], init[:4, :4])
+    assert np.all(out[-4:, :-4] == 0)
+
+
+def test_gaussian_sampler_streams(golden):
+    smp = S.GaussianCEMSampler(ghp(rejection_sampling=False), 4, 4)
+    np.random.seed(7)
+    np.testing.assert_array_equal(smp.sample_initial_actions(1, 16, None), golden["gauss_init_actions_seed7"])
+    np.random.seed(11)
+    nxt = smp.sample_next_actions(16, golden["gauss_fit_elites"], np.arange(10.0))
+    np.testing.assert_allclose(smp._mean, golden["gauss_fit_mean"], atol=1e-15)
+    np.testing.assert_allclose(smp._sigma, golden["gauss_fit_sigma"], rtol=1e-12, atol=1e-16)
+    np.testing.assert_allclose(nxt, golden["gauss_next_actions_seed11"], rtol=1e-9, atol=1e-12)
+    smp2 = S.GaussianCEMSampler(ghp(rejection_sampling=False, cov_blockdiag=True, smooth_cov=True), 4, 4)
+    np.random.seed(7)
+    smp2.sample_initial_actions(1, 16, None)
+    smp2._fit(golden["gauss_fit_elites"])
+    np.testing.assert_allclose(smp2._sigma, golden["gauss_fit_sigma_blockdiag_smooth"], rtol=1e-12, atol=1e-16)
+
+
+def test_gaussian_reuse_mean(golden):
+    smp = S.GaussianCEMSampler(ghp(rejection_sampling=False, reuse_mean=True), 4, 4)
+    smp.log_best_action(np.zeros(4), golden["gauss_reuse_plan"])
+    np.random.seed(3)
+    a = smp.sample_initial_actions(4, 16, None)
+    np.testing.assert_array_equal(smp._mean, golden["gauss_reuse_mean"])
+    np.testing.assert_array_equal(a, golden["gauss_reuse_actions_seed3"])
+    assert a.shape[0] == 16      # first call: no previous mean -> cold start (reference gaussian_sampler.py:23)
+    b = smp.sample_initial_actions(5, 16, None)      # second call warm-starts from the logged plan
+    assert b.shape[0] == 8       # reuse_factor 0.5
+    plan = golden["gauss_reuse_plan"][0]
+    want = np.zeros((5, 4))
+    want[:5] = np.concatenate([plan, np.zeros((2, 4))])[::3][:5]
+    np.testing.assert_array_equal(smp._mean, want.reshape(-1))
+
+
+def test_rejection_sampler_bounds():
+    smp = S.GaussianCEMSampler(ghp(), 4, 4)
+    np.random.seed(0)
+    a = smp.sample_initial_actions(0, 6, None)
+    assert a.shape == (6, 15, 4)
+    assert np.abs(a[:, :, :2]).max() <= 1.5 * 0.05 and np.abs(a[:, :, 2]).max() <= 1.5 * 0.15
+
+
+def test_correlated_noise_sampler(golden):
+    hp = HParams(**S.CorrelatedNoiseSampler.get_default_hparams())
+    cs = S.CorrelatedNoiseSampler(hp, 4, 4)
+    np.random.seed(5)
+    np.testing.assert_array_equal(cs.sample_initial_actions(1, 12, None), golden["corr_init_seed5"])
+    np.random.seed(6)
+    np.testing.assert_allclose(cs.sample_next_actions(12, golden["corr_best"], golden["corr_scores"]),
+                               golden["corr_next_seed6"], rtol=1e-12, atol=1e-15)
+
+
+def test_policy_arg_resolution():
+    pol = NullPolicy({"adim": 4}, {})
+    assert get_policy_args(pol, {}, 0, 0) == {}
+    assert pol.act()["actions"].shape == (4,)
+
+    class Wants(NullPolicy):
+        def act(self, t, i_tr, images, goal_pix=None, obs=None, extra=7):
+            return {}
+    kw = get_policy_args(Wants({"adim": 2}, {}), {"images": "IM"}, 3, 9, {"goal_pix": "GP"})
+    assert kw == {"t": 3, "i_tr": 9, "images": "IM", "goal_pix": "GP", "obs": {"images": "IM"}, "extra": 7}
+
+
+def test_required_param_raises():
+    class Needs(NullPolicy):
+        def act(self, t, unknown_thing):
+            return {}
+    with pytest.raises(ValueError):
+        get_policy_args(Needs({"adim": 2}, {}), {}, 0, 0, {})
+
+
+class _Injected(BlobPredictor):
+    """BlobPredictor plus the rollout-evaluator backend attribute the controller looks for."""
+    def __init__(self, *a, **k):
+        BlobPredictor.__init__(self, *a, **k)
+        self.backend = OracleBackend(self)
+
+
+AG = {"adim": 4, "sdim": 4, "image_height": 48, "image_width": 64, "gpu_id": 0}
+PP = {"predictor_class": _Injected, "rejection_sampling": False, "verbose": False, "num_samples": 24,
+      "minimum_selection": 5, "device_cem": False}
+
+
+def test_override_semantics(golden):
+    for bad, want in zip(({"iterations": 3}, {"not_a_param": 1}), golden["override_errors"]):
+        with pytest.raises({"ValueError": ValueError, "AttributeError": AttributeError}[str(want)]):
+            PixelCostController(AG, dict(PP, **bad), 0, 1)
+
+
+def test_full_act_matches_reference(golden):
+    """Three MPC steps through get_policy_args -> act() with the seeded global RNG: actions sampled,
+    context handed to the predictor, scores, elite indices and the returned action all equal the
+    reference controller's."""
+    pol = PixelCostController(AG, dict(PP), 0, 1)
+    pol.reset()
+    assert pol._hp.start_planning == int(golden["act_start_planning"])
+    images, state = golden["act_images"], golden["act_state"]
+    np.random.seed(42)
+    for t in range(3):
+        obs = {"images": images[:t + 1], "state": state[:t + 1]}
+        kw = get_policy_args(pol, obs, t, 0, {"desig_pix": golden["act_desig"], "goal_pix": golden["act_goal"]})
+        assert sorted(kw) == sorted(["t", "i_tr", "desig_pix", "goal_pix", "images", "state", "verbose_worker"])
+        out = pol.act(**kw)
+        np.testing.assert_allclose(out["actions"], golden["act_t%d_action" % t], rtol=1e-9, atol=1e-12)
+        if t >= 1:
+            call = pol.predictor.calls[-1]
+            np.testing.assert_allclose(call["actions"], golden["act_t%d_last_actions" % t], rtol=1e-9, atol=1e-12)
+            np.testing.assert_array_equal(call["context_pixel_distributions"], golden["act_t%d_ctx_distrib" % t])
+            np.testing.assert_allclose(call["context_actions"], golden["act_t%d_ctx_actions" % t], rtol=1e-9, atol=1e-12)
+            for i in range(3):
+                np.testing.assert_allclose(out["plan_stat"]["scores_itr%d" % i], golden["act_t%d_scores_itr%d" % (t, i)], rtol=1e-9)
+            np.testing.assert_array_equal(pol._best_indices, golden["act_t%d_best_indices" % t])
+            np.testing.assert_allclose(pol._best_actions, golden["act_t%d_best_actions" % t], rtol=1e-9, atol=1e-12)

@@ -1,0 +1,152 @@
+// cem.cu — CEM sampler / elite selection / Gaussian refit kernels (float64, tiny, latency-bound).
+//
+// Sampling law.  The reference draws x ~ N(mu, Sigma) with np.random.multivariate_normal
+// (gaussian_sampler.py:82).  Iteration 0 has a diagonal Sigma (construct_initial_sigma,
+// controller_utils.py:47-84) so x = mu + sigma .* z.  After a refit on K elites,
+// Sigma = Xc^T Xc / (K-1) (np.cov, gaussian_sampler.py:101) has rank <= K-1, and
+// x = mu + (Xc^T / sqrt(K-1)) z with z in R^K has exactly that law — no factorisation needed.
+// Noise is Philox4x32-10 keyed by (seed; global sample index, draw index, iteration, plan index), so a
+// sample's actions do not depend on how samples are sharded over GPUs; any rank can regenerate
+// any elite's action row, which is what makes the refit communication-free.
+#include "vf_common.cuh"
+
+namespace vf {
+namespace {
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+  const uint32_t n1 = (uint32_t)p1;
+  const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+  const uint32_t n3 = (uint32_t)p0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// standard normal #j of (sample, iteration, plan): Box-Muller on two 32-bit uniforms, float64
+__device__ double philox_normal(uint64_t seed, uint32_t plan, uint32_t iter, uint32_t sample, uint32_t j) {
+  uint32_t c[4] = {sample, j >> 1, iter, plan};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const double u1 = ((double)c[0] + 0.5) * (1.0 / 4294967296.0);
+  const double u2 = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
+  const double r = sqrt(-2.0 * log(u1));
+  const double th = 6.283185307179586476925286766559 * u2;
+  return (j & 1) ? r * sin(th) : r * cos(th);
+}
+
+// thread per (row i, coordinate d)
+__global__ void k_sample_actions(SampleArgs a, int n) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n * a.D) return;
+  const int i = tid / a.D, d = tid % a.D;
+  const int gidx = a.indices ? a.indices[i] : a.offset + i;
+  double x = a.mean[d];
+  if (a.K == 0) {
+    const double z = a.noise ? (double)a.noise[(long long)gidx * a.noise_stride + d]
+                             : philox_normal(a.seed, a.plan_index, a.iteration, (uint32_t)gidx, (uint32_t)d);
+    x += a.std0[d] * z;
+  } else {
+    for (int k = 0; k < a.K; ++k) {
+      const double z = a.noise ? (double)a.noise[(long long)gidx * a.noise_stride + k]
+                               : philox_normal(a.seed, a.plan_index, a.iteration, (uint32_t)gidx, (uint32_t)k);
+      x += a.factor[d * a.K + k] * z;
+    }
+  }
+  const int ad = d % a.adim, na = d / a.adim;
+  x = fmin(fmax(x, a.clip_lo[ad]), a.clip_hi[ad]);       // truncate_movement
+  a.out_nr[(long long)i * a.D + d] = x;
+  const int T = a.nactions * a.repeat;
+  for (int r = 0; r < a.repeat; ++r) {                     // np.repeat(actions, repeat, axis=1)
+    const long long o = ((long long)i * T + na * a.repeat + r) * a.adim + ad;
+    if (a.out_actions) a.out_actions[o] = (float)x;
+    if (a.out_actions64) a.out_actions64[o] = x;
+  }
+}
+
+// strict total order: (score asc, NaN last, index asc) == np.argsort(kind='stable')
+__device__ __forceinline__ bool key_less(double a, int ia, double b, int ib) {
+  const bool na = a != a, nb = b != b;
+  if (na != nb) return nb;
+  if (!na && a != b) return a < b;
+  return ia < ib;
+}
+
+// single block bitonic sort over a power-of-two padded (key, index) array held in global/L2
+__global__ void __launch_bounds__(1024) k_topk(const double* __restrict__ scores, int n, int npad, int k, int* out_idx,
+                                               double* keys, int* idx) {
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+    keys[i] = i < n ? scores[i] : __longlong_as_double(0x7ff0000000000000LL);   // +inf pad
+    idx[i] = i < n ? i : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int size = 2; size <= npad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < npad / 2; t += blockDim.x) {
+        const int lo = (t / stride) * 2 * stride + (t % stride);
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const double ka = keys[lo], kb = keys[hi];
+        const int ia = idx[lo], ib = idx[hi];
+        const bool swap = up ? key_less(kb, ib, ka, ia) : key_less(ka, ia, kb, ib);
+        if (swap) { keys[lo] = kb; keys[hi] = ka; idx[lo] = ib; idx[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) out_idx[i] = idx[i];
+}
+
+// single block.  mean, unbiased covariance (np.cov(rowvar=False, bias=False)), factor = Xc^T / sqrt(K-1)
+__global__ void k_refit(const double* __restrict__ x, int K, int D, double* mean, double* factor, double* cov) {
+  extern __shared__ double sm[];   // [D]
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += x[(long long)k * D + d];
+    sm[d] = s / (double)K;
+    mean[d] = sm[d];
+  }
+  __syncthreads();
+  const double denom = (double)(K > 1 ? K - 1 : 1);
+  const double isq = 1.0 / sqrt(denom);
+  for (int i = threadIdx.x; i < D * K; i += blockDim.x) {
+    const int d = i / K, k = i % K;
+    factor[i] = (x[(long long)k * D + d] - sm[d]) * isq;
+  }
+  if (cov)
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+      const int d = i / D, e = i % D;
+      double s = 0.0;
+      for (int k = 0; k < K; ++k) s += (x[(long long)k * D + d] - sm[d]) * (x[(long long)k * D + e] - sm[e]);
+      cov[i] = s / denom;
+    }
+}
+
+}  // namespace
+
+void launch_sample_actions(const SampleArgs& a, int n, cudaStream_t s) {
+  ++g_launch_counter;
+  const int total = n * a.D;
+  k_sample_actions<<<(total + 127) / 128, 128, 0, s>>>(a, n);
+}
+int topk_padded(int n) {
+  int p = 2;
+  while (p < n) p <<= 1;
+  return p;
+}
+void launch_topk(const double* scores, int n, int k, int* out_idx, double* work_keys, int* work_idx, cudaStream_t s) {
+  ++g_launch_counter;
+  k_topk<<<1, 1024, 0, s>>>(scores, n, topk_padded(n), k, out_idx, work_keys, work_idx);
+}
+void launch_refit(const double* elites_nr, int K, int D, double* mean, double* factor, double* cov, cudaStream_t s) {
+  ++g_launch_counter;
+  k_refit<<<1, 256, D * sizeof(double), s>>>(elites_nr, K, D, mean, factor, cov);
+}
+
+}  // namespace vf

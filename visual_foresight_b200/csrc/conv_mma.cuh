@@ -1,0 +1,33 @@
+// conv_mma.cuh — tcgen05 (5th-gen tensor core) implicit-GEMM convolution: host-side interface.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "vf_common.cuh"
+
+namespace vf {
+
+// fp16 hi/lo split copies of one conv layer's spatial weights, laid out for the UMMA B operand
+struct MmaConvWeights {
+  bool ready = false;
+  int k = 0, cin = 0, cout = 0;
+  __half* w_hi = nullptr;   // [k*k][cout][cin]  (K-major rows), scaled by 2^scale_log2
+  __half* w_lo = nullptr;
+  int scale_log2 = 0;
+};
+
+struct MmaConvCall {
+  View src, out;
+  const float* sabias;
+  const float* bias;
+  int H, W;
+  int passes;   // 3 = hi*hi + lo*hi + hi*lo (fp32-grade), 1 = hi*hi
+};
+
+bool mma_conv_supported(int k, int cin, int cout, int H, int W);
+// returns 0 on success; device allocations are appended to *allocs (owned by the engine handle)
+int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaConvWeights* out,
+                             std::vector<void*>* allocs, std::string* err);
+int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaStream_t s);
+
+}  // namespace vf

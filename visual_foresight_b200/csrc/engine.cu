@@ -1,0 +1,1106 @@
+// engine.cu — the vfengine handle: weight preprocessing, the conv-LSTM/CDNA rollout schedule, costs,
+// the device-resident CEM loop, and the extern "C" boundary declared in include/vfengine.h.
+//
+// Data layout in HBM (per handle, B = max_samples):
+//   ctx_frames  f32 [C][ncam][H][W][3]        context, shared by all samples (sample_stride 0 views)
+//   gen_images  f32 [B][P][ncam][H][W][3]     every predicted frame, reference output layout
+//   gen_distrib f32 [B][P][ncam][H][W][nd]    (vpred_model_interface.py:75-88)
+//   per view / rnn layer: lstm_in [B][h][w][2F]  = [x | h_prev] conv input, c [B][h][w][F]
+//   raw         f32 [B][H*W*Cout max]         conv output scratch (pre-norm)
+//   mask_in     f32 [B][H][W][ngf+3*(nt+3)]   [h_masks | T_0..T_nt-1 | prev | first | scratch]
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vfengine.h"
+#include "vf_common.cuh"
+#include "conv_mma.cuh"
+
+using namespace vf;
+
+namespace {
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct ConvLayer {
+  std::string name;
+  int k = 0, H = 0, W = 0, cin_sp = 0, cin_const = 0, cout = 0;
+  bool lstm = false;
+  float* w_sp = nullptr;    // [k*k][cin_sp][cout]
+  float* wcls = nullptr;    // [k*k][A][cout]
+  float* bias = nullptr;
+  float *gamma = nullptr, *beta = nullptr;          // conv norm  (or gates norm for lstm)
+  float *cgamma = nullptr, *cbeta = nullptr;        // cell norm (lstm)
+  float* sabias = nullptr;  // [B][k*k][cout]
+  MmaConvWeights mma;       // tensor-core operand copies (precision != SIMT)
+};
+
+struct RnnState {
+  float* lstm_in = nullptr;   // [B][h][w][2F]
+  float* c = nullptr;         // [B][h][w][F]
+  int h = 0, w = 0, F = 0;
+};
+
+struct ViewNet {
+  std::vector<ConvLayer> enc_conv, dec_conv;
+  std::vector<ConvLayer> enc_lstm, dec_lstm;     // entries with k == 0 for non-rnn layers
+  std::vector<RnnState> enc_rnn, dec_rnn;
+  ConvLayer scratch0, scratch1, masks0, masks1;
+  float *cdna_w = nullptr, *cdna_b = nullptr;
+};
+
+struct DebugEntry {
+  View v;
+  int H, W;
+};
+
+}  // namespace
+
+struct vf_engine {
+  vf_config cfg;
+  char err[512];
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<void*> allocs;
+  std::map<std::string, HostTensor> host_w;
+  bool weights_ready = false, context_set = false, distrib_set = false, predicted = false;
+  int last_M = 0;
+
+  // derived
+  int B, H, W, ncam, nd, adim, sdim, nz, A, S, C, P, ngf, nt, kc, nm, n_enc;
+  std::vector<ViewNet> views;
+  float *w_state = nullptr, *b_state = nullptr;
+
+  // shared scratch
+  float *raw = nullptr, *dec_in = nullptr, *stats = nullptr, *cstats = nullptr;
+  std::vector<float*> act_enc, act_dec;
+  float *scr_h = nullptr, *mask_in = nullptr, *logits = nullptr, *kern = nullptr, *partial = nullptr;
+  int nblk = 0;
+
+  // context / outputs
+  uint8_t* ctx_u8 = nullptr;
+  float *ctx_frames = nullptr, *ctx_distrib = nullptr, *ctx_states = nullptr, *ctx_actions = nullptr;
+  int n_ctx_actions = 0;
+  int* desig_pix_dev = nullptr;
+  float *gen_images = nullptr, *gen_distrib = nullptr, *gen_states = nullptr;
+  float *sa = nullptr, *state_cur = nullptr, *zs = nullptr;
+  float* actions = nullptr;   // [B][Tcap][adim]
+  int Tcap = 0, T = 0;
+  float* cost = nullptr;      // [B][P][ntask]
+  double *goal_dev = nullptr, *taskw_dev = nullptr;
+  float* goal_img = nullptr;
+  double* scores_tmp = nullptr;   // [B]
+  int* fetch_idx = nullptr;
+  float* fetch_buf = nullptr;
+
+  // CEM
+  vf_cem_params cem;
+  bool cem_active = false;
+  int cem_D = 0, cem_T = 0, cem_Dmax = 0, cem_act_cap = 0;
+  double *cem_mean = nullptr, *cem_factor = nullptr, *cem_std0 = nullptr, *cem_cov = nullptr;
+  double *cem_scores = nullptr;     // [iters][Mg]
+  size_t cem_scores_cap = 0;
+  float* cem_noise = nullptr;
+  size_t cem_noise_cap = 0;
+  bool cem_has_noise = false;
+  int* cem_elite_idx = nullptr;
+  double *cem_elites_nr = nullptr, *cem_best64 = nullptr, *cem_local_nr = nullptr, *cem_actions64 = nullptr;
+  double* topk_keys = nullptr;
+  int* topk_idx = nullptr;
+  size_t topk_cap = 0;
+  float* cem_goal_host_copy = nullptr;
+
+  std::map<std::string, DebugEntry> debug[4];
+
+  // profiling (vf_profile_*)
+  bool prof_on = false;
+  struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_pool;
+};
+
+namespace {
+
+int fail(vf_engine* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(h, VF_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+template <typename T>
+int dalloc(vf_engine* h, T** p, size_t n) {
+  void* q = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) return fail(h, VF_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return VF_OK;
+}
+#define DA(p, n)                          \
+  do {                                    \
+    int r__ = dalloc(h, &(p), (size_t)(n)); \
+    if (r__) return r__;                  \
+  } while (0)
+
+const HostTensor* find_w(vf_engine* h, int view, const std::string& name) {
+  char pre[32];
+  snprintf(pre, sizeof(pre), "view%d.", view);
+  auto it = h->host_w.find(std::string(pre) + name);
+  if (it != h->host_w.end()) return &it->second;
+  if (view == 0) {
+    it = h->host_w.find(name);
+    if (it != h->host_w.end()) return &it->second;
+  }
+  return nullptr;
+}
+
+int upload(vf_engine* h, float** dst, const std::vector<float>& v) {
+  DA(*dst, v.size());
+  CU(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return VF_OK;
+}
+
+// Split an HWIO conv weight into the spatial part [k*k][cin_sp][cout] and the border-class sums of the
+// tiled action/state channels wcls[cls][a][cout] (see conv_simt.cu header).
+int prepare_conv(vf_engine* h, int view, ConvLayer& L) {
+  const int A = L.cin_const, k = L.k, kk = k * k;
+  const HostTensor* w = find_w(h, view, L.name + ".w");
+  if (!w) return fail(h, VF_ERR_STATE, "missing weight view%d.%s.w", view, L.name.c_str());
+  const int cin_total = L.cin_sp + A;
+  if (w->shape.size() != 4 || w->shape[0] != k || w->shape[1] != k || w->shape[2] != cin_total || w->shape[3] != L.cout)
+    return fail(h, VF_ERR_INVALID, "weight %s.w has wrong shape (want %d,%d,%d,%d)", L.name.c_str(), k, k, cin_total, L.cout);
+  // channel order: conv [spatial, sa]; lstm [x, sa, h]
+  const int xch = L.lstm ? L.cin_sp / 2 : L.cin_sp;
+  std::vector<float> wsp((size_t)kk * L.cin_sp * L.cout);
+  for (int t = 0; t < kk; ++t)
+    for (int c = 0; c < L.cin_sp; ++c) {
+      const int src_c = (c < xch) ? c : c + A;
+      memcpy(&wsp[((size_t)t * L.cin_sp + c) * L.cout], &w->data[((size_t)t * cin_total + src_c) * L.cout], L.cout * sizeof(float));
+    }
+  int r = upload(h, &L.w_sp, wsp);
+  if (r) return r;
+  if (A > 0) {
+    const int pad = k / 2;
+    std::vector<float> wc((size_t)kk * A * L.cout);
+    for (int cy = 0; cy < k; ++cy)
+      for (int cx = 0; cx < k; ++cx) {
+        const int yr = cy < pad ? cy : (cy > pad ? L.H - 1 - (k - 1 - cy) : pad);
+        const int xr = cx < pad ? cx : (cx > pad ? L.W - 1 - (k - 1 - cx) : pad);
+        for (int a = 0; a < A; ++a)
+          for (int n = 0; n < L.cout; ++n) {
+            double s = 0.0;
+            for (int dy = 0; dy < k; ++dy) {
+              const int yy = yr + dy - pad;
+              if (yy < 0 || yy >= L.H) continue;
+              for (int dx = 0; dx < k; ++dx) {
+                const int xx = xr + dx - pad;
+                if (xx < 0 || xx >= L.W) continue;
+                s += (double)w->data[((size_t)(dy * k + dx) * cin_total + xch + a) * L.cout + n];
+              }
+            }
+            wc[((size_t)(cy * k + cx) * A + a) * L.cout + n] = (float)s;
+          }
+      }
+    r = upload(h, &L.wcls, wc);
+    if (r) return r;
+    DA(L.sabias, (size_t)h->B * kk * L.cout);
+  }
+  auto opt = [&](const char* suffix, float** dst, int n) -> int {
+    const HostTensor* t = find_w(h, view, L.name + suffix);
+    if (!t) return fail(h, VF_ERR_STATE, "missing weight view%d.%s%s", view, L.name.c_str(), suffix);
+    if ((int)t->data.size() != n) return fail(h, VF_ERR_INVALID, "weight %s%s has %zu elements, want %d", L.name.c_str(), suffix, t->data.size(), n);
+    return upload(h, dst, t->data);
+  };
+  if (L.lstm) {
+    if ((r = opt(".gates_gamma", &L.gamma, L.cout))) return r;
+    if ((r = opt(".gates_beta", &L.beta, L.cout))) return r;
+    if ((r = opt(".cell_gamma", &L.cgamma, L.cout / 4))) return r;
+    if ((r = opt(".cell_beta", &L.cbeta, L.cout / 4))) return r;
+  } else {
+    if ((r = opt(".b", &L.bias, L.cout))) return r;
+    if (find_w(h, view, L.name + ".gamma")) {
+      if ((r = opt(".gamma", &L.gamma, L.cout))) return r;
+      if ((r = opt(".beta", &L.beta, L.cout))) return r;
+    }
+  }
+  if (h->cfg.precision != VF_PREC_FP32_SIMT && mma_conv_supported(L.k, L.cin_sp, L.cout, L.H, L.W)) {
+    std::string e;
+    if (mma_conv_prepare_weights(wsp.data(), L.k, L.cin_sp, L.cout, &L.mma, &h->allocs, &e))
+      return fail(h, VF_ERR_CUDA, "mma weight prep %s: %s", L.name.c_str(), e.c_str());
+  }
+  return VF_OK;
+}
+
+ConvLayer mk(const std::string& name, int k, int H, int W, int cin_sp, int cin_const, int cout, bool lstm) {
+  ConvLayer L;
+  L.name = name; L.k = k; L.H = H; L.W = W; L.cin_sp = cin_sp; L.cin_const = cin_const; L.cout = cout; L.lstm = lstm;
+  return L;
+}
+
+int build_net(vf_engine* h) {
+  const vf_config& c = h->cfg;
+  const int n = c.n_enc, A = h->A, B = h->B;
+  h->views.resize(h->ncam);
+  size_t raw_max = 0, decin_max = 0, cmax = 0, fmax_ = 0;
+  auto upd = [&](const ConvLayer& L) {
+    raw_max = std::max(raw_max, (size_t)L.H * L.W * L.cout);
+    cmax = std::max(cmax, (size_t)L.cout);
+  };
+  for (int v = 0; v < h->ncam; ++v) {
+    ViewNet& net = h->views[v];
+    int hh = h->H, ww = h->W, cprev = 6;
+    std::vector<int> enc_out;
+    net.enc_lstm.resize(n); net.enc_rnn.resize(n); net.dec_lstm.resize(n); net.dec_rnn.resize(n);
+    for (int i = 0; i < n; ++i) {
+      const int oc = c.enc_channels[i];
+      char nm[64];
+      snprintf(nm, sizeof(nm), "enc%d.conv", i);
+      net.enc_conv.push_back(mk(nm, i == 0 ? 5 : 3, hh, ww, cprev, A, oc, false));
+      upd(net.enc_conv.back());
+      hh /= 2; ww /= 2;
+      if (c.enc_rnn[i]) {
+        snprintf(nm, sizeof(nm), "enc%d.lstm", i);
+        net.enc_lstm[i] = mk(nm, c.lstm_ksize, hh, ww, 2 * oc, A, 4 * oc, true);
+        upd(net.enc_lstm[i]);
+        RnnState& r = net.enc_rnn[i];
+        r.h = hh; r.w = ww; r.F = oc;
+        DA(r.lstm_in, (size_t)B * hh * ww * 2 * oc);
+        DA(r.c, (size_t)B * hh * ww * oc);
+        fmax_ = std::max(fmax_, (size_t)oc);
+      }
+      enc_out.push_back(oc);
+      cprev = oc;
+    }
+    for (int i = 0; i < n; ++i) {
+      const int oc = c.dec_channels[i];
+      const int cin = cprev + (i > 0 ? enc_out[n - 1 - i] : 0);
+      hh *= 2; ww *= 2;
+      decin_max = std::max(decin_max, (size_t)hh * ww * cin);
+      char nm[64];
+      snprintf(nm, sizeof(nm), "dec%d.conv", i);
+      net.dec_conv.push_back(mk(nm, 3, hh, ww, cin, A, oc, false));
+      upd(net.dec_conv.back());
+      if (c.dec_rnn[i]) {
+        snprintf(nm, sizeof(nm), "dec%d.lstm", i);
+        net.dec_lstm[i] = mk(nm, c.lstm_ksize, hh, ww, 2 * oc, A, 4 * oc, true);
+        upd(net.dec_lstm[i]);
+        RnnState& r = net.dec_rnn[i];
+        r.h = hh; r.w = ww; r.F = oc;
+        DA(r.lstm_in, (size_t)B * hh * ww * 2 * oc);
+        DA(r.c, (size_t)B * hh * ww * oc);
+        fmax_ = std::max(fmax_, (size_t)oc);
+      }
+      cprev = oc;
+    }
+    const int g = h->ngf;
+    net.scratch0 = mk("scratch.conv0", 3, h->H, h->W, g, 0, g, false);
+    net.scratch1 = mk("scratch.conv1", 3, h->H, h->W, g, 0, 3, false);
+    net.masks0 = mk("masks.conv0", 3, h->H, h->W, g, 0, g, false);
+    net.masks1 = mk("masks.conv1", 3, h->H, h->W, g + 3 * h->nm, 0, h->nm, false);
+    upd(net.scratch0);
+  }
+  // shared scratch (first view's shapes == all views' shapes)
+  DA(h->raw, (size_t)B * raw_max);
+  DA(h->dec_in, (size_t)B * decin_max);
+  DA(h->stats, (size_t)B * cmax * 2);
+  DA(h->cstats, (size_t)B * std::max(fmax_, (size_t)1) * 2);
+  h->act_enc.assign(n, nullptr);
+  h->act_dec.assign(n, nullptr);
+  {
+    int hh = h->H, ww = h->W;
+    for (int i = 0; i < n; ++i) {
+      hh /= 2; ww /= 2;
+      if (!c.enc_rnn[i]) DA(h->act_enc[i], (size_t)B * hh * ww * c.enc_channels[i]);
+    }
+    for (int i = 0; i < n; ++i) {
+      hh *= 2; ww *= 2;
+      if (!c.dec_rnn[i]) DA(h->act_dec[i], (size_t)B * hh * ww * c.dec_channels[i]);
+    }
+  }
+  const size_t px = (size_t)h->H * h->W;
+  DA(h->scr_h, (size_t)B * px * h->ngf);
+  DA(h->mask_in, (size_t)B * px * (h->ngf + 3 * h->nm));
+  DA(h->logits, (size_t)B * px * h->nm);
+  DA(h->kern, (size_t)B * h->nt * h->kc * h->kc);
+  h->nblk = composite_blocks(h->H, h->W);
+  DA(h->partial, (size_t)B * h->nd * h->nblk);
+  return VF_OK;
+}
+
+int finalize_weights(vf_engine* h) {
+  if (h->weights_ready) return VF_OK;
+  for (int v = 0; v < h->ncam; ++v) {
+    ViewNet& net = h->views[v];
+    int r;
+    for (auto& L : net.enc_conv) if ((r = prepare_conv(h, v, L))) return r;
+    for (auto& L : net.dec_conv) if ((r = prepare_conv(h, v, L))) return r;
+    for (auto& L : net.enc_lstm) if (L.k && (r = prepare_conv(h, v, L))) return r;
+    for (auto& L : net.dec_lstm) if (L.k && (r = prepare_conv(h, v, L))) return r;
+    if ((r = prepare_conv(h, v, net.scratch0))) return r;
+    if ((r = prepare_conv(h, v, net.scratch1))) return r;
+    if ((r = prepare_conv(h, v, net.masks0))) return r;
+    if ((r = prepare_conv(h, v, net.masks1))) return r;
+    const HostTensor* cw = find_w(h, v, "cdna.dense.w");
+    const HostTensor* cb = find_w(h, v, "cdna.dense.b");
+    if (!cw || !cb) return fail(h, VF_ERR_STATE, "missing weight view%d.cdna.dense.{w,b}", v);
+    const int nout = h->kc * h->kc * h->nt;
+    const RnnState& sm = net.enc_rnn[h->n_enc - 1];
+    const size_t feat = (size_t)(h->H >> h->n_enc) * (h->W >> h->n_enc) * h->cfg.enc_channels[h->n_enc - 1];
+    (void)sm;
+    if (cw->data.size() != feat * nout || (int)cb->data.size() != nout)
+      return fail(h, VF_ERR_INVALID, "cdna.dense has wrong shape (want %zu x %d)", feat, nout);
+    if ((r = upload(h, &net.cdna_w, cw->data))) return r;
+    if ((r = upload(h, &net.cdna_b, cb->data))) return r;
+  }
+  if (h->sdim > 0) {
+    const HostTensor* sw = find_w(h, 0, "state.dense.w");
+    const HostTensor* sb = find_w(h, 0, "state.dense.b");
+    if (!sw || !sb) return fail(h, VF_ERR_STATE, "missing weight state.dense.{w,b}");
+    if ((int)sw->data.size() != (h->adim + h->sdim) * h->sdim || (int)sb->data.size() != h->sdim)
+      return fail(h, VF_ERR_INVALID, "state.dense has wrong shape");
+    int r;
+    if ((r = upload(h, &h->w_state, sw->data))) return r;
+    if ((r = upload(h, &h->b_state, sb->data))) return r;
+  }
+  h->host_w.clear();
+  h->weights_ready = true;
+  return VF_OK;
+}
+
+View dense_view(float* p, int hw, int C) { return make_view(p, (long long)hw * C, C, 0, C); }
+
+void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act);
+
+cudaEvent_t prof_event(vf_engine* h) {
+  if (!h->prof_pool.empty()) { cudaEvent_t e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void run_conv(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act = ACT_NONE) {
+  if (!h->prof_on) { run_conv_impl(h, L, s0, s1, out, B, act); return; }
+  vf_engine::ProfRec r;
+  r.a = prof_event(h); r.b = prof_event(h);
+  r.cls = L.lstm ? 0 : 1;
+  r.flops = 2.0 * B * L.H * L.W * L.k * L.k * (double)L.cin_sp * L.cout;
+  cudaEventRecord(r.a, h->stream);
+  run_conv_impl(h, L, s0, s1, out, B, act);
+  cudaEventRecord(r.b, h->stream);
+  h->prof.push_back(r);
+}
+
+void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act) {
+  if (h->cfg.precision != VF_PREC_FP32_SIMT && L.mma.ready) {
+    MmaConvCall c;
+    c.src = s0; c.out = out; c.sabias = L.sabias; c.bias = L.bias; c.H = L.H; c.W = L.W;
+    c.passes = (h->cfg.precision == VF_PREC_F16X3) ? 3 : 1;
+    mma_conv_launch(L.mma, c, B, h->stream);
+    return;
+  }
+  ConvArgs a;
+  a.src0 = s0; a.src1 = s1; a.w = L.w_sp; a.bias = L.bias; a.sabias = L.sabias; a.out = out;
+  a.H = L.H; a.W = L.W; a.Cin = L.cin_sp; a.Cout = L.cout; a.k = L.k; a.act = act;
+  launch_conv_simt(a, B, h->stream);
+}
+
+void run_lstm(vf_engine* h, int v, const ConvLayer& L, RnnState& r, int B, const std::string& dbg) {
+  const int hw = r.h * r.w, F = r.F;
+  View in = dense_view(r.lstm_in, hw, 2 * F);
+  View gates = dense_view(h->raw, hw, 4 * F);
+  View none = make_view(nullptr, 0, 0, 0, 0);
+  run_conv(h, L, in, none, gates, B);
+  launch_plane_stats(gates, B, r.h, r.w, 0, h->cfg.norm_eps, h->stats, h->stream);
+  launch_lstm_gates(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->stream);
+  launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cfg.norm_eps, h->cstats, h->stream);
+  View hv = make_view(r.lstm_in, (long long)hw * 2 * F, 2 * F, F, F);
+  launch_lstm_out(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cstats, L.cgamma, L.cbeta, r.c, hv, h->stream);
+  h->debug[v][dbg + ".h"] = DebugEntry{hv, r.h, r.w};
+  h->debug[v][dbg + ".c"] = DebugEntry{dense_view(r.c, hw, F), r.h, r.w};
+}
+
+// one cell step of one view (spec P1-P8)
+void run_step(vf_engine* h, int v, int tau, int B) {
+  const vf_config& c = h->cfg;
+  ViewNet& net = h->views[v];
+  const int n = h->n_enc, H = h->H, W = h->W, nd = h->nd;
+  const long long px = (long long)H * W;
+  View none = make_view(nullptr, 0, 0, 0, 0);
+  // P1 inputs
+  View image, distrib;
+  if (tau < h->C) {
+    image = make_view(h->ctx_frames + ((long long)tau * h->ncam + v) * px * 3, 0, 3, 0, 3);
+    distrib = make_view(h->ctx_distrib + ((long long)tau * h->ncam + v) * px * nd, 0, nd, 0, nd);
+  } else {
+    const int t = tau - h->C;
+    image = make_view(h->gen_images + ((long long)t * h->ncam + v) * px * 3, (long long)h->P * h->ncam * px * 3, 3, 0, 3);
+    distrib = make_view(h->gen_distrib + ((long long)t * h->ncam + v) * px * nd, (long long)h->P * h->ncam * px * nd, nd, 0, nd);
+  }
+  View first = make_view(h->ctx_frames + (long long)v * px * 3, 0, 3, 0, 3);
+  View first_d = make_view(h->ctx_distrib + (long long)v * px * nd, 0, nd, 0, nd);
+
+  // per-layer border-class bias of the tiled action/state vector
+  auto sab = [&](ConvLayer& L) {
+    if (L.k && L.wcls) launch_sabias(h->sa, h->A, L.wcls, L.bias, L.k * L.k, L.cout, B, L.sabias, h->stream);
+  };
+  for (int i = 0; i < n; ++i) { sab(net.enc_conv[i]); sab(net.enc_lstm[i]); sab(net.dec_conv[i]); sab(net.dec_lstm[i]); }
+
+  // P2 encoder
+  std::vector<View> enc_out(n);
+  std::vector<int> enc_h(n), enc_w(n);
+  View x0 = image, x1 = first;
+  int hh = H, ww = W;
+  for (int i = 0; i < n; ++i) {
+    ConvLayer& L = net.enc_conv[i];
+    const int oc = L.cout;
+    View rawv = dense_view(h->raw, hh * ww, oc);
+    run_conv(h, L, x0, x1, rawv, B);
+    hh /= 2; ww /= 2;
+    launch_plane_stats(rawv, B, hh, ww, 1, c.norm_eps, h->stats, h->stream);
+    View dst = c.enc_rnn[i] ? make_view(net.enc_rnn[i].lstm_in, (long long)hh * ww * 2 * oc, 2 * oc, 0, oc)
+                            : dense_view(h->act_enc[i], hh * ww, oc);
+    launch_norm_act(rawv, B, hh, ww, 1, h->stats, L.gamma, L.beta, ACT_RELU, dst, h->stream);
+    h->debug[v][L.name] = DebugEntry{dst, hh, ww};
+    View out = dst;
+    if (c.enc_rnn[i]) {
+      run_lstm(h, v, net.enc_lstm[i], net.enc_rnn[i], B, net.enc_lstm[i].name);
+      out = make_view(net.enc_rnn[i].lstm_in, (long long)hh * ww * 2 * oc, 2 * oc, oc, oc);
+    }
+    enc_out[i] = out; enc_h[i] = hh; enc_w[i] = ww;
+    x0 = out; x1 = none;
+  }
+  // P4 decoder
+  View x = enc_out[n - 1];
+  for (int i = 0; i < n; ++i) {
+    ConvLayer& L = net.dec_conv[i];
+    const int oc = L.cout;
+    View skip = i > 0 ? enc_out[n - 1 - i] : none;
+    View din = dense_view(h->dec_in, 4 * hh * ww, x.C + skip.C);
+    launch_upsample2x(x, skip, B, hh, ww, din, h->stream);
+    hh *= 2; ww *= 2;
+    View rawv = dense_view(h->raw, hh * ww, oc);
+    run_conv(h, L, din, none, rawv, B);
+    launch_plane_stats(rawv, B, hh, ww, 0, c.norm_eps, h->stats, h->stream);
+    View dst = c.dec_rnn[i] ? make_view(net.dec_rnn[i].lstm_in, (long long)hh * ww * 2 * oc, 2 * oc, 0, oc)
+                            : dense_view(h->act_dec[i], hh * ww, oc);
+    launch_norm_act(rawv, B, hh, ww, 0, h->stats, L.gamma, L.beta, ACT_RELU, dst, h->stream);
+    h->debug[v][L.name] = DebugEntry{dst, hh, ww};
+    x = dst;
+    if (c.dec_rnn[i]) {
+      run_lstm(h, v, net.dec_lstm[i], net.dec_rnn[i], B, net.dec_lstm[i].name);
+      x = make_view(net.dec_rnn[i].lstm_in, (long long)hh * ww * 2 * oc, 2 * oc, oc, oc);
+    }
+  }
+  if (tau < h->C - 1) return;   // warm-up step: its prediction is never consumed
+  const int t_out = tau - (h->C - 1);
+  const int g = h->ngf, nm = h->nm, cm = g + 3 * nm;
+  View h_last = x;
+  // P5/P6
+  launch_cdna_kernels(enc_out[n - 1], enc_h[n - 1] * enc_w[n - 1], net.cdna_w, net.cdna_b, h->kc, h->nt, B, h->kern, h->stream);
+  View mask_in = dense_view(h->mask_in, (int)px, cm);
+  launch_cdna_apply(image, first, h->kern, h->kc, h->nt, B, H, W, mask_in, g, h->stream);
+  // P7 scratch image
+  View rawg = dense_view(h->raw, (int)px, g);
+  run_conv(h, net.scratch0, h_last, none, rawg, B);
+  launch_plane_stats(rawg, B, H, W, 0, c.norm_eps, h->stats, h->stream);
+  View scr = dense_view(h->scr_h, (int)px, g);
+  launch_norm_act(rawg, B, H, W, 0, h->stats, net.scratch0.gamma, net.scratch0.beta, ACT_RELU, scr, h->stream);
+  View scratch_out = make_view(h->mask_in, px * cm, cm, g + 3 * (h->nt + 2), 3);
+  run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
+  // P8 masks
+  run_conv(h, net.masks0, h_last, none, rawg, B);
+  launch_plane_stats(rawg, B, H, W, 0, c.norm_eps, h->stats, h->stream);
+  View hm = make_view(h->mask_in, px * cm, cm, 0, g);
+  launch_norm_act(rawg, B, H, W, 0, h->stats, net.masks0.gamma, net.masks0.beta, ACT_RELU, hm, h->stream);
+  View lg = dense_view(h->logits, (int)px, nm);
+  run_conv(h, net.masks1, mask_in, none, lg, B);
+  CompositeArgs ca;
+  ca.logits = lg;
+  ca.layers = make_view(h->mask_in, px * cm, cm, g, 3 * nm);
+  ca.prev_d = distrib; ca.first_d = first_d; ca.kern = h->kern;
+  ca.gen_image = make_view(h->gen_images + ((long long)t_out * h->ncam + v) * px * 3, (long long)h->P * h->ncam * px * 3, 3, 0, 3);
+  ca.gen_distrib = make_view(h->gen_distrib + ((long long)t_out * h->ncam + v) * px * nd, (long long)h->P * h->ncam * px * nd, nd, 0, nd);
+  ca.partial = h->partial; ca.nt = h->nt; ca.ksize = h->kc; ca.nd = nd; ca.H = H; ca.W = W;
+  launch_composite(ca, B, h->stream);
+  launch_distrib_normalize(ca.gen_distrib, h->partial, h->nblk, B, H, W, nd, h->stream);
+  h->debug[v]["scratch"] = DebugEntry{scratch_out, H, W};
+  h->debug[v]["mask_logits"] = DebugEntry{lg, H, W};
+  h->debug[v]["gen_image"] = DebugEntry{ca.gen_image, H, W};
+  h->debug[v]["gen_distrib"] = DebugEntry{ca.gen_distrib, H, W};
+  h->debug[v]["cdna.kernels"] = DebugEntry{make_view(h->kern, (long long)h->nt * h->kc * h->kc, h->nt * h->kc * h->kc, 0, h->nt * h->kc * h->kc), 1, 1};
+  h->debug[v]["dec_last"] = DebugEntry{h_last, H, W};
+}
+
+// rolls S-1 cell steps for M samples whose actions are in h->actions [M][T][adim]
+int rollout(vf_engine* h, int M, int T) {
+  if (!h->weights_ready) { int r = finalize_weights(h); if (r) return r; }
+  if (!h->context_set) return fail(h, VF_ERR_STATE, "vf_set_context must be called before predicting");
+  if (!h->distrib_set) return fail(h, VF_ERR_STATE, "no designated-pixel distribution: pass pix_distrib to vf_set_context or call vf_set_desig");
+  const int need = h->S - 1 - h->n_ctx_actions;
+  if (T < need) return fail(h, VF_ERR_INVALID, "need %d actions per sample (S-1-n_ctx_actions), got T=%d", need, T);
+  for (auto& net : h->views) {
+    for (auto& r : net.enc_rnn) if (r.c) {
+      CU(cudaMemsetAsync(r.c, 0, (size_t)M * r.h * r.w * r.F * sizeof(float), h->stream));
+      CU(cudaMemsetAsync(r.lstm_in, 0, (size_t)M * r.h * r.w * 2 * r.F * sizeof(float), h->stream));
+    }
+    for (auto& r : net.dec_rnn) if (r.c) {
+      CU(cudaMemsetAsync(r.c, 0, (size_t)M * r.h * r.w * r.F * sizeof(float), h->stream));
+      CU(cudaMemsetAsync(r.lstm_in, 0, (size_t)M * r.h * r.w * 2 * r.F * sizeof(float), h->stream));
+    }
+  }
+  SaArgs sa;
+  sa.actions = h->actions; sa.T = T; sa.adim = h->adim; sa.sdim = h->sdim; sa.nz = h->nz;
+  sa.n_ctx_actions = h->n_ctx_actions; sa.C = h->C; sa.ctx_actions = h->ctx_actions; sa.ctx_states = h->ctx_states;
+  sa.zs = h->nz ? h->zs : nullptr; sa.w_state = h->w_state; sa.b_state = h->b_state; sa.state_cur = h->state_cur;
+  sa.sa = h->sa; sa.gen_states_all = h->sdim ? h->gen_states : nullptr; sa.P = h->P;
+  for (int tau = 0; tau < h->S - 1; ++tau) {
+    launch_build_sa(sa, M, tau, h->stream);
+    for (int v = 0; v < h->ncam; ++v) run_step(h, v, tau, M);
+  }
+  CU(cudaGetLastError());
+  h->predicted = true;
+  h->last_M = M;
+  return VF_OK;
+}
+
+int ensure_actions(vf_engine* h, int T) {
+  if (T > h->Tcap) {
+    DA(h->actions, (size_t)h->B * T * h->adim);
+    h->Tcap = T;
+  }
+  return VF_OK;
+}
+
+int score_device(vf_engine* h, int cost_kind, const float* goal, const float* task_weights, float finalweight,
+                 const float* distrib, int M, int P, double* scores_dev) {
+  const int ntask = h->ncam * h->nd;
+  if (cost_kind == VF_COST_PIXEL_DISTANCE) {
+    double g[VF_MAX_TASKS * 2], tw[VF_MAX_TASKS];
+    for (int i = 0; i < ntask * 2; ++i) g[i] = (double)goal[i];
+    for (int i = 0; i < ntask; ++i) tw[i] = task_weights ? (double)task_weights[i] : 1.0 / ntask;
+    CU(cudaMemcpyAsync(h->goal_dev, g, sizeof(double) * ntask * 2, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->taskw_dev, tw, sizeof(double) * ntask, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // g/tw live on this stack frame
+    launch_pixel_cost(distrib, M, P, h->ncam, h->H, h->W, h->nd, h->goal_dev, h->cost, h->stream);
+    launch_score_final(h->cost, M, P, ntask, h->taskw_dev, (double)finalweight, scores_dev, h->stream);
+  } else if (cost_kind == VF_COST_GOAL_IMAGE) {
+    const size_t n = (size_t)h->ncam * h->H * h->W * 3;
+    CU(cudaMemcpyAsync(h->goal_img, goal, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    launch_goal_image_cost(h->gen_images, M, P, h->ncam, h->H, h->W, h->goal_img, scores_dev, h->stream);
+  } else {
+    return fail(h, VF_ERR_INVALID, "unknown cost kind %d", cost_kind);
+  }
+  CU(cudaGetLastError());
+  return VF_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int vf_abi_version(void) { return VF_ABI_VERSION; }
+
+const char* vf_last_error(const vf_engine* h) { return h ? h->err : "null handle"; }
+
+int vf_create(const vf_config* cfg, vf_engine** out) {
+  if (!cfg || !out) return VF_ERR_INVALID;
+  *out = nullptr;
+  vf_engine* h = new vf_engine();
+  h->err[0] = 0;
+  h->cfg = *cfg;
+  *out = h;   // returned even on failure so the caller can read vf_last_error, then vf_destroy
+  if (cfg->abi_version != VF_ABI_VERSION) return fail(h, VF_ERR_INVALID, "ABI version %d != %d", cfg->abi_version, VF_ABI_VERSION);
+  h->B = cfg->max_samples; h->H = cfg->height; h->W = cfg->width; h->ncam = cfg->ncam; h->nd = cfg->ndesig;
+  h->adim = cfg->adim; h->sdim = cfg->sdim; h->nz = cfg->nz; h->A = cfg->adim + cfg->sdim + cfg->nz;
+  h->S = cfg->seq_len; h->C = cfg->context_frames; h->P = h->S - h->C; h->ngf = cfg->ngf;
+  h->nt = cfg->num_transformed; h->kc = cfg->cdna_ksize; h->nm = h->nt + 3; h->n_enc = cfg->n_enc;
+  if (h->B < 1 || h->H < 8 || h->W < 8 || h->ncam < 1 || h->ncam > 4 || h->nd < 1 || h->nd > 4 || h->ncam * h->nd > VF_MAX_TASKS)
+    return fail(h, VF_ERR_INVALID, "bad sizes (max_samples %d, %dx%d, ncam %d, ndesig %d)", h->B, h->H, h->W, h->ncam, h->nd);
+  if (h->adim < 1 || h->adim > 8 || h->sdim < 0 || h->sdim > 16 || h->nz < 0) return fail(h, VF_ERR_INVALID, "bad adim/sdim/nz");
+  if (h->C < 1 || h->S <= h->C) return fail(h, VF_ERR_INVALID, "need seq_len > context_frames >= 1");
+  if (cfg->n_enc < 1 || cfg->n_enc > VF_MAX_LAYERS || cfg->n_dec != cfg->n_enc) return fail(h, VF_ERR_INVALID, "n_enc/n_dec");
+  if ((h->H % (1 << cfg->n_enc)) || (h->W % (1 << cfg->n_enc))) return fail(h, VF_ERR_INVALID, "H, W must be divisible by 2^n_enc");
+  if ((h->H >> cfg->n_enc) < 4 || (h->W >> cfg->n_enc) < 4) return fail(h, VF_ERR_INVALID, "coarsest feature map must be at least 4x4");
+  if (cfg->dec_channels[cfg->n_dec - 1] != cfg->ngf) return fail(h, VF_ERR_INVALID, "last decoder layer must have ngf channels");
+  if (!cfg->enc_rnn[cfg->n_enc - 1]) return fail(h, VF_ERR_INVALID, "the last encoder layer must be recurrent (CDNA feature)");
+  if (h->nt < 1 || h->nt > 8 || h->kc * h->kc * h->nt > 128 || (h->kc % 2) == 0 || (cfg->lstm_ksize != 5 && cfg->lstm_ksize != 3))
+    return fail(h, VF_ERR_INVALID, "unsupported CDNA/LSTM kernel configuration");
+  if (cfg->precision < 0 || cfg->precision > VF_PREC_F16X1) return fail(h, VF_ERR_INVALID, "bad precision");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(h, VF_ERR_CUDA, "no CUDA device available (%s): vfengine has no CPU path", cudaGetErrorString(e));
+  CU(cudaSetDevice(cfg->device));
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  int r = build_net(h);
+  if (r) return r;
+  const size_t px = (size_t)h->H * h->W;
+  DA(h->ctx_u8, (size_t)h->C * h->ncam * px * 3);
+  DA(h->ctx_frames, (size_t)h->C * h->ncam * px * 3);
+  DA(h->ctx_distrib, (size_t)h->C * h->ncam * px * h->nd);
+  DA(h->ctx_states, (size_t)h->C * std::max(h->sdim, 1));
+  DA(h->ctx_actions, (size_t)std::max(h->S, 1) * h->adim);
+  DA(h->desig_pix_dev, (size_t)h->ncam * h->nd * 2);
+  DA(h->gen_images, (size_t)h->B * h->P * h->ncam * px * 3);
+  DA(h->gen_distrib, (size_t)h->B * h->P * h->ncam * px * h->nd);
+  DA(h->gen_states, (size_t)h->B * h->P * std::max(h->sdim, 1));
+  DA(h->sa, (size_t)h->B * h->A);
+  DA(h->state_cur, (size_t)h->B * std::max(h->sdim, 1));
+  if (h->nz) DA(h->zs, (size_t)h->B * (h->S - 1) * h->nz);
+  DA(h->cost, (size_t)h->B * h->P * h->ncam * h->nd);
+  DA(h->goal_dev, VF_MAX_TASKS * 2);
+  DA(h->taskw_dev, VF_MAX_TASKS);
+  DA(h->goal_img, (size_t)h->ncam * px * 3);
+  DA(h->scores_tmp, (size_t)h->B);
+  DA(h->fetch_idx, (size_t)h->B);
+  return VF_OK;
+}
+
+int vf_destroy(vf_engine* h) {
+  if (!h) return VF_OK;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return VF_OK;
+}
+
+int vf_set_stream(vf_engine* h, void* s) {
+  if (!h) return VF_ERR_INVALID;
+  if (h->stream) CU(cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (s) { h->stream = (cudaStream_t)s; h->own_stream = false; }
+  else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  return VF_OK;
+}
+
+int vf_synchronize(vf_engine* h) {
+  if (!h) return VF_ERR_INVALID;
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+int vf_load_weights(vf_engine* h, const vf_tensor* t, int32_t n) {
+  if (!h || (!t && n > 0)) return VF_ERR_INVALID;
+  if (h->weights_ready) return fail(h, VF_ERR_STATE, "weights already finalised for this handle");
+  for (int i = 0; i < n; ++i) {
+    if (!t[i].name || !t[i].data || t[i].dtype != VF_F32 || t[i].ndim < 1 || t[i].ndim > 6)
+      return fail(h, VF_ERR_INVALID, "tensor %d is malformed", i);
+    HostTensor ht;
+    size_t cnt = 1;
+    for (int d = 0; d < t[i].ndim; ++d) { ht.shape.push_back(t[i].shape[d]); cnt *= (size_t)t[i].shape[d]; }
+    ht.data.assign((const float*)t[i].data, (const float*)t[i].data + cnt);
+    h->host_w[t[i].name] = std::move(ht);
+  }
+  return VF_OK;
+}
+
+int vf_set_context(vf_engine* h, const uint8_t* frames, const float* states, const float* ctx_actions, int32_t nca,
+                   const float* pix_distrib) {
+  if (!h || !frames) return fail(h, VF_ERR_INVALID, "frames_u8 is required");
+  if (h->sdim > 0 && !states) return fail(h, VF_ERR_INVALID, "states required when sdim > 0");
+  if (nca < 0 || nca > h->S - 1 || (nca > 0 && !ctx_actions)) return fail(h, VF_ERR_INVALID, "bad n_ctx_actions %d", nca);
+  const size_t px = (size_t)h->H * h->W, nf = (size_t)h->C * h->ncam * px * 3;
+  CU(cudaMemcpyAsync(h->ctx_u8, frames, nf, cudaMemcpyHostToDevice, h->stream));
+  launch_u8_to_f32(h->ctx_u8, h->ctx_frames, (long long)nf, 255.0f, h->stream);
+  if (h->sdim > 0) CU(cudaMemcpyAsync(h->ctx_states, states, sizeof(float) * h->C * h->sdim, cudaMemcpyHostToDevice, h->stream));
+  if (nca > 0) CU(cudaMemcpyAsync(h->ctx_actions, ctx_actions, sizeof(float) * nca * h->adim, cudaMemcpyHostToDevice, h->stream));
+  h->n_ctx_actions = nca;
+  if (pix_distrib) {
+    CU(cudaMemcpyAsync(h->ctx_distrib, pix_distrib, sizeof(float) * h->C * h->ncam * px * h->nd, cudaMemcpyHostToDevice, h->stream));
+    h->distrib_set = true;
+  }
+  CU(cudaStreamSynchronize(h->stream));   // caller buffers may be pageable / short-lived
+  h->context_set = true;
+  return VF_OK;
+}
+
+int vf_set_desig(vf_engine* h, const float* desig) {
+  if (!h || !desig) return VF_ERR_INVALID;
+  int pix[VF_MAX_TASKS * 2];
+  for (int i = 0; i < h->ncam * h->nd; ++i) {
+    // np.clip(desig, 0, [H-1, W-1]).astype(int): truncation toward zero of the clipped float
+    float y = desig[2 * i], x = desig[2 * i + 1];
+    y = fminf(fmaxf(y, 0.f), (float)(h->H - 1));
+    x = fminf(fmaxf(x, 0.f), (float)(h->W - 1));
+    pix[2 * i] = (int)y;
+    pix[2 * i + 1] = (int)x;
+  }
+  const size_t n = (size_t)h->C * h->ncam * h->H * h->W * h->nd;
+  CU(cudaMemsetAsync(h->ctx_distrib, 0, n * sizeof(float), h->stream));
+  CU(cudaMemcpyAsync(h->desig_pix_dev, pix, sizeof(int) * h->ncam * h->nd * 2, cudaMemcpyHostToDevice, h->stream));
+  launch_onehot(h->ctx_distrib, h->C, h->ncam, h->H, h->W, h->nd, h->desig_pix_dev, h->stream);
+  CU(cudaStreamSynchronize(h->stream));
+  h->distrib_set = true;
+  return VF_OK;
+}
+
+int vf_predict(vf_engine* h, const float* actions, int32_t M, int32_t T, const float* zs, float* of, float* od, float* os) {
+  if (!h || !actions) return fail(h, VF_ERR_INVALID, "actions is required");
+  if (M < 1 || M > h->B) return fail(h, VF_ERR_INVALID, "M=%d outside [1, max_samples=%d]", M, h->B);
+  if (h->nz > 0 && !zs) return fail(h, VF_ERR_INVALID, "zs required when nz > 0");
+  int r = ensure_actions(h, T);
+  if (r) return r;
+  CU(cudaMemcpyAsync(h->actions, actions, sizeof(float) * (size_t)M * T * h->adim, cudaMemcpyHostToDevice, h->stream));
+  if (h->nz) CU(cudaMemcpyAsync(h->zs, zs, sizeof(float) * (size_t)M * (h->S - 1) * h->nz, cudaMemcpyHostToDevice, h->stream));
+  h->T = T;
+  r = rollout(h, M, T);
+  if (r) return r;
+  const size_t px = (size_t)h->H * h->W;
+  if (of) CU(cudaMemcpyAsync(of, h->gen_images, sizeof(float) * (size_t)M * h->P * h->ncam * px * 3, cudaMemcpyDeviceToHost, h->stream));
+  if (od) CU(cudaMemcpyAsync(od, h->gen_distrib, sizeof(float) * (size_t)M * h->P * h->ncam * px * h->nd, cudaMemcpyDeviceToHost, h->stream));
+  if (os && h->sdim) CU(cudaMemcpyAsync(os, h->gen_states, sizeof(float) * (size_t)M * h->P * h->sdim, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+int vf_score(vf_engine* h, int32_t kind, const float* goal, const float* tw, float fw, double* out) {
+  if (!h || !goal || !out) return fail(h, VF_ERR_INVALID, "goal and out_scores are required");
+  if (!h->predicted) return fail(h, VF_ERR_STATE, "vf_score before vf_predict");
+  int r = score_device(h, kind, goal, tw, fw, h->gen_distrib, h->last_M, h->P, h->scores_tmp);
+  if (r) return r;
+  CU(cudaMemcpyAsync(out, h->scores_tmp, sizeof(double) * h->last_M, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+int vf_score_external(vf_engine* h, const float* distrib, int32_t M, int32_t P, const float* goal, const float* tw,
+                      float fw, double* out) {
+  if (!h || !distrib || !goal || !out) return fail(h, VF_ERR_INVALID, "null argument");
+  if (M < 1 || P < 1 || M > h->B || (long long)M * P > (long long)h->B * h->P) return fail(h, VF_ERR_INVALID, "M*P exceeds capacity");
+  const size_t n = (size_t)M * P * h->ncam * h->H * h->W * h->nd;
+  CU(cudaMemcpyAsync(h->gen_distrib, distrib, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  h->predicted = false;   // gen_distrib no longer holds a rollout
+  double* sc = h->scores_tmp;
+  int r = score_device(h, VF_COST_PIXEL_DISTANCE, goal, tw, fw, h->gen_distrib, M, P, sc);
+  if (r) return r;
+  CU(cudaMemcpyAsync(out, sc, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+int vf_fetch(vf_engine* h, const int32_t* idx, int32_t n, float* of, float* od) {
+  if (!h || !idx || n < 1) return VF_ERR_INVALID;
+  if (!h->predicted) return fail(h, VF_ERR_STATE, "vf_fetch before a rollout");
+  const size_t px = (size_t)h->H * h->W;
+  const size_t rf = (size_t)h->P * h->ncam * px * 3, rd = (size_t)h->P * h->ncam * px * h->nd;
+  for (int i = 0; i < n; ++i) {
+    if (idx[i] < 0 || idx[i] >= h->last_M) return fail(h, VF_ERR_INVALID, "index %d out of range", idx[i]);
+    if (of) CU(cudaMemcpyAsync(of + (size_t)i * rf, h->gen_images + (size_t)idx[i] * rf, rf * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (od) CU(cudaMemcpyAsync(od + (size_t)i * rd, h->gen_distrib + (size_t)idx[i] * rd, rd * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+// ---- CEM -----------------------------------------------------------------------------------------
+
+static void fill_sample_args(vf_engine* h, SampleArgs& a, int iteration) {
+  const vf_cem_params& p = h->cem;
+  a.D = h->cem_D; a.nactions = p.nactions; a.adim = h->adim; a.repeat = p.repeat;
+  a.K = iteration == 0 ? 0 : p.num_elites;
+  a.mean = h->cem_mean; a.factor = h->cem_factor; a.std0 = h->cem_std0;
+  a.noise = h->cem_has_noise ? h->cem_noise + (size_t)iteration * p.global_samples * h->cem_Dmax : nullptr;
+  a.noise_stride = h->cem_Dmax;
+  a.indices = nullptr; a.offset = p.sample_offset;
+  for (int i = 0; i < 8; ++i) {
+    a.clip_lo[i] = p.action_bound ? (double)p.clip_lo[i] : -INFINITY;
+    a.clip_hi[i] = p.action_bound ? (double)p.clip_hi[i] : INFINITY;
+  }
+  a.seed = p.seed; a.plan_index = p.plan_index; a.iteration = (uint32_t)iteration;
+  a.out_nr = nullptr; a.out_actions = nullptr; a.out_actions64 = nullptr;
+}
+
+int vf_cem_begin(vf_engine* h, const vf_cem_params* p, const float* goal, const float* noise) {
+  if (!h || !p || !goal) return fail(h, VF_ERR_INVALID, "params and goal are required");
+  const int M = p->num_samples, Mg = p->global_samples, K = p->num_elites;
+  if (M < 1 || M > h->B) return fail(h, VF_ERR_INVALID, "num_samples=%d outside [1, max_samples=%d]", M, h->B);
+  if (Mg < M || p->sample_offset < 0 || p->sample_offset + M > Mg) return fail(h, VF_ERR_INVALID, "bad shard (offset %d, M %d, global %d)", p->sample_offset, M, Mg);
+  if (K < 1 || K > Mg) return fail(h, VF_ERR_INVALID, "num_elites=%d outside [1, %d]", K, Mg);
+  if (p->iterations < 1 || p->nactions < 1 || p->repeat < 1) return fail(h, VF_ERR_INVALID, "bad iterations/nactions/repeat");
+  const int D = p->nactions * h->adim;
+  if (D > 128) return fail(h, VF_ERR_INVALID, "nactions*adim=%d > 128", D);
+  if (p->n_ctx_actions != h->n_ctx_actions) return fail(h, VF_ERR_INVALID, "n_ctx_actions (%d) differs from vf_set_context (%d)", p->n_ctx_actions, h->n_ctx_actions);
+  h->cem = *p;
+  h->cem_D = D; h->cem_T = p->nactions * p->repeat; h->cem_Dmax = std::max(D, K);
+  int r = ensure_actions(h, h->cem_T);
+  if (r) return r;
+  if (!h->cem_mean) {
+    DA(h->cem_mean, 128); DA(h->cem_std0, 128); DA(h->cem_cov, 128 * 128);
+  }
+  // per-call sized buffers (grow only)
+  const size_t need_scores = (size_t)p->iterations * Mg;
+  if (need_scores > h->cem_scores_cap) { DA(h->cem_scores, need_scores); h->cem_scores_cap = need_scores; }
+  const size_t npad = (size_t)topk_padded(Mg);
+  if (npad > h->topk_cap) {
+    DA(h->topk_keys, npad); DA(h->topk_idx, npad); h->topk_cap = npad;
+    DA(h->cem_elite_idx, Mg);
+    DA(h->cem_factor, (size_t)128 * Mg); DA(h->cem_elites_nr, (size_t)Mg * 128);
+    DA(h->cem_best64, (size_t)Mg * 128 * 8);
+  }
+  if (!h->cem_local_nr) { DA(h->cem_local_nr, (size_t)h->B * 128); }
+  if (h->cem_T > h->cem_act_cap) { DA(h->cem_actions64, (size_t)h->B * h->cem_T * h->adim); h->cem_act_cap = h->cem_T; }
+  if ((size_t)K * h->cem_T * h->adim > (size_t)Mg * 128 * 8) return fail(h, VF_ERR_INVALID, "elite buffer too small");
+  h->cem_has_noise = noise != nullptr;
+  if (noise) {
+    const size_t nn = (size_t)p->iterations * Mg * h->cem_Dmax;
+    if (nn > h->cem_noise_cap) { DA(h->cem_noise, nn); h->cem_noise_cap = nn; }
+    CU(cudaMemcpyAsync(h->cem_noise, noise, nn * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  double mean[128], std0[128];
+  for (int d = 0; d < D; ++d) {
+    mean[d] = p->use_mean0 ? (double)p->mean0[d] : 0.0;
+    double s = (double)p->initial_std[d % h->adim];
+    // construct_initial_sigma scales the VARIANCE of all but the last action block (controller_utils.py:76-81)
+    if (p->reduce_std_scale != 1.0f && d < (p->nactions - 1) * h->adim) s *= sqrt((double)p->reduce_std_scale);
+    std0[d] = s;
+  }
+  CU(cudaMemcpyAsync(h->cem_mean, mean, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->cem_std0, std0, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+  // goal / task weights
+  const int ntask = h->ncam * h->nd;
+  if (p->cost_kind == VF_COST_PIXEL_DISTANCE) {
+    double g[VF_MAX_TASKS * 2], tw[VF_MAX_TASKS];
+    double wsum = 0;
+    for (int i = 0; i < ntask; ++i) wsum += p->task_weights[i];
+    for (int i = 0; i < ntask * 2; ++i) g[i] = (double)goal[i];
+    for (int i = 0; i < ntask; ++i) tw[i] = wsum > 0 ? (double)p->task_weights[i] : 1.0 / ntask;
+    CU(cudaMemcpyAsync(h->goal_dev, g, sizeof(double) * ntask * 2, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->taskw_dev, tw, sizeof(double) * ntask, cudaMemcpyHostToDevice, h->stream));
+  } else if (p->cost_kind == VF_COST_GOAL_IMAGE) {
+    CU(cudaMemcpyAsync(h->goal_img, goal, sizeof(float) * (size_t)h->ncam * h->H * h->W * 3, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    return fail(h, VF_ERR_INVALID, "unknown cost kind");
+  }
+  CU(cudaStreamSynchronize(h->stream));   // host staging arrays above are on this stack frame
+  h->cem_active = true;
+  return VF_OK;
+}
+
+int vf_cem_iter_rollout(vf_engine* h, int32_t it) {
+  if (!h || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
+  const vf_cem_params& p = h->cem;
+  if (it < 0 || it >= p.iterations) return fail(h, VF_ERR_INVALID, "iteration %d out of range", it);
+  SampleArgs a;
+  fill_sample_args(h, a, it);
+  a.out_nr = h->cem_local_nr; a.out_actions = h->actions; a.out_actions64 = h->cem_actions64;
+  launch_sample_actions(a, p.num_samples, h->stream);
+  h->T = h->cem_T;
+  int r = rollout(h, p.num_samples, h->cem_T);
+  if (r) return r;
+  double* sc = h->cem_scores + (size_t)it * p.global_samples + p.sample_offset;
+  const int ntask = h->ncam * h->nd;
+  if (p.cost_kind == VF_COST_PIXEL_DISTANCE) {
+    launch_pixel_cost(h->gen_distrib, p.num_samples, h->P, h->ncam, h->H, h->W, h->nd, h->goal_dev, h->cost, h->stream);
+    launch_score_final(h->cost, p.num_samples, h->P, ntask, h->taskw_dev, (double)p.finalweight, sc, h->stream);
+  } else {
+    launch_goal_image_cost(h->gen_images, p.num_samples, h->P, h->ncam, h->H, h->W, h->goal_img, sc, h->stream);
+  }
+  CU(cudaGetLastError());
+  return VF_OK;
+}
+
+int vf_cem_iter_select(vf_engine* h, int32_t it) {
+  if (!h || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
+  const vf_cem_params& p = h->cem;
+  if (it < 0 || it >= p.iterations) return fail(h, VF_ERR_INVALID, "iteration %d out of range", it);
+  const int K = p.num_elites;
+  launch_topk(h->cem_scores + (size_t)it * p.global_samples, p.global_samples, K, h->cem_elite_idx, h->topk_keys, h->topk_idx, h->stream);
+  // regenerate the elites' action rows from their global indices (no exchange of actions between ranks)
+  SampleArgs a;
+  fill_sample_args(h, a, it);
+  a.indices = h->cem_elite_idx;
+  a.out_nr = h->cem_elites_nr; a.out_actions64 = h->cem_best64;
+  launch_sample_actions(a, K, h->stream);
+  if (it < p.iterations - 1) launch_refit(h->cem_elites_nr, K, h->cem_D, h->cem_mean, h->cem_factor, nullptr, h->stream);
+  CU(cudaGetLastError());
+  return VF_OK;
+}
+
+int vf_cem_finish(vf_engine* h, double* best, int32_t* eidx, double* scores) {
+  if (!h || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
+  const vf_cem_params& p = h->cem;
+  if (best) CU(cudaMemcpyAsync(best, h->cem_best64, sizeof(double) * (size_t)p.num_elites * h->cem_T * h->adim, cudaMemcpyDeviceToHost, h->stream));
+  if (eidx) CU(cudaMemcpyAsync(eidx, h->cem_elite_idx, sizeof(int) * p.num_elites, cudaMemcpyDeviceToHost, h->stream));
+  if (scores) CU(cudaMemcpyAsync(scores, h->cem_scores, sizeof(double) * (size_t)p.iterations * p.global_samples, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+int vf_cem_scores_dev(vf_engine* h, void** dev) {
+  if (!h || !dev || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
+  *dev = h->cem_scores;
+  return VF_OK;
+}
+
+int vf_cem_scores_read(vf_engine* h, int32_t it, int32_t off, int32_t n, double* out) {
+  if (!h || !out || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
+  if (it < 0 || it >= h->cem.iterations || off < 0 || n < 1 || off + n > h->cem.global_samples) return fail(h, VF_ERR_INVALID, "bad score segment");
+  CU(cudaMemcpyAsync(out, h->cem_scores + (size_t)it * h->cem.global_samples + off, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+int vf_cem_scores_write(vf_engine* h, int32_t it, int32_t off, int32_t n, const double* in) {
+  if (!h || !in || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
+  if (it < 0 || it >= h->cem.iterations || off < 0 || n < 1 || off + n > h->cem.global_samples) return fail(h, VF_ERR_INVALID, "bad score segment");
+  CU(cudaMemcpyAsync(h->cem_scores + (size_t)it * h->cem.global_samples + off, in, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+int vf_cem_actions(vf_engine* h, double* out) {
+  if (!h || !out || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
+  CU(cudaMemcpyAsync(out, h->cem_actions64, sizeof(double) * (size_t)h->cem.num_samples * h->cem_T * h->adim, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+int vf_cem_plan(vf_engine* h, const vf_cem_params* p, const float* goal, const float* noise, double* best, int32_t* eidx,
+                double* scores) {
+  int r = vf_cem_begin(h, p, goal, noise);
+  if (r) return r;
+  if (p->global_samples != p->num_samples)
+    return fail(h, VF_ERR_INVALID, "vf_cem_plan is the single-rank form; sharded plans use begin/iter_rollout/<all-gather>/iter_select/finish");
+  for (int it = 0; it < p->iterations; ++it) {
+    if ((r = vf_cem_iter_rollout(h, it))) return r;
+    if ((r = vf_cem_iter_select(h, it))) return r;
+  }
+  return vf_cem_finish(h, best, eidx, scores);
+}
+
+int vf_topk(vf_engine* h, const double* scores, int32_t n, int32_t k, int32_t* out) {
+  if (!h || !scores || !out || n < 1 || k < 1 || k > n) return fail(h, VF_ERR_INVALID, "bad topk arguments");
+  double *ds, *keys;
+  int *idx, *oi;
+  const int npad = topk_padded(n);
+  DA(ds, n); DA(keys, npad); DA(idx, npad); DA(oi, k);
+  CU(cudaMemcpyAsync(ds, scores, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  launch_topk(ds, n, k, oi, keys, idx, h->stream);
+  CU(cudaMemcpyAsync(out, oi, sizeof(int) * k, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+int vf_refit(vf_engine* h, const double* elites, int32_t K, int32_t nactions, int32_t repeat, int32_t adim, double* om,
+             double* oc, double* of) {
+  if (!h || !elites || K < 1 || nactions < 1 || repeat < 1 || adim < 1) return fail(h, VF_ERR_INVALID, "bad refit arguments");
+  const int D = nactions * adim, T = nactions * repeat;
+  if (D > 128) return fail(h, VF_ERR_INVALID, "D > 128");
+  // _fit_gaussians keeps the LAST action of every repeat group (gaussian_sampler.py:97-99)
+  std::vector<double> nr((size_t)K * D);
+  for (int k = 0; k < K; ++k)
+    for (int a = 0; a < nactions; ++a)
+      for (int d = 0; d < adim; ++d) nr[((size_t)k * nactions + a) * adim + d] = elites[((size_t)k * T + a * repeat + repeat - 1) * adim + d];
+  double *dx, *dm, *df, *dc;
+  DA(dx, (size_t)K * D); DA(dm, D); DA(df, (size_t)D * K); DA(dc, (size_t)D * D);
+  CU(cudaMemcpyAsync(dx, nr.data(), sizeof(double) * K * D, cudaMemcpyHostToDevice, h->stream));
+  launch_refit(dx, K, D, dm, df, dc, h->stream);
+  if (om) CU(cudaMemcpyAsync(om, dm, sizeof(double) * D, cudaMemcpyDeviceToHost, h->stream));
+  if (oc) CU(cudaMemcpyAsync(oc, dc, sizeof(double) * D * D, cudaMemcpyDeviceToHost, h->stream));
+  if (of) CU(cudaMemcpyAsync(of, df, sizeof(double) * D * K, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+// ---- debug -----------------------------------------------------------------------------------------
+
+int vf_debug_conv2d(vf_engine* h, int32_t impl, const float* x, const float* w, const float* bias, int32_t B, int32_t H,
+                    int32_t W, int32_t Cin, int32_t Cout, int32_t k, float* y) {
+  if (!h || !x || !w || !y || (k != 3 && k != 5)) return fail(h, VF_ERR_INVALID, "bad conv arguments");
+  float *dx, *dw, *db = nullptr, *dy;
+  const size_t nx = (size_t)B * H * W * Cin, nw = (size_t)k * k * Cin * Cout, ny = (size_t)B * H * W * Cout;
+  DA(dx, nx); DA(dw, nw); DA(dy, ny);
+  CU(cudaMemcpyAsync(dx, x, nx * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(dw, w, nw * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (bias) { DA(db, Cout); CU(cudaMemcpyAsync(db, bias, Cout * sizeof(float), cudaMemcpyHostToDevice, h->stream)); }
+  View vx = make_view(dx, (long long)H * W * Cin, Cin, 0, Cin), vy = make_view(dy, (long long)H * W * Cout, Cout, 0, Cout);
+  if (impl == VF_PREC_FP32_SIMT) {
+    ConvArgs a;
+    a.src0 = vx; a.src1 = make_view(nullptr, 0, 0, 0, 0); a.w = dw; a.bias = db; a.sabias = nullptr; a.out = vy;
+    a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.k = k; a.act = ACT_NONE;
+    launch_conv_simt(a, B, h->stream);
+  } else {
+    if (!mma_conv_supported(k, Cin, Cout, H, W)) return fail(h, VF_ERR_UNSUPPORTED, "shape not supported by the tcgen05 conv");
+    MmaConvWeights mw;
+    std::string e;
+    std::vector<float> wh(w, w + nw);
+    if (mma_conv_prepare_weights(wh.data(), k, Cin, Cout, &mw, &h->allocs, &e)) return fail(h, VF_ERR_CUDA, "mma weight prep: %s", e.c_str());
+    MmaConvCall c;
+    c.src = vx; c.out = vy; c.sabias = nullptr; c.bias = db; c.H = H; c.W = W; c.passes = impl == VF_PREC_F16X3 ? 3 : 1;
+    if (mma_conv_launch(mw, c, B, h->stream)) return fail(h, VF_ERR_CUDA, "mma conv launch failed");
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(y, dy, ny * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return VF_OK;
+}
+
+int64_t vf_debug_fetch(vf_engine* h, const char* name, int32_t view, float* out, int64_t cap) {
+  if (!h || !name || view < 0 || view >= h->ncam) return VF_ERR_INVALID;
+  auto it = h->debug[view].find(name);
+  if (it == h->debug[view].end()) return fail(h, VF_ERR_INVALID, "no debug tensor '%s'", name);
+  const DebugEntry& d = it->second;
+  const int M = h->last_M;
+  const int64_t n = (int64_t)M * d.H * d.W * d.v.C;
+  if (!out) return n;
+  if (cap < n) return fail(h, VF_ERR_INVALID, "capacity %lld < %lld", (long long)cap, (long long)n);
+  const size_t rowbytes = (size_t)d.v.C * sizeof(float);
+  for (int b = 0; b < M; ++b) {
+    cudaError_t e = cudaMemcpy2DAsync(out + (size_t)b * d.H * d.W * d.v.C, rowbytes,
+                                      d.v.p + (size_t)b * d.v.sample_stride + d.v.ch_off, (size_t)d.v.pix_stride * sizeof(float),
+                                      rowbytes, (size_t)d.H * d.W, cudaMemcpyDeviceToHost, h->stream);
+    if (e != cudaSuccess) return fail(h, VF_ERR_CUDA, "debug fetch: %s", cudaGetErrorString(e));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return n;
+}
+
+int vf_profile_enable(vf_engine* h, int32_t on) {
+  if (!h) return VF_ERR_INVALID;
+  CU(cudaStreamSynchronize(h->stream));
+  for (auto& r : h->prof) { h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b); }
+  h->prof.clear();
+  h->prof_on = on != 0;
+  return VF_OK;
+}
+
+int vf_profile_read(vf_engine* h, double* ms, double* flops, int64_t* launches, int32_t nclass) {
+  if (!h || !ms || !flops || !launches || nclass < 2) return VF_ERR_INVALID;
+  CU(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < nclass; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+  for (auto& r : h->prof) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t; flops[r.cls] += r.flops; launches[r.cls] += 1;
+  }
+  return VF_OK;
+}
+
+int64_t vf_launch_count(const vf_engine* h) { (void)h; return g_launch_counter; }
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+// pointwise.cu — instance-norm statistics, normalise+activation, conv-LSTM pointwise, bilinear x2
+// upsample, and the action/state vector with its per-layer border-class bias.  All HBM/L2-bound:
+// threads run along the channel dimension (NHWC innermost) so every warp access is contiguous.
+#include "vf_common.cuh"
+
+namespace vf {
+namespace {
+
+__device__ __forceinline__ const float* vptr(const View& v, int b, long long pix) {
+  return v.p + (long long)b * v.sample_stride + pix * v.pix_stride + v.ch_off;
+}
+
+__device__ __forceinline__ float pooled(const View& x, int b, int W, int pool, int y, int xx, int c) {
+  if (!pool) return __ldg(vptr(x, b, (long long)y * W + xx) + c);
+  const int Wi = W * 2;
+  const float* p00 = vptr(x, b, (long long)(2 * y) * Wi + 2 * xx) + c;
+  const float a = __ldg(p00), bq = __ldg(p00 + x.pix_stride);
+  const float cq = __ldg(p00 + (long long)Wi * x.pix_stride), d = __ldg(p00 + (long long)(Wi + 1) * x.pix_stride);
+  return ((a + bq) + (cq + d)) * 0.25f;
+}
+
+// grid (B, ceil(C/32)), block (32, 8).  Two passes (mean, then centred variance) like the oracle's
+// instance norm; fixed summation order -> bit-reproducible, independent of sample count and GPU count.
+__global__ void k_plane_stats(View x, int H, int W, int pool, float eps, float* stats) {
+  const int b = blockIdx.x;
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  const int npix = H * W;
+  __shared__ float red[8][33];
+  const bool ok = c < x.C;
+  float s = 0.f;
+  if (ok)
+    for (int p = threadIdx.y; p < npix; p += 8) s += pooled(x, b, W, pool, p / W, p % W, c);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mean += red[i][threadIdx.x];
+  mean /= (float)npix;
+  __syncthreads();
+  float v = 0.f;
+  if (ok)
+    for (int p = threadIdx.y; p < npix; p += 8) {
+      const float d = pooled(x, b, W, pool, p / W, p % W, c) - mean;
+      v = fmaf(d, d, v);
+    }
+  red[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  if (threadIdx.y == 0 && ok) {
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) var += red[i][threadIdx.x];
+    var /= (float)npix;
+    stats[((long long)b * x.C + c) * 2 + 0] = mean;
+    stats[((long long)b * x.C + c) * 2 + 1] = 1.0f / sqrtf(var + eps);
+  }
+}
+
+__global__ void k_norm_act(View x, int B, int H, int W, int pool, const float* __restrict__ stats,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, int act, View y) {
+  const long long total = (long long)B * H * W * x.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % x.C);
+    const long long pixb = i / x.C;
+    const int pix = (int)(pixb % (H * W));
+    const int b = (int)(pixb / (H * W));
+    const float v = pooled(x, b, W, pool, pix / W, pix % W, c);
+    const float mean = stats[((long long)b * x.C + c) * 2], rstd = stats[((long long)b * x.C + c) * 2 + 1];
+    float o = (v - mean) * rstd * gamma[c] + beta[c];
+    if (act == ACT_RELU) o = fmaxf(o, 0.f);
+    y.p[(long long)b * y.sample_stride + (long long)pix * y.pix_stride + y.ch_off + c] = o;
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+__device__ __forceinline__ float gate_norm(const View& g, int b, long long pix, int ch, const float* gstats,
+                                           const float* gg, const float* gb) {
+  const float v = __ldg(vptr(g, b, pix) + ch);
+  const float* st = gstats + ((long long)b * g.C + ch) * 2;
+  return (v - st[0]) * st[1] * gg[ch] + gb[ch];
+}
+
+// gate order along channels: i, j, f, o   (spec P3)
+__global__ void k_lstm_gates(View gates, int B, int HW, int F, const float* __restrict__ gstats,
+                             const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c) {
+  const long long total = (long long)B * HW * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long long pixb = i / F;
+    const int pix = (int)(pixb % HW);
+    const int b = (int)(pixb / HW);
+    const float gi = gate_norm(gates, b, pix, f, gstats, gg, gb);
+    const float gj = gate_norm(gates, b, pix, F + f, gstats, gg, gb);
+    const float gf = gate_norm(gates, b, pix, 2 * F + f, gstats, gg, gb);
+    c[i] = c[i] * sigmoidf_(gf + fb) + sigmoidf_(gi) * tanhf(gj);
+  }
+}
+
+__global__ void k_lstm_out(View gates, int B, int HW, int F, const float* __restrict__ gstats,
+                           const float* __restrict__ gg, const float* __restrict__ gb,
+                           const float* __restrict__ cstats, const float* __restrict__ cg,
+                           const float* __restrict__ cb, float* c, View h) {
+  const long long total = (long long)B * HW * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long long pixb = i / F;
+    const int pix = (int)(pixb % HW);
+    const int b = (int)(pixb / HW);
+    const float* st = cstats + ((long long)b * F + f) * 2;
+    const float cn = (c[i] - st[0]) * st[1] * cg[f] + cb[f];
+    c[i] = cn;
+    const float go = gate_norm(gates, b, pix, 3 * F + f, gstats, gg, gb);
+    h.p[(long long)b * h.sample_stride + (long long)pix * h.pix_stride + h.ch_off + f] = tanhf(cn) * sigmoidf_(go);
+  }
+}
+
+// PyTorch upsample_bilinear2d(align_corners=False, scale 2): src = max(0.5*(dst+0.5)-0.5, 0)
+__device__ __forceinline__ void bil_idx(int d, int n, int& i0, int& i1, float& l0, float& l1) {
+  float src = 0.5f * ((float)d + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  i1 = i0 + ((i0 < n - 1) ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__global__ void k_upsample2x(View s0, View s1, int B, int H, int W, View out) {
+  const int C = s0.C + s1.C;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)B * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pixb = i / C;
+    const int pix = (int)(pixb % (Ho * Wo));
+    const int b = (int)(pixb / (Ho * Wo));
+    const int Y = pix / Wo, X = pix % Wo;
+    int y0, y1, x0, x1;
+    float hl0, hl1, wl0, wl1;
+    bil_idx(Y, H, y0, y1, hl0, hl1);
+    bil_idx(X, W, x0, x1, wl0, wl1);
+    const View& s = (c < s0.C) ? s0 : s1;
+    const int cc = (c < s0.C) ? c : c - s0.C;
+    const float v00 = __ldg(vptr(s, b, (long long)y0 * W + x0) + cc), v01 = __ldg(vptr(s, b, (long long)y0 * W + x1) + cc);
+    const float v10 = __ldg(vptr(s, b, (long long)y1 * W + x0) + cc), v11 = __ldg(vptr(s, b, (long long)y1 * W + x1) + cc);
+    out.p[(long long)b * out.sample_stride + (long long)pix * out.pix_stride + out.ch_off + c] =
+        hl0 * (wl0 * v00 + wl1 * v01) + hl1 * (wl0 * v10 + wl1 * v11);
+  }
+}
+
+// sa[m] = concat(action_tau, state_tau[, z_tau]);  gen_state = dense(concat(action, state))   (P1, P9)
+__global__ void k_build_sa(SaArgs a, int M, int tau) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int A = a.adim + a.sdim + a.nz;
+  float* sa = a.sa + (long long)m * A;
+  float act[8], st[16];
+  for (int i = 0; i < a.adim; ++i) {
+    float v;
+    if (tau < a.n_ctx_actions) v = a.ctx_actions[tau * a.adim + i];
+    else v = a.actions[((long long)m * a.T + (tau - a.n_ctx_actions)) * a.adim + i];
+    act[i] = v;
+    sa[i] = v;
+  }
+  for (int i = 0; i < a.sdim; ++i) {
+    const float v = (tau < a.C) ? a.ctx_states[tau * a.sdim + i] : a.state_cur[(long long)m * a.sdim + i];
+    st[i] = v;
+    sa[a.adim + i] = v;
+  }
+  for (int i = 0; i < a.nz; ++i) sa[a.adim + a.sdim + i] = a.zs ? a.zs[((long long)m * (a.P + a.C - 1) + tau) * a.nz + i] : 0.f;
+  for (int j = 0; j < a.sdim; ++j) {
+    float acc = 0.f;
+    for (int i = 0; i < a.adim; ++i) acc = fmaf(act[i], a.w_state[i * a.sdim + j], acc);
+    for (int i = 0; i < a.sdim; ++i) acc = fmaf(st[i], a.w_state[(a.adim + i) * a.sdim + j], acc);
+    acc += a.b_state[j];
+    a.state_cur[(long long)m * a.sdim + j] = acc;
+    if (a.gen_states_all && tau >= a.C - 1) a.gen_states_all[((long long)m * a.P + (tau - (a.C - 1))) * a.sdim + j] = acc;
+  }
+}
+
+__global__ void k_sabias(const float* __restrict__ sa, int A, const float* __restrict__ wcls,
+                         const float* __restrict__ bias, int ncls, int Cout, int B, float* out) {
+  const long long total = (long long)B * ncls * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % Cout);
+    const int cls = (int)((i / Cout) % ncls);
+    const int b = (int)(i / ((long long)Cout * ncls));
+    float acc = 0.f;
+    for (int k = 0; k < A; ++k) acc = fmaf(sa[(long long)b * A + k], __ldg(wcls + ((long long)cls * A + k) * Cout + n), acc);
+    out[i] = acc + (bias ? bias[n] : 0.f);
+  }
+}
+
+__global__ void k_u8_to_f32(const uint8_t* in, float* out, long long n, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (float)in[i] / scale;
+}
+__global__ void k_fill(float* p, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_onehot(float* d, int C, int ncam, int H, int W, int nd, const int* pix) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * ncam * nd) return;
+  const int p = i % nd, cam = (i / nd) % ncam, t = i / (nd * ncam);
+  const int y = pix[(cam * nd + p) * 2], x = pix[(cam * nd + p) * 2 + 1];
+  d[((((long long)t * ncam + cam) * H + y) * W + x) * nd + p] = 1.f;
+}
+__global__ void k_gather_rows(const float* src, long long row, const int* idx, int n, float* dst) {
+  const long long total = (long long)n * row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / row);
+    dst[i] = src[(long long)idx[r] * row + (i % row)];
+  }
+}
+
+inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+void launch_plane_stats(View x, int B, int H, int W, int pool, float eps, float* stats, cudaStream_t s) {
+  ++g_launch_counter;
+  dim3 grid(B, (x.C + 31) / 32), block(32, 8);
+  k_plane_stats<<<grid, block, 0, s>>>(x, H, W, pool, eps, stats);
+}
+void launch_norm_act(View x, int B, int H, int W, int pool, const float* stats, const float* gamma,
+                     const float* beta, int act, View y, cudaStream_t s) {
+  ++g_launch_counter;
+  k_norm_act<<<grid_for((long long)B * H * W * x.C), 256, 0, s>>>(x, B, H, W, pool, stats, gamma, beta, act, y);
+}
+void launch_lstm_gates(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
+                       float fb, float* c, cudaStream_t s) {
+  ++g_launch_counter;
+  k_lstm_gates<<<grid_for((long long)B * HW * F), 256, 0, s>>>(gates, B, HW, F, gstats, gg, gb, fb, c);
+}
+void launch_lstm_out(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
+                     const float* cstats, const float* cg, const float* cb, float* c, View h, cudaStream_t s) {
+  ++g_launch_counter;
+  k_lstm_out<<<grid_for((long long)B * HW * F), 256, 0, s>>>(gates, B, HW, F, gstats, gg, gb, cstats, cg, cb, c, h);
+}
+void launch_upsample2x(View s0, View s1, int B, int H, int W, View out, cudaStream_t s) {
+  ++g_launch_counter;
+  k_upsample2x<<<grid_for((long long)B * 4 * H * W * (s0.C + s1.C)), 256, 0, s>>>(s0, s1, B, H, W, out);
+}
+void launch_build_sa(const SaArgs& a, int M, int tau, cudaStream_t s) {
+  ++g_launch_counter;
+  k_build_sa<<<(M + 127) / 128, 128, 0, s>>>(a, M, tau);
+}
+void launch_sabias(const float* sa, int A, const float* wcls, const float* bias, int ncls, int Cout, int B,
+                   float* out, cudaStream_t s) {
+  ++g_launch_counter;
+  k_sabias<<<grid_for((long long)B * ncls * Cout), 256, 0, s>>>(sa, A, wcls, bias, ncls, Cout, B, out);
+}
+void launch_u8_to_f32(const uint8_t* in, float* out, long long n, float scale, cudaStream_t s) {
+  ++g_launch_counter;
+  k_u8_to_f32<<<grid_for(n), 256, 0, s>>>(in, out, n, scale);
+}
+void launch_fill(float* p, long long n, float v, cudaStream_t s) {
+  ++g_launch_counter;
+  k_fill<<<grid_for(n), 256, 0, s>>>(p, n, v);
+}
+void launch_onehot(float* d, int C, int ncam, int H, int W, int nd, const int* pix, cudaStream_t s) {
+  ++g_launch_counter;
+  k_onehot<<<(C * ncam * nd + 63) / 64, 64, 0, s>>>(d, C, ncam, H, W, nd, pix);
+}
+void launch_gather_rows(const float* src, long long row, const int* idx, int n, float* dst, cudaStream_t s) {
+  ++g_launch_counter;
+  k_gather_rows<<<grid_for((long long)n * row), 256, 0, s>>>(src, row, idx, n, dst);
+}
+
+}  // namespace vf

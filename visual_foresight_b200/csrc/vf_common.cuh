@@ -1,0 +1,147 @@
+// vf_common.cuh — shared types and launcher declarations of the vfengine CUDA kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace vf {
+
+// NHWC activation view: element (b, y, x, c) lives at
+//   p[b * sample_stride + (y * W + x) * pix_stride + ch_off + c]
+// sample_stride == 0 broadcasts one image to every sample (context frames are shared by all
+// action samples — the reference tf.tile()s them per tower, setup_predictor.py:40-44).
+struct View {
+  float* p;
+  long long sample_stride;
+  int pix_stride;
+  int ch_off;
+  int C;
+};
+
+__host__ __device__ inline View make_view(float* p, long long ss, int ps, int co, int C) {
+  View v; v.p = p; v.sample_stride = ss; v.pix_stride = ps; v.ch_off = co; v.C = C; return v;
+}
+
+// border class of pixel coordinate y for a SAME zero-padded k-tap filter (k odd): which taps fall
+// inside the image.  Classes 0..pad-1 = first rows, pad = interior, pad+1..k-1 = last rows.
+__host__ __device__ inline int border_class(int y, int H, int pad) {
+  if (y < pad) return y;
+  if (y >= H - pad) return 2 * pad - (H - 1 - y);
+  return pad;
+}
+
+struct ConvArgs {
+  View src0, src1;        // input channels = src0.C + src1.C (src1.C may be 0)
+  const float* w;         // [k*k][Cin][Cout]
+  const float* bias;      // [Cout] or null
+  const float* sabias;    // [B][k*k classes][Cout] (includes bias) or null
+  View out;               // raw output
+  int H, W, Cin, Cout, k;
+  int act;                // 0 none, 1 sigmoid (small kernel only)
+};
+
+enum { ACT_NONE = 0, ACT_SIGMOID = 1, ACT_RELU = 2 };
+
+// ---- convolution (SIMT fp32) ---------------------------------------------------------------
+void launch_conv_simt(const ConvArgs& a, int B, cudaStream_t s);
+
+// ---- normalisation / pointwise --------------------------------------------------------------
+// stats[(b*C + c)*2 + {0,1}] = mean, rstd of (optionally 2x2 avg-pooled) x over the plane
+void launch_plane_stats(View x, int B, int H, int W, int pool, float eps, float* stats, cudaStream_t s);
+// y = act((pool(x) - mean) * rstd * gamma + beta)
+void launch_norm_act(View x, int B, int H, int W, int pool, const float* stats, const float* gamma,
+                     const float* beta, int act, View y, cudaStream_t s);
+// conv-LSTM pointwise, part 1: c <- c*sigmoid(f+fb) + sigmoid(i)*tanh(j) with gates instance-normalised
+void launch_lstm_gates(View gates, int B, int HW, int F, const float* gstats, const float* ggamma,
+                       const float* gbeta, float forget_bias, float* c, cudaStream_t s);
+// part 2: c <- IN(c);  h <- tanh(c) * sigmoid(IN(o))
+void launch_lstm_out(View gates, int B, int HW, int F, const float* gstats, const float* ggamma,
+                     const float* gbeta, const float* cstats, const float* cgamma, const float* cbeta,
+                     float* c, View h, cudaStream_t s);
+// out[b, 2H, 2W, C0+C1] = bilinear_x2(concat(src0, src1))   (half-pixel centres, edge clamp)
+void launch_upsample2x(View src0, View src1, int B, int H, int W, View out, cudaStream_t s);
+
+// ---- action/state vector and its per-layer border-class bias ----------------------------------
+struct SaArgs {
+  const float* actions;    // [M][T][adim] local samples
+  int T, adim, sdim, nz, n_ctx_actions, C;
+  const float* ctx_actions;  // [n_ctx_actions][adim]
+  const float* ctx_states;   // [C][sdim]
+  const float* zs;           // [M][S-1][nz] or null
+  const float* w_state;      // [(adim+sdim)][sdim]
+  const float* b_state;      // [sdim]
+  float* state_cur;          // [M][sdim]  (gen_state of the previous step, in/out)
+  float* sa;                 // [M][A] out
+  float* gen_states_all;     // [M][P][sdim] or null
+  int P;
+};
+void launch_build_sa(const SaArgs& a, int M, int tau, cudaStream_t s);
+// sabias[b][cls][n] = bias[n] + sum_a sa[b][a] * wcls[cls][a][n]
+void launch_sabias(const float* sa, int A, const float* wcls, const float* bias, int ncls, int Cout,
+                   int B, float* out, cudaStream_t s);
+
+// ---- CDNA ------------------------------------------------------------------------------------
+// kern[b][n][k*k]: dense(feat) + identity, relu-shift, L1 normalise   (spec P5)
+void launch_cdna_kernels(View feat, int npix, const float* w, const float* bias, int ksize, int nt,
+                         int B, float* kern, cudaStream_t s);
+// mask_in[.., base + 3n + c] = T_n(image)[c]; then prev image, first image   (spec P6)
+void launch_cdna_apply(View image, View first, const float* kern, int ksize, int nt, int B, int H, int W,
+                       View mask_in, int base, cudaStream_t s);
+struct CompositeArgs {
+  View logits;            // [B,H,W,n_masks]
+  View layers;            // mask_in view positioned at the first transformed image, C = 3*n_masks
+  View prev_d, first_d;   // distributions [.,H,W,nd]
+  const float* kern;      // [B][nt][k*k]
+  View gen_image;         // out [B,H,W,3]
+  View gen_distrib;       // out raw [B,H,W,nd]
+  float* partial;         // [B][nd][nblk] plane sums of the raw distribution
+  int nt, ksize, nd, H, W;
+};
+int composite_blocks(int H, int W);
+void launch_composite(const CompositeArgs& a, int B, cudaStream_t s);
+// distrib /= sum_hw(distrib)   (renormalize_pixdistrib)
+void launch_distrib_normalize(View d, const float* partial, int nblk, int B, int H, int W, int nd, cudaStream_t s);
+
+// ---- costs -------------------------------------------------------------------------------------
+// cost[m][t][task] = sum(p*d)/sum(p) on distrib (M,P,ncam,H,W,nd);  goal (ncam,nd,2) doubles
+void launch_pixel_cost(const float* distrib, int M, int P, int ncam, int H, int W, int nd,
+                       const double* goal, float* cost, cudaStream_t s);
+// scores[m] = sum_task w_task * (sum_t cost*t_mult) / sum(t_mult)     (float64 like numpy>=2)
+void launch_score_final(const float* cost, int M, int P, int ntask, const double* task_w, double finalweight,
+                        double* scores, cudaStream_t s);
+// scores[m] = mean((frames[m, P-1, cam0] - goal)^2)
+void launch_goal_image_cost(const float* frames, int M, int P, int ncam, int H, int W, const float* goal,
+                            double* scores, cudaStream_t s);
+
+// ---- CEM ---------------------------------------------------------------------------------------
+struct SampleArgs {
+  int D, nactions, adim, repeat, K;   // K = columns of the factor (0 -> diagonal, iteration 0)
+  const double* mean;      // [D]
+  const double* factor;    // [D][K]  (iteration > 0)
+  const double* std0;      // [D]     (iteration 0)
+  const float* noise;      // external standard normals for this iteration or null -> Philox
+  int noise_stride;        // doubles per sample in the noise row
+  const int* indices;      // global sample indices to generate (null -> offset + i)
+  int offset;
+  double clip_lo[8], clip_hi[8];
+  uint64_t seed; uint32_t plan_index; uint32_t iteration;
+  double* out_nr;          // [n][D] non-repeated actions (float64, post clip)
+  float* out_actions;      // [n][T][adim] repeated, f32 (network input) or null
+  double* out_actions64;   // [n][T][adim] or null
+};
+void launch_sample_actions(const SampleArgs& a, int n, cudaStream_t s);
+// stable ascending top-k (ties -> lower index, NaN last) == np.argsort(kind='stable')[:k]
+void launch_topk(const double* scores, int n, int k, int* out_idx, double* work_keys, int* work_idx, cudaStream_t s);
+int topk_padded(int n);
+// mean[D], factor[D][K] = Xc^T / sqrt(K-1), cov[D][D] (unbiased)
+void launch_refit(const double* elites_nr, int K, int D, double* mean, double* factor, double* cov, cudaStream_t s);
+
+// ---- misc --------------------------------------------------------------------------------------
+void launch_u8_to_f32(const uint8_t* in, float* out, long long n, float scale, cudaStream_t s);
+void launch_fill(float* p, long long n, float v, cudaStream_t s);
+void launch_onehot(float* distrib, int C, int ncam, int H, int W, int nd, const int* pix, cudaStream_t s);
+void launch_gather_rows(const float* src, long long row, const int* idx, int n, float* dst, cudaStream_t s);
+
+extern long long g_launch_counter;   // incremented by every launcher
+
+}  // namespace vf
