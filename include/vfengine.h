@@ -98,15 +98,17 @@ typedef struct vf_cem_params {
   int32_t num_elites;               /* K = max(int(selection_frac*M), minimum_selection), cem_base_controller.py:89-91 */
   int32_t nactions, repeat;         /* T = nactions*repeat */
   int32_t action_bound;             /* truncate_movement, controller_utils.py:6-44 */
-  float initial_std[8];             /* per action dim: sqrt of construct_initial_sigma diag, controller_utils.py:47-84 */
-  float clip_lo[8], clip_hi[8];     /* per action dim bounds (+-inf = unbounded) */
-  float mean0[128];                 /* initial mean (nactions*adim), zeros unless reuse_mean */
   int32_t use_mean0;
-  float reduce_std_scale;           /* multiplies std of all but the last action block when t>=2 */
   int32_t cost_kind;                /* enum vf_cost_kind */
-  float finalweight;                /* pixel_cost_controller.py:63,175-176 */
-  float task_weights[VF_MAX_TASKS]; /* per (cam, desig); 1/n reproduces np.mean, pixel_cost_controller.py:153 */
   int32_t n_ctx_actions;            /* context actions prepended to the plan (C-1 for PixelCostController, 0 legacy) */
+  int32_t pad0;
+  /* float64 like the reference's sampler state (gaussian_sampler.py works in float64 throughout) */
+  double initial_std[8];            /* per action dim: sqrt of construct_initial_sigma diag, controller_utils.py:47-84 */
+  double clip_lo[8], clip_hi[8];    /* per action dim bounds (+-inf = unbounded) */
+  double mean0[128];                /* initial mean (nactions*adim), zeros unless reuse_mean */
+  double reduce_std_scale;          /* multiplies the VARIANCE of all but the last action block when t>=2 */
+  double finalweight;               /* pixel_cost_controller.py:63,175-176 */
+  double task_weights[VF_MAX_TASKS];/* per (cam, desig); 1/n reproduces np.mean, pixel_cost_controller.py:153 */
   uint64_t seed;                    /* Philox key */
   uint32_t plan_index;              /* Philox counter word: MPC step */
   int32_t reserved[8];

@@ -57,8 +57,8 @@ def main():
     for gi, goal in enumerate([np.array([36, 48]), np.array([0, 0]), np.array([47.0, 10.0])]):
         G["distgrid_goal%d" % gi] = goal.astype(np.float64)
         G["distgrid_out%d" % gi] = quiet(ctrl._get_distancegrid, goal)
-    agc = dict(ag, image_height=24, image_width=32)          # small planes keep the fixture < 1 MB
-    gen = (rng.rand(8, 13, 1, 24, 32, 2).astype(np.float32) ** 3) + 1e-4
+    agc = dict(ag, image_height=32, image_width=32)          # small planes keep the fixture < 1 MB
+    gen = (rng.rand(8, 13, 1, 32, 32, 2).astype(np.float32) ** 3) + 1e-4
     G["cost_gen_distrib"] = gen
     G["cost_goal_pix"] = np.array([[[18, 24], [5, 7]]])
     ctrl2 = quiet(PixelCostController, agc, dict(pp, designated_pixel_count=2), 0, 1)

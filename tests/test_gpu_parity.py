@@ -74,12 +74,12 @@ def test_pixel_cost_vs_reference_golden(golden):
     """device cost kernel on the reference's own input -> the reference's own scores."""
     from visual_foresight_b200.engine import Engine
     gen = golden["cost_gen_distrib"]
-    e = Engine(S.spec_64(height=24, width=32, ndesig=2, seq_len=15), gen.shape[0])
+    e = Engine(S.spec_64(height=32, width=32, ndesig=2, seq_len=15), gen.shape[0])
     for fw, key in ((10.0, "cost_scores_2desig"), (3.0, "cost_scores_2desig_fw3")):
         sc = e.score_external(gen, golden["cost_goal_pix"], finalweight=fw)
         np.testing.assert_allclose(sc, golden[key], rtol=1e-5)
     # ragged / edge: a single plane, goal outside the image, one-hot distribution
-    one = np.zeros((1, 1, 1, 24, 32, 2), np.float32)
+    one = np.zeros((1, 1, 1, 32, 32, 2), np.float32)
     one[0, 0, 0, 3, 4, 0] = 1
     one[0, 0, 0, 23, 31, 1] = 2
     sc = e.score_external(one, np.array([[[40.0, -3.0], [0, 0]]]), finalweight=10.0)
@@ -300,3 +300,45 @@ def test_controller_device_path_end_to_end():
         outs.append(np.stack(acts))
         pol.predictor.backend.engine.close()
     np.testing.assert_array_equal(outs[0], outs[1])
+
+
+# ---- tcgen05 implicit-GEMM convolution ------------------------------------------------------------------------
+MMA_SHAPES = [(3, 32, 32, 64, 128, 5), (2, 16, 16, 128, 256, 5), (5, 8, 8, 256, 512, 5), (2, 16, 16, 64, 128, 3),
+              (4, 6, 8, 64, 128, 5), (7, 8, 8, 32, 128, 5), (2, 12, 16, 32, 128, 5), (1, 24, 32, 32, 128, 3)]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", MMA_SHAPES)
+@pytest.mark.parametrize("impl,tol", [(1, 2e-5), (2, 6e-3)])
+def test_conv_mma_vs_fp64(eng_small, B, H, W, Cin, Cout, k, impl, tol):
+    """tcgen05 conv (fp16 hi/lo split x3 = fp32-grade; single pass = fp16-grade) vs a float64 convolution and
+    vs the fp32 FFMA kernel on the same inputs."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(B * 100 + Cin + k)
+    x = rng.standard_normal((B, H, W, Cin)).astype(np.float32)
+    w = (rng.standard_normal((k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    y = eng_small.debug_conv2d(x, w, b, impl=impl)
+    ref = F.conv2d(torch.from_numpy(x).double().permute(0, 3, 1, 2), torch.from_numpy(w).double().permute(3, 2, 0, 1),
+                   torch.from_numpy(b).double(), padding=k // 2).permute(0, 2, 3, 1).numpy()
+    err = np.abs(y - ref).max()
+    assert err < tol, "max abs err %g" % err
+    if impl == 1:
+        ys = eng_small.debug_conv2d(x, w, b, impl=0)
+        assert np.abs(y - ys).max() < 2e-5
+
+
+@pytest.mark.parametrize("precision,tol", [("f16x3", FRAME_TOL), ("f16x1", 5e-2)])
+def test_rollout_tensor_core_path_vs_oracle(precision, tol):
+    """Full predictor rollout with the conv-LSTM convolutions on tcgen05: the fp32-grade mode holds the 1e-4
+    frame tolerance of BASELINE.json; the single-pass mode is reported with its own (looser) bound."""
+    sp = S.spec_64(height=64, width=64, seq_len=6)
+    w = Hh.make_weights(sp, seed=11)
+    inp = Hh.synth_inputs(sp, seed=11)
+    acts = Hh.gaussian_actions(sp, 5, 15, seed=11)
+    e, (gi, gd, gs) = _engine_rollout(sp, w, inp, acts, precision=precision)
+    oi, od, os_ = Hh.oracle_rollout(sp, w, inp, acts)
+    err = float(np.abs(gi - oi).max())
+    print("precision %s: frames max-abs err %.3g, distrib %.3g" % (precision, err, float(np.abs(gd - od).max())))
+    assert err <= tol
+    e.close()

@@ -56,6 +56,8 @@ struct ViewNet {
   std::vector<RnnState> enc_rnn, dec_rnn;
   ConvLayer scratch0, scratch1, masks0, masks1;
   float *cdna_w = nullptr, *cdna_b = nullptr;
+  float *w_state = nullptr, *b_state = nullptr;   // per-view state head (IndepMultiSAVP: independent weight sets)
+  float* state_cur = nullptr;                      // [B][sdim] this view's predicted state
 };
 
 struct DebugEntry {
@@ -78,7 +80,6 @@ struct vf_engine {
   // derived
   int B, H, W, ncam, nd, adim, sdim, nz, A, S, C, P, ngf, nt, kc, nm, n_enc;
   std::vector<ViewNet> views;
-  float *w_state = nullptr, *b_state = nullptr;
 
   // shared scratch
   float *raw = nullptr, *dec_in = nullptr, *stats = nullptr, *cstats = nullptr;
@@ -373,15 +374,16 @@ int finalize_weights(vf_engine* h) {
     if ((r = upload(h, &net.cdna_w, cw->data))) return r;
     if ((r = upload(h, &net.cdna_b, cb->data))) return r;
   }
-  if (h->sdim > 0) {
-    const HostTensor* sw = find_w(h, 0, "state.dense.w");
-    const HostTensor* sb = find_w(h, 0, "state.dense.b");
-    if (!sw || !sb) return fail(h, VF_ERR_STATE, "missing weight state.dense.{w,b}");
+  for (int v = 0; v < h->ncam && h->sdim > 0; ++v) {
+    const HostTensor* sw = find_w(h, v, "state.dense.w");
+    const HostTensor* sb = find_w(h, v, "state.dense.b");
+    if (!sw || !sb) return fail(h, VF_ERR_STATE, "missing weight view%d.state.dense.{w,b}", v);
     if ((int)sw->data.size() != (h->adim + h->sdim) * h->sdim || (int)sb->data.size() != h->sdim)
       return fail(h, VF_ERR_INVALID, "state.dense has wrong shape");
     int r;
-    if ((r = upload(h, &h->w_state, sw->data))) return r;
-    if ((r = upload(h, &h->b_state, sb->data))) return r;
+    if ((r = upload(h, &h->views[v].w_state, sw->data))) return r;
+    if ((r = upload(h, &h->views[v].b_state, sb->data))) return r;
+    DA(h->views[v].state_cur, (size_t)h->B * h->sdim);
   }
   h->host_w.clear();
   h->weights_ready = true;
@@ -412,7 +414,7 @@ void run_conv(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int 
 }
 
 void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act) {
-  if (h->cfg.precision != VF_PREC_FP32_SIMT && L.mma.ready) {
+  if (h->cfg.precision != VF_PREC_FP32_SIMT && L.mma.ready && s1.C == 0) {
     MmaConvCall c;
     c.src = s0; c.out = out; c.sabias = L.sabias; c.bias = L.bias; c.H = L.H; c.W = L.W;
     c.passes = (h->cfg.precision == VF_PREC_F16X3) ? 3 : 1;
@@ -572,11 +574,17 @@ int rollout(vf_engine* h, int M, int T) {
   SaArgs sa;
   sa.actions = h->actions; sa.T = T; sa.adim = h->adim; sa.sdim = h->sdim; sa.nz = h->nz;
   sa.n_ctx_actions = h->n_ctx_actions; sa.C = h->C; sa.ctx_actions = h->ctx_actions; sa.ctx_states = h->ctx_states;
-  sa.zs = h->nz ? h->zs : nullptr; sa.w_state = h->w_state; sa.b_state = h->b_state; sa.state_cur = h->state_cur;
-  sa.sa = h->sa; sa.gen_states_all = h->sdim ? h->gen_states : nullptr; sa.P = h->P;
+  sa.zs = h->nz ? h->zs : nullptr; sa.sa = h->sa; sa.P = h->P;
   for (int tau = 0; tau < h->S - 1; ++tau) {
-    launch_build_sa(sa, M, tau, h->stream);
-    for (int v = 0; v < h->ncam; ++v) run_step(h, v, tau, M);
+    for (int v = 0; v < h->ncam; ++v) {
+      // every view runs its own state recurrence with its own state head; the states returned to the
+      // caller are view 0's (vpred_model_interface.py:80-82 reads outputs['gen_states'] of the first model)
+      sa.w_state = h->views[v].w_state; sa.b_state = h->views[v].b_state;
+      sa.state_cur = h->sdim ? h->views[v].state_cur : h->state_cur;
+      sa.gen_states_all = (h->sdim && v == 0) ? h->gen_states : nullptr;
+      launch_build_sa(sa, M, tau, h->stream);
+      run_step(h, v, tau, M);
+    }
   }
   CU(cudaGetLastError());
   h->predicted = true;
@@ -876,7 +884,7 @@ int vf_cem_begin(vf_engine* h, const vf_cem_params* p, const float* goal, const 
     mean[d] = p->use_mean0 ? (double)p->mean0[d] : 0.0;
     double s = (double)p->initial_std[d % h->adim];
     // construct_initial_sigma scales the VARIANCE of all but the last action block (controller_utils.py:76-81)
-    if (p->reduce_std_scale != 1.0f && d < (p->nactions - 1) * h->adim) s *= sqrt((double)p->reduce_std_scale);
+    if (p->reduce_std_scale != 1.0 && d < (p->nactions - 1) * h->adim) s *= sqrt(p->reduce_std_scale);
     std0[d] = s;
   }
   CU(cudaMemcpyAsync(h->cem_mean, mean, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));

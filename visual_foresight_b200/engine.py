@@ -52,12 +52,12 @@ class VfCemParams(C.Structure):
     _fields_ = [
         ("num_samples", C.c_int32), ("global_samples", C.c_int32), ("sample_offset", C.c_int32),
         ("iterations", C.c_int32), ("num_elites", C.c_int32), ("nactions", C.c_int32), ("repeat", C.c_int32),
-        ("action_bound", C.c_int32),
-        ("initial_std", C.c_float * 8), ("clip_lo", C.c_float * 8), ("clip_hi", C.c_float * 8),
-        ("mean0", C.c_float * 128), ("use_mean0", C.c_int32), ("reduce_std_scale", C.c_float),
-        ("cost_kind", C.c_int32), ("finalweight", C.c_float), ("task_weights", C.c_float * VF_MAX_TASKS),
-        ("n_ctx_actions", C.c_int32), ("seed", C.c_uint64), ("plan_index", C.c_uint32),
-        ("reserved", C.c_int32 * 8),
+        ("action_bound", C.c_int32), ("use_mean0", C.c_int32), ("cost_kind", C.c_int32),
+        ("n_ctx_actions", C.c_int32), ("pad0", C.c_int32),
+        ("initial_std", C.c_double * 8), ("clip_lo", C.c_double * 8), ("clip_hi", C.c_double * 8),
+        ("mean0", C.c_double * 128), ("reduce_std_scale", C.c_double), ("finalweight", C.c_double),
+        ("task_weights", C.c_double * VF_MAX_TASKS),
+        ("seed", C.c_uint64), ("plan_index", C.c_uint32), ("reserved", C.c_int32 * 8),
     ]
 
 
@@ -281,6 +281,7 @@ class Engine:
         best = np.empty((K, T, self.spec.adim), np.float64)
         eidx = np.empty((K,), np.int32)
         scores = np.empty((params.iterations, params.global_samples), np.float64)
+        self._cem_params = params
         self._check(self.lib.vf_cem_plan(self._h, C.byref(params), _ptr(g), _ptr(nz), _ptr(best), _ptr(eidx), _ptr(scores)))
         return best, eidx, scores
 
