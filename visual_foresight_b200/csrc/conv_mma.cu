@@ -343,9 +343,12 @@ bool plan_geometry(int k, int Cin, int Cout, int H, int W, int B, int passes, Ge
   }
   g.img_pix = g.v_cnt + (k - 1) * g.Wp + (k - 1);
   g.img_pix = (g.img_pix + 7) / 8 * 8;
-  int npix = g.G * g.img_pix;
-  while (npix % 8 != 2) ++npix;                          // conflict-free 16-byte stores across k-chunks
-  g.npix = npix;
+  for (;; --g.G) {                                       // shrink the image group until the staging buffers fit
+    int npix = g.G * g.img_pix;
+    while (npix % 8 != 2) ++npix;                        // conflict-free 16-byte stores across k-chunks
+    g.npix = npix;
+    if (g.G == 1 || (size_t)4 * KC * npix * 16 + (size_t)NSTAGE * STAGE_BYTES + 256 <= (size_t)227 * 1024) break;
+  }
   g.ngroups = (B + g.G - 1) / g.G;
   g.nitems = g.n_mt * g.ngroups * g.npass;
   *out = g;
