@@ -5,23 +5,30 @@
 //   * Output channels sit on the MMA M dimension (UMMA_M = 128 TMEM lanes), pixels on N (TMEM columns).  One
 //     epilogue thread therefore owns one output channel of every pixel in the tile: per-channel work is
 //     thread-local, and a warp writes 32 consecutive channels of one pixel = one 128-byte NHWC line.
-//   * No im2col and no per-tap re-fetch.  A tile's input pixels (+halo) are staged ONCE per 32-channel chunk in
-//     shared memory as a FLAT zero-padded image (row pitch Wp = W + k - 1) in the UMMA "interleaved" (no-swizzle)
-//     K-major layout [k-chunk of 8 ch][pixel][16 B].  In that layout the operand row of pixel p is at byte offset
-//     16*p, so filter tap (dy,dx) is the SAME buffer read through a matrix descriptor whose start address is
-//     advanced by (dy*Wp + dx)*16 bytes: 25 taps = 25 descriptors, zero data movement.  The k-1 wrap-around
-//     columns per image row are computed and discarded (W/Wp efficiency: 89% at 32x32, 80% at 16x16).
+//   * No im2col and no per-tap re-fetch.  A tile's input pixels (+halo) are staged ONCE per channel chunk in
+//     shared memory as a FLAT zero-padded image (row pitch Wp = W + k - 1), one operand row per pixel.  Filter tap
+//     (dy,dx) is the SAME buffer read through a matrix descriptor whose start address is advanced by
+//     (dy*Wp + dx) pixel rows: 25 taps = 25 descriptors, zero data movement.  The k-1 wrap-around columns per image
+//     row are computed and discarded (W/Wp efficiency: 89% at 32x32, 80% at 16x16).
 //   * fp32-grade arithmetic on fp16 tensor cores: both operands are split x = hi + lo (fp16 each, weights
 //     pre-scaled by a power of two so lo stays normal) and three MMAs hi*hi + hi*lo + lo*hi accumulate into the
-//     same fp32 TMEM accumulator (relative error ~2^-21 per product; the dropped lo*lo term is ~2^-22).
+//     same fp32 TMEM accumulator.
 //   * Weights are pre-packed on the host in exactly the shared-memory operand layout, so a pipeline stage is one
-//     contiguous 16 KB cp.async.bulk (TMA 1-D) completing on an mbarrier: no tensor maps.
+//     contiguous cp.async.bulk (TMA 1-D) completing on an mbarrier: no tensor maps.
 //   * Warp roles: warp 0 = weight producer (bulk copies), warp 1 = MMA issuer (one elected thread) + TMEM
 //     allocator, warps 2-5 = activation stagers (fp32 -> fp16 hi/lo split on the fly) then epilogue
 //     (tcgen05.ld -> scale, + border-class bias -> coalesced NHWC stores).  Persistent CTAs, one per SM.
+//
+// Operand layouts (VF_MMA_LAYOUT, default chosen from hardware measurements — see DESIGN.md):
+//   0  interleave / no swizzle, 32-channel chunks [k-chunk][pixel][16 B]           (correct, operand fetch ~16 B/clk)
+//   1  SWIZZLE_64B,  32-channel chunks, pixel rows of 64 B
+//   2  SWIZZLE_128B, 64-channel chunks, pixel rows of 128 B
+// For the swizzled layouts the 16-byte chunks of a row are XOR-permuted with the row's shared-memory ADDRESS bits
+// ([7,9) / [7,10)); the stager applies the same permutation so that every tap-shifted descriptor sees consistent data.
 #include <cuda.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -31,17 +38,16 @@
 namespace vf {
 namespace {
 
-constexpr int CH = 32;                 // input channels per chunk
-constexpr int KC = CH / 8;             // 16-byte k-chunks per chunk
 constexpr int MT = 128;                // cout tile (UMMA M)
-constexpr int NSTAGE = 4;              // weight pipeline stages
-constexpr int A_HALF_BYTES = KC * MT * 16;          // one hi (or lo) weight block: 8 KB
-constexpr int STAGE_BYTES = 2 * A_HALF_BYTES;       // hi + lo: 16 KB
-constexpr int NTHREADS = 192;
-constexpr int NLOAD = 128;             // stager/epilogue threads (warps 2..5)
+constexpr int NTHREADS = 384;
+constexpr int NLOAD = 128;             // threads per role group (4 epilogue warps, 4 stager warps)
 constexpr int MAX_SEG = 8;
+constexpr int MAX_STAGE = 4;
+constexpr int MAX_UNIT = 4;            // (images x column segments) per item
 
 struct Geometry {
+  int layout, bo_mode;
+  int ch, kc, ksteps, row_bytes, swz_mask, half_bytes, stage_bytes, nstage, nbuf, plane_bytes;
   int H, W, k, pad, Wp;
   int Cin, Cout;
   int nchunk, ntap, n_mt;
@@ -49,12 +55,13 @@ struct Geometry {
   int v_cnt;        // virtual pixels per image per item (multiple of 32)
   int npass;        // passes over the image's virtual pixel range
   int img_pix;      // staged flat pixels per image
-  int npix;         // pixels per k-chunk plane (G*img_pix rounded so that npix % 8 == 2)
+  int npix;         // staged pixel rows per plane
   int nseg;         // MMA column segments per image
   int seg_n[MAX_SEG];
   int seg_off[MAX_SEG];
   int ngroups, nitems;
   int passes;       // 1 or 3 MMA passes
+  int nacc;         // TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs)
   float out_scale;  // 2^-scale_log2
 };
 
@@ -63,7 +70,7 @@ struct Params {
   View src, out;
   const float* sabias;
   const float* bias;
-  const __half* w;     // packed [mt][chunk][tap][hi|lo][kc][128][8]
+  const __half* w;     // packed [mt][chunk][tap][hi|lo][operand tile]
   int B;
 };
 
@@ -91,8 +98,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (!done && spins > (1u << 26)) __trap();      // a lost arrival must fail loudly, never hang the GPU
   }
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -121,32 +128,66 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, no swizzle ("interleave"): 8-row core matrices of 16-byte rows.  LBO = byte distance between the two
-// 16-byte K chunks of one MMA (K = 16 halves), SBO = byte distance between 8-row groups.  version = 1 (sm_100).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (K-major).  version = 1 (sm_100).  layout_type: 0 none, 4 = 64B, 2 = 128B swizzle.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type,
+                                              uint32_t base_offset) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)(base_offset & 7) << 49) |
+         ((uint64_t)(layout_type & 7) << 61);
 }
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(MT >> 4) << 24); }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// All MMAs of one filter tap (one weight stage): PASSES x KSTEPS x U instructions, straight-line, issued by the single
+// elected thread.  Descriptors only differ in their low word (start address >> 4), advanced by pre-shifted offsets.
+template <int PASSES, int KSTEPS, int U>
+__device__ __forceinline__ void issue_tap(uint64_t da_st, uint64_t db_tap, uint64_t a_half, uint64_t b_plane, uint64_t kstep_a,
+                                          uint64_t kstep_b, const uint32_t (&ucol)[MAX_UNIT], const uint64_t (&uoff)[MAX_UNIT],
+                                          const uint32_t (&uidesc)[MAX_UNIT], uint32_t acc_first) {
+#pragma unroll
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const uint64_t da_p = da_st + (pass == 2 ? a_half : 0);
+    const uint64_t db_p = db_tap + (pass == 1 ? b_plane : 0);
+#pragma unroll
+    for (int j = 0; j < KSTEPS; ++j) {
+      const uint64_t da = da_p + j * kstep_a, db = db_p + j * kstep_b;
+#pragma unroll
+      for (int u = 0; u < U; ++u) tc_mma_f16(ucol[u], da, db + uoff[u], uidesc[u], (pass | j) == 0 ? acc_first : 1u);
+    }
+  }
+}
+
+// thread layout: warp 0 weight producer, warp 1 MMA issuer (+TMEM alloc), warps 2,3 idle, warps 4..7 epilogue
+// (warp % 4 = TMEM lane quarter), warps 8..11 activation stagers
+constexpr int EPI_WARP0 = 4, STG_WARP0 = 8;
+
 __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ uint8_t smem_raw[];
   const Geometry& g = P.g;
-  const int plane_bytes = KC * g.npix * 16;            // one hi (or lo) activation plane of one chunk buffer
-  uint8_t* act[2] = {smem, smem + 2 * plane_bytes};    // [buf] -> hi plane, lo plane follows
-  uint8_t* wst = smem + 4 * plane_bytes;               // weight stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + NSTAGE * STAGE_BYTES);
-  uint64_t *w_full = bars, *w_empty = bars + NSTAGE, *a_full = bars + 2 * NSTAGE, *a_empty = a_full + 2;
-  uint64_t *acc_full = a_empty + 2, *acc_empty = acc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;        // 1024-aligned: swizzle phases are address based
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t act_base = sbase;                                       // [buf][hi|lo] planes
+  const uint32_t wst_base = sbase + (uint32_t)(g.nbuf * 2 * g.plane_bytes);
+  uint8_t* tail = smem + g.nbuf * 2 * g.plane_bytes + g.nstage * g.stage_bytes;
+  float* s_sab = reinterpret_cast<float*>(tail);                         // [25 classes][128 channels] border-class bias
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 25 * MT * sizeof(float));
+  uint64_t *w_full = bars, *w_empty = bars + MAX_STAGE, *a_full = bars + 2 * MAX_STAGE, *a_empty = a_full + 2;
+  uint64_t *acc_full = a_empty + 2, *acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], NLOAD); mbar_init(&a_empty[i], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, NLOAD);
+    for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], NLOAD); mbar_init(&a_empty[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NLOAD);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -159,149 +200,215 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
   const uint32_t tmem_base = *tmem_slot;
 
   const int per_mt = g.ngroups * g.npass;
+  const uint32_t ltype = g.layout == 0 ? 0u : (g.layout == 1 ? 4u : 2u);
+  const int acc_cols = g.G * g.v_cnt;                    // TMEM columns of one accumulator set
+  const int nacc = g.nacc;                               // 2 when two sets fit in the 512 columns
 
   if (warp == 0) {
     // ===== weight producer =====
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t bytes = g.passes == 3 ? STAGE_BYTES : A_HALF_BYTES;
+      const uint32_t bytes = g.passes == 3 ? (uint32_t)g.stage_bytes : (uint32_t)g.half_bytes;
       for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
         const int mt = item / per_mt;
-        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.w) + (size_t)mt * g.nchunk * g.ntap * STAGE_BYTES;
+        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.w) + (size_t)mt * g.nchunk * g.ntap * g.stage_bytes;
         for (int ct = 0; ct < g.nchunk * g.ntap; ++ct) {
           mbar_wait(&w_empty[s], ph ^ 1);
           mbar_expect_tx(&w_full[s], bytes);
-          bulk_g2s(wst + s * STAGE_BYTES, wbase + (size_t)ct * STAGE_BYTES, bytes, &w_full[s]);
-          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          bulk_g2s(wst_base + s * g.stage_bytes, wbase + (size_t)ct * g.stage_bytes, bytes, &w_full[s]);
+          if (++s == g.nstage) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0, aph[2] = {0, 0}, acc_ph = 0;
-      const uint32_t lbo_b = (uint32_t)g.npix * 16;
-      for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
-        mbar_wait(acc_empty, acc_ph ^ 1);
-        acc_ph ^= 1;
-        tc_fence_after();
-        for (int c = 0; c < g.nchunk; ++c) {
-          const int buf = c & 1;
-          mbar_wait(&a_full[buf], aph[buf]);
-          aph[buf] ^= 1;
-          tc_fence_after();
-          const uint32_t b_hi = smem_u32(act[buf]), b_lo = b_hi + plane_bytes;
-          for (int tap = 0; tap < g.ntap; ++tap) {
-            mbar_wait(&w_full[s], ph);
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(wst + s * STAGE_BYTES), a_lo = a_hi + A_HALF_BYTES;
-            const uint32_t tap_off = (uint32_t)((tap / g.k) * g.Wp + (tap % g.k)) * 16;
-            for (int pass = 0; pass < g.passes; ++pass) {
-              const uint32_t a0 = pass == 2 ? a_lo : a_hi;
-              const uint32_t b0 = pass == 1 ? b_lo : b_hi;
+    // ===== MMA issuer: the whole warp walks the loops (warp-uniform), one elected lane issues =====
+    const uint32_t lbo_b = g.layout == 0 ? (uint32_t)g.npix * 16 : 16u;
+    const uint32_t sbo_b = g.layout == 0 ? 128u : (uint32_t)(8 * g.row_bytes);
+    const uint32_t a_lbo = g.layout == 0 ? (uint32_t)(MT * 16) : 16u;
+    const uint64_t kstep_b = (g.layout == 0 ? 2 * lbo_b : 32u) >> 4;     // start-address advance per K=16 step (16-byte units)
+    const uint64_t kstep_a = (g.layout == 0 ? 2 * a_lbo : 32u) >> 4;
+    const uint32_t pix_b = g.layout == 0 ? 16u : (uint32_t)g.row_bytes;
+    const uint64_t da_zero = make_desc(0, a_lbo, sbo_b, ltype, 0);
+    const uint64_t db_zero = make_desc(0, lbo_b, sbo_b, ltype, 0);
+    const uint64_t a_half = (uint64_t)(g.half_bytes >> 4), b_plane = (uint64_t)(g.plane_bytes >> 4);
+    const int U = g.G * g.nseg;                                          // accumulator units per item (<= MAX_UNIT)
+    uint32_t ucol0[MAX_UNIT], ucol[MAX_UNIT], uidesc[MAX_UNIT];
+    uint64_t uoff[MAX_UNIT];
 #pragma unroll
-              for (int j = 0; j < CH / 16; ++j) {
-                const uint64_t da = make_desc(a0 + j * 2 * (MT * 16), MT * 16, 128);
-                const uint32_t first = (c | tap | pass | j) == 0 ? 0u : 1u;
-                for (int im = 0; im < g.G; ++im) {
-                  for (int sg = 0; sg < g.nseg; ++sg) {
-                    const uint32_t col = (uint32_t)(im * g.v_cnt + g.seg_off[sg]);
-                    const uint32_t baddr = b0 + j * 2 * lbo_b + tap_off + (uint32_t)(im * g.img_pix + g.seg_off[sg]) * 16;
-                    tc_mma_f16(tmem_base + col, da, make_desc(baddr, lbo_b, 128), make_idesc(g.seg_n[sg]), first);
-                  }
-                }
-              }
+    for (int u = 0; u < MAX_UNIT; ++u) {
+      const int im = u / g.nseg, sg = u % g.nseg;
+      ucol0[u] = tmem_base + (uint32_t)(im * g.v_cnt + g.seg_off[sg]);
+      uoff[u] = (uint64_t)(((uint32_t)(im * g.img_pix + g.seg_off[sg]) * pix_b) >> 4);
+      uidesc[u] = make_idesc(g.seg_n[sg]);
+    }
+    const int ntap = g.ntap, kk = g.k, Wp = g.Wp;
+    const int variant = (g.passes == 3 ? 4 : 0) + (U - 1);              // KSTEPS is fixed per layout below
+    int s = 0;
+    uint32_t ph = 0, job = 0, it = 0;
+    for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
+      const int a = it % nacc;
+      mbar_wait(&acc_empty[a], ((it / nacc) & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int u = 0; u < MAX_UNIT; ++u) ucol[u] = ucol0[u] + (uint32_t)(a * acc_cols);
+      uint32_t acc = 0;                                                  // first MMA of every unit overwrites
+      for (int c = 0; c < g.nchunk; ++c, ++job) {
+        const int buf = job % g.nbuf;
+        mbar_wait(&a_full[buf], (job / g.nbuf) & 1);
+        tc_fence_after();
+        const uint64_t db_buf = db_zero + (uint64_t)((act_base + (uint32_t)(buf * 2 * g.plane_bytes)) >> 4);
+        int ty = 0, tx = 0;
+        for (int tap = 0; tap < ntap; ++tap) {
+          mbar_wait(&w_full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da_st = da_zero + (uint64_t)((wst_base + (uint32_t)(s * g.stage_bytes)) >> 4);
+            const uint64_t db_tap = db_buf + (uint64_t)(((uint32_t)(ty * Wp + tx) * pix_b) >> 4);
+#define VF_ISSUE(PA, UU)                                                                                              \
+  if (g.ksteps == 2) issue_tap<PA, 2, UU>(da_st, db_tap, a_half, b_plane, kstep_a, kstep_b, ucol, uoff, uidesc, acc);  \
+  else issue_tap<PA, 4, UU>(da_st, db_tap, a_half, b_plane, kstep_a, kstep_b, ucol, uoff, uidesc, acc)
+            switch (variant) {
+              case 0: VF_ISSUE(1, 1); break;
+              case 1: VF_ISSUE(1, 2); break;
+              case 2: VF_ISSUE(1, 3); break;
+              case 3: VF_ISSUE(1, 4); break;
+              case 4: VF_ISSUE(3, 1); break;
+              case 5: VF_ISSUE(3, 2); break;
+              case 6: VF_ISSUE(3, 3); break;
+              default: VF_ISSUE(3, 4); break;
             }
+#undef VF_ISSUE
             tc_commit(&w_empty[s]);                 // stage reusable once these MMAs retire
-            if (++s == NSTAGE) { s = 0; ph ^= 1; }
           }
-          tc_commit(&a_empty[buf]);                 // chunk buffer reusable
+          __syncwarp();
+          acc = 1;
+          if (++s == g.nstage) { s = 0; ph ^= 1; }
+          if (++tx == kk) { tx = 0; ++ty; }
         }
-        tc_commit(acc_full);                        // accumulators complete -> epilogue
+        if (elect_one()) tc_commit(&a_empty[buf]);  // chunk buffer reusable
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(&acc_full[a]);     // accumulators complete -> epilogue
+      __syncwarp();
+    }
+  } else if (warp >= STG_WARP0) {
+    // ===== activation stagers: fp32 NHWC -> fp16 hi/lo operand rows of the flat zero-padded image =====
+    const int t = threadIdx.x - STG_WARP0 * 32;     // 0..127
+    const int kc8 = t % g.kc;                       // this thread always handles the same 16-byte k-chunk
+    const int pl0 = t / g.kc, pl_step = NLOAD / g.kc;
+    uint32_t job = 0;
+    for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
+      const int rem = item % per_mt;
+      const int grp = rem / g.npass, ps = rem % g.npass;
+      const int b0 = grp * g.G, v_lo = ps * g.v_cnt;
+      const int npl = g.G * g.img_pix;
+      for (int c = 0; c < g.nchunk; ++c, ++job) {
+        const int buf = job % g.nbuf;
+        mbar_wait(&a_empty[buf], ((job / g.nbuf) & 1) ^ 1);
+        const uint32_t hi_addr = act_base + (uint32_t)(buf * 2 * g.plane_bytes);
+        uint8_t* hi_ptr = smem + buf * 2 * g.plane_bytes;
+        const int choff = P.src.ch_off + c * g.ch + kc8 * 8;
+        for (int plb = pl0; plb < npl; plb += 4 * pl_step) {
+          float4 f[4][2];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {             // issue all loads of the batch first (memory-level parallelism)
+            const int pl = plb + u * pl_step;
+            const int im = pl / g.img_pix, ql = pl - im * g.img_pix;
+            const int q = v_lo + ql;                // flat index in the zero-padded image
+            const int qy = q / g.Wp;
+            const int yy = qy - g.pad, xx = q - qy * g.Wp - g.pad;
+            const int b = b0 + im;
+            ok[u] = pl < npl && b < P.B && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W;
+            if (ok[u]) {
+              const float4* sp = reinterpret_cast<const float4*>(P.src.p + (long long)b * P.src.sample_stride +
+                                                                 (long long)(yy * g.W + xx) * P.src.pix_stride + choff);
+              f[u][0] = __ldg(sp);
+              f[u][1] = __ldg(sp + 1);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int pl = plb + u * pl_step;
+            if (pl >= npl) break;
+            uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
+            if (ok[u]) {
+              const float x[8] = {f[u][0].x, f[u][0].y, f[u][0].z, f[u][0].w, f[u][1].x, f[u][1].y, f[u][1].z, f[u][1].w};
+              __half h[8], l[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                h[e] = __float2half_rn(x[e]);
+                l[e] = __float2half_rn(x[e] - __half2float(h[e]));
+              }
+              vh = *reinterpret_cast<uint4*>(h);
+              vl = *reinterpret_cast<uint4*>(l);
+            }
+            uint32_t off;
+            if (g.layout == 0) {
+              off = (uint32_t)(kc8 * g.npix + pl) * 16;
+            } else {
+              const uint32_t rowoff = (uint32_t)pl * g.row_bytes;
+              off = rowoff + (((uint32_t)kc8 ^ (((hi_addr + rowoff) >> 7) & (uint32_t)g.swz_mask)) << 4);
+            }
+            *reinterpret_cast<uint4*>(hi_ptr + off) = vh;
+            *reinterpret_cast<uint4*>(hi_ptr + g.plane_bytes + off) = vl;   // plane_bytes % 1024 == 0: same swizzle phase
+          }
+        }
+        fence_proxy_async();                        // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(&a_full[buf]);
       }
     }
-  } else {
-    // ===== activation stagers, then epilogue (warps 2..5) =====
-    const int t = threadIdx.x - 64;                 // 0..127
+  } else if (warp >= EPI_WARP0) {
+    // ===== epilogue: TMEM -> registers -> (x 2^-s, + border-class bias) -> NHWC global =====
     const int q4 = warp & 3;                        // TMEM lane quarter this warp may read
     const int row = q4 * 32 + lane;                 // output channel within the cout tile
-    uint32_t aeph[2] = {0, 0}, accf_ph = 0;
-    for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
+    const int center = g.pad * g.k + g.pad;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
       const int mt = item / per_mt;
       const int rem = item % per_mt;
       const int grp = rem / g.npass, ps = rem % g.npass;
-      const int b0 = grp * g.G;
-      const int v_lo = ps * g.v_cnt;
-      // ---- stage input chunks ----
-      for (int c = 0; c < g.nchunk; ++c) {
-        const int buf = c & 1;
-        mbar_wait(&a_empty[buf], aeph[buf] ^ 1);
-        aeph[buf] ^= 1;
-        uint4* hi = reinterpret_cast<uint4*>(act[buf]);
-        uint4* lo = reinterpret_cast<uint4*>(act[buf] + plane_bytes);
-        const int total = g.G * g.img_pix * KC;
-        for (int idx = t; idx < total; idx += NLOAD) {
-          const int kc = idx & (KC - 1);
-          const int pl = idx >> 2;                   // pixel slot in the plane
-          const int im = pl / g.img_pix, ql = pl - im * g.img_pix;
-          const int q = v_lo + ql;                   // flat index in the zero-padded image
-          const int yy = q / g.Wp - g.pad, xx = q % g.Wp - g.pad;
-          const int b = b0 + im;
-          uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
-          if (b < P.B && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) {
-            const float* sp = P.src.p + (long long)b * P.src.sample_stride + (long long)(yy * g.W + xx) * P.src.pix_stride +
-                              P.src.ch_off + c * CH + kc * 8;
-            const float4 f0 = __ldg(reinterpret_cast<const float4*>(sp));
-            const float4 f1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
-            const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-            __half h[8], l[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              h[e] = __float2half_rn(f[e]);
-              l[e] = __float2half_rn(f[e] - __half2float(h[e]));
-            }
-            vh = *reinterpret_cast<uint4*>(h);
-            vl = *reinterpret_cast<uint4*>(l);
-          }
-          hi[kc * g.npix + pl] = vh;
-          lo[kc * g.npix + pl] = vl;
-        }
-        fence_proxy_async();                         // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(&a_full[buf]);
-      }
-      // ---- epilogue ----
-      mbar_wait(acc_full, accf_ph);
-      accf_ph ^= 1;
-      tc_fence_after();
+      const int b0 = grp * g.G, v_lo = ps * g.v_cnt;
       const int n = mt * MT + row;
+      const int a = it % nacc;
+      mbar_wait(&acc_full[a], (it / nacc) & 1);
+      tc_fence_after();
       for (int im = 0; im < g.G; ++im) {
         const int b = b0 + im;
+        const bool live = b < P.B;
+        float sb_c = 0.f;
+        if (live) {
+          if (P.sabias) {                           // this thread's column of the per-sample class table (private: no sync)
+            const float* sp = P.sabias + (long long)b * g.ntap * g.Cout + n;
+            for (int cls = 0; cls < g.ntap; ++cls) s_sab[cls * MT + row] = __ldg(sp + (long long)cls * g.Cout);
+            sb_c = s_sab[center * MT + row];
+          } else if (P.bias) {
+            sb_c = __ldg(P.bias + n);
+          }
+        }
+        float* op = P.out.p + (long long)b * P.out.sample_stride + P.out.ch_off + n;
         for (int cc = 0; cc < g.v_cnt; cc += 32) {
           uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(im * g.v_cnt + cc), r);
-          if (b >= P.B) continue;
-          int v = v_lo + cc;
+          tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + im * g.v_cnt + cc), r);
+          if (!live) continue;
+          const int v = v_lo + cc;
           int oy = v / g.Wp, ox = v - oy * g.Wp;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (ox < g.W && oy < g.H) {
               float val = __uint_as_float(r[j]) * g.out_scale;
-              if (P.sabias) {
-                const int cls = border_class(oy, g.H, g.pad) * g.k + border_class(ox, g.W, g.pad);
-                val += __ldg(P.sabias + ((long long)b * g.ntap + cls) * g.Cout + n);
-              } else if (P.bias) {
-                val += __ldg(P.bias + n);
-              }
-              P.out.p[(long long)b * P.out.sample_stride + (long long)(oy * g.W + ox) * P.out.pix_stride + P.out.ch_off + n] = val;
+              const int cy = border_class(oy, g.H, g.pad), cx = border_class(ox, g.W, g.pad);
+              const int cls = cy * g.k + cx;
+              val += (cls == center || !P.sabias) ? sb_c : s_sab[cls * MT + row];
+              op[(long long)(oy * g.W + ox) * P.out.pix_stride] = val;
             }
             if (++ox == g.Wp) { ox = 0; ++oy; }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(acc_empty);
+      mbar_arrive(&acc_empty[a]);
     }
   }
   __syncthreads();
@@ -312,23 +419,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 int g_num_sms = 0;
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr size_t SMEM_SLACK = 1024 + 25 * MT * 4 + 256;      // alignment slack + bias table + barriers
 
-bool plan_geometry(int k, int Cin, int Cout, int H, int W, int B, int passes, Geometry* out) {
+void current_mode(int* layout, int* bo) {
+  static int s_layout = -1, s_bo = 0;
+  if (s_layout < 0) {
+    const char* e = getenv("VF_MMA_LAYOUT");
+    s_layout = e ? atoi(e) : 1;     // SWIZZLE_64B: verified correct with tap-shifted descriptors on B200
+    if (s_layout < 0 || s_layout > 2) s_layout = 0;
+    const char* b = getenv("VF_MMA_BO");
+    s_bo = b ? atoi(b) : 0;
+  }
+  *layout = s_layout; *bo = s_bo;
+}
+
+bool plan_geometry(int layout, int bo_mode, int k, int Cin, int Cout, int H, int W, int B, int passes, Geometry* out) {
   Geometry g;
   memset(&g, 0, sizeof(g));
+  g.layout = layout; g.bo_mode = bo_mode;
+  g.ch = layout == 2 ? 64 : 32;
+  if (Cin % g.ch || Cout % MT) return false;
+  g.kc = g.ch / 8; g.ksteps = g.ch / 16; g.row_bytes = g.ch * 2; g.swz_mask = layout == 2 ? 7 : (layout == 1 ? 3 : 0);
+  g.half_bytes = MT * g.ch * 2; g.stage_bytes = 2 * g.half_bytes;
   g.H = H; g.W = W; g.k = k; g.pad = k / 2; g.Wp = W + k - 1; g.Cin = Cin; g.Cout = Cout;
-  g.nchunk = Cin / CH; g.ntap = k * k; g.n_mt = Cout / MT; g.passes = passes;
+  g.nchunk = Cin / g.ch; g.ntap = k * k; g.n_mt = Cout / MT; g.passes = passes;
   const int V = H * g.Wp;                               // virtual pixels per image (incl. k-1 wrap columns per row)
   // (G, v_cnt, npass): several whole small images per item, or an (almost) even slice of one large image.
   // v_cnt is rounded up to 32 columns; the overshoot reads zero-filled staging rows and is masked in the epilogue.
-  if (V <= 256) {
+  if (V <= 128) {
     g.v_cnt = (V + 31) / 32 * 32;
-    g.G = std::max(1, std::min(512 / g.v_cnt, 3));
+    g.G = std::max(1, std::min(256 / g.v_cnt, 3));
     g.npass = 1;
   } else {
-    g.G = 1;
-    g.npass = (V + 511) / 512;
-    g.v_cnt = ((V + g.npass - 1) / g.npass + 31) / 32 * 32;
+    g.G = 1;                                            // <= 256 columns per item: two TMEM accumulator sets
+    const int np0 = (V + 255) / 256;
+    int best_waste = 1 << 30;
+    for (int np = np0; np <= np0 + 2; ++np) {           // least padded columns, then fewest passes
+      const int v = ((V + np - 1) / np + 31) / 32 * 32;
+      if (v > 256) continue;
+      if (np * v - V < best_waste) { best_waste = np * v - V; g.npass = np; g.v_cnt = v; }
+    }
   }
   // MMA column segments: n <= 256, multiple of 16
   g.nseg = 0;
@@ -343,12 +474,24 @@ bool plan_geometry(int k, int Cin, int Cout, int H, int W, int B, int passes, Ge
   }
   g.img_pix = g.v_cnt + (k - 1) * g.Wp + (k - 1);
   g.img_pix = (g.img_pix + 7) / 8 * 8;
-  for (;; --g.G) {                                       // shrink the image group until the staging buffers fit
+  // buffers: prefer double-buffered activations + as many weight stages as fit (>= 2)
+  bool ok = false;
+  for (; g.G >= 1 && !ok; --g.G) {
     int npix = g.G * g.img_pix;
-    while (npix % 8 != 2) ++npix;                        // conflict-free 16-byte stores across k-chunks
+    if (layout == 0) while (npix % 8 != 2) ++npix;      // conflict-free 16-byte stores across k-chunks
     g.npix = npix;
-    if (g.G == 1 || (size_t)4 * KC * npix * 16 + (size_t)NSTAGE * STAGE_BYTES + 256 <= (size_t)227 * 1024) break;
+    g.plane_bytes = (npix * g.ch * 2 + 1023) / 1024 * 1024;
+    for (g.nbuf = 2; g.nbuf >= 1; --g.nbuf) {
+      const size_t act = (size_t)g.nbuf * 2 * g.plane_bytes;
+      if (act + 2 * (size_t)g.stage_bytes + SMEM_SLACK > SMEM_LIMIT) continue;
+      g.nstage = (int)std::min<size_t>(MAX_STAGE, (SMEM_LIMIT - SMEM_SLACK - act) / g.stage_bytes);
+      ok = true;
+      break;
+    }
+    if (ok) break;
   }
+  if (!ok || g.G * g.nseg > MAX_UNIT) return false;
+  g.nacc = (2 * g.G * g.v_cnt <= 512) ? 2 : 1;
   g.ngroups = (B + g.G - 1) / g.G;
   g.nitems = g.n_mt * g.ngroups * g.npass;
   *out = g;
@@ -357,43 +500,52 @@ bool plan_geometry(int k, int Cin, int Cout, int H, int W, int B, int passes, Ge
 
 // >= 116 KB so that exactly one CTA is resident per SM: every CTA allocates all 512 TMEM columns
 size_t smem_bytes(const Geometry& g) {
-  return std::max((size_t)4 * KC * g.npix * 16 + (size_t)NSTAGE * STAGE_BYTES + 256, (size_t)116 * 1024);
+  return std::max((size_t)g.nbuf * 2 * g.plane_bytes + (size_t)g.nstage * g.stage_bytes + SMEM_SLACK, (size_t)116 * 1024);
 }
 
 }  // namespace
 
 bool mma_conv_supported(int k, int cin, int cout, int H, int W) {
-  if ((k != 3 && k != 5) || cin % CH || cout % MT) return false;
+  if (k != 3 && k != 5) return false;
+  int layout, bo;
+  current_mode(&layout, &bo);
   Geometry g;
-  if (!plan_geometry(k, cin, cout, H, W, 1, 3, &g)) return false;
-  return smem_bytes(g) <= 227 * 1024;
+  return plan_geometry(layout, bo, k, cin, cout, H, W, 1, 3, &g);
 }
 
 int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaConvWeights* out, std::vector<void*>* allocs,
                              std::string* err) {
-  if (cin % CH || cout % MT) { if (err) *err = "cin % 32 or cout % 128"; return -1; }
-  const int kk = k * k, nchunk = cin / CH, n_mt = cout / MT;
+  int layout, bo;
+  current_mode(&layout, &bo);
+  const int ch = layout == 2 ? 64 : 32;
+  if (cin % ch || cout % MT) { if (err) *err = "cin % chunk or cout % 128"; return -1; }
+  const int kk = k * k, nchunk = cin / ch, n_mt = cout / MT, kc = ch / 8, rb = ch * 2;
+  const int swz = layout == 2 ? 7 : (layout == 1 ? 3 : 0);
   float amax = 0.f;
   for (size_t i = 0; i < (size_t)kk * cin * cout; ++i) amax = std::max(amax, fabsf(w_sp[i]));
   int sl = 0;
   if (amax > 0.f) sl = (int)floorf(log2f(16384.0f / amax));           // max |w| * 2^sl in [8192, 16384]
   sl = std::max(-24, std::min(sl, 24));
   const float scale = ldexpf(1.0f, sl);
-  const size_t total = (size_t)n_mt * nchunk * kk * 2 * KC * MT * 8;
+  const size_t half_elems = (size_t)MT * ch;
+  const size_t total = (size_t)n_mt * nchunk * kk * 2 * half_elems;
   std::vector<__half> packed(total);
   for (int mt = 0; mt < n_mt; ++mt)
     for (int c = 0; c < nchunk; ++c)
       for (int t = 0; t < kk; ++t) {
-        const size_t blk = ((((size_t)mt * nchunk + c) * kk + t) * 2) * KC * MT * 8;
-        for (int kc = 0; kc < KC; ++kc)
+        const size_t blk = (((size_t)mt * nchunk + c) * kk + t) * 2 * half_elems;
+        for (int kc8 = 0; kc8 < kc; ++kc8)
           for (int r = 0; r < MT; ++r)
             for (int e = 0; e < 8; ++e) {
-              const int ci = c * CH + kc * 8 + e, n = mt * MT + r;
+              const int ci = c * ch + kc8 * 8 + e, n = mt * MT + r;
               const float v = w_sp[((size_t)t * cin + ci) * cout + n] * scale;
               const __half h = __float2half_rn(v);
               const __half l = __float2half_rn(v - __half2float(h));
-              packed[blk + ((size_t)kc * MT + r) * 8 + e] = h;
-              packed[blk + (size_t)KC * MT * 8 + ((size_t)kc * MT + r) * 8 + e] = l;
+              size_t pos;                                              // element index inside the 128-row operand tile
+              if (layout == 0) pos = ((size_t)kc8 * MT + r) * 8 + e;
+              else pos = ((size_t)r * rb + (size_t)((kc8 ^ ((r * rb >> 7) & swz)) << 4)) / 2 + e;
+              packed[blk + pos] = h;
+              packed[blk + half_elems + pos] = l;
             }
       }
   void* d = nullptr;
@@ -410,14 +562,16 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaCon
 
 int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaStream_t s) {
   Params P;
-  if (!plan_geometry(w.k, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
+  int layout, bo;
+  current_mode(&layout, &bo);
+  if (!plan_geometry(layout, bo, w.k, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
   P.g.out_scale = ldexpf(1.0f, -w.scale_log2);
   P.src = c.src; P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B;
   if ((c.src.pix_stride % 4) || (c.src.ch_off % 4) || (c.src.sample_stride % 4)) return -2;      // float4 loads
   const size_t smem = smem_bytes(P.g);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_conv_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -3;
+    if (cudaFuncSetAttribute(k_conv_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) != cudaSuccess) return -3;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
