@@ -304,7 +304,10 @@ def test_controller_device_path_end_to_end():
 
 # ---- tcgen05 implicit-GEMM convolution ------------------------------------------------------------------------
 MMA_SHAPES = [(3, 32, 32, 64, 128, 5), (2, 16, 16, 128, 256, 5), (5, 8, 8, 256, 512, 5), (2, 16, 16, 64, 128, 3),
-              (4, 6, 8, 64, 128, 5), (7, 8, 8, 32, 128, 5), (2, 12, 16, 32, 128, 5), (1, 24, 32, 32, 128, 3)]
+              (4, 6, 8, 64, 128, 5), (7, 8, 8, 32, 128, 5), (2, 12, 16, 32, 128, 5), (1, 24, 32, 32, 128, 3),
+              # zero-padded channel chunks / output tiles (thin layers: Cout 3, 7, 32, 64; Cin 40, 56)
+              (2, 16, 16, 56, 7, 3), (3, 16, 16, 32, 3, 3), (2, 32, 32, 40, 32, 3), (1, 64, 64, 64, 32, 3),
+              (2, 16, 16, 128, 64, 3), (1, 32, 32, 128, 160, 3)]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k", MMA_SHAPES)

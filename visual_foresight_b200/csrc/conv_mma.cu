@@ -44,6 +44,7 @@ constexpr int NLOAD = 128;             // threads per role group (4 epilogue war
 constexpr int MAX_SEG = 8;
 constexpr int MAX_STAGE = 4;
 constexpr int MAX_UNIT = 4;            // (images x column segments) per item
+constexpr int MAX_UNIT_B = 8;          // swapped orientation: 128-pixel units per item
 
 struct Geometry {
   int layout, bo_mode;
@@ -62,6 +63,9 @@ struct Geometry {
   int ngroups, nitems;
   int passes;       // 1 or 3 MMA passes
   int nacc;         // TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs)
+  int swap;         // 1: pixels on the MMA M dimension (TMEM lanes), output channels on N — thin layers (Cout <= 64)
+  int np;           // swap: output channels padded to a multiple of 16 (MMA N, TMEM columns per 128-pixel unit)
+  int units;        // swap: 128-pixel units per item
   float out_scale;  // 2^-scale_log2
 };
 
@@ -72,6 +76,7 @@ struct Params {
   const float* bias;
   const __half* w;     // packed [mt][chunk][tap][hi|lo][operand tile]
   int B;
+  int act;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -128,6 +133,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor (K-major).  version = 1 (sm_100).  layout_type: 0 none, 4 = 64B, 2 = 128B swizzle.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type,
                                               uint32_t base_offset) {
@@ -159,6 +174,25 @@ __device__ __forceinline__ void issue_tap(uint64_t da_st, uint64_t db_tap, uint6
       const uint64_t da = da_p + j * kstep_a, db = db_p + j * kstep_b;
 #pragma unroll
       for (int u = 0; u < U; ++u) tc_mma_f16(ucol[u], da, db + uoff[u], uidesc[u], (pass | j) == 0 ? acc_first : 1u);
+    }
+  }
+}
+
+// Swapped orientation: A = activation rows (128 pixels per unit, tap-shifted), B = the weight tile (np output channels).
+template <int PASSES, int U>
+__device__ __forceinline__ void issue_tap_swap(uint64_t da_tap, uint64_t db_st, uint64_t a_plane, uint64_t b_half, uint64_t kstep,
+                                               int ksteps, uint64_t unit_step, uint32_t tmem_acc, uint32_t np, uint32_t idesc,
+                                               uint32_t acc_first) {
+#pragma unroll
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const uint64_t da_p = da_tap + (pass == 1 ? a_plane : 0);
+    const uint64_t db_p = db_st + (pass == 2 ? b_half : 0);
+#pragma unroll 2
+    for (int j = 0; j < ksteps; ++j) {
+      const uint64_t da = da_p + j * kstep, db = db_p + j * kstep;
+#pragma unroll
+      for (int u = 0; u < U; ++u)      // unit u: pixel rows [128u, 128u+128) of the item -> TMEM columns [u*np, (u+1)*np)
+        tc_mma_f16(tmem_acc + u * np, da + (uint64_t)u * unit_step, db, idesc, (pass | j) == 0 ? acc_first : 1u);
     }
   }
 }
@@ -201,7 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
 
   const int per_mt = g.ngroups * g.npass;
   const uint32_t ltype = g.layout == 0 ? 0u : (g.layout == 1 ? 4u : 2u);
-  const int acc_cols = g.G * g.v_cnt;                    // TMEM columns of one accumulator set
+  const int acc_cols = g.swap ? g.units * g.np : g.G * g.v_cnt;   // TMEM columns of one accumulator set
   const int nacc = g.nacc;                               // 2 when two sets fit in the 512 columns
 
   if (warp == 0) {
@@ -242,6 +276,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
       uoff[u] = (uint64_t)(((uint32_t)(im * g.img_pix + g.seg_off[sg]) * pix_b) >> 4);
       uidesc[u] = make_idesc(g.seg_n[sg]);
     }
+    if (g.swap) {
+      const uint64_t unit_step = (uint64_t)((128u * pix_b) >> 4);
+      const uint32_t idesc_b = make_idesc(g.np);
+      const int units = g.units;
+      int s = 0;
+      uint32_t ph = 0, job = 0, it = 0;
+      for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
+        const int a = it % nacc;
+        mbar_wait(&acc_empty[a], ((it / nacc) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(a * acc_cols);
+        uint32_t acc = 0;
+        for (int c = 0; c < g.nchunk; ++c, ++job) {
+          const int buf = job % g.nbuf;
+          mbar_wait(&a_full[buf], (job / g.nbuf) & 1);
+          tc_fence_after();
+          const uint64_t da_buf = db_zero + (uint64_t)((act_base + (uint32_t)(buf * 2 * g.plane_bytes)) >> 4);
+          int ty = 0, tx = 0;
+          for (int tap = 0; tap < g.ntap; ++tap) {
+            mbar_wait(&w_full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t db_st = da_zero + (uint64_t)((wst_base + (uint32_t)(s * g.stage_bytes)) >> 4);
+              const uint64_t da_tap = da_buf + (uint64_t)(((uint32_t)(ty * g.Wp + tx) * pix_b) >> 4);
+#define VF_SW(PA, UU) issue_tap_swap<PA, UU>(da_tap, db_st, b_plane, a_half, kstep_b, g.ksteps, unit_step, tacc, (uint32_t)g.np, idesc_b, acc)
+              if (g.passes == 3) {
+                switch (units) {
+                  case 1: VF_SW(3, 1); break; case 2: VF_SW(3, 2); break; case 3: VF_SW(3, 3); break; case 4: VF_SW(3, 4); break;
+                  case 5: VF_SW(3, 5); break; case 6: VF_SW(3, 6); break; case 7: VF_SW(3, 7); break; default: VF_SW(3, 8); break;
+                }
+              } else {
+                switch (units) {
+                  case 1: VF_SW(1, 1); break; case 2: VF_SW(1, 2); break; case 3: VF_SW(1, 3); break; case 4: VF_SW(1, 4); break;
+                  case 5: VF_SW(1, 5); break; case 6: VF_SW(1, 6); break; case 7: VF_SW(1, 7); break; default: VF_SW(1, 8); break;
+                }
+              }
+#undef VF_SW
+              tc_commit(&w_empty[s]);
+            }
+            __syncwarp();
+            acc = 1;
+            if (++s == g.nstage) { s = 0; ph ^= 1; }
+            if (++tx == g.k) { tx = 0; ++ty; }
+          }
+          if (elect_one()) tc_commit(&a_empty[buf]);
+          __syncwarp();
+        }
+        if (elect_one()) tc_commit(&acc_full[a]);
+        __syncwarp();
+      }
+    } else {
     const int ntap = g.ntap, kk = g.k, Wp = g.Wp;
     const int variant = (g.passes == 3 ? 4 : 0) + (U - 1);              // KSTEPS is fixed per layout below
     int s = 0;
@@ -292,6 +377,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
       if (elect_one()) tc_commit(&acc_full[a]);     // accumulators complete -> epilogue
       __syncwarp();
     }
+    }
   } else if (warp >= STG_WARP0) {
     // ===== activation stagers: fp32 NHWC -> fp16 hi/lo operand rows of the flat zero-padded image =====
     const int t = threadIdx.x - STG_WARP0 * 32;     // 0..127
@@ -309,6 +395,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
         const uint32_t hi_addr = act_base + (uint32_t)(buf * 2 * g.plane_bytes);
         uint8_t* hi_ptr = smem + buf * 2 * g.plane_bytes;
         const int choff = P.src.ch_off + c * g.ch + kc8 * 8;
+        const bool ch_ok = c * g.ch + kc8 * 8 < g.Cin;          // zero-padded channel units of the last chunk
         for (int plb = pl0; plb < npl; plb += 4 * pl_step) {
           float4 f[4][2];
           bool ok[4];
@@ -320,7 +407,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
             const int qy = q / g.Wp;
             const int yy = qy - g.pad, xx = q - qy * g.Wp - g.pad;
             const int b = b0 + im;
-            ok[u] = pl < npl && b < P.B && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W;
+            ok[u] = ch_ok && pl < npl && b < P.B && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W;
             if (ok[u]) {
               const float4* sp = reinterpret_cast<const float4*>(P.src.p + (long long)b * P.src.sample_stride +
                                                                  (long long)(yy * g.W + xx) * P.src.pix_stride + choff);
@@ -363,7 +450,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
     // ===== epilogue: TMEM -> registers -> (x 2^-s, + border-class bias) -> NHWC global =====
     const int q4 = warp & 3;                        // TMEM lane quarter this warp may read
     const int row = q4 * 32 + lane;                 // output channel within the cout tile
-    const int center = g.pad * g.k + g.pad;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
       const int mt = item / per_mt;
@@ -374,36 +460,105 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
       const int a = it % nacc;
       mbar_wait(&acc_full[a], (it / nacc) & 1);
       tc_fence_after();
+      if (g.swap) {
+        // pixels on lanes: this thread owns pixel row `row` of every 128-pixel unit and all output channels of it
+        const int b = b0;
+        const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.pad;
+        const float scale = g.out_scale;
+        const bool sigm = P.act == ACT_SIGMOID;
+        const bool vec4 = ((g.Cout | P.out.ch_off | ps) & 3) == 0 && (P.out.sample_stride & 3) == 0;
+        for (int u = 0; u < g.units; ++u) {
+          const int v = v_lo + u * 128 + row;
+          const int oy = v / Wp, ox = v - oy * Wp;
+          const bool valid = b < P.B && ox < W && oy < H;
+          const float* sb = nullptr;
+          float* op = nullptr;
+          if (valid) {
+            if (P.sabias) {
+              const int cls = border_class(oy, H, pad) * g.k + border_class(ox, W, pad);
+              sb = P.sabias + ((long long)b * g.ntap + cls) * g.Cout;
+            } else {
+              sb = P.bias;
+            }
+            op = P.out.p + (long long)b * P.out.sample_stride + (long long)(oy * W + ox) * ps + P.out.ch_off;
+          }
+          for (int c16 = 0; c16 < g.np; c16 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + u * g.np + c16), r);
+            if (!valid) continue;
+            if (vec4) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                if (c16 + j < g.Cout) {
+                  const float4 bb = sb ? __ldg(reinterpret_cast<const float4*>(sb + c16 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  float4 o;
+                  o.x = fmaf(__uint_as_float(r[j]), scale, bb.x);
+                  o.y = fmaf(__uint_as_float(r[j + 1]), scale, bb.y);
+                  o.z = fmaf(__uint_as_float(r[j + 2]), scale, bb.z);
+                  o.w = fmaf(__uint_as_float(r[j + 3]), scale, bb.w);
+                  if (sigm) {
+                    o.x = __fdividef(1.f, 1.f + __expf(-o.x)); o.y = __fdividef(1.f, 1.f + __expf(-o.y));
+                    o.z = __fdividef(1.f, 1.f + __expf(-o.z)); o.w = __fdividef(1.f, 1.f + __expf(-o.w));
+                  }
+                  *reinterpret_cast<float4*>(op + c16 + j) = o;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (c16 + j < g.Cout) {
+                  float o = fmaf(__uint_as_float(r[j]), scale, sb ? __ldg(sb + c16 + j) : 0.f);
+                  if (sigm) o = __fdividef(1.f, 1.f + __expf(-o));
+                  op[c16 + j] = o;
+                }
+              }
+            }
+          }
+        }
+      } else
       for (int im = 0; im < g.G; ++im) {
         const int b = b0 + im;
-        const bool live = b < P.B;
-        float sb_c = 0.f;
-        if (live) {
-          if (P.sabias) {                           // this thread's column of the per-sample class table (private: no sync)
+        const bool live = b < P.B && n < g.Cout;
+        if (live) {                                 // this thread's column of the per-sample class table (private: no sync)
+          if (P.sabias) {
             const float* sp = P.sabias + (long long)b * g.ntap * g.Cout + n;
             for (int cls = 0; cls < g.ntap; ++cls) s_sab[cls * MT + row] = __ldg(sp + (long long)cls * g.Cout);
-            sb_c = s_sab[center * MT + row];
-          } else if (P.bias) {
-            sb_c = __ldg(P.bias + n);
+          } else {
+            const float bv = P.bias ? __ldg(P.bias + n) : 0.f;
+            for (int cls = 0; cls < g.ntap; ++cls) s_sab[cls * MT + row] = bv;
           }
         }
         float* op = P.out.p + (long long)b * P.out.sample_stride + P.out.ch_off + n;
+        const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.pad, kk = g.k;
+        const float scale = g.out_scale;
+        const bool sigm = P.act == ACT_SIGMOID;
         for (int cc = 0; cc < g.v_cnt; cc += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + im * g.v_cnt + cc), r);
           if (!live) continue;
+          // Every lane handles the SAME pixel (a different channel).  Branch-free and without loop-carried state so the
+          // 32 elements overlap: a 32-column chunk spans at most 4 image rows (Wp >= 10), selected by compare-and-add.
           const int v = v_lo + cc;
-          int oy = v / g.Wp, ox = v - oy * g.Wp;
+          const int oy0 = v / Wp, ox0 = v - oy0 * Wp;
+          int cyk[4], rbase[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            cyk[w] = border_class(oy0 + w, H, pad) * kk;
+            rbase[w] = (oy0 + w) * W * ps;
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (ox < g.W && oy < g.H) {
-              float val = __uint_as_float(r[j]) * g.out_scale;
-              const int cy = border_class(oy, g.H, g.pad), cx = border_class(ox, g.W, g.pad);
-              const int cls = cy * g.k + cx;
-              val += (cls == center || !P.sabias) ? sb_c : s_sab[cls * MT + row];
-              op[(long long)(oy * g.W + ox) * P.out.pix_stride] = val;
-            }
-            if (++ox == g.Wp) { ox = 0; ++oy; }
+            const int x0 = ox0 + j;
+            const int wr = (x0 >= Wp) + (x0 >= 2 * Wp) + (x0 >= 3 * Wp);
+            const int x = x0 - wr * Wp;
+            const bool valid = (x < W) & (oy0 + wr < H);
+            const int cx = x < pad ? x : (x >= W - pad ? x - (W - 1 - 2 * pad) : pad);
+            const int cyw = wr == 0 ? cyk[0] : (wr == 1 ? cyk[1] : (wr == 2 ? cyk[2] : cyk[3]));
+            const int rb = wr == 0 ? rbase[0] : (wr == 1 ? rbase[1] : (wr == 2 ? rbase[2] : rbase[3]));
+            const float bias = s_sab[(valid ? cyw + cx : 0) * MT + row];
+            float val = fmaf(__uint_as_float(r[j]), scale, bias);
+            if (sigm) val = __fdividef(1.f, 1.f + __expf(-val));
+            if (valid) op[rb + x * ps] = val;
           }
         }
       }
@@ -439,11 +594,44 @@ bool plan_geometry(int layout, int bo_mode, int k, int Cin, int Cout, int H, int
   memset(&g, 0, sizeof(g));
   g.layout = layout; g.bo_mode = bo_mode;
   g.ch = layout == 2 ? 64 : 32;
-  if (Cin % g.ch || Cout % MT) return false;
+  if (Cin % 8) return false;                            // 16-byte staging units; channels/cout beyond the real extent are zero-padded
   g.kc = g.ch / 8; g.ksteps = g.ch / 16; g.row_bytes = g.ch * 2; g.swz_mask = layout == 2 ? 7 : (layout == 1 ? 3 : 0);
   g.half_bytes = MT * g.ch * 2; g.stage_bytes = 2 * g.half_bytes;
   g.H = H; g.W = W; g.k = k; g.pad = k / 2; g.Wp = W + k - 1; g.Cin = Cin; g.Cout = Cout;
-  g.nchunk = Cin / g.ch; g.ntap = k * k; g.n_mt = Cout / MT; g.passes = passes;
+  g.nchunk = (Cin + g.ch - 1) / g.ch; g.ntap = k * k; g.n_mt = (Cout + MT - 1) / MT; g.passes = passes;
+  if (Cout <= 64 && layout >= 1) {
+    // ---- swapped orientation (thin layers): pixels on M in 128-row units, np = Cout padded to 16 on N ----
+    g.swap = 1;
+    g.np = (Cout + 15) / 16 * 16;
+    g.half_bytes = g.np * g.row_bytes; g.stage_bytes = 2 * g.half_bytes;
+    g.n_mt = 1; g.G = 1;
+    const int Vs = H * g.Wp;
+    const int umax = std::min(MAX_UNIT_B, 256 / g.np);
+    for (int units = umax; units >= 1; --units) {
+      g.npass = (Vs + 128 * units - 1) / (128 * units);
+      g.units = ((Vs + g.npass - 1) / g.npass + 127) / 128;
+      g.v_cnt = g.units * 128;
+      g.img_pix = (g.v_cnt + (k - 1) * g.Wp + (k - 1) + 7) / 8 * 8;
+      g.npix = g.img_pix;
+      g.plane_bytes = (g.npix * g.ch * 2 + 1023) / 1024 * 1024;
+      bool fit = false;
+      for (g.nbuf = 2; g.nbuf >= 1; --g.nbuf) {
+        const size_t act = (size_t)g.nbuf * 2 * g.plane_bytes;
+        if (act + 2 * (size_t)g.stage_bytes + SMEM_SLACK > SMEM_LIMIT) continue;
+        g.nstage = (int)std::min<size_t>(MAX_STAGE, (SMEM_LIMIT - SMEM_SLACK - act) / g.stage_bytes);
+        fit = true;
+        break;
+      }
+      if (fit && g.nbuf == 2) break;                      // largest unit count that still double-buffers the staging
+      if (fit && units == 1) break;
+      if (!fit && units == 1) return false;
+    }
+    g.nacc = (2 * g.units * g.np <= 512) ? 2 : 1;
+    g.ngroups = B;
+    g.nitems = g.ngroups * g.npass;
+    *out = g;
+    return true;
+  }
   const int V = H * g.Wp;                               // virtual pixels per image (incl. k-1 wrap columns per row)
   // (G, v_cnt, npass): several whole small images per item, or an (almost) even slice of one large image.
   // v_cnt is rounded up to 32 columns; the overshoot reads zero-filled staging rows and is masked in the epilogue.
@@ -518,8 +706,10 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaCon
   int layout, bo;
   current_mode(&layout, &bo);
   const int ch = layout == 2 ? 64 : 32;
-  if (cin % ch || cout % MT) { if (err) *err = "cin % chunk or cout % 128"; return -1; }
-  const int kk = k * k, nchunk = cin / ch, n_mt = cout / MT, kc = ch / 8, rb = ch * 2;
+  if (cin % 8) { if (err) *err = "cin % 8"; return -1; }
+  const bool swap = cout <= 64 && layout >= 1;
+  const int rows = swap ? (cout + 15) / 16 * 16 : MT;                 // operand tile rows (output channels)
+  const int kk = k * k, nchunk = (cin + ch - 1) / ch, n_mt = swap ? 1 : (cout + MT - 1) / MT, kc = ch / 8, rb = ch * 2;
   const int swz = layout == 2 ? 7 : (layout == 1 ? 3 : 0);
   float amax = 0.f;
   for (size_t i = 0; i < (size_t)kk * cin * cout; ++i) amax = std::max(amax, fabsf(w_sp[i]));
@@ -527,7 +717,7 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaCon
   if (amax > 0.f) sl = (int)floorf(log2f(16384.0f / amax));           // max |w| * 2^sl in [8192, 16384]
   sl = std::max(-24, std::min(sl, 24));
   const float scale = ldexpf(1.0f, sl);
-  const size_t half_elems = (size_t)MT * ch;
+  const size_t half_elems = (size_t)rows * ch;
   const size_t total = (size_t)n_mt * nchunk * kk * 2 * half_elems;
   std::vector<__half> packed(total);
   for (int mt = 0; mt < n_mt; ++mt)
@@ -535,14 +725,14 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaCon
       for (int t = 0; t < kk; ++t) {
         const size_t blk = (((size_t)mt * nchunk + c) * kk + t) * 2 * half_elems;
         for (int kc8 = 0; kc8 < kc; ++kc8)
-          for (int r = 0; r < MT; ++r)
+          for (int r = 0; r < rows; ++r)
             for (int e = 0; e < 8; ++e) {
-              const int ci = c * ch + kc8 * 8 + e, n = mt * MT + r;
-              const float v = w_sp[((size_t)t * cin + ci) * cout + n] * scale;
+              const int ci = c * ch + kc8 * 8 + e, n = mt * rows + r;
+              const float v = (ci < cin && n < cout) ? w_sp[((size_t)t * cin + ci) * cout + n] * scale : 0.f;
               const __half h = __float2half_rn(v);
               const __half l = __float2half_rn(v - __half2float(h));
               size_t pos;                                              // element index inside the 128-row operand tile
-              if (layout == 0) pos = ((size_t)kc8 * MT + r) * 8 + e;
+              if (layout == 0) pos = ((size_t)kc8 * rows + r) * 8 + e;
               else pos = ((size_t)r * rb + (size_t)((kc8 ^ ((r * rb >> 7) & swz)) << 4)) / 2 + e;
               packed[blk + pos] = h;
               packed[blk + half_elems + pos] = l;
@@ -566,7 +756,7 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   current_mode(&layout, &bo);
   if (!plan_geometry(layout, bo, w.k, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
   P.g.out_scale = ldexpf(1.0f, -w.scale_log2);
-  P.src = c.src; P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B;
+  P.src = c.src; P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B; P.act = c.act;
   if ((c.src.pix_stride % 4) || (c.src.ch_off % 4) || (c.src.sample_stride % 4)) return -2;      // float4 loads
   const size_t smem = smem_bytes(P.g);
   static bool attr_set = false;

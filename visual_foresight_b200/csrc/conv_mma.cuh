@@ -22,6 +22,7 @@ struct MmaConvCall {
   const float* bias;
   int H, W;
   int passes;   // 3 = hi*hi + lo*hi + hi*lo (fp32-grade), 1 = hi*hi
+  int act = 0;  // ACT_NONE / ACT_SIGMOID applied in the epilogue
 };
 
 bool mma_conv_supported(int k, int cin, int cout, int H, int W);

@@ -34,6 +34,7 @@ struct HostTensor {
 struct ConvLayer {
   std::string name;
   int k = 0, H = 0, W = 0, cin_sp = 0, cin_const = 0, cout = 0;
+  int cin_w = 0;            // spatial channels present in the weight tensor (cin_sp may be zero-padded beyond it)
   bool lstm = false;
   float* w_sp = nullptr;    // [k*k][cin_sp][cout]
   float* wcls = nullptr;    // [k*k][A][cout]
@@ -78,11 +79,12 @@ struct vf_engine {
   int last_M = 0;
 
   // derived
-  int B, H, W, ncam, nd, adim, sdim, nz, A, S, C, P, ngf, nt, kc, nm, n_enc;
+  int B, H, W, ncam, nd, adim, sdim, nz, A, S, C, P, ngf, nt, kc, nm, n_enc, cm;
   std::vector<ViewNet> views;
 
   // shared scratch
   float *raw = nullptr, *dec_in = nullptr, *stats = nullptr, *cstats = nullptr;
+  double* stats_partial = nullptr;
   std::vector<float*> act_enc, act_dec;
   float *scr_h = nullptr, *mask_in = nullptr, *logits = nullptr, *kern = nullptr, *partial = nullptr;
   int nblk = 0;
@@ -188,14 +190,15 @@ int prepare_conv(vf_engine* h, int view, ConvLayer& L) {
   const int A = L.cin_const, k = L.k, kk = k * k;
   const HostTensor* w = find_w(h, view, L.name + ".w");
   if (!w) return fail(h, VF_ERR_STATE, "missing weight view%d.%s.w", view, L.name.c_str());
-  const int cin_total = L.cin_sp + A;
+  if (!L.cin_w) L.cin_w = L.cin_sp;
+  const int cin_total = L.cin_w + A;
   if (w->shape.size() != 4 || w->shape[0] != k || w->shape[1] != k || w->shape[2] != cin_total || w->shape[3] != L.cout)
     return fail(h, VF_ERR_INVALID, "weight %s.w has wrong shape (want %d,%d,%d,%d)", L.name.c_str(), k, k, cin_total, L.cout);
   // channel order: conv [spatial, sa]; lstm [x, sa, h]
-  const int xch = L.lstm ? L.cin_sp / 2 : L.cin_sp;
-  std::vector<float> wsp((size_t)kk * L.cin_sp * L.cout);
+  const int xch = L.lstm ? L.cin_w / 2 : L.cin_w;
+  std::vector<float> wsp((size_t)kk * L.cin_sp * L.cout, 0.f);
   for (int t = 0; t < kk; ++t)
-    for (int c = 0; c < L.cin_sp; ++c) {
+    for (int c = 0; c < L.cin_w; ++c) {
       const int src_c = (c < xch) ? c : c + A;
       memcpy(&wsp[((size_t)t * L.cin_sp + c) * L.cout], &w->data[((size_t)t * cin_total + src_c) * L.cout], L.cout * sizeof(float));
     }
@@ -318,13 +321,15 @@ int build_net(vf_engine* h) {
     net.scratch0 = mk("scratch.conv0", 3, h->H, h->W, g, 0, g, false);
     net.scratch1 = mk("scratch.conv1", 3, h->H, h->W, g, 0, 3, false);
     net.masks0 = mk("masks.conv0", 3, h->H, h->W, g, 0, g, false);
-    net.masks1 = mk("masks.conv1", 3, h->H, h->W, g + 3 * h->nm, 0, h->nm, false);
+    net.masks1 = mk("masks.conv1", 3, h->H, h->W, h->cm, 0, h->nm, false);
+    net.masks1.cin_w = g + 3 * h->nm;        // mask_in rows are padded to a multiple of 8 channels (16-byte staging units)
     upd(net.scratch0);
   }
   // shared scratch (first view's shapes == all views' shapes)
   DA(h->raw, (size_t)B * raw_max);
   DA(h->dec_in, (size_t)B * decin_max);
   DA(h->stats, (size_t)B * cmax * 2);
+  DA(h->stats_partial, plane_stats_partial_doubles(B, (int)cmax));
   DA(h->cstats, (size_t)B * std::max(fmax_, (size_t)1) * 2);
   h->act_enc.assign(n, nullptr);
   h->act_dec.assign(n, nullptr);
@@ -341,7 +346,8 @@ int build_net(vf_engine* h) {
   }
   const size_t px = (size_t)h->H * h->W;
   DA(h->scr_h, (size_t)B * px * h->ngf);
-  DA(h->mask_in, (size_t)B * px * (h->ngf + 3 * h->nm));
+  DA(h->mask_in, (size_t)B * px * h->cm);
+  if (cudaMemset(h->mask_in, 0, (size_t)B * px * h->cm * sizeof(float)) != cudaSuccess) return fail(h, VF_ERR_CUDA, "memset mask_in");
   DA(h->logits, (size_t)B * px * h->nm);
   DA(h->kern, (size_t)B * h->nt * h->kc * h->kc);
   h->nblk = composite_blocks(h->H, h->W);
@@ -418,6 +424,7 @@ void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out,
     MmaConvCall c;
     c.src = s0; c.out = out; c.sabias = L.sabias; c.bias = L.bias; c.H = L.H; c.W = L.W;
     c.passes = (h->cfg.precision == VF_PREC_F16X3) ? 3 : 1;
+    c.act = act;
     mma_conv_launch(L.mma, c, B, h->stream);
     return;
   }
@@ -433,9 +440,9 @@ void run_lstm(vf_engine* h, int v, const ConvLayer& L, RnnState& r, int B, const
   View gates = dense_view(h->raw, hw, 4 * F);
   View none = make_view(nullptr, 0, 0, 0, 0);
   run_conv(h, L, in, none, gates, B);
-  launch_plane_stats(gates, B, r.h, r.w, 0, h->cfg.norm_eps, h->stats, h->stream);
+  launch_plane_stats(gates, B, r.h, r.w, 0, h->cfg.norm_eps, h->stats, h->stats_partial, h->stream);
   launch_lstm_gates(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->stream);
-  launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cfg.norm_eps, h->cstats, h->stream);
+  launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cfg.norm_eps, h->cstats, h->stats_partial, h->stream);
   View hv = make_view(r.lstm_in, (long long)hw * 2 * F, 2 * F, F, F);
   launch_lstm_out(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cstats, L.cgamma, L.cbeta, r.c, hv, h->stream);
   h->debug[v][dbg + ".h"] = DebugEntry{hv, r.h, r.w};
@@ -479,7 +486,7 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     View rawv = dense_view(h->raw, hh * ww, oc);
     run_conv(h, L, x0, x1, rawv, B);
     hh /= 2; ww /= 2;
-    launch_plane_stats(rawv, B, hh, ww, 1, c.norm_eps, h->stats, h->stream);
+    launch_plane_stats(rawv, B, hh, ww, 1, c.norm_eps, h->stats, h->stats_partial, h->stream);
     View dst = c.enc_rnn[i] ? make_view(net.enc_rnn[i].lstm_in, (long long)hh * ww * 2 * oc, 2 * oc, 0, oc)
                             : dense_view(h->act_enc[i], hh * ww, oc);
     launch_norm_act(rawv, B, hh, ww, 1, h->stats, L.gamma, L.beta, ACT_RELU, dst, h->stream);
@@ -503,7 +510,7 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     hh *= 2; ww *= 2;
     View rawv = dense_view(h->raw, hh * ww, oc);
     run_conv(h, L, din, none, rawv, B);
-    launch_plane_stats(rawv, B, hh, ww, 0, c.norm_eps, h->stats, h->stream);
+    launch_plane_stats(rawv, B, hh, ww, 0, c.norm_eps, h->stats, h->stats_partial, h->stream);
     View dst = c.dec_rnn[i] ? make_view(net.dec_rnn[i].lstm_in, (long long)hh * ww * 2 * oc, 2 * oc, 0, oc)
                             : dense_view(h->act_dec[i], hh * ww, oc);
     launch_norm_act(rawv, B, hh, ww, 0, h->stats, L.gamma, L.beta, ACT_RELU, dst, h->stream);
@@ -516,7 +523,7 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   }
   if (tau < h->C - 1) return;   // warm-up step: its prediction is never consumed
   const int t_out = tau - (h->C - 1);
-  const int g = h->ngf, nm = h->nm, cm = g + 3 * nm;
+  const int g = h->ngf, nm = h->nm, cm = h->cm;
   View h_last = x;
   // P5/P6
   launch_cdna_kernels(enc_out[n - 1], enc_h[n - 1] * enc_w[n - 1], net.cdna_w, net.cdna_b, h->kc, h->nt, B, h->kern, h->stream);
@@ -525,14 +532,14 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   // P7 scratch image
   View rawg = dense_view(h->raw, (int)px, g);
   run_conv(h, net.scratch0, h_last, none, rawg, B);
-  launch_plane_stats(rawg, B, H, W, 0, c.norm_eps, h->stats, h->stream);
+  launch_plane_stats(rawg, B, H, W, 0, c.norm_eps, h->stats, h->stats_partial, h->stream);
   View scr = dense_view(h->scr_h, (int)px, g);
   launch_norm_act(rawg, B, H, W, 0, h->stats, net.scratch0.gamma, net.scratch0.beta, ACT_RELU, scr, h->stream);
   View scratch_out = make_view(h->mask_in, px * cm, cm, g + 3 * (h->nt + 2), 3);
   run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
   // P8 masks
   run_conv(h, net.masks0, h_last, none, rawg, B);
-  launch_plane_stats(rawg, B, H, W, 0, c.norm_eps, h->stats, h->stream);
+  launch_plane_stats(rawg, B, H, W, 0, c.norm_eps, h->stats, h->stats_partial, h->stream);
   View hm = make_view(h->mask_in, px * cm, cm, 0, g);
   launch_norm_act(rawg, B, H, W, 0, h->stats, net.masks0.gamma, net.masks0.beta, ACT_RELU, hm, h->stream);
   View lg = dense_view(h->logits, (int)px, nm);
@@ -645,6 +652,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
   h->adim = cfg->adim; h->sdim = cfg->sdim; h->nz = cfg->nz; h->A = cfg->adim + cfg->sdim + cfg->nz;
   h->S = cfg->seq_len; h->C = cfg->context_frames; h->P = h->S - h->C; h->ngf = cfg->ngf;
   h->nt = cfg->num_transformed; h->kc = cfg->cdna_ksize; h->nm = h->nt + 3; h->n_enc = cfg->n_enc;
+  h->cm = (cfg->ngf + 3 * h->nm + 7) / 8 * 8;
   if (h->B < 1 || h->H < 8 || h->W < 8 || h->ncam < 1 || h->ncam > 4 || h->nd < 1 || h->nd > 4 || h->ncam * h->nd > VF_MAX_TASKS)
     return fail(h, VF_ERR_INVALID, "bad sizes (max_samples %d, %dx%d, ncam %d, ndesig %d)", h->B, h->H, h->W, h->ncam, h->nd);
   if (h->adim < 1 || h->adim > 8 || h->sdim < 0 || h->sdim > 16 || h->nz < 0) return fail(h, VF_ERR_INVALID, "bad adim/sdim/nz");

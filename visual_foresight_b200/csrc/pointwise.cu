@@ -19,40 +19,48 @@ __device__ __forceinline__ float pooled(const View& x, int b, int W, int pool, i
   return ((a + bq) + (cq + d)) * 0.25f;
 }
 
-// grid (B, ceil(C/32)), block (32, 8).  Two passes (mean, then centred variance) like the oracle's
-// instance norm; fixed summation order -> bit-reproducible, independent of sample count and GPU count.
-__global__ void k_plane_stats(View x, int H, int W, int pool, float eps, float* stats) {
+// Instance-norm statistics, one pass: grid (B, ceil(C/32), S pixel splits), block (32, 8).  Every thread accumulates
+// sum and sum-of-squares of its pixels in float64 (no cancellation in E[x^2]-mean^2 at fp32 data precision), the 8
+// rows are combined in a fixed order, and the S partials of a (sample, channel) are combined in a fixed order by
+// k_stats_finalize: bit-reproducible, independent of sample count and GPU count.
+constexpr int STATS_MAX_SPLIT = 8;
+__global__ void k_plane_stats(View x, int H, int W, int pool, double* partial) {
   const int b = blockIdx.x;
   const int c = blockIdx.y * 32 + threadIdx.x;
+  const int S = gridDim.z, sp = blockIdx.z;
   const int npix = H * W;
-  __shared__ float red[8][33];
-  const bool ok = c < x.C;
-  float s = 0.f;
-  if (ok)
-    for (int p = threadIdx.y; p < npix; p += 8) s += pooled(x, b, W, pool, p / W, p % W, c);
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  float mean = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) mean += red[i][threadIdx.x];
-  mean /= (float)npix;
-  __syncthreads();
-  float v = 0.f;
-  if (ok)
-    for (int p = threadIdx.y; p < npix; p += 8) {
-      const float d = pooled(x, b, W, pool, p / W, p % W, c) - mean;
-      v = fmaf(d, d, v);
+  const int p0 = (int)((long long)npix * sp / S), p1 = (int)((long long)npix * (sp + 1) / S);
+  __shared__ double red[2][8][33];
+  double s = 0.0, q = 0.0;
+  if (c < x.C)
+    for (int p = p0 + threadIdx.y; p < p1; p += 8) {
+      const double v = (double)pooled(x, b, W, pool, p / W, p % W, c);
+      s += v;
+      q = fma(v, v, q);
     }
-  red[threadIdx.y][threadIdx.x] = v;
+  red[0][threadIdx.y][threadIdx.x] = s;
+  red[1][threadIdx.y][threadIdx.x] = q;
   __syncthreads();
-  if (threadIdx.y == 0 && ok) {
-    float var = 0.f;
+  if (threadIdx.y == 0 && c < x.C) {
+    double ts = 0.0, tq = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) var += red[i][threadIdx.x];
-    var /= (float)npix;
-    stats[((long long)b * x.C + c) * 2 + 0] = mean;
-    stats[((long long)b * x.C + c) * 2 + 1] = 1.0f / sqrtf(var + eps);
+    for (int i = 0; i < 8; ++i) { ts += red[0][i][threadIdx.x]; tq += red[1][i][threadIdx.x]; }
+    double* o = partial + (((long long)b * x.C + c) * S + sp) * 2;
+    o[0] = ts;
+    o[1] = tq;
   }
+}
+
+__global__ void k_stats_finalize(const double* __restrict__ partial, int n, int S, int npix, float eps, float* stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double ts = 0.0, tq = 0.0;
+  for (int k = 0; k < S; ++k) { ts += partial[((long long)i * S + k) * 2]; tq += partial[((long long)i * S + k) * 2 + 1]; }
+  const double mean = ts / npix;
+  double var = tq / npix - mean * mean;            // biased variance
+  if (var < 0.0) var = 0.0;
+  stats[(long long)i * 2] = (float)mean;
+  stats[(long long)i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 __global__ void k_norm_act(View x, int B, int H, int W, int pool, const float* __restrict__ stats,
@@ -221,11 +229,17 @@ inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
 
 }  // namespace
 
-void launch_plane_stats(View x, int B, int H, int W, int pool, float eps, float* stats, cudaStream_t s) {
-  ++g_launch_counter;
-  dim3 grid(B, (x.C + 31) / 32), block(32, 8);
-  k_plane_stats<<<grid, block, 0, s>>>(x, H, W, pool, eps, stats);
+void launch_plane_stats(View x, int B, int H, int W, int pool, float eps, float* stats, double* partial, cudaStream_t s) {
+  g_launch_counter += 2;
+  const int npix = H * W;
+  int S = npix >= 2048 ? 8 : (npix >= 512 ? 4 : (npix >= 128 ? 2 : 1));
+  while (S < STATS_MAX_SPLIT && (long long)B * ((x.C + 31) / 32) * S < 296 && npix / (2 * S) >= 16) S *= 2;   // fill the 148 SMs
+  dim3 grid(B, (x.C + 31) / 32, S), block(32, 8);
+  k_plane_stats<<<grid, block, 0, s>>>(x, H, W, pool, partial);
+  const int n = B * x.C;
+  k_stats_finalize<<<(n + 255) / 256, 256, 0, s>>>(partial, n, S, npix, eps, stats);
 }
+size_t plane_stats_partial_doubles(int B, int C) { return (size_t)B * C * STATS_MAX_SPLIT * 2; }
 void launch_norm_act(View x, int B, int H, int W, int pool, const float* stats, const float* gamma,
                      const float* beta, int act, View y, cudaStream_t s) {
   ++g_launch_counter;

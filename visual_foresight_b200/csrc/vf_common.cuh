@@ -47,7 +47,9 @@ void launch_conv_simt(const ConvArgs& a, int B, cudaStream_t s);
 
 // ---- normalisation / pointwise --------------------------------------------------------------
 // stats[(b*C + c)*2 + {0,1}] = mean, rstd of (optionally 2x2 avg-pooled) x over the plane
-void launch_plane_stats(View x, int B, int H, int W, int pool, float eps, float* stats, cudaStream_t s);
+// (partial: scratch of plane_stats_partial_doubles(B, C) float64)
+void launch_plane_stats(View x, int B, int H, int W, int pool, float eps, float* stats, double* partial, cudaStream_t s);
+size_t plane_stats_partial_doubles(int B, int C);
 // y = act((pool(x) - mean) * rstd * gamma + beta)
 void launch_norm_act(View x, int B, int H, int W, int pool, const float* stats, const float* gamma,
                      const float* beta, int act, View y, cudaStream_t s);
