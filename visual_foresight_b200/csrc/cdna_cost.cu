@@ -13,43 +13,61 @@ __device__ __forceinline__ const float* vptr(const View& v, int b, long long pix
 // TF 'SYMMETRIC' padding index: -1 -> 0, -2 -> 1, n -> n-1, n+1 -> n-2
 __device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -1 - i : (i >= n ? 2 * n - 1 - i : i); }
 
-// block per sample, 1024 threads = 128 output lanes x 8 K-groups
+// CDNA kernel head (spec P5): dense(flatten(h)) -> +identity -> relu-shift -> L1 normalise.
+// Block = CK_S samples x all outputs: every weight element fetched from L2 feeds CK_S FMAs.  1024 threads =
+// 128 output lanes x CK_G K-groups; the feature chunk of the CK_S samples is staged in shared memory (broadcast reads).
+constexpr int CK_S = 4, CK_G = 8, CK_T = 1024;
 __global__ void __launch_bounds__(1024) k_cdna_kernels(View feat, int npix, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, int ksize, int nt, float* kern) {
-  const int b = blockIdx.x;
+                                                      const float* __restrict__ bias, int ksize, int nt, int B, float* kern) {
+  const int b0 = blockIdx.x * CK_S;
   const int nout = ksize * ksize * nt;          // <= 128
-  const int j = threadIdx.x % 128, g = threadIdx.x / 128;
+  const int j = threadIdx.x & 127, g = threadIdx.x >> 7;
   const int K = npix * feat.C;
-  const int per = (K + 7) / 8;
-  __shared__ float part[8][128];
-  __shared__ float raw[128];
-  float acc = 0.f;
-  if (j < nout) {
-    const int k1 = min(K, (g + 1) * per);
-    for (int k = g * per; k < k1; ++k) {
-      const float f = __ldg(vptr(feat, b, k / feat.C) + (k % feat.C));
-      acc = fmaf(f, __ldg(w + (long long)k * nout + j), acc);
+  __shared__ float sf[CK_S][CK_T];
+  __shared__ float part[CK_G][CK_S][128];
+  float acc[CK_S];
+#pragma unroll
+  for (int sI = 0; sI < CK_S; ++sI) acc[sI] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += CK_T) {
+    for (int i = threadIdx.x; i < CK_S * CK_T; i += 1024) {
+      const int sI = i / CK_T, kk = i - sI * CK_T, k = k0 + kk, b = b0 + sI;
+      sf[sI][kk] = (b < B && k < K) ? __ldg(vptr(feat, b, k / feat.C) + (k % feat.C)) : 0.f;
+    }
+    __syncthreads();
+    if (j < nout) {
+      constexpr int KG = CK_T / CK_G;
+      const int ke = min(KG, max(0, K - k0 - g * KG));
+      const float* wp = w + (long long)(k0 + g * KG) * nout + j;
+      for (int kk = 0; kk < ke; ++kk) {
+        const float wv = __ldg(wp + (long long)kk * nout);
+#pragma unroll
+        for (int sI = 0; sI < CK_S; ++sI) acc[sI] = fmaf(sf[sI][g * KG + kk], wv, acc[sI]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int sI = 0; sI < CK_S; ++sI) part[g][sI][j] = acc[sI];
+  __syncthreads();
+  // raw kernel taps: dense output reshaped (k, k, nt): j = (u*k + v)*nt + n ; + identity at the centre tap
+  for (int i = threadIdx.x; i < CK_S * 128; i += 1024) {
+    const int sI = i >> 7, jj = i & 127;
+    if (jj < nout) {
+      float v = bias[jj];
+#pragma unroll
+      for (int gg = 0; gg < CK_G; ++gg) v += part[gg][sI][jj];      // fixed order
+      if (jj / nt == (ksize / 2) * ksize + ksize / 2) v += 1.0f;
+      part[0][sI][jj] = fmaxf(v - 1e-12f, 0.f) + 1e-12f;
     }
   }
-  part[g][j] = acc;
   __syncthreads();
-  if (g == 0 && j < nout) {
-    float v = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v += part[i][j];
-    v += bias[j];
-    // dense output reshaped (k, k, nt): j = (u*k + v)*nt + n ; + identity at the centre tap
-    const int tap = j / nt;
-    if (tap == (ksize / 2) * ksize + ksize / 2) v += 1.0f;
-    v = fmaxf(v - 1e-12f, 0.f) + 1e-12f;
-    raw[j] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < nt) {
-    const int n = threadIdx.x;
-    float s = 0.f;
-    for (int t = 0; t < ksize * ksize; ++t) s += raw[t * nt + n];
-    for (int t = 0; t < ksize * ksize; ++t) kern[((long long)b * nt + n) * ksize * ksize + t] = raw[t * nt + n] / s;
+  if (threadIdx.x < CK_S * nt) {
+    const int sI = threadIdx.x / nt, n = threadIdx.x % nt, b = b0 + sI;
+    if (b < B) {
+      float sum = 0.f;
+      for (int t = 0; t < ksize * ksize; ++t) sum += part[0][sI][t * nt + n];
+      for (int t = 0; t < ksize * ksize; ++t) kern[((long long)b * nt + n) * ksize * ksize + t] = part[0][sI][t * nt + n] / sum;
+    }
   }
 }
 
@@ -253,7 +271,7 @@ __global__ void __launch_bounds__(256) k_goal_image_cost(const float* __restrict
 void launch_cdna_kernels(View feat, int npix, const float* w, const float* bias, int ksize, int nt, int B, float* kern,
                          cudaStream_t s) {
   ++g_launch_counter;
-  k_cdna_kernels<<<B, 1024, 0, s>>>(feat, npix, w, bias, ksize, nt, kern);
+  k_cdna_kernels<<<(B + CK_S - 1) / CK_S, 1024, 0, s>>>(feat, npix, w, bias, ksize, nt, B, kern);
 }
 void launch_cdna_apply(View image, View first, const float* kern, int ksize, int nt, int B, int H, int W, View mask_in,
                        int base, cudaStream_t s) {

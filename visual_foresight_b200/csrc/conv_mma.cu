@@ -42,7 +42,7 @@ constexpr int MT = 128;                // cout tile (UMMA M)
 constexpr int NTHREADS = 384;
 constexpr int NLOAD = 128;             // threads per role group (4 epilogue warps, 4 stager warps)
 constexpr int MAX_SEG = 8;
-constexpr int MAX_STAGE = 4;
+constexpr int MAX_STAGE = 8;
 constexpr int MAX_UNIT = 4;            // (images x column segments) per item
 constexpr int MAX_UNIT_B = 8;          // swapped orientation: 128-pixel units per item
 

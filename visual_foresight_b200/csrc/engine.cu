@@ -86,6 +86,7 @@ struct vf_engine {
   float *raw = nullptr, *dec_in = nullptr, *stats = nullptr, *cstats = nullptr;
   double* stats_partial = nullptr;
   std::vector<float*> act_enc, act_dec;
+  float* pack0 = nullptr;    // [B][H][W][8] packed (image, first) input of enc0 (tensor-core path)
   float *scr_h = nullptr, *mask_in = nullptr, *logits = nullptr, *kern = nullptr, *partial = nullptr;
   int nblk = 0;
 
@@ -281,6 +282,10 @@ int build_net(vf_engine* h) {
       char nm[64];
       snprintf(nm, sizeof(nm), "enc%d.conv", i);
       net.enc_conv.push_back(mk(nm, i == 0 ? 5 : 3, hh, ww, cprev, A, oc, false));
+      if (i == 0 && c.precision != VF_PREC_FP32_SIMT) {      // (image, first) packed to 8 channels for the tensor-core path
+        net.enc_conv.back().cin_sp = 8;
+        net.enc_conv.back().cin_w = 6;
+      }
       upd(net.enc_conv.back());
       hh /= 2; ww /= 2;
       if (c.enc_rnn[i]) {
@@ -346,6 +351,7 @@ int build_net(vf_engine* h) {
   }
   const size_t px = (size_t)h->H * h->W;
   DA(h->scr_h, (size_t)B * px * h->ngf);
+  if (c.precision != VF_PREC_FP32_SIMT) DA(h->pack0, (size_t)B * px * 8);
   DA(h->mask_in, (size_t)B * px * h->cm);
   if (cudaMemset(h->mask_in, 0, (size_t)B * px * h->cm * sizeof(float)) != cudaSuccess) return fail(h, VF_ERR_CUDA, "memset mask_in");
   DA(h->logits, (size_t)B * px * h->nm);
@@ -479,6 +485,11 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   std::vector<View> enc_out(n);
   std::vector<int> enc_h(n), enc_w(n);
   View x0 = image, x1 = first;
+  if (h->pack0) {
+    launch_pack_rgb2(image, first, B, H * W, h->pack0, h->stream);
+    x0 = dense_view(h->pack0, H * W, 8);
+    x1 = none;
+  }
   int hh = H, ww = W;
   for (int i = 0; i < n; ++i) {
     ConvLayer& L = net.enc_conv[i];

@@ -63,19 +63,35 @@ __global__ void k_stats_finalize(const double* __restrict__ partial, int n, int 
   stats[(long long)i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-__global__ void k_norm_act(View x, int B, int H, int W, int pool, const float* __restrict__ stats,
-                           const float* __restrict__ gamma, const float* __restrict__ beta, int act, View y) {
-  const long long total = (long long)B * H * W * x.C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % x.C);
-    const long long pixb = i / x.C;
-    const int pix = (int)(pixb % (H * W));
-    const int b = (int)(pixb / (H * W));
-    const float v = pooled(x, b, W, pool, pix / W, pix % W, c);
-    const float mean = stats[((long long)b * x.C + c) * 2], rstd = stats[((long long)b * x.C + c) * 2 + 1];
-    float o = (v - mean) * rstd * gamma[c] + beta[c];
-    if (act == ACT_RELU) o = fmaxf(o, 0.f);
-    y.p[(long long)b * y.sample_stride + (long long)pix * y.pix_stride + y.ch_off + c] = o;
+// one thread = 4 consecutive channels of one output pixel; grid.y = sample
+__global__ void __launch_bounds__(256) k_norm_act(View x, int H, int W, int pool, const float* __restrict__ stats,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta, int act, View y) {
+  const int b = blockIdx.y;
+  const int C4 = x.C >> 2;
+  const int total = H * W * C4;
+  const float* st = stats + (long long)b * x.C * 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (i % C4) << 2;
+    const int pix = i / C4;
+    float4 v;
+    if (!pool) {
+      v = __ldg(reinterpret_cast<const float4*>(vptr(x, b, pix) + c));
+    } else {
+      const int py = pix / W, px = pix - py * W, Wi = 2 * W;
+      const float* p00 = vptr(x, b, (long long)(2 * py) * Wi + 2 * px) + c;
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(p00)), a1 = __ldg(reinterpret_cast<const float4*>(p00 + x.pix_stride));
+      const float4 a2 = __ldg(reinterpret_cast<const float4*>(p00 + (long long)Wi * x.pix_stride));
+      const float4 a3 = __ldg(reinterpret_cast<const float4*>(p00 + (long long)(Wi + 1) * x.pix_stride));
+      v.x = ((a0.x + a1.x) + (a2.x + a3.x)) * 0.25f; v.y = ((a0.y + a1.y) + (a2.y + a3.y)) * 0.25f;
+      v.z = ((a0.z + a1.z) + (a2.z + a3.z)) * 0.25f; v.w = ((a0.w + a1.w) + (a2.w + a3.w)) * 0.25f;
+    }
+    const float4 s0 = *reinterpret_cast<const float4*>(st + 2 * c), s1 = *reinterpret_cast<const float4*>(st + 2 * c + 4);
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c)), b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 o;                                            // stats layout: (mean, rstd) pairs
+    o.x = (v.x - s0.x) * s0.y * g4.x + b4.x; o.y = (v.y - s0.z) * s0.w * g4.y + b4.y;
+    o.z = (v.z - s1.x) * s1.y * g4.z + b4.z; o.w = (v.w - s1.z) * s1.w * g4.w + b4.w;
+    if (act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    *reinterpret_cast<float4*>(y.p + (long long)b * y.sample_stride + (long long)pix * y.pix_stride + y.ch_off + c) = o;
   }
 }
 
@@ -88,37 +104,36 @@ __device__ __forceinline__ float gate_norm(const View& g, int b, long long pix, 
   return (v - st[0]) * st[1] * gg[ch] + gb[ch];
 }
 
-// gate order along channels: i, j, f, o   (spec P3)
-__global__ void k_lstm_gates(View gates, int B, int HW, int F, const float* __restrict__ gstats,
-                             const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c) {
-  const long long total = (long long)B * HW * F;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int f = (int)(i % F);
-    const long long pixb = i / F;
-    const int pix = (int)(pixb % HW);
-    const int b = (int)(pixb / HW);
+// gate order along channels: i, j, f, o   (spec P3).  grid.y = sample; threads run along f (coalesced)
+__global__ void __launch_bounds__(256) k_lstm_gates(View gates, int HW, int F, const float* __restrict__ gstats,
+                                                    const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c) {
+  const int b = blockIdx.y;
+  const int total = HW * F;
+  float* cb_ = c + (long long)b * total;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int f = i % F, pix = i / F;
     const float gi = gate_norm(gates, b, pix, f, gstats, gg, gb);
     const float gj = gate_norm(gates, b, pix, F + f, gstats, gg, gb);
     const float gf = gate_norm(gates, b, pix, 2 * F + f, gstats, gg, gb);
-    c[i] = c[i] * sigmoidf_(gf + fb) + sigmoidf_(gi) * tanhf(gj);
+    cb_[i] = cb_[i] * sigmoidf_(gf + fb) + sigmoidf_(gi) * tanhf(gj);
   }
 }
 
-__global__ void k_lstm_out(View gates, int B, int HW, int F, const float* __restrict__ gstats,
-                           const float* __restrict__ gg, const float* __restrict__ gb,
-                           const float* __restrict__ cstats, const float* __restrict__ cg,
-                           const float* __restrict__ cb, float* c, View h) {
-  const long long total = (long long)B * HW * F;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int f = (int)(i % F);
-    const long long pixb = i / F;
-    const int pix = (int)(pixb % HW);
-    const int b = (int)(pixb / HW);
+__global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, const float* __restrict__ gstats,
+                                                  const float* __restrict__ gg, const float* __restrict__ gb,
+                                                  const float* __restrict__ cstats, const float* __restrict__ cg,
+                                                  const float* __restrict__ cb, float* c, View h) {
+  const int b = blockIdx.y;
+  const int total = HW * F;
+  float* cb_ = c + (long long)b * total;
+  float* hb = h.p + (long long)b * h.sample_stride + h.ch_off;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int f = i % F, pix = i / F;
     const float* st = cstats + ((long long)b * F + f) * 2;
-    const float cn = (c[i] - st[0]) * st[1] * cg[f] + cb[f];
-    c[i] = cn;
+    const float cn = (cb_[i] - st[0]) * st[1] * cg[f] + cb[f];
+    cb_[i] = cn;
     const float go = gate_norm(gates, b, pix, 3 * F + f, gstats, gg, gb);
-    h.p[(long long)b * h.sample_stride + (long long)pix * h.pix_stride + h.ch_off + f] = tanhf(cn) * sigmoidf_(go);
+    hb[(long long)pix * h.pix_stride + f] = tanhf(cn) * sigmoidf_(go);
   }
 }
 
@@ -132,26 +147,32 @@ __device__ __forceinline__ void bil_idx(int d, int n, int& i0, int& i1, float& l
   l0 = 1.f - l1;
 }
 
-__global__ void k_upsample2x(View s0, View s1, int B, int H, int W, View out) {
-  const int C = s0.C + s1.C;
+// one thread = 4 consecutive channels of one output pixel (both sources have C % 4 == 0); grid.y = sample
+__global__ void __launch_bounds__(256) k_upsample2x(View s0, View s1, int H, int W, View out) {
+  const int b = blockIdx.y;
+  const int C = s0.C + s1.C, C4 = C >> 2;
   const int Ho = 2 * H, Wo = 2 * W;
-  const long long total = (long long)B * Ho * Wo * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const long long pixb = i / C;
-    const int pix = (int)(pixb % (Ho * Wo));
-    const int b = (int)(pixb / (Ho * Wo));
-    const int Y = pix / Wo, X = pix % Wo;
+  const int total = Ho * Wo * C4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (i % C4) << 2;
+    const int pix = i / C4;
+    const int Y = pix / Wo, X = pix - Y * Wo;
     int y0, y1, x0, x1;
     float hl0, hl1, wl0, wl1;
     bil_idx(Y, H, y0, y1, hl0, hl1);
     bil_idx(X, W, x0, x1, wl0, wl1);
     const View& s = (c < s0.C) ? s0 : s1;
     const int cc = (c < s0.C) ? c : c - s0.C;
-    const float v00 = __ldg(vptr(s, b, (long long)y0 * W + x0) + cc), v01 = __ldg(vptr(s, b, (long long)y0 * W + x1) + cc);
-    const float v10 = __ldg(vptr(s, b, (long long)y1 * W + x0) + cc), v11 = __ldg(vptr(s, b, (long long)y1 * W + x1) + cc);
-    out.p[(long long)b * out.sample_stride + (long long)pix * out.pix_stride + out.ch_off + c] =
-        hl0 * (wl0 * v00 + wl1 * v01) + hl1 * (wl0 * v10 + wl1 * v11);
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(vptr(s, b, y0 * W + x0) + cc));
+    const float4 v01 = __ldg(reinterpret_cast<const float4*>(vptr(s, b, y0 * W + x1) + cc));
+    const float4 v10 = __ldg(reinterpret_cast<const float4*>(vptr(s, b, y1 * W + x0) + cc));
+    const float4 v11 = __ldg(reinterpret_cast<const float4*>(vptr(s, b, y1 * W + x1) + cc));
+    float4 o;
+    o.x = hl0 * (wl0 * v00.x + wl1 * v01.x) + hl1 * (wl0 * v10.x + wl1 * v11.x);
+    o.y = hl0 * (wl0 * v00.y + wl1 * v01.y) + hl1 * (wl0 * v10.y + wl1 * v11.y);
+    o.z = hl0 * (wl0 * v00.z + wl1 * v01.z) + hl1 * (wl0 * v10.z + wl1 * v11.z);
+    o.w = hl0 * (wl0 * v00.w + wl1 * v01.w) + hl1 * (wl0 * v10.w + wl1 * v11.w);
+    *reinterpret_cast<float4*>(out.p + (long long)b * out.sample_stride + (long long)pix * out.pix_stride + out.ch_off + c) = o;
   }
 }
 
@@ -198,6 +219,17 @@ __global__ void k_sabias(const float* __restrict__ sa, int A, const float* __res
   }
 }
 
+// out[b, pix, 0..7] = (image rgb, first rgb, 0, 0): 8-channel (16-byte-unit) input of the first encoder conv
+__global__ void k_pack_rgb2(View image, View first, int HW, float* out) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const float* ip = vptr(image, b, pix);
+  const float* fp = vptr(first, b, pix);
+  float4* o = reinterpret_cast<float4*>(out + ((long long)b * HW + pix) * 8);
+  o[0] = make_float4(__ldg(ip), __ldg(ip + 1), __ldg(ip + 2), __ldg(fp));
+  o[1] = make_float4(__ldg(fp + 1), __ldg(fp + 2), 0.f, 0.f);
+}
 __global__ void k_u8_to_f32(const uint8_t* in, float* out, long long n, float scale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = (float)in[i] / scale;
@@ -243,21 +275,25 @@ size_t plane_stats_partial_doubles(int B, int C) { return (size_t)B * C * STATS_
 void launch_norm_act(View x, int B, int H, int W, int pool, const float* stats, const float* gamma,
                      const float* beta, int act, View y, cudaStream_t s) {
   ++g_launch_counter;
-  k_norm_act<<<grid_for((long long)B * H * W * x.C), 256, 0, s>>>(x, B, H, W, pool, stats, gamma, beta, act, y);
+  dim3 grid(grid_for((long long)H * W * (x.C >> 2), 256, 64), B);
+  k_norm_act<<<grid, 256, 0, s>>>(x, H, W, pool, stats, gamma, beta, act, y);
 }
 void launch_lstm_gates(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
                        float fb, float* c, cudaStream_t s) {
   ++g_launch_counter;
-  k_lstm_gates<<<grid_for((long long)B * HW * F), 256, 0, s>>>(gates, B, HW, F, gstats, gg, gb, fb, c);
+  dim3 grid(grid_for((long long)HW * F, 256, 64), B);
+  k_lstm_gates<<<grid, 256, 0, s>>>(gates, HW, F, gstats, gg, gb, fb, c);
 }
 void launch_lstm_out(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
                      const float* cstats, const float* cg, const float* cb, float* c, View h, cudaStream_t s) {
   ++g_launch_counter;
-  k_lstm_out<<<grid_for((long long)B * HW * F), 256, 0, s>>>(gates, B, HW, F, gstats, gg, gb, cstats, cg, cb, c, h);
+  dim3 grid(grid_for((long long)HW * F, 256, 64), B);
+  k_lstm_out<<<grid, 256, 0, s>>>(gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h);
 }
 void launch_upsample2x(View s0, View s1, int B, int H, int W, View out, cudaStream_t s) {
   ++g_launch_counter;
-  k_upsample2x<<<grid_for((long long)B * 4 * H * W * (s0.C + s1.C)), 256, 0, s>>>(s0, s1, B, H, W, out);
+  dim3 grid(grid_for((long long)4 * H * W * ((s0.C + s1.C) >> 2), 256, 64), B);
+  k_upsample2x<<<grid, 256, 0, s>>>(s0, s1, H, W, out);
 }
 void launch_build_sa(const SaArgs& a, int M, int tau, cudaStream_t s) {
   ++g_launch_counter;
@@ -267,6 +303,11 @@ void launch_sabias(const float* sa, int A, const float* wcls, const float* bias,
                    float* out, cudaStream_t s) {
   ++g_launch_counter;
   k_sabias<<<grid_for((long long)B * ncls * Cout), 256, 0, s>>>(sa, A, wcls, bias, ncls, Cout, B, out);
+}
+void launch_pack_rgb2(View image, View first, int B, int HW, float* out, cudaStream_t s) {
+  ++g_launch_counter;
+  dim3 grid((HW + 255) / 256, B);
+  k_pack_rgb2<<<grid, 256, 0, s>>>(image, first, HW, out);
 }
 void launch_u8_to_f32(const uint8_t* in, float* out, long long n, float scale, cudaStream_t s) {
   ++g_launch_counter;

@@ -138,6 +138,8 @@ int topk_padded(int n);
 // mean[D], factor[D][K] = Xc^T / sqrt(K-1), cov[D][D] (unbiased)
 void launch_refit(const double* elites_nr, int K, int D, double* mean, double* factor, double* cov, cudaStream_t s);
 
+void launch_pack_rgb2(View image, View first, int B, int HW, float* out, cudaStream_t s);
+
 // ---- misc --------------------------------------------------------------------------------------
 void launch_u8_to_f32(const uint8_t* in, float* out, long long n, float scale, cudaStream_t s);
 void launch_fill(float* p, long long n, float v, cudaStream_t s);
