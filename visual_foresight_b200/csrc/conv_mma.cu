@@ -39,7 +39,7 @@ namespace vf {
 namespace {
 
 constexpr int MT = 128;                // cout tile (UMMA M)
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 512;
 constexpr int NLOAD = 128;             // threads per role group (4 epilogue warps, 4 stager warps)
 constexpr int MAX_SEG = 8;
 constexpr int MAX_STAGE = 8;
@@ -91,8 +91,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+  if (mbar_try(addr, parity)) return;             // fast path: already complete
   uint32_t done = 0;
   for (uint32_t spins = 0; !done; ++spins) {
     asm volatile(
@@ -197,9 +207,108 @@ __device__ __forceinline__ void issue_tap_swap(uint64_t da_tap, uint64_t db_st, 
   }
 }
 
-// thread layout: warp 0 weight producer, warp 1 MMA issuer (+TMEM alloc), warps 2,3 idle, warps 4..7 epilogue
-// (warp % 4 = TMEM lane quarter), warps 8..11 activation stagers
-constexpr int EPI_WARP0 = 4, STG_WARP0 = 8;
+struct IssueCtx {
+  uint64_t da_zero, db_zero, a_half, b_plane, kstep_a, kstep_b;
+  uint32_t act_base, wst_base, tmem_base, pix_b;
+  uint64_t* w_full; uint64_t* w_empty; uint64_t* a_full; uint64_t* a_empty; uint64_t* acc_full; uint64_t* acc_empty;
+};
+
+// Whole-kernel MMA issue loop, specialised at compile time on (passes, k-steps, accumulator units): inside the tap loop
+// there is one mbarrier wait, one election, PASSES*KSTEPS*U back-to-back UTCHMMA and one commit.
+template <int PASSES, int KSTEPS, int U>
+__device__ __noinline__ void issuer_loop(const Geometry& g, const IssueCtx& cx, int acc_cols) {
+  uint32_t ucol0[MAX_UNIT], ucol[MAX_UNIT], uidesc[MAX_UNIT];
+  uint64_t uoff[MAX_UNIT];
+#pragma unroll
+  for (int u = 0; u < MAX_UNIT; ++u) {
+    const int im = u / g.nseg, sg = u % g.nseg;
+    ucol0[u] = cx.tmem_base + (uint32_t)(im * g.v_cnt + g.seg_off[sg]);
+    uoff[u] = (uint64_t)(((uint32_t)(im * g.img_pix + g.seg_off[sg]) * cx.pix_b) >> 4);
+    uidesc[u] = make_idesc(g.seg_n[sg]);
+  }
+  const int nitems = g.nitems, nchunk = g.nchunk, ntap = g.ntap, kk = g.k, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
+  const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
+  const uint64_t pix16 = (uint64_t)(cx.pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.k) * cx.pix_b) >> 4);
+  const uint64_t da_base = cx.da_zero + (uint64_t)(cx.wst_base >> 4), db_base = cx.db_zero + (uint64_t)(cx.act_base >> 4);
+  int s = 0;
+  uint32_t ph = 0, job = 0, it = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+    const int a = it % nacc;
+    mbar_wait(&cx.acc_empty[a], ((it / nacc) & 1) ^ 1);
+    tc_fence_after();
+#pragma unroll
+    for (int u = 0; u < MAX_UNIT; ++u) ucol[u] = ucol0[u] + (uint32_t)(a * acc_cols);
+    uint32_t acc = 0;                                                    // first MMA of every unit overwrites
+    for (int c = 0; c < nchunk; ++c, ++job) {
+      const int buf = job % nbuf;
+      mbar_wait(&cx.a_full[buf], (job / nbuf) & 1);
+      tc_fence_after();
+      uint64_t db_tap = db_base + (uint64_t)(buf * buf16);
+      int tx = 0;
+      for (int tap = 0; tap < ntap; ++tap) {
+        mbar_wait(&cx.w_full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_tap<PASSES, KSTEPS, U>(da_base + (uint64_t)(s * stage16), db_tap, cx.a_half, cx.b_plane, cx.kstep_a, cx.kstep_b,
+                                       ucol, uoff, uidesc, acc);
+          tc_commit(&cx.w_empty[s]);                                     // stage reusable once these MMAs retire
+        }
+        acc = 1;
+        if (++s == nstage) { s = 0; ph ^= 1; }
+        db_tap += pix16;
+        if (++tx == kk) { tx = 0; db_tap += rowskip16; }
+      }
+      if (elect_one()) tc_commit(&cx.a_empty[buf]);                      // chunk buffer reusable
+    }
+    if (elect_one()) tc_commit(&cx.acc_full[a]);                         // accumulators complete -> epilogue
+  }
+}
+
+template <int PASSES, int U>
+__device__ __noinline__ void issuer_loop_swap(const Geometry& g, const IssueCtx& cx, int acc_cols) {
+  const uint64_t unit_step = (uint64_t)((128u * cx.pix_b) >> 4);
+  const uint32_t idesc_b = make_idesc(g.np), np = (uint32_t)g.np;
+  const int nitems = g.nitems, nchunk = g.nchunk, ntap = g.ntap, kk = g.k, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
+  const int ksteps = g.ksteps;
+  const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
+  const uint64_t pix16 = (uint64_t)(cx.pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.k) * cx.pix_b) >> 4);
+  const uint64_t dw_base = cx.da_zero + (uint64_t)(cx.wst_base >> 4), dx_base = cx.db_zero + (uint64_t)(cx.act_base >> 4);
+  int s = 0;
+  uint32_t ph = 0, job = 0, it = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+    const int a = it % nacc;
+    mbar_wait(&cx.acc_empty[a], ((it / nacc) & 1) ^ 1);
+    tc_fence_after();
+    const uint32_t tacc = cx.tmem_base + (uint32_t)(a * acc_cols);
+    uint32_t acc = 0;
+    for (int c = 0; c < nchunk; ++c, ++job) {
+      const int buf = job % nbuf;
+      mbar_wait(&cx.a_full[buf], (job / nbuf) & 1);
+      tc_fence_after();
+      uint64_t da_tap = dx_base + (uint64_t)(buf * buf16);
+      int tx = 0;
+      for (int tap = 0; tap < ntap; ++tap) {
+        mbar_wait(&cx.w_full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_tap_swap<PASSES, U>(da_tap, dw_base + (uint64_t)(s * stage16), cx.b_plane, cx.a_half, cx.kstep_b, ksteps, unit_step,
+                                    tacc, np, idesc_b, acc);
+          tc_commit(&cx.w_empty[s]);
+        }
+        acc = 1;
+        if (++s == nstage) { s = 0; ph ^= 1; }
+        da_tap += pix16;
+        if (++tx == kk) { tx = 0; da_tap += rowskip16; }
+      }
+      if (elect_one()) tc_commit(&cx.a_empty[buf]);
+    }
+    if (elect_one()) tc_commit(&cx.acc_full[a]);
+  }
+}
+
+// thread layout: warp 0 weight producer, warp 1 MMA issuer (+TMEM alloc), warps 2,3 idle, warps 4..11 epilogue
+// (warp % 4 = TMEM lane quarter, two warps per quarter split the columns / units), warps 12..15 activation stagers
+constexpr int EPI_WARP0 = 4, STG_WARP0 = 12, NEPI = 256;
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
   extern __shared__ uint8_t smem_raw[];
@@ -209,8 +318,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
   const uint32_t act_base = sbase;                                       // [buf][hi|lo] planes
   const uint32_t wst_base = sbase + (uint32_t)(g.nbuf * 2 * g.plane_bytes);
   uint8_t* tail = smem + g.nbuf * 2 * g.plane_bytes + g.nstage * g.stage_bytes;
-  float* s_sab = reinterpret_cast<float*>(tail);                         // [25 classes][128 channels] border-class bias
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 25 * MT * sizeof(float));
+  float* s_sab_all = reinterpret_cast<float*>(tail);                     // [2 halves][25 classes][128 channels] border-class bias
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * 25 * MT * sizeof(float));
   uint64_t *w_full = bars, *w_empty = bars + MAX_STAGE, *a_full = bars + 2 * MAX_STAGE, *a_empty = a_full + 2;
   uint64_t *acc_full = a_empty + 2, *acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
@@ -220,7 +329,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
     for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], NLOAD); mbar_init(&a_empty[i], 1);
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NLOAD);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -260,123 +369,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
     const uint32_t lbo_b = g.layout == 0 ? (uint32_t)g.npix * 16 : 16u;
     const uint32_t sbo_b = g.layout == 0 ? 128u : (uint32_t)(8 * g.row_bytes);
     const uint32_t a_lbo = g.layout == 0 ? (uint32_t)(MT * 16) : 16u;
-    const uint64_t kstep_b = (g.layout == 0 ? 2 * lbo_b : 32u) >> 4;     // start-address advance per K=16 step (16-byte units)
-    const uint64_t kstep_a = (g.layout == 0 ? 2 * a_lbo : 32u) >> 4;
-    const uint32_t pix_b = g.layout == 0 ? 16u : (uint32_t)g.row_bytes;
-    const uint64_t da_zero = make_desc(0, a_lbo, sbo_b, ltype, 0);
-    const uint64_t db_zero = make_desc(0, lbo_b, sbo_b, ltype, 0);
-    const uint64_t a_half = (uint64_t)(g.half_bytes >> 4), b_plane = (uint64_t)(g.plane_bytes >> 4);
-    const int U = g.G * g.nseg;                                          // accumulator units per item (<= MAX_UNIT)
-    uint32_t ucol0[MAX_UNIT], ucol[MAX_UNIT], uidesc[MAX_UNIT];
-    uint64_t uoff[MAX_UNIT];
-#pragma unroll
-    for (int u = 0; u < MAX_UNIT; ++u) {
-      const int im = u / g.nseg, sg = u % g.nseg;
-      ucol0[u] = tmem_base + (uint32_t)(im * g.v_cnt + g.seg_off[sg]);
-      uoff[u] = (uint64_t)(((uint32_t)(im * g.img_pix + g.seg_off[sg]) * pix_b) >> 4);
-      uidesc[u] = make_idesc(g.seg_n[sg]);
-    }
+    IssueCtx cx;
+    cx.kstep_b = (g.layout == 0 ? 2 * lbo_b : 32u) >> 4;                  // start-address advance per K=16 step (16-byte units)
+    cx.kstep_a = (g.layout == 0 ? 2 * a_lbo : 32u) >> 4;
+    cx.pix_b = g.layout == 0 ? 16u : (uint32_t)g.row_bytes;
+    cx.da_zero = make_desc(0, a_lbo, sbo_b, ltype, 0);
+    cx.db_zero = make_desc(0, lbo_b, sbo_b, ltype, 0);
+    cx.a_half = (uint64_t)(g.half_bytes >> 4); cx.b_plane = (uint64_t)(g.plane_bytes >> 4);
+    cx.act_base = act_base; cx.wst_base = wst_base; cx.tmem_base = tmem_base;
+    cx.w_full = w_full; cx.w_empty = w_empty; cx.a_full = a_full; cx.a_empty = a_empty; cx.acc_full = acc_full; cx.acc_empty = acc_empty;
     if (g.swap) {
-      const uint64_t unit_step = (uint64_t)((128u * pix_b) >> 4);
-      const uint32_t idesc_b = make_idesc(g.np);
-      const int units = g.units;
-      int s = 0;
-      uint32_t ph = 0, job = 0, it = 0;
-      for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
-        const int a = it % nacc;
-        mbar_wait(&acc_empty[a], ((it / nacc) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(a * acc_cols);
-        uint32_t acc = 0;
-        for (int c = 0; c < g.nchunk; ++c, ++job) {
-          const int buf = job % g.nbuf;
-          mbar_wait(&a_full[buf], (job / g.nbuf) & 1);
-          tc_fence_after();
-          const uint64_t da_buf = db_zero + (uint64_t)((act_base + (uint32_t)(buf * 2 * g.plane_bytes)) >> 4);
-          int ty = 0, tx = 0;
-          for (int tap = 0; tap < g.ntap; ++tap) {
-            mbar_wait(&w_full[s], ph);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t db_st = da_zero + (uint64_t)((wst_base + (uint32_t)(s * g.stage_bytes)) >> 4);
-              const uint64_t da_tap = da_buf + (uint64_t)(((uint32_t)(ty * g.Wp + tx) * pix_b) >> 4);
-#define VF_SW(PA, UU) issue_tap_swap<PA, UU>(da_tap, db_st, b_plane, a_half, kstep_b, g.ksteps, unit_step, tacc, (uint32_t)g.np, idesc_b, acc)
-              if (g.passes == 3) {
-                switch (units) {
-                  case 1: VF_SW(3, 1); break; case 2: VF_SW(3, 2); break; case 3: VF_SW(3, 3); break; case 4: VF_SW(3, 4); break;
-                  case 5: VF_SW(3, 5); break; case 6: VF_SW(3, 6); break; case 7: VF_SW(3, 7); break; default: VF_SW(3, 8); break;
-                }
-              } else {
-                switch (units) {
-                  case 1: VF_SW(1, 1); break; case 2: VF_SW(1, 2); break; case 3: VF_SW(1, 3); break; case 4: VF_SW(1, 4); break;
-                  case 5: VF_SW(1, 5); break; case 6: VF_SW(1, 6); break; case 7: VF_SW(1, 7); break; default: VF_SW(1, 8); break;
-                }
-              }
+#define VF_SW(PA, UU) issuer_loop_swap<PA, UU>(g, cx, acc_cols)
+      if (g.passes == 3) {
+        switch (g.units) {
+          case 1: VF_SW(3, 1); break; case 2: VF_SW(3, 2); break; case 3: VF_SW(3, 3); break; case 4: VF_SW(3, 4); break;
+          case 5: VF_SW(3, 5); break; case 6: VF_SW(3, 6); break; case 7: VF_SW(3, 7); break; default: VF_SW(3, 8); break;
+        }
+      } else {
+        switch (g.units) {
+          case 1: VF_SW(1, 1); break; case 2: VF_SW(1, 2); break; case 3: VF_SW(1, 3); break; case 4: VF_SW(1, 4); break;
+          case 5: VF_SW(1, 5); break; case 6: VF_SW(1, 6); break; case 7: VF_SW(1, 7); break; default: VF_SW(1, 8); break;
+        }
+      }
 #undef VF_SW
-              tc_commit(&w_empty[s]);
-            }
-            __syncwarp();
-            acc = 1;
-            if (++s == g.nstage) { s = 0; ph ^= 1; }
-            if (++tx == g.k) { tx = 0; ++ty; }
-          }
-          if (elect_one()) tc_commit(&a_empty[buf]);
-          __syncwarp();
-        }
-        if (elect_one()) tc_commit(&acc_full[a]);
-        __syncwarp();
-      }
     } else {
-    const int ntap = g.ntap, kk = g.k, Wp = g.Wp;
-    const int variant = (g.passes == 3 ? 4 : 0) + (U - 1);              // KSTEPS is fixed per layout below
-    int s = 0;
-    uint32_t ph = 0, job = 0, it = 0;
-    for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
-      const int a = it % nacc;
-      mbar_wait(&acc_empty[a], ((it / nacc) & 1) ^ 1);
-      tc_fence_after();
-#pragma unroll
-      for (int u = 0; u < MAX_UNIT; ++u) ucol[u] = ucol0[u] + (uint32_t)(a * acc_cols);
-      uint32_t acc = 0;                                                  // first MMA of every unit overwrites
-      for (int c = 0; c < g.nchunk; ++c, ++job) {
-        const int buf = job % g.nbuf;
-        mbar_wait(&a_full[buf], (job / g.nbuf) & 1);
-        tc_fence_after();
-        const uint64_t db_buf = db_zero + (uint64_t)((act_base + (uint32_t)(buf * 2 * g.plane_bytes)) >> 4);
-        int ty = 0, tx = 0;
-        for (int tap = 0; tap < ntap; ++tap) {
-          mbar_wait(&w_full[s], ph);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t da_st = da_zero + (uint64_t)((wst_base + (uint32_t)(s * g.stage_bytes)) >> 4);
-            const uint64_t db_tap = db_buf + (uint64_t)(((uint32_t)(ty * Wp + tx) * pix_b) >> 4);
-#define VF_ISSUE(PA, UU)                                                                                              \
-  if (g.ksteps == 2) issue_tap<PA, 2, UU>(da_st, db_tap, a_half, b_plane, kstep_a, kstep_b, ucol, uoff, uidesc, acc);  \
-  else issue_tap<PA, 4, UU>(da_st, db_tap, a_half, b_plane, kstep_a, kstep_b, ucol, uoff, uidesc, acc)
-            switch (variant) {
-              case 0: VF_ISSUE(1, 1); break;
-              case 1: VF_ISSUE(1, 2); break;
-              case 2: VF_ISSUE(1, 3); break;
-              case 3: VF_ISSUE(1, 4); break;
-              case 4: VF_ISSUE(3, 1); break;
-              case 5: VF_ISSUE(3, 2); break;
-              case 6: VF_ISSUE(3, 3); break;
-              default: VF_ISSUE(3, 4); break;
-            }
-#undef VF_ISSUE
-            tc_commit(&w_empty[s]);                 // stage reusable once these MMAs retire
-          }
-          __syncwarp();
-          acc = 1;
-          if (++s == g.nstage) { s = 0; ph ^= 1; }
-          if (++tx == kk) { tx = 0; ++ty; }
-        }
-        if (elect_one()) tc_commit(&a_empty[buf]);  // chunk buffer reusable
-        __syncwarp();
+      const int U = g.G * g.nseg;
+#define VF_IS(PA, UU)                                       \
+  if (g.ksteps == 2) issuer_loop<PA, 2, UU>(g, cx, acc_cols); \
+  else issuer_loop<PA, 4, UU>(g, cx, acc_cols)
+      if (g.passes == 3) {
+        switch (U) { case 1: VF_IS(3, 1); break; case 2: VF_IS(3, 2); break; case 3: VF_IS(3, 3); break; default: VF_IS(3, 4); break; }
+      } else {
+        switch (U) { case 1: VF_IS(1, 1); break; case 2: VF_IS(1, 2); break; case 3: VF_IS(1, 3); break; default: VF_IS(1, 4); break; }
       }
-      if (elect_one()) tc_commit(&acc_full[a]);     // accumulators complete -> epilogue
-      __syncwarp();
-    }
+#undef VF_IS
     }
   } else if (warp >= STG_WARP0) {
     // ===== activation stagers: fp32 NHWC -> fp16 hi/lo operand rows of the flat zero-padded image =====
@@ -450,6 +476,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
     // ===== epilogue: TMEM -> registers -> (x 2^-s, + border-class bias) -> NHWC global =====
     const int q4 = warp & 3;                        // TMEM lane quarter this warp may read
     const int row = q4 * 32 + lane;                 // output channel within the cout tile
+    const int half = (warp - EPI_WARP0) >> 2;       // the two warps of a quarter take alternate column chunks / units
+    float* s_sab = s_sab_all + half * 25 * MT;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
       const int mt = item / per_mt;
@@ -467,7 +495,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
         const float scale = g.out_scale;
         const bool sigm = P.act == ACT_SIGMOID;
         const bool vec4 = ((g.Cout | P.out.ch_off | ps) & 3) == 0 && (P.out.sample_stride & 3) == 0;
-        for (int u = 0; u < g.units; ++u) {
+        for (int u = half; u < g.units; u += 2) {
           const int v = v_lo + u * 128 + row;
           const int oy = v / Wp, ox = v - oy * Wp;
           const bool valid = b < P.B && ox < W && oy < H;
@@ -483,6 +511,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
             op = P.out.p + (long long)b * P.out.sample_stride + (long long)(oy * W + ox) * ps + P.out.ch_off;
           }
           for (int c16 = 0; c16 < g.np; c16 += 16) {
+            float4 bbv[4];
+            if (valid && vec4) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                bbv[j4] = (sb && c16 + 4 * j4 < g.Cout) ? __ldg(reinterpret_cast<const float4*>(sb + c16 + 4 * j4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             uint32_t r[16];
             tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + u * g.np + c16), r);
             if (!valid) continue;
@@ -490,7 +524,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
                 if (c16 + j < g.Cout) {
-                  const float4 bb = sb ? __ldg(reinterpret_cast<const float4*>(sb + c16 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  const float4 bb = bbv[j >> 2];
                   float4 o;
                   o.x = fmaf(__uint_as_float(r[j]), scale, bb.x);
                   o.y = fmaf(__uint_as_float(r[j + 1]), scale, bb.y);
@@ -532,7 +566,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
         const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.pad, kk = g.k;
         const float scale = g.out_scale;
         const bool sigm = P.act == ACT_SIGMOID;
-        for (int cc = 0; cc < g.v_cnt; cc += 32) {
+        for (int cc = half * 32; cc < g.v_cnt; cc += 64) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + im * g.v_cnt + cc), r);
           if (!live) continue;
@@ -575,7 +609,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
 // ---- host side ---------------------------------------------------------------------------------------------------
 int g_num_sms = 0;
 constexpr size_t SMEM_LIMIT = 227 * 1024;
-constexpr size_t SMEM_SLACK = 1024 + 25 * MT * 4 + 256;      // alignment slack + bias table + barriers
+constexpr size_t SMEM_SLACK = 1024 + 2 * 25 * MT * 4 + 256;  // alignment slack + bias tables + barriers
 
 void current_mode(int* layout, int* bo) {
   static int s_layout = -1, s_bo = 0;
