@@ -216,7 +216,7 @@ struct IssueCtx {
 // Whole-kernel MMA issue loop, specialised at compile time on (passes, k-steps, accumulator units): inside the tap loop
 // there is one mbarrier wait, one election, PASSES*KSTEPS*U back-to-back UTCHMMA and one commit.
 template <int PASSES, int KSTEPS, int U>
-__device__ __noinline__ void issuer_loop(const Geometry& g, const IssueCtx& cx, int acc_cols) {
+__device__ __forceinline__ void issuer_loop(const Geometry& g, const IssueCtx& cx, int acc_cols) {
   uint32_t ucol0[MAX_UNIT], ucol[MAX_UNIT], uidesc[MAX_UNIT];
   uint64_t uoff[MAX_UNIT];
 #pragma unroll
@@ -265,7 +265,7 @@ __device__ __noinline__ void issuer_loop(const Geometry& g, const IssueCtx& cx, 
 }
 
 template <int PASSES, int U>
-__device__ __noinline__ void issuer_loop_swap(const Geometry& g, const IssueCtx& cx, int acc_cols) {
+__device__ __forceinline__ void issuer_loop_swap(const Geometry& g, const IssueCtx& cx, int acc_cols) {
   const uint64_t unit_step = (uint64_t)((128u * cx.pix_b) >> 4);
   const uint32_t idesc_b = make_idesc(g.np), np = (uint32_t)g.np;
   const int nitems = g.nitems, nchunk = g.nchunk, ntap = g.ntap, kk = g.k, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
