@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("VF_PRECISION", "fp32_simt"), choices=["fp32_simt", "f16x3", "f16x1"])
+    ap.add_argument("--precision", default=os.environ.get("VF_PRECISION", "f16x3"), choices=["fp32_simt", "f16x3", "f16x1"])
     ap.add_argument("--samples", type=int, default=0, help="override per-GPU M (debug)")
     ap.add_argument("--cpu-samples", type=int, default=8)
     ap.add_argument("--ref-samples", type=int, default=8)

@@ -89,7 +89,7 @@ def test_pixel_cost_vs_reference_golden(golden):
 
 
 # ---- predictor ----------------------------------------------------------------------------------------
-def _engine_rollout(sp, weights, inp, acts, precision="fp32_simt"):
+def _engine_rollout(sp, weights, inp, acts, precision="fp32_simt"):  # fp32 FFMA checker path unless a test asks for the tensor-core path
     from visual_foresight_b200.engine import Engine
     e = Engine(sp, acts.shape[0], precision=precision)
     e.load_weights(weights)
@@ -182,7 +182,7 @@ def test_cem_plan_vs_oracle_explicit_noise():
     M, K, iters = 12, 4, 3
     kw = _plan_kwargs(sp, M, K, iters)
     noise = np.random.default_rng(9).standard_normal((iters, M, 20)).astype(np.float32)
-    be = EngineBackend(sp, w, M)
+    be = EngineBackend(sp, w, M, precision="fp32_simt")
     ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"],
            "context_pixel_distributions": OC.switch_on_pix(inp["desig"], 2, 1, 32, 32, 1)}
     res = be.plan(ctx, goal_pix=inp["goal"], noise=noise, **kw)
@@ -199,7 +199,8 @@ def test_cem_plan_vs_oracle_explicit_noise():
     be.engine.close()
 
 
-def test_philox_sampling_matches_restatement_and_shards_are_invariant():
+@pytest.mark.parametrize("PREC", ["fp32_simt", "f16x3"])
+def test_philox_sampling_matches_restatement_and_shards_are_invariant(PREC):
     """Device Philox normals == numpy restatement; a plan split into two shards (run back to back on one
     GPU, scores exchanged through the host) gives bit-identical scores and elites to the unsharded plan."""
     from visual_foresight_b200.predictor import EngineBackend, cem_params
@@ -210,7 +211,7 @@ def test_philox_sampling_matches_restatement_and_shards_are_invariant():
     kw = _plan_kwargs(sp, M, K, iters, seed=1234567890123)
     ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"],
            "context_pixel_distributions": OC.switch_on_pix(inp["desig"], 2, 1, 32, 32, 1)}
-    full = EngineBackend(sp, w, M)
+    full = EngineBackend(sp, w, M, precision=PREC)
     res = full.plan(ctx, goal_pix=inp["goal"], **kw)
     # iteration-0 actions of the full plan vs the numpy Philox restatement
     full.set_context(ctx)
@@ -225,7 +226,7 @@ def test_philox_sampling_matches_restatement_and_shards_are_invariant():
             want = np.clip(std[d % 4] * z, kw["clip"][0][d % 4], kw["clip"][1][d % 4])
             np.testing.assert_allclose(a0[m, (d // 4) * 3, d % 4], want, rtol=1e-10, atol=1e-14)
     # two shards
-    halves = [EngineBackend(sp, w, M // 2), EngineBackend(sp, w, M // 2)]
+    halves = [EngineBackend(sp, w, M // 2, precision=PREC), EngineBackend(sp, w, M // 2, precision=PREC)]
     for r, b in enumerate(halves):
         b.set_context(ctx)
         pr = cem_params(sp, n_ctx_actions=1, global_samples=M, sample_offset=r * (M // 2),

@@ -198,7 +198,7 @@ class PixelCostController(CEMBaseController):
                          verbose_img_height=128, predictor_propagation=False, only_take_first_view=False,
                          state_append=None, finalweight=10., use_predictor_ncam=False, device_cem=True,
                          cem_seed=0, task_weights=None, log_to_stdout=False, model_spec=None, model_seed=0,
-                         precision="fp32_simt").items():
+                         precision="f16x3").items():
             hp.add_hparam(k, v)
         return hp
 

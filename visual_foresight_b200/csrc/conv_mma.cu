@@ -77,6 +77,8 @@ struct Params {
   const __half* w;     // packed [mt][chunk][tap][hi|lo][operand tile]
   int B;
   int act;
+  double* stats_partial;   // optional: per-(sample, channel) sum / sum-of-squares partials of the stored outputs
+  int stats_S;             // partial slots per (sample, channel)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -482,8 +484,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
     for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
       const int mt = item / per_mt;
       const int rem = item % per_mt;
-      const int grp = rem / g.npass, ps = rem % g.npass;
-      const int b0 = grp * g.G, v_lo = ps * g.v_cnt;
+      const int grp = rem / g.npass, ps_ = rem % g.npass;
+      const int b0 = grp * g.G, v_lo = ps_ * g.v_cnt;
       const int n = mt * MT + row;
       const int a = it % nacc;
       mbar_wait(&acc_full[a], (it / nacc) & 1);
@@ -566,6 +568,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
         const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.pad, kk = g.k;
         const float scale = g.out_scale;
         const bool sigm = P.act == ACT_SIGMOID;
+        double st_s = 0.0, st_q = 0.0;              // instance-norm statistics of this thread's channel (fused: no extra pass)
         for (int cc = half * 32; cc < g.v_cnt; cc += 64) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + im * g.v_cnt + cc), r);
@@ -580,6 +583,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
             cyk[w] = border_class(oy0 + w, H, pad) * kk;
             rbase[w] = (oy0 + w) * W * ps;
           }
+          float cs = 0.f, cq = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int x0 = ox0 + j;
@@ -592,8 +596,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
             const float bias = s_sab[(valid ? cyw + cx : 0) * MT + row];
             float val = fmaf(__uint_as_float(r[j]), scale, bias);
             if (sigm) val = __fdividef(1.f, 1.f + __expf(-val));
-            if (valid) op[rb + x * ps] = val;
+            if (valid) {
+              op[rb + x * ps] = val;
+              cs += val;                            // fp32 within the 32-element chunk, float64 across chunks
+              cq = fmaf(val, val, cq);
+            }
           }
+          st_s += (double)cs;
+          st_q += (double)cq;
+        }
+        if (P.stats_partial && live) {              // slot = (pass, column-half): every slot is written exactly once
+          double* o = P.stats_partial + (((long long)b * g.Cout + n) * P.stats_S + (ps_ * 2 + half)) * 2;
+          o[0] = st_s;
+          o[1] = st_q;
         }
       }
       tc_fence_before();
@@ -791,6 +806,9 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   if (!plan_geometry(layout, bo, w.k, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
   P.g.out_scale = ldexpf(1.0f, -w.scale_log2);
   P.src = c.src; P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B; P.act = c.act;
+  P.stats_partial = nullptr; P.stats_S = 0;
+  if (c.stats_partial && !P.g.swap) { P.stats_partial = c.stats_partial; P.stats_S = P.g.npass * 2; }
+  if (c.stats_slots) *c.stats_slots = P.stats_S;
   if ((c.src.pix_stride % 4) || (c.src.ch_off % 4) || (c.src.sample_stride % 4)) return -2;      // float4 loads
   const size_t smem = smem_bytes(P.g);
   static bool attr_set = false;

@@ -23,6 +23,8 @@ struct MmaConvCall {
   int H, W;
   int passes;   // 3 = hi*hi + lo*hi + hi*lo (fp32-grade), 1 = hi*hi
   int act = 0;  // ACT_NONE / ACT_SIGMOID applied in the epilogue
+  double* stats_partial = nullptr;   // in: scratch for fused instance-norm partial sums (null = not requested)
+  int* stats_slots = nullptr;        // out: partial slots per (sample, channel) written (0 = this launch did not fuse them)
 };
 
 bool mma_conv_supported(int k, int cin, int cout, int H, int W);

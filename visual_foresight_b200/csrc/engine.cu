@@ -404,7 +404,7 @@ int finalize_weights(vf_engine* h) {
 
 View dense_view(float* p, int hw, int C) { return make_view(p, (long long)hw * C, C, 0, C); }
 
-void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act);
+void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act, double* stats_partial, int* stats_slots);
 
 cudaEvent_t prof_event(vf_engine* h) {
   if (!h->prof_pool.empty()) { cudaEvent_t e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
@@ -413,24 +413,28 @@ cudaEvent_t prof_event(vf_engine* h) {
   return e;
 }
 
-void run_conv(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act = ACT_NONE) {
-  if (!h->prof_on) { run_conv_impl(h, L, s0, s1, out, B, act); return; }
+void run_conv(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act = ACT_NONE, double* stats_partial = nullptr,
+              int* stats_slots = nullptr) {
+  if (stats_slots) *stats_slots = 0;
+  if (!h->prof_on) { run_conv_impl(h, L, s0, s1, out, B, act, stats_partial, stats_slots); return; }
   vf_engine::ProfRec r;
   r.a = prof_event(h); r.b = prof_event(h);
   r.cls = L.lstm ? 0 : 1;
   r.flops = 2.0 * B * L.H * L.W * L.k * L.k * (double)L.cin_sp * L.cout;
   cudaEventRecord(r.a, h->stream);
-  run_conv_impl(h, L, s0, s1, out, B, act);
+  run_conv_impl(h, L, s0, s1, out, B, act, stats_partial, stats_slots);
   cudaEventRecord(r.b, h->stream);
   h->prof.push_back(r);
 }
 
-void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act) {
+void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act, double* stats_partial, int* stats_slots) {
   if (h->cfg.precision != VF_PREC_FP32_SIMT && L.mma.ready && s1.C == 0) {
     MmaConvCall c;
     c.src = s0; c.out = out; c.sabias = L.sabias; c.bias = L.bias; c.H = L.H; c.W = L.W;
     c.passes = (h->cfg.precision == VF_PREC_F16X3) ? 3 : 1;
     c.act = act;
+    c.stats_partial = stats_partial;
+    c.stats_slots = stats_slots;
     mma_conv_launch(L.mma, c, B, h->stream);
     return;
   }
@@ -445,10 +449,17 @@ void run_lstm(vf_engine* h, int v, const ConvLayer& L, RnnState& r, int B, const
   View in = dense_view(r.lstm_in, hw, 2 * F);
   View gates = dense_view(h->raw, hw, 4 * F);
   View none = make_view(nullptr, 0, 0, 0, 0);
-  run_conv(h, L, in, none, gates, B);
-  launch_plane_stats(gates, B, r.h, r.w, 0, h->cfg.norm_eps, h->stats, h->stats_partial, h->stream);
-  launch_lstm_gates(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->stream);
-  launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cfg.norm_eps, h->cstats, h->stats_partial, h->stream);
+  int slots = 0;
+  run_conv(h, L, in, none, gates, B, ACT_NONE, h->stats_partial, &slots);
+  if (slots > 0) launch_stats_finalize(h->stats_partial, B * 4 * F, slots, hw, h->cfg.norm_eps, h->stats, h->stream);
+  else launch_plane_stats(gates, B, r.h, r.w, 0, h->cfg.norm_eps, h->stats, h->stats_partial, h->stream);
+  if (256 % F == 0) {     // cell-state statistics fused into the pointwise kernel
+    const int S = launch_lstm_gates(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->stats_partial, h->stream);
+    launch_stats_finalize(h->stats_partial, B * F, S, hw, h->cfg.norm_eps, h->cstats, h->stream);
+  } else {
+    launch_lstm_gates_generic(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->stream);
+    launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cfg.norm_eps, h->cstats, h->stats_partial, h->stream);
+  }
   View hv = make_view(r.lstm_in, (long long)hw * 2 * F, 2 * F, F, F);
   launch_lstm_out(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cstats, L.cgamma, L.cbeta, r.c, hv, h->stream);
   h->debug[v][dbg + ".h"] = DebugEntry{hv, r.h, r.w};

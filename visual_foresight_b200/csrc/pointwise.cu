@@ -104,9 +104,49 @@ __device__ __forceinline__ float gate_norm(const View& g, int b, long long pix, 
   return (v - st[0]) * st[1] * gg[ch] + gb[ch];
 }
 
-// gate order along channels: i, j, f, o   (spec P3).  grid.y = sample; threads run along f (coalesced)
+// gate order along channels: i, j, f, o   (spec P3).  grid (pixel blocks, sample); 256 threads = (256/F) pixel lanes x F
+// channels (F in {32, 64, 128}: each thread keeps ONE channel).  The instance-norm statistics of the new cell state
+// are accumulated on the fly (float64 per thread, lanes combined in a fixed order) -> partial[(b*F+f)*S + block].
 __global__ void __launch_bounds__(256) k_lstm_gates(View gates, int HW, int F, const float* __restrict__ gstats,
-                                                    const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c) {
+                                                    const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c,
+                                                    double* partial) {
+  const int b = blockIdx.y;
+  const int lanes = 256 / F;
+  const int f = threadIdx.x % F, pl = threadIdx.x / F;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  float* cb_ = c + (long long)b * HW * F;
+  const float* st = gstats + (long long)b * gates.C * 2;
+  const float mi = st[2 * f], ri = st[2 * f + 1], mj = st[2 * (F + f)], rj = st[2 * (F + f) + 1];
+  const float mf = st[2 * (2 * F + f)], rf = st[2 * (2 * F + f) + 1];
+  const float gi_g = gg[f], gi_b = gb[f], gj_g = gg[F + f], gj_b = gb[F + f], gf_g = gg[2 * F + f], gf_b = gb[2 * F + f];
+  double s = 0.0, q = 0.0;
+  for (int pix = p0 + pl; pix < p1; pix += lanes) {
+    const float* gp = vptr(gates, b, pix);
+    const float gi = (__ldg(gp + f) - mi) * ri * gi_g + gi_b;
+    const float gj = (__ldg(gp + F + f) - mj) * rj * gj_g + gj_b;
+    const float gf = (__ldg(gp + 2 * F + f) - mf) * rf * gf_g + gf_b;
+    const int i = pix * F + f;
+    const float cn = cb_[i] * sigmoidf_(gf + fb) + sigmoidf_(gi) * tanhf(gj);
+    cb_[i] = cn;
+    s += (double)cn;
+    q = fma((double)cn, (double)cn, q);
+  }
+  __shared__ double red[2][256];
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = q;
+  __syncthreads();
+  if (pl == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int l = 0; l < lanes; ++l) { ts += red[0][l * F + f]; tq += red[1][l * F + f]; }
+    double* o = partial + (((long long)b * F + f) * gridDim.x + blockIdx.x) * 2;
+    o[0] = ts;
+    o[1] = tq;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_lstm_gates_generic(View gates, int HW, int F, const float* __restrict__ gstats,
+                                                            const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c) {
   const int b = blockIdx.y;
   const int total = HW * F;
   float* cb_ = c + (long long)b * total;
@@ -271,18 +311,30 @@ void launch_plane_stats(View x, int B, int H, int W, int pool, float eps, float*
   const int n = B * x.C;
   k_stats_finalize<<<(n + 255) / 256, 256, 0, s>>>(partial, n, S, npix, eps, stats);
 }
-size_t plane_stats_partial_doubles(int B, int C) { return (size_t)B * C * STATS_MAX_SPLIT * 2; }
+size_t plane_stats_partial_doubles(int B, int C) { return (size_t)B * C * 16 * 2; }   // up to 16 slots per (sample, channel)
 void launch_norm_act(View x, int B, int H, int W, int pool, const float* stats, const float* gamma,
                      const float* beta, int act, View y, cudaStream_t s) {
   ++g_launch_counter;
   dim3 grid(grid_for((long long)H * W * (x.C >> 2), 256, 64), B);
   k_norm_act<<<grid, 256, 0, s>>>(x, H, W, pool, stats, gamma, beta, act, y);
 }
-void launch_lstm_gates(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
-                       float fb, float* c, cudaStream_t s) {
+int launch_lstm_gates(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
+                      float fb, float* c, double* partial, cudaStream_t s) {
+  ++g_launch_counter;
+  int S = HW >= 1024 ? 8 : (HW >= 256 ? 4 : (HW >= 64 ? 2 : 1));      // pixel blocks per sample = stats partial slots
+  dim3 grid(S, B);
+  k_lstm_gates<<<grid, 256, 0, s>>>(gates, HW, F, gstats, gg, gb, fb, c, partial);
+  return S;
+}
+void launch_lstm_gates_generic(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
+                               float fb, float* c, cudaStream_t s) {
   ++g_launch_counter;
   dim3 grid(grid_for((long long)HW * F, 256, 64), B);
-  k_lstm_gates<<<grid, 256, 0, s>>>(gates, HW, F, gstats, gg, gb, fb, c);
+  k_lstm_gates_generic<<<grid, 256, 0, s>>>(gates, HW, F, gstats, gg, gb, fb, c);
+}
+void launch_stats_finalize(const double* partial, int n, int S, int npix, float eps, float* stats, cudaStream_t s) {
+  ++g_launch_counter;
+  k_stats_finalize<<<(n + 255) / 256, 256, 0, s>>>(partial, n, S, npix, eps, stats);
 }
 void launch_lstm_out(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
                      const float* cstats, const float* cg, const float* cb, float* c, View h, cudaStream_t s) {

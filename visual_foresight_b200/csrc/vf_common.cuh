@@ -54,8 +54,12 @@ size_t plane_stats_partial_doubles(int B, int C);
 void launch_norm_act(View x, int B, int H, int W, int pool, const float* stats, const float* gamma,
                      const float* beta, int act, View y, cudaStream_t s);
 // conv-LSTM pointwise, part 1: c <- c*sigmoid(f+fb) + sigmoid(i)*tanh(j) with gates instance-normalised
-void launch_lstm_gates(View gates, int B, int HW, int F, const float* gstats, const float* ggamma,
-                       const float* gbeta, float forget_bias, float* c, cudaStream_t s);
+// also accumulates the instance-norm partial sums of the new cell state; returns the partial slots per (sample, channel)
+int launch_lstm_gates(View gates, int B, int HW, int F, const float* gstats, const float* ggamma,
+                      const float* gbeta, float forget_bias, float* c, double* partial, cudaStream_t s);
+void launch_lstm_gates_generic(View gates, int B, int HW, int F, const float* gstats, const float* ggamma,
+                               const float* gbeta, float forget_bias, float* c, cudaStream_t s);
+void launch_stats_finalize(const double* partial, int n, int S, int npix, float eps, float* stats, cudaStream_t s);
 // part 2: c <- IN(c);  h <- tanh(c) * sigmoid(IN(o))
 void launch_lstm_out(View gates, int B, int HW, int F, const float* gstats, const float* ggamma,
                      const float* gbeta, const float* cstats, const float* cgamma, const float* cbeta,

@@ -152,7 +152,7 @@ def spec_to_config(spec: PredictorSpec, max_samples: int, device: int = 0, preci
 class Engine:
     """Owns one vf_engine handle.  All array arguments/results are NumPy (host) arrays."""
 
-    def __init__(self, spec: PredictorSpec, max_samples: int, device: int = 0, precision="fp32_simt"):
+    def __init__(self, spec: PredictorSpec, max_samples: int, device: int = 0, precision="f16x3"):
         self.lib = load_library()
         self.spec = spec
         self.max_samples = int(max_samples)

@@ -90,7 +90,7 @@ class EngineBackend:
     """Rollout evaluator on one GPU: owns the vf_engine handle for one (spec, max_samples)."""
 
     def __init__(self, spec: PredictorSpec, weights_per_view, max_samples: int, device: int = 0,
-                 precision="fp32_simt", state_append=None):
+                 precision="f16x3", state_append=None):
         self.spec = spec
         self.engine = Engine(spec, max_samples, device=device, precision=precision)
         self.engine.load_weights(weights_per_view)
@@ -211,7 +211,7 @@ class B200VPredEvaluation:
         self.n_context = self.spec.context_frames
         self.sequence_length = self.spec.seq_len
         self.n_cam = self.spec.ncam
-        self._precision = pol.get("precision", self._hp.get("precision", "fp32_simt"))
+        self._precision = pol.get("precision", self._hp.get("precision", "f16x3"))
         self._max_samples = int(pol.get("num_samples", self._hp.get("run_batch_size", 200)))
         self._state_append = pol.get("state_append")
 
@@ -243,7 +243,7 @@ def setup_predictor(hyperparams, conf, gpu_id=0, ngpu=1, logger=None):
                                adim=conf["adim"], sdim=conf["sdim"], seq_len=conf["sequence_length"],
                                context_frames=conf["context_frames"])
         weights = [specmod.init_weights(spec, int(conf.get("model_seed", 0)), v) for v in range(spec.ncam)]
-    backend = EngineBackend(spec, weights, int(conf["batch_size"]), device=gpu_id, precision=conf.get("precision", "fp32_simt"))
+    backend = EngineBackend(spec, weights, int(conf["batch_size"]), device=gpu_id, precision=conf.get("precision", "f16x3"))
 
     def predictor_func(input_images=None, input_one_hot_images=None, input_state=None, input_actions=None):
         frames = np.asarray(input_images)[0]                        # (C,ncam,H,W,3) float in [0,1] (get_context)
