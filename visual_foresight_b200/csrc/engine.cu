@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -124,6 +125,12 @@ struct vf_engine {
   float* cem_goal_host_copy = nullptr;
 
   std::map<std::string, DebugEntry> debug[4];
+
+  // CUDA graph of one rollout (S-1 cell steps): captured on the second call with a given key, replayed afterwards
+  cudaGraphExec_t graph_exec = nullptr;
+  long long graph_key = -1, graph_seen_key = -1;
+  long long graph_launches = 0;
+  bool use_graph = true;
 
   // profiling (vf_profile_*)
   bool prof_on = false;
@@ -584,12 +591,7 @@ void run_step(vf_engine* h, int v, int tau, int B) {
 }
 
 // rolls S-1 cell steps for M samples whose actions are in h->actions [M][T][adim]
-int rollout(vf_engine* h, int M, int T) {
-  if (!h->weights_ready) { int r = finalize_weights(h); if (r) return r; }
-  if (!h->context_set) return fail(h, VF_ERR_STATE, "vf_set_context must be called before predicting");
-  if (!h->distrib_set) return fail(h, VF_ERR_STATE, "no designated-pixel distribution: pass pix_distrib to vf_set_context or call vf_set_desig");
-  const int need = h->S - 1 - h->n_ctx_actions;
-  if (T < need) return fail(h, VF_ERR_INVALID, "need %d actions per sample (S-1-n_ctx_actions), got T=%d", need, T);
+int rollout_body(vf_engine* h, int M, int T) {
   for (auto& net : h->views) {
     for (auto& r : net.enc_rnn) if (r.c) {
       CU(cudaMemsetAsync(r.c, 0, (size_t)M * r.h * r.w * r.F * sizeof(float), h->stream));
@@ -615,11 +617,51 @@ int rollout(vf_engine* h, int M, int T) {
       run_step(h, v, tau, M);
     }
   }
+  return VF_OK;
+}
+
+// rolls S-1 cell steps for M samples whose actions are in h->actions [M][T][adim].  The launch sequence of a rollout is
+// static for a given (M, T, n_ctx_actions), so it is captured into a CUDA graph the second time a key is seen and replayed
+// afterwards (~3300 kernel launches per plan collapse into 3 graph launches).
+int rollout(vf_engine* h, int M, int T) {
+  if (!h->weights_ready) { int r = finalize_weights(h); if (r) return r; }
+  if (!h->context_set) return fail(h, VF_ERR_STATE, "vf_set_context must be called before predicting");
+  if (!h->distrib_set) return fail(h, VF_ERR_STATE, "no designated-pixel distribution: pass pix_distrib to vf_set_context or call vf_set_desig");
+  const int need = h->S - 1 - h->n_ctx_actions;
+  if (T < need) return fail(h, VF_ERR_INVALID, "need %d actions per sample (S-1-n_ctx_actions), got T=%d", need, T);
+  const long long key = ((long long)M << 24) | ((long long)T << 8) | (long long)h->n_ctx_actions;
+  int r = VF_OK;
+  if (!h->use_graph || h->prof_on) {
+    r = rollout_body(h, M, T);
+  } else if (h->graph_exec && h->graph_key == key) {
+    CU(cudaGraphLaunch(h->graph_exec, h->stream));
+    g_launch_counter += h->graph_launches;
+  } else if (h->graph_seen_key != key) {
+    h->graph_seen_key = key;                       // first sighting: run eagerly (one-time attribute setup, JIT-free warm-up)
+    r = rollout_body(h, M, T);
+  } else {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; h->graph_key = -1; }
+    cudaGraph_t graph = nullptr;
+    const long long before = g_launch_counter;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    r = rollout_body(h, M, T);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (e != cudaSuccess) return fail(h, VF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    h->graph_launches = g_launch_counter - before;
+    e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { h->graph_exec = nullptr; return fail(h, VF_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+    h->graph_key = key;
+    CU(cudaGraphLaunch(h->graph_exec, h->stream));
+  }
+  if (r) return r;
   CU(cudaGetLastError());
   h->predicted = true;
   h->last_M = M;
   return VF_OK;
 }
+
 
 int ensure_actions(vf_engine* h, int T) {
   if (T > h->Tcap) {
@@ -675,6 +717,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
   h->S = cfg->seq_len; h->C = cfg->context_frames; h->P = h->S - h->C; h->ngf = cfg->ngf;
   h->nt = cfg->num_transformed; h->kc = cfg->cdna_ksize; h->nm = h->nt + 3; h->n_enc = cfg->n_enc;
   h->cm = (cfg->ngf + 3 * h->nm + 7) / 8 * 8;
+  { const char* e = getenv("VF_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
   if (h->B < 1 || h->H < 8 || h->W < 8 || h->ncam < 1 || h->ncam > 4 || h->nd < 1 || h->nd > 4 || h->ncam * h->nd > VF_MAX_TASKS)
     return fail(h, VF_ERR_INVALID, "bad sizes (max_samples %d, %dx%d, ncam %d, ndesig %d)", h->B, h->H, h->W, h->ncam, h->nd);
   if (h->adim < 1 || h->adim > 8 || h->sdim < 0 || h->sdim > 16 || h->nz < 0) return fail(h, VF_ERR_INVALID, "bad adim/sdim/nz");
@@ -721,6 +764,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
 int vf_destroy(vf_engine* h) {
   if (!h) return VF_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   for (void* p : h->allocs) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
