@@ -180,13 +180,13 @@ def run_ours(args, rank, world, local_rank):
     M_local = CFG["M"] if not args.samples else args.samples
     M_global = M_local * world
     be = EngineBackend(spec, w, M_local, device=local_rank, precision=args.precision)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                      # engine kernels, the NCCL all-gather and the timing events share it
     be.engine.set_stream(stream.cuda_stream)
     ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"]}
     desig = inp["desig"].astype(np.float32)
     kw = plan_kwargs(spec, M_local)
     goal = inp["goal"].astype(np.float32)
-    shard = EngineShard(be)
+    shard = EngineShard(be, stream=stream)
     planner = ShardedCEMPlanner(shard, rank, world)
     frames_per_plan = CFG["iters"] * M_global * spec.n_pred * spec.ncam
 

@@ -181,6 +181,9 @@ VF_API int vf_cem_iter_select(vf_engine* h, int32_t iteration);
 VF_API int vf_cem_finish(vf_engine* h, double* out_best_actions, int32_t* out_elite_idx, double* out_scores);
 /* device pointer to the (iterations, global_samples) f64 score matrix, for the collective */
 VF_API int vf_cem_scores_dev(vf_engine* h, void** scores_dev);
+/* adopt a caller-owned DEVICE buffer of at least iterations*global_samples float64 as the score matrix of the following
+ * vf_cem_begin calls (e.g. a torch tensor the collective library already knows); NULL -> back to the engine-owned one */
+VF_API int vf_cem_bind_scores(vf_engine* h, void* scores_dev);
 /* host access to one row segment of the score matrix: scores[iteration][offset : offset+n] (used by
  * the host-staged exchange when no device collective is available, and by the shard tests) */
 VF_API int vf_cem_scores_read(vf_engine* h, int32_t iteration, int32_t offset, int32_t n, double* out);

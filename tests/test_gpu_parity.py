@@ -369,3 +369,19 @@ def test_rollout_tensor_core_path_vs_oracle(precision, tol):
     print("precision %s: frames max-abs err %.3g, distrib %.3g" % (precision, err, float(np.abs(gd - od).max())))
     assert err <= tol
     e.close()
+
+
+# ---- multi-GPU (only when the box has >= 2 GPUs; the 1-GPU round-end run skips it) ------------------------------
+def test_two_gpu_sharded_plan_is_bit_identical():
+    """torchrun x2: contiguous shards + NCCL in-place all-gather of the float64 scores per CEM iteration give the
+    same scores / elite indices / best actions, bit for bit, as the single-GPU plan (tests/multigpu_check.py)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29531", os.path.join(here, "multigpu_check.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert "MULTIGPU_CHECK_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

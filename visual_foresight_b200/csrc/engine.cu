@@ -112,7 +112,8 @@ struct vf_engine {
   bool cem_active = false;
   int cem_D = 0, cem_T = 0, cem_Dmax = 0, cem_act_cap = 0;
   double *cem_mean = nullptr, *cem_factor = nullptr, *cem_std0 = nullptr, *cem_cov = nullptr;
-  double *cem_scores = nullptr;     // [iters][Mg]
+  double *cem_scores = nullptr;     // [iters][Mg] (engine-owned or bound by vf_cem_bind_scores)
+  double *cem_scores_own = nullptr, *cem_scores_ext = nullptr;
   size_t cem_scores_cap = 0;
   float* cem_noise = nullptr;
   size_t cem_noise_cap = 0;
@@ -936,7 +937,8 @@ int vf_cem_begin(vf_engine* h, const vf_cem_params* p, const float* goal, const 
   }
   // per-call sized buffers (grow only)
   const size_t need_scores = (size_t)p->iterations * Mg;
-  if (need_scores > h->cem_scores_cap) { DA(h->cem_scores, need_scores); h->cem_scores_cap = need_scores; }
+  if (need_scores > h->cem_scores_cap) { DA(h->cem_scores_own, need_scores); h->cem_scores_cap = need_scores; }
+  h->cem_scores = h->cem_scores_ext ? h->cem_scores_ext : h->cem_scores_own;
   const size_t npad = (size_t)topk_padded(Mg);
   if (npad > h->topk_cap) {
     DA(h->topk_keys, npad); DA(h->topk_idx, npad); h->topk_cap = npad;
@@ -1036,6 +1038,13 @@ int vf_cem_finish(vf_engine* h, double* best, int32_t* eidx, double* scores) {
 int vf_cem_scores_dev(vf_engine* h, void** dev) {
   if (!h || !dev || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
   *dev = h->cem_scores;
+  return VF_OK;
+}
+
+int vf_cem_bind_scores(vf_engine* h, void* dev) {
+  if (!h) return VF_ERR_INVALID;
+  h->cem_scores_ext = (double*)dev;
+  h->cem_active = false;            // the binding takes effect at the next vf_cem_begin
   return VF_OK;
 }
 

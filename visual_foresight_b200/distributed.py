@@ -47,42 +47,48 @@ class ShardedCEMPlanner:
 class EngineShard:
     """One rank's engine.  ``backend`` is a predictor.EngineBackend whose context is already set."""
 
-    def __init__(self, backend, device_collective: bool = True):
+    def __init__(self, backend, device_collective: bool = True, stream=None):
         self.backend = backend
         self.engine = backend.engine
         self.device_collective = device_collective
         self._scores_t = None
+        self.stream = stream
+        if device_collective:
+            # The collective is ordered against a torch stream, so the engine must run on that same stream.  torch's
+            # default stream has handle 0 (which vf_set_stream reads as "use your own stream"), hence a dedicated one.
+            import torch
+            if self.stream is None:
+                self.stream = torch.cuda.Stream()
+            self.engine.set_stream(self.stream.cuda_stream)
 
     def begin(self, *, global_samples, offset, local, iterations, goal, noise=None, **params):
         from .predictor import cem_params
         p = cem_params(self.backend.spec, num_samples=local, global_samples=global_samples, sample_offset=offset,
                        iterations=iterations, n_ctx_actions=self.backend._n_ctx_actions, **params)
         self._p = p
+        if global_samples > local and self.device_collective:
+            # the (iterations, global) float64 score matrix lives in a torch tensor the collective library owns;
+            # the engine writes its shard straight into it (vf_cem_bind_scores)
+            import torch
+            if self._scores_t is None or tuple(self._scores_t.shape) != (iterations, global_samples):
+                self._scores_t = torch.zeros((iterations, global_samples), dtype=torch.float64, device="cuda")
+            self.engine.cem_bind_scores(self._scores_t.data_ptr())
+        else:
+            self.engine.cem_bind_scores(0)
         self.engine.cem_begin(p, goal, noise)
-        self._scores_t = None
 
     def rollout(self, it):
         self.engine.cem_iter_rollout(it)
 
-    def _scores_tensor(self):
-        """torch view of the engine's (iterations, global) float64 score matrix (no copy)."""
-        if self._scores_t is None:
-            import torch
-
-            class _Raw:
-                pass
-            raw = _Raw()
-            raw.__cuda_array_interface__ = {"shape": (self._p.iterations, self._p.global_samples), "typestr": "<f8",
-                                            "data": (self.engine.cem_scores_dev(), False), "version": 2}
-            self._scores_t = torch.as_tensor(raw, device="cuda")
-        return self._scores_t
-
     def exchange(self, it, offset, local, group=None):
         import torch.distributed as dist
         if self.device_collective and dist.get_backend(group) == "nccl":
-            row = self._scores_tensor()[it]
-            # NCCL in-place all-gather: each rank's segment already sits at row[offset : offset+local]
-            dist.all_gather_into_tensor(row, row[offset:offset + local], group=group)
+            import torch
+            row = self._scores_t[it]
+            # NCCL in-place all-gather, ordered on the engine's stream: each rank's segment already sits at
+            # row[offset : offset+local]
+            with torch.cuda.stream(self.stream):
+                dist.all_gather_into_tensor(row, row[offset:offset + local], group=group)
         else:           # host-staged exchange (gloo)
             import torch
             mine = torch.from_numpy(self.engine.cem_scores_read(it, offset, local))

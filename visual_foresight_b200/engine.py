@@ -84,6 +84,7 @@ _SIGS = {
     "vf_cem_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vf_cem_scores_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "vf_cem_actions": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vf_cem_bind_scores": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vf_cem_scores_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vf_cem_scores_write": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vf_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
@@ -310,6 +311,9 @@ class Engine:
         p = C.c_void_p()
         self._check(self.lib.vf_cem_scores_dev(self._h, C.byref(p)))
         return int(p.value)
+
+    def cem_bind_scores(self, dev_ptr: int):
+        self._check(self.lib.vf_cem_bind_scores(self._h, C.c_void_p(dev_ptr) if dev_ptr else None))
 
     def cem_scores_read(self, it: int, offset: int, n: int):
         out = np.empty((n,), np.float64)
