@@ -13,71 +13,142 @@ __device__ __forceinline__ const float* vptr(const View& v, int b, long long pix
 // TF 'SYMMETRIC' padding index: -1 -> 0, -2 -> 1, n -> n-1, n+1 -> n-2
 __device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -1 - i : (i >= n ? 2 * n - 1 - i : i); }
 
-// CDNA kernel head (spec P5): dense(flatten(h)) -> +identity -> relu-shift -> L1 normalise.
-// Block = CK_S samples x all outputs: every weight element fetched from L2 feeds CK_S FMAs.  1024 threads =
-// 128 output lanes x CK_G K-groups; the feature chunk of the CK_S samples is staged in shared memory (broadcast reads).
-constexpr int CK_S = 4, CK_G = 8, CK_T = 1024;
-__global__ void __launch_bounds__(1024) k_cdna_kernels(View feat, int npix, const float* __restrict__ w,
-                                                      const float* __restrict__ bias, int ksize, int nt, int B, float* kern) {
-  const int b0 = blockIdx.x * CK_S;
-  const int nout = ksize * ksize * nt;          // <= 128
-  const int j = threadIdx.x & 127, g = threadIdx.x >> 7;
+// ---- CDNA kernel head (spec P5): dense(flatten(h)) -> +identity -> relu-shift -> L1 normalise -----------------------
+// Split-K partial products: grid (K slices of CK_KC, sample groups of CK_S) fills the 148 SMs (c2: 16 x 25 blocks); every
+// weight element fetched from L2 feeds CK_S FMAs.  part[ks][b][128] is combined in a fixed order by cdna_finalize(), which
+// the consumers (CDNA apply) run in their prologue: no separate finalize launch.
+constexpr int CK_S = 8, CK_KC = 512;
+__global__ void __launch_bounds__(256) k_cdna_partial(View feat, int npix, const float* __restrict__ w, int nout, int B,
+                                                      float* __restrict__ part) {
+  const int ks = blockIdx.x, k0 = ks * CK_KC, b0 = blockIdx.y * CK_S;
   const int K = npix * feat.C;
-  __shared__ float sf[CK_S][CK_T];
-  __shared__ float part[CK_G][CK_S][128];
+  __shared__ float sf[CK_S][CK_KC];
+  __shared__ float red[CK_S][128];
+  for (int i = threadIdx.x; i < CK_S * CK_KC; i += 256) {
+    const int sI = i / CK_KC, kk = i - sI * CK_KC, k = k0 + kk, b = b0 + sI;
+    sf[sI][kk] = (b < B && k < K) ? vld1(feat, voff(feat, b, k / feat.C) + (k % feat.C)) : 0.f;
+  }
+  __syncthreads();
+  const int j = threadIdx.x & 127, g = threadIdx.x >> 7;          // 128 output lanes x 2 K halves
   float acc[CK_S];
 #pragma unroll
   for (int sI = 0; sI < CK_S; ++sI) acc[sI] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += CK_T) {
-    for (int i = threadIdx.x; i < CK_S * CK_T; i += 1024) {
-      const int sI = i / CK_T, kk = i - sI * CK_T, k = k0 + kk, b = b0 + sI;
-      sf[sI][kk] = (b < B && k < K) ? __ldg(vptr(feat, b, k / feat.C) + (k % feat.C)) : 0.f;
-    }
-    __syncthreads();
-    if (j < nout) {
-      constexpr int KG = CK_T / CK_G;
-      const int ke = min(KG, max(0, K - k0 - g * KG));
-      const float* wp = w + (long long)(k0 + g * KG) * nout + j;
-      for (int kk = 0; kk < ke; ++kk) {
-        const float wv = __ldg(wp + (long long)kk * nout);
+  if (j < nout) {
+    const int kb = g * (CK_KC / 2);
+    const int ke = min(CK_KC / 2, max(0, K - k0 - kb));
+    const float* wp = w + (long long)(k0 + kb) * nout + j;
+#pragma unroll 4
+    for (int kk = 0; kk < ke; ++kk) {
+      const float wv = __ldg(wp + (long long)kk * nout);
 #pragma unroll
-        for (int sI = 0; sI < CK_S; ++sI) acc[sI] = fmaf(sf[sI][g * KG + kk], wv, acc[sI]);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int sI = 0; sI < CK_S; ++sI) part[g][sI][j] = acc[sI];
-  __syncthreads();
-  // raw kernel taps: dense output reshaped (k, k, nt): j = (u*k + v)*nt + n ; + identity at the centre tap
-  for (int i = threadIdx.x; i < CK_S * 128; i += 1024) {
-    const int sI = i >> 7, jj = i & 127;
-    if (jj < nout) {
-      float v = bias[jj];
-#pragma unroll
-      for (int gg = 0; gg < CK_G; ++gg) v += part[gg][sI][jj];      // fixed order
-      if (jj / nt == (ksize / 2) * ksize + ksize / 2) v += 1.0f;
-      part[0][sI][jj] = fmaxf(v - 1e-12f, 0.f) + 1e-12f;
+      for (int sI = 0; sI < CK_S; ++sI) acc[sI] = fmaf(sf[sI][kb + kk], wv, acc[sI]);
     }
   }
+  if (g == 1) {
+#pragma unroll
+    for (int sI = 0; sI < CK_S; ++sI) red[sI][j] = acc[sI];
+  }
   __syncthreads();
-  if (threadIdx.x < CK_S * nt) {
-    const int sI = threadIdx.x / nt, n = threadIdx.x % nt, b = b0 + sI;
-    if (b < B) {
-      float sum = 0.f;
-      for (int t = 0; t < ksize * ksize; ++t) sum += part[0][sI][t * nt + n];
-      for (int t = 0; t < ksize * ksize; ++t) kern[((long long)b * nt + n) * ksize * ksize + t] = part[0][sI][t * nt + n] / sum;
-    }
+  if (g == 0 && j < nout) {
+#pragma unroll
+    for (int sI = 0; sI < CK_S; ++sI)
+      if (b0 + sI < B) part[((long long)ks * B + b0 + sI) * 128 + j] = acc[sI] + red[sI][j];
   }
 }
 
-__global__ void k_cdna_apply(View image, View first, const float* __restrict__ kern, int ksize, int nt, int H, int W,
-                             View mask_in, int base) {
-  extern __shared__ float sk[];   // [nt][k*k]
+// Block-wide (>= 128 threads): sk[t*nt + n] = normalised CDNA kernel tap t of transformed image n for sample b.
+// Dense output j = (u*k + v)*nt + n.  tmp: 128 floats, sums: 8 floats of shared memory.
+__device__ __forceinline__ void cdna_finalize(const float* __restrict__ part, int nks, int B, int b,
+                                              const float* __restrict__ bias, int ksize, int nt, float* sk, float* tmp, float* sums) {
+  const int kk = ksize * ksize, nout = kk * nt, j = threadIdx.x;
+  if (j < nout) {
+    float v = bias[j];
+    for (int ks = 0; ks < nks; ++ks) v += part[((long long)ks * B + b) * 128 + j];       // fixed order
+    if (j / nt == (ksize / 2) * ksize + ksize / 2) v += 1.0f;
+    tmp[j] = fmaxf(v - 1e-12f, 0.f) + 1e-12f;
+  }
+  __syncthreads();
+  if (j < nt) {
+    float sum = 0.f;
+    for (int t = 0; t < kk; ++t) sum += tmp[t * nt + j];
+    sums[j] = sum;
+  }
+  __syncthreads();
+  if (j < nout) sk[j] = tmp[j] / sums[j % nt];
+  __syncthreads();
+}
+
+// CDNA application (spec P6), nt = 4 transformed images, 5x5 kernels: block = (band of TR rows, sample).  The band
+// (+2 halo rows, SYMMETRIC-mirrored) is staged in shared memory as float4 pixels, the four kernels of a tap are one
+// float4: 2 LDS.128 + 12 FMA per tap.  Writes layers[.., 0..17] = T_0..T_3 (rgb each), prev image, first image.
+__global__ void __launch_bounds__(256) k_cdna_apply4(View image, View first, const float* __restrict__ part, int nks,
+                                                     const float* __restrict__ bias, int B, int H, int W, int TR, View layers,
+                                                     float* __restrict__ kern_out) {
+  extern __shared__ float4 sm4[];
+  float4* sk4 = sm4;                       // [25]
+  float* tmp = reinterpret_cast<float*>(sm4 + 25);    // [128] + sums [8]
+  float* sums = tmp + 128;
+  float4* img = sm4 + 25 + 34;             // [(TR+4)][W]
+  const int b = blockIdx.y, y0 = blockIdx.x * TR;
+  for (int i = threadIdx.x; i < (TR + 4) * W; i += 256) {
+    const int r = i / W, x = i - r * W;
+    const int yy = mirror(y0 - 2 + r, H);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < H) {                // rows far below the image (last band) stay zero: never used by valid pixels
+      const float* ip = vptr(image, b, (long long)yy * W + x);
+      v = make_float4(__ldg(ip), __ldg(ip + 1), __ldg(ip + 2), 0.f);
+    }
+    img[i] = v;
+  }
+  cdna_finalize(part, nks, B, b, bias, 5, 4, reinterpret_cast<float*>(sk4), tmp, sums);
+  if (blockIdx.x == 0 && threadIdx.x < 100) {     // materialise kern[b][n][tap] for the composite kernel / debugging
+    const int t = threadIdx.x >> 2, n = threadIdx.x & 3;
+    kern_out[((long long)b * 4 + n) * 25 + t] = reinterpret_cast<const float*>(sk4)[threadIdx.x];
+  }
+  for (int p = threadIdx.x; p < TR * W; p += 256) {
+    const int r = p / W, x = p - r * W, y = y0 + r;
+    if (y >= H) break;
+    float a[4][3];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) a[n][0] = a[n][1] = a[n][2] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        const int xx = mirror(x + v - 2, W);
+        const float4 px = img[(r + u) * W + xx];
+        const float4 kv = sk4[u * 5 + v];
+        a[0][0] = fmaf(px.x, kv.x, a[0][0]); a[0][1] = fmaf(px.y, kv.x, a[0][1]); a[0][2] = fmaf(px.z, kv.x, a[0][2]);
+        a[1][0] = fmaf(px.x, kv.y, a[1][0]); a[1][1] = fmaf(px.y, kv.y, a[1][1]); a[1][2] = fmaf(px.z, kv.y, a[1][2]);
+        a[2][0] = fmaf(px.x, kv.z, a[2][0]); a[2][1] = fmaf(px.y, kv.z, a[2][1]); a[2][2] = fmaf(px.z, kv.z, a[2][2]);
+        a[3][0] = fmaf(px.x, kv.w, a[3][0]); a[3][1] = fmaf(px.y, kv.w, a[3][1]); a[3][2] = fmaf(px.z, kv.w, a[3][2]);
+      }
+    }
+    const float4 pv = img[(r + 2) * W + x];
+    const float* fp = vptr(first, b, (long long)y * W + x);
+    const float f0 = __ldg(fp), f1 = __ldg(fp + 1), f2 = __ldg(fp + 2);
+    const long long o = voff(layers, b, (long long)y * W + x);
+    vst4(layers, o, make_float4(a[0][0], a[0][1], a[0][2], a[1][0]));
+    vst4(layers, o + 4, make_float4(a[1][1], a[1][2], a[2][0], a[2][1]));
+    vst4(layers, o + 8, make_float4(a[2][2], a[3][0], a[3][1], a[3][2]));
+    vst4(layers, o + 12, make_float4(pv.x, pv.y, pv.z, f0));
+    vst1(layers, o + 16, f1);
+    vst1(layers, o + 17, f2);
+  }
+}
+
+// generic (any nt <= 8, odd ksize): one thread per pixel, global loads
+__global__ void __launch_bounds__(128) k_cdna_apply(View image, View first, const float* __restrict__ part, int nks,
+                                                    const float* __restrict__ bias, int ksize, int nt, int B, int H, int W,
+                                                    View layers, float* __restrict__ kern_out) {
+  __shared__ float sk[128], tmp[128], sums[8];
   const int b = blockIdx.y;
   const int kk = ksize * ksize;
-  for (int i = threadIdx.x; i < nt * kk; i += blockDim.x) sk[i] = kern[(long long)b * nt * kk + i];
-  __syncthreads();
+  cdna_finalize(part, nks, B, b, bias, ksize, nt, sk, tmp, sums);
+  if (blockIdx.x == 0 && threadIdx.x < kk * nt) {
+    const int t = threadIdx.x / nt, n = threadIdx.x % nt;
+    kern_out[((long long)b * nt + n) * kk + t] = sk[threadIdx.x];
+  }
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= H * W) return;
   const int y = pix / W, x = pix % W, pad = ksize / 2;
@@ -90,74 +161,100 @@ __global__ void k_cdna_apply(View image, View first, const float* __restrict__ k
       const float* ip = vptr(image, b, (long long)yy * W + xx);
       const float r = __ldg(ip), g = __ldg(ip + 1), bl = __ldg(ip + 2);
       for (int n = 0; n < nt; ++n) {
-        const float kv = sk[n * kk + u * ksize + v];
+        const float kv = sk[(u * ksize + v) * nt + n];
         acc[n][0] = fmaf(r, kv, acc[n][0]);
         acc[n][1] = fmaf(g, kv, acc[n][1]);
         acc[n][2] = fmaf(bl, kv, acc[n][2]);
       }
     }
   }
-  float* o = mask_in.p + (long long)b * mask_in.sample_stride + (long long)pix * mask_in.pix_stride + mask_in.ch_off + base;
+  const long long o = voff(layers, b, pix);
   for (int n = 0; n < nt; ++n)
-    for (int c = 0; c < 3; ++c) o[3 * n + c] = acc[n][c];
+    for (int c = 0; c < 3; ++c) vst1(layers, o + 3 * n + c, acc[n][c]);
   const float* ip = vptr(image, b, pix);
   const float* fp = vptr(first, b, pix);
   for (int c = 0; c < 3; ++c) {
-    o[3 * nt + c] = __ldg(ip + c);
-    o[3 * nt + 3 + c] = __ldg(fp + c);
+    vst1(layers, o + 3 * nt + c, __ldg(ip + c));
+    vst1(layers, o + 3 * nt + 3 + c, __ldg(fp + c));
   }
 }
 
 constexpr int COMP_THREADS = 256;
 
-// one thread per pixel.  masks = softmax(logits); gen_image = sum_n m_n * layer_n;
+// masks = softmax(logits); gen_image = sum_n m_n * layer_n;
 // gen_distrib = sum_{n<nt} m_n * T_n(prev_d) + m_nt*prev_d + m_{nt+1}*first_d + m_{nt+2}*prev_d   (spec P8)
-__global__ void __launch_bounds__(COMP_THREADS) k_composite(CompositeArgs a) {
-  extern __shared__ float sk[];
+// Block = (band of TR rows, sample); the previous distribution's band (+halo, SYMMETRIC-mirrored) is staged in shared
+// memory; kernels as [tap][nt].  Per-thread sums of the raw distribution are combined by a fixed shuffle tree + fixed
+// warp order -> partial[b][p][band].
+__global__ void __launch_bounds__(COMP_THREADS) k_composite(CompositeArgs a, int TR) {
+  extern __shared__ float smc[];
   __shared__ float red[COMP_THREADS / 32];
-  const int b = blockIdx.y;
-  const int kk = a.ksize * a.ksize, nm = a.nt + 3;
-  for (int i = threadIdx.x; i < a.nt * kk; i += blockDim.x) sk[i] = a.kern[(long long)b * a.nt * kk + i];
+  const int b = blockIdx.y, y0 = blockIdx.x * TR;
+  const int kk = a.ksize * a.ksize, nm = a.nt + 3, pad = a.ksize / 2, W = a.W, H = a.H;
+  const int BR = TR + 2 * pad;
+  float* sk = smc;                         // [kk][nt]
+  float* band = smc + ((kk * a.nt + 3) & ~3);   // [nd][BR][W]
+  for (int i = threadIdx.x; i < a.nt * kk; i += COMP_THREADS) {
+    const int t = i / a.nt, n = i - t * a.nt;
+    sk[i] = a.kern[((long long)b * a.nt + n) * kk + t];
+  }
+  for (int i = threadIdx.x; i < a.nd * BR * W; i += COMP_THREADS) {
+    const int p = i / (BR * W), rem = i - p * BR * W, r = rem / W, x = rem - r * W;
+    const int yy = mirror(y0 - pad + r, H);
+    band[i] = (yy >= 0 && yy < H) ? __ldg(vptr(a.prev_d, b, (long long)yy * W + x) + p) : 0.f;
+  }
   __syncthreads();
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool ok = pix < a.H * a.W;
-  float m[16];
   float dsum[4] = {0.f, 0.f, 0.f, 0.f};
-  if (ok) {
-    const int y = pix / a.W, x = pix % a.W, pad = a.ksize / 2;
+  for (int q = threadIdx.x; q < TR * W; q += COMP_THREADS) {
+    const int r = q / W, x = q - r * W, y = y0 + r;
+    if (y >= H) break;
+    const long long pix = (long long)y * W + x;
+    float m[16];
     const float* lg = vptr(a.logits, b, pix);
     float mx = -3.4e38f;
     for (int n = 0; n < nm; ++n) { m[n] = __ldg(lg + n); mx = fmaxf(mx, m[n]); }
     float se = 0.f;
     for (int n = 0; n < nm; ++n) { m[n] = expf(m[n] - mx); se += m[n]; }
     for (int n = 0; n < nm; ++n) m[n] = m[n] / se;
-    const float* ly = vptr(a.layers, b, pix);
-    float* gi = a.gen_image.p + (long long)b * a.gen_image.sample_stride + (long long)pix * a.gen_image.pix_stride + a.gen_image.ch_off;
-    for (int c = 0; c < 3; ++c) {
-      float v = 0.f;
-      for (int n = 0; n < nm; ++n) v += m[n] * __ldg(ly + 3 * n + c);
-      gi[c] = v;
+    const long long lo = voff(a.layers, b, pix);
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (nm == 7) {                           // 21 channels = 6 vector loads (the buffer is padded to 24 channels)
+      float l[24];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float4 v4 = vld4(a.layers, lo + 4 * j);
+        l[4 * j] = v4.x; l[4 * j + 1] = v4.y; l[4 * j + 2] = v4.z; l[4 * j + 3] = v4.w;
+      }
+#pragma unroll
+      for (int n = 0; n < 7; ++n) { g0 += m[n] * l[3 * n]; g1 += m[n] * l[3 * n + 1]; g2 += m[n] * l[3 * n + 2]; }
+    } else {
+      for (int n = 0; n < nm; ++n) {
+        g0 += m[n] * vld1(a.layers, lo + 3 * n);
+        g1 += m[n] * vld1(a.layers, lo + 3 * n + 1);
+        g2 += m[n] * vld1(a.layers, lo + 3 * n + 2);
+      }
     }
-    float* gd = a.gen_distrib.p + (long long)b * a.gen_distrib.sample_stride + (long long)pix * a.gen_distrib.pix_stride + a.gen_distrib.ch_off;
+    float* gi = a.gen_image.p + voff(a.gen_image, b, pix);
+    gi[0] = g0; gi[1] = g1; gi[2] = g2;
+    float* gd = a.gen_distrib.p + voff(a.gen_distrib, b, pix);
     for (int p = 0; p < a.nd; ++p) {
+      const float* bp = band + p * BR * W;
       float t[8];
       for (int n = 0; n < a.nt; ++n) t[n] = 0.f;
-      for (int u = 0; u < a.ksize; ++u) {
-        const int yy = mirror(y + u - pad, a.H);
+      for (int u = 0; u < a.ksize; ++u)
         for (int v = 0; v < a.ksize; ++v) {
-          const int xx = mirror(x + v - pad, a.W);
-          const float d = __ldg(vptr(a.prev_d, b, (long long)yy * a.W + xx) + p);
-          for (int n = 0; n < a.nt; ++n) t[n] = fmaf(d, sk[n * kk + u * a.ksize + v], t[n]);
+          const float d = bp[(r + u) * W + mirror(x + v - pad, W)];
+          const float* kp = sk + (u * a.ksize + v) * a.nt;
+          for (int n = 0; n < a.nt; ++n) t[n] = fmaf(d, kp[n], t[n]);
         }
-      }
-      const float pd = __ldg(vptr(a.prev_d, b, pix) + p), fd = __ldg(vptr(a.first_d, b, pix) + p);
+      const float pd = bp[(r + pad) * W + x], fd = __ldg(vptr(a.first_d, b, pix) + p);
       float v = 0.f;
       for (int n = 0; n < a.nt; ++n) v += m[n] * t[n];
       v += m[a.nt] * pd;
       v += m[a.nt + 1] * fd;
       v += m[a.nt + 2] * pd;
       gd[p] = v;
-      dsum[p] = v;
+      dsum[p] += v;
     }
   }
   // block sums of the raw distribution (fixed shuffle tree + fixed warp order)
@@ -268,22 +365,39 @@ __global__ void __launch_bounds__(256) k_goal_image_cost(const float* __restrict
 
 }  // namespace
 
-void launch_cdna_kernels(View feat, int npix, const float* w, const float* bias, int ksize, int nt, int B, float* kern,
-                         cudaStream_t s) {
-  ++g_launch_counter;
-  k_cdna_kernels<<<(B + CK_S - 1) / CK_S, 1024, 0, s>>>(feat, npix, w, bias, ksize, nt, B, kern);
+inline int band_rows(int H, int W) {                 // rows per block of the banded CDNA / composite kernels
+  int tr = 16;
+  while (tr > 4 && (long long)(tr + 4) * W * 16 > 40 * 1024) tr /= 2;
+  return tr;
 }
-void launch_cdna_apply(View image, View first, const float* kern, int ksize, int nt, int B, int H, int W, View mask_in,
-                       int base, cudaStream_t s) {
+size_t cdna_partial_floats(int K, int B) { return (size_t)((K + CK_KC - 1) / CK_KC) * B * 128; }
+void launch_cdna_kernels(View feat, int npix, const float* w, int ksize, int nt, int B, float* part, cudaStream_t s) {
   ++g_launch_counter;
-  dim3 grid((H * W + 127) / 128, B);
-  k_cdna_apply<<<grid, 128, nt * ksize * ksize * sizeof(float), s>>>(image, first, kern, ksize, nt, H, W, mask_in, base);
+  const int K = npix * feat.C;
+  dim3 grid((K + CK_KC - 1) / CK_KC, (B + CK_S - 1) / CK_S);
+  k_cdna_partial<<<grid, 256, 0, s>>>(feat, npix, w, ksize * ksize * nt, B, part);
 }
-int composite_blocks(int H, int W) { return (H * W + COMP_THREADS - 1) / COMP_THREADS; }
+void launch_cdna_apply(View image, View first, const float* part, int K, const float* bias, float* kern, int ksize, int nt,
+                       int B, int H, int W, View layers, cudaStream_t s) {
+  ++g_launch_counter;
+  const int nks = (K + CK_KC - 1) / CK_KC;
+  if (nt == 4 && ksize == 5 && W >= 8) {
+    const int TR = band_rows(H, W);
+    dim3 grid((H + TR - 1) / TR, B);
+    const size_t smem = (size_t)(25 + 34 + (TR + 4) * W) * sizeof(float4);
+    k_cdna_apply4<<<grid, 256, smem, s>>>(image, first, part, nks, bias, B, H, W, TR, layers, kern);
+  } else {
+    dim3 grid((H * W + 127) / 128, B);
+    k_cdna_apply<<<grid, 128, 0, s>>>(image, first, part, nks, bias, ksize, nt, B, H, W, layers, kern);
+  }
+}
+int composite_blocks(int H, int W) { const int TR = band_rows(H, W); return (H + TR - 1) / TR; }
 void launch_composite(const CompositeArgs& a, int B, cudaStream_t s) {
   ++g_launch_counter;
-  dim3 grid(composite_blocks(a.H, a.W), B);
-  k_composite<<<grid, COMP_THREADS, a.nt * a.ksize * a.ksize * sizeof(float), s>>>(a);
+  const int TR = band_rows(a.H, a.W);
+  dim3 grid((a.H + TR - 1) / TR, B);
+  const size_t smem = (size_t)(((a.nt * a.ksize * a.ksize + 3) & ~3) + a.nd * (TR + a.ksize - 1) * a.W) * sizeof(float);
+  k_composite<<<grid, COMP_THREADS, smem, s>>>(a, TR);
 }
 void launch_distrib_normalize(View d, const float* partial, int nblk, int B, int H, int W, int nd, cudaStream_t s) {
   ++g_launch_counter;

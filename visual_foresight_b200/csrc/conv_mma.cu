@@ -1,30 +1,32 @@
-// conv_mma.cu — tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a.
+// conv_mma.cu — tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a, operands fed by TMA.
 //
 // D[cout, pixel] = sum_{tap, cin} W[cout, (tap, cin)] * X[(tap, cin), pixel]      (SAME zero padding, stride 1)
 //
-//   * Output channels sit on the MMA M dimension (UMMA_M = 128 TMEM lanes), pixels on N (TMEM columns).  One
-//     epilogue thread therefore owns one output channel of every pixel in the tile: per-channel work is
-//     thread-local, and a warp writes 32 consecutive channels of one pixel = one 128-byte NHWC line.
-//   * No im2col and no per-tap re-fetch.  A tile's input pixels (+halo) are staged ONCE per channel chunk in
-//     shared memory as a FLAT zero-padded image (row pitch Wp = W + k - 1), one operand row per pixel.  Filter tap
-//     (dy,dx) is the SAME buffer read through a matrix descriptor whose start address is advanced by
-//     (dy*Wp + dx) pixel rows: 25 taps = 25 descriptors, zero data movement.  The k-1 wrap-around columns per image
-//     row are computed and discarded (W/Wp efficiency: 89% at 32x32, 80% at 16x16).
-//   * fp32-grade arithmetic on fp16 tensor cores: both operands are split x = hi + lo (fp16 each, weights
-//     pre-scaled by a power of two so lo stays normal) and three MMAs hi*hi + hi*lo + lo*hi accumulate into the
-//     same fp32 TMEM accumulator.
+//   * Activations live in HBM in "split-half" storage (vf_common.cuh): two fp16 planes hi = rn16(x), lo = rn16(x - hi),
+//     written once by the producing kernel.  The conv fetches a tile's input rows (+halo) per 32-channel chunk with ONE
+//     cp.async.bulk.tensor (5-D tensor map: channel, x, y, sample, plane) per plane, box = 32 ch x (W+k-1) x R rows starting
+//     at x = -pad: the hardware zero-fills the SAME padding and writes the SWIZZLE_64B operand layout directly.  No
+//     register staging, no conversion pass, no im2col.
+//   * The box in shared memory is a FLAT zero-padded image (row pitch Wp = W + k - 1), one operand row per pixel.  Filter
+//     tap (dy,dx) is the SAME buffer read through a matrix descriptor whose start address is advanced by (dy*Wp + dx)
+//     pixel rows: 25 taps = 25 descriptors, zero data movement.  The k-1 wrap-around columns per image row are computed
+//     and discarded (W/Wp efficiency: 89% at 32x32, 80% at 16x16).
+//   * Two orientations.  Cout >= 128: output channels on the MMA M dimension (TMEM lanes), pixels on N; a warp stores 32
+//     consecutive channels of one pixel = one 128-byte NHWC line.  Cout <= 64 ("swap"): pixels on M in 128-row units,
+//     channels on N; one epilogue thread owns one pixel and writes its channels with 16-byte stores.
+//   * fp32-grade arithmetic on fp16 tensor cores: three MMAs hi*hi + hi*lo + lo*hi accumulate into the same fp32 TMEM
+//     accumulator (weights pre-scaled by a power of two so their lo part stays normal).
 //   * Weights are pre-packed on the host in exactly the shared-memory operand layout, so a pipeline stage is one
-//     contiguous cp.async.bulk (TMA 1-D) completing on an mbarrier: no tensor maps.
-//   * Warp roles: warp 0 = weight producer (bulk copies), warp 1 = MMA issuer (one elected thread) + TMEM
-//     allocator, warps 2-5 = activation stagers (fp32 -> fp16 hi/lo split on the fly) then epilogue
-//     (tcgen05.ld -> scale, + border-class bias -> coalesced NHWC stores).  Persistent CTAs, one per SM.
+//     contiguous cp.async.bulk (TMA 1-D) completing on an mbarrier.
+//   * Warp roles (384 threads, persistent CTAs, one per SM): warp 0 = weight producer, warp 1 = MMA issuer (one elected
+//     thread) + TMEM allocator, warp 2 = activation producer (tensor TMA), warps 4-11 = epilogue (tcgen05.ld -> scale,
+//     + border-class bias, optional sigmoid / instance-norm partial sums -> NHWC stores).  Two TMEM accumulator sets and two
+//     activation buffers: the epilogue of item i and the loads of item i+1 overlap the MMAs.
 //
-// Operand layouts (VF_MMA_LAYOUT, default chosen from hardware measurements — see DESIGN.md):
-//   0  interleave / no swizzle, 32-channel chunks [k-chunk][pixel][16 B]           (correct, operand fetch ~16 B/clk)
-//   1  SWIZZLE_64B,  32-channel chunks, pixel rows of 64 B
-//   2  SWIZZLE_128B, 64-channel chunks, pixel rows of 128 B
-// For the swizzled layouts the 16-byte chunks of a row are XOR-permuted with the row's shared-memory ADDRESS bits
-// ([7,9) / [7,10)); the stager applies the same permutation so that every tap-shifted descriptor sees consistent data.
+// Operand layouts (VF_MMA_LAYOUT): 1 = SWIZZLE_64B, 32-channel chunks, pixel rows of 64 B (default);
+//                                  2 = SWIZZLE_128B, 64-channel chunks, pixel rows of 128 B.
+// The swizzle XOR acts on absolute shared-memory address bits for TMA and for the MMA descriptors alike (measured:
+// tap-shifted descriptors are exact with base_offset = 0), so arbitrary 64-byte row shifts stay consistent.
 #include <cuda.h>
 #include <math.h>
 #include <stdio.h>
@@ -39,8 +41,7 @@ namespace vf {
 namespace {
 
 constexpr int MT = 128;                // cout tile (UMMA M)
-constexpr int NTHREADS = 512;
-constexpr int NLOAD = 128;             // threads per role group (4 epilogue warps, 4 stager warps)
+constexpr int NTHREADS = 384;
 constexpr int MAX_SEG = 8;
 constexpr int MAX_STAGE = 8;
 constexpr int MAX_UNIT = 4;            // (images x column segments) per item
@@ -55,8 +56,10 @@ struct Geometry {
   int G;            // images per item
   int v_cnt;        // virtual pixels per image per item (multiple of 32)
   int npass;        // passes over the image's virtual pixel range
-  int img_pix;      // staged flat pixels per image
-  int npix;         // staged pixel rows per plane
+  int img_pix;      // shared-memory pixel rows reserved per image (>= R*Wp, multiple of 8)
+  int R;            // rows of the TMA box (covers v_cnt + halo for every pass offset)
+  int box_bytes;    // bytes one TMA box delivers (R * Wp * row_bytes)
+  int nchunk0;      // channel chunks taken from the first source (the rest come from the second)
   int nseg;         // MMA column segments per image
   int seg_n[MAX_SEG];
   int seg_off[MAX_SEG];
@@ -70,8 +73,10 @@ struct Geometry {
 };
 
 struct Params {
+  alignas(64) CUtensorMap tmap0;   // activations of source 0: (channel, x, y, sample, plane)
+  alignas(64) CUtensorMap tmap1;   // source 1 (channel chunks >= nchunk0) or a copy of tmap0
   Geometry g;
-  View src, out;
+  View out;
   const float* sabias;
   const float* bias;
   const __half* w;     // packed [mt][chunk][tap][hi|lo][operand tile]
@@ -119,7 +124,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -236,6 +247,8 @@ __device__ __forceinline__ void issuer_loop(const Geometry& g, const IssueCtx& c
   uint32_t ph = 0, job = 0, it = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
     const int a = it % nacc;
+    // the box starts at the image row containing the item's first virtual pixel: skip (v_lo mod Wp) pixel rows
+    const uint64_t item_off16 = (uint64_t)(((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
     mbar_wait(&cx.acc_empty[a], ((it / nacc) & 1) ^ 1);
     tc_fence_after();
 #pragma unroll
@@ -245,7 +258,7 @@ __device__ __forceinline__ void issuer_loop(const Geometry& g, const IssueCtx& c
       const int buf = job % nbuf;
       mbar_wait(&cx.a_full[buf], (job / nbuf) & 1);
       tc_fence_after();
-      uint64_t db_tap = db_base + (uint64_t)(buf * buf16);
+      uint64_t db_tap = db_base + (uint64_t)(buf * buf16) + item_off16;
       int tx = 0;
       for (int tap = 0; tap < ntap; ++tap) {
         mbar_wait(&cx.w_full[s], ph);
@@ -282,12 +295,13 @@ __device__ __forceinline__ void issuer_loop_swap(const Geometry& g, const IssueC
     mbar_wait(&cx.acc_empty[a], ((it / nacc) & 1) ^ 1);
     tc_fence_after();
     const uint32_t tacc = cx.tmem_base + (uint32_t)(a * acc_cols);
+    const uint64_t item_off16 = (uint64_t)(((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
     uint32_t acc = 0;
     for (int c = 0; c < nchunk; ++c, ++job) {
       const int buf = job % nbuf;
       mbar_wait(&cx.a_full[buf], (job / nbuf) & 1);
       tc_fence_after();
-      uint64_t da_tap = dx_base + (uint64_t)(buf * buf16);
+      uint64_t da_tap = dx_base + (uint64_t)(buf * buf16) + item_off16;
       int tx = 0;
       for (int tap = 0; tap < ntap; ++tap) {
         mbar_wait(&cx.w_full[s], ph);
@@ -308,11 +322,11 @@ __device__ __forceinline__ void issuer_loop_swap(const Geometry& g, const IssueC
   }
 }
 
-// thread layout: warp 0 weight producer, warp 1 MMA issuer (+TMEM alloc), warps 2,3 idle, warps 4..11 epilogue
-// (warp % 4 = TMEM lane quarter, two warps per quarter split the columns / units), warps 12..15 activation stagers
-constexpr int EPI_WARP0 = 4, STG_WARP0 = 12, NEPI = 256;
+// thread layout: warp 0 weight producer, warp 1 MMA issuer (+TMEM alloc), warp 2 activation producer (tensor TMA),
+// warp 3 idle, warps 4..11 epilogue (warp % 4 = TMEM lane quarter, two warps per quarter split the columns / units)
+constexpr int EPI_WARP0 = 4, NEPI = 256;
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant__ Params P) {
   extern __shared__ uint8_t smem_raw[];
   const Geometry& g = P.g;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;        // 1024-aligned: swizzle phases are address based
@@ -330,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], NLOAD); mbar_init(&a_empty[i], 1);
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
       mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -345,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
   const uint32_t tmem_base = *tmem_slot;
 
   const int per_mt = g.ngroups * g.npass;
-  const uint32_t ltype = g.layout == 0 ? 0u : (g.layout == 1 ? 4u : 2u);
+  const uint32_t ltype = g.layout == 1 ? 4u : 2u;
   const int acc_cols = g.swap ? g.units * g.np : g.G * g.v_cnt;   // TMEM columns of one accumulator set
   const int nacc = g.nacc;                               // 2 when two sets fit in the 512 columns
 
@@ -368,15 +382,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp walks the loops (warp-uniform), one elected lane issues =====
-    const uint32_t lbo_b = g.layout == 0 ? (uint32_t)g.npix * 16 : 16u;
-    const uint32_t sbo_b = g.layout == 0 ? 128u : (uint32_t)(8 * g.row_bytes);
-    const uint32_t a_lbo = g.layout == 0 ? (uint32_t)(MT * 16) : 16u;
+    const uint32_t sbo_b = (uint32_t)(8 * g.row_bytes);                   // 8-row core-matrix group pitch
     IssueCtx cx;
-    cx.kstep_b = (g.layout == 0 ? 2 * lbo_b : 32u) >> 4;                  // start-address advance per K=16 step (16-byte units)
-    cx.kstep_a = (g.layout == 0 ? 2 * a_lbo : 32u) >> 4;
-    cx.pix_b = g.layout == 0 ? 16u : (uint32_t)g.row_bytes;
-    cx.da_zero = make_desc(0, a_lbo, sbo_b, ltype, 0);
-    cx.db_zero = make_desc(0, lbo_b, sbo_b, ltype, 0);
+    cx.kstep_a = cx.kstep_b = 32u >> 4;                                   // start-address advance per K=16 step (16-byte units)
+    cx.pix_b = (uint32_t)g.row_bytes;
+    cx.da_zero = make_desc(0, 16u, sbo_b, ltype, 0);
+    cx.db_zero = make_desc(0, 16u, sbo_b, ltype, 0);
     cx.a_half = (uint64_t)(g.half_bytes >> 4); cx.b_plane = (uint64_t)(g.plane_bytes >> 4);
     cx.act_base = act_base; cx.wst_base = wst_base; cx.tmem_base = tmem_base;
     cx.w_full = w_full; cx.w_empty = w_empty; cx.a_full = a_full; cx.a_empty = a_empty; cx.acc_full = acc_full; cx.acc_empty = acc_empty;
@@ -406,72 +417,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
       }
 #undef VF_IS
     }
-  } else if (warp >= STG_WARP0) {
-    // ===== activation stagers: fp32 NHWC -> fp16 hi/lo operand rows of the flat zero-padded image =====
-    const int t = threadIdx.x - STG_WARP0 * 32;     // 0..127
-    const int kc8 = t % g.kc;                       // this thread always handles the same 16-byte k-chunk
-    const int pl0 = t / g.kc, pl_step = NLOAD / g.kc;
-    uint32_t job = 0;
-    for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
-      const int rem = item % per_mt;
-      const int grp = rem / g.npass, ps = rem % g.npass;
-      const int b0 = grp * g.G, v_lo = ps * g.v_cnt;
-      const int npl = g.G * g.img_pix;
-      for (int c = 0; c < g.nchunk; ++c, ++job) {
-        const int buf = job % g.nbuf;
-        mbar_wait(&a_empty[buf], ((job / g.nbuf) & 1) ^ 1);
-        const uint32_t hi_addr = act_base + (uint32_t)(buf * 2 * g.plane_bytes);
-        uint8_t* hi_ptr = smem + buf * 2 * g.plane_bytes;
-        const int choff = P.src.ch_off + c * g.ch + kc8 * 8;
-        const bool ch_ok = c * g.ch + kc8 * 8 < g.Cin;          // zero-padded channel units of the last chunk
-        for (int plb = pl0; plb < npl; plb += 4 * pl_step) {
-          float4 f[4][2];
-          bool ok[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {             // issue all loads of the batch first (memory-level parallelism)
-            const int pl = plb + u * pl_step;
-            const int im = pl / g.img_pix, ql = pl - im * g.img_pix;
-            const int q = v_lo + ql;                // flat index in the zero-padded image
-            const int qy = q / g.Wp;
-            const int yy = qy - g.pad, xx = q - qy * g.Wp - g.pad;
-            const int b = b0 + im;
-            ok[u] = ch_ok && pl < npl && b < P.B && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W;
-            if (ok[u]) {
-              const float4* sp = reinterpret_cast<const float4*>(P.src.p + (long long)b * P.src.sample_stride +
-                                                                 (long long)(yy * g.W + xx) * P.src.pix_stride + choff);
-              f[u][0] = __ldg(sp);
-              f[u][1] = __ldg(sp + 1);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int pl = plb + u * pl_step;
-            if (pl >= npl) break;
-            uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
-            if (ok[u]) {
-              const float x[8] = {f[u][0].x, f[u][0].y, f[u][0].z, f[u][0].w, f[u][1].x, f[u][1].y, f[u][1].z, f[u][1].w};
-              __half h[8], l[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                h[e] = __float2half_rn(x[e]);
-                l[e] = __float2half_rn(x[e] - __half2float(h[e]));
-              }
-              vh = *reinterpret_cast<uint4*>(h);
-              vl = *reinterpret_cast<uint4*>(l);
-            }
-            uint32_t off;
-            if (g.layout == 0) {
-              off = (uint32_t)(kc8 * g.npix + pl) * 16;
-            } else {
-              const uint32_t rowoff = (uint32_t)pl * g.row_bytes;
-              off = rowoff + (((uint32_t)kc8 ^ (((hi_addr + rowoff) >> 7) & (uint32_t)g.swz_mask)) << 4);
-            }
-            *reinterpret_cast<uint4*>(hi_ptr + off) = vh;
-            *reinterpret_cast<uint4*>(hi_ptr + g.plane_bytes + off) = vl;   // plane_bytes % 1024 == 0: same swizzle phase
-          }
+  } else if (warp == 2) {
+    // ===== activation producer: one tensor-TMA box per (image, plane) and channel chunk =====
+    if (lane == 0) {
+      const int nplanes = g.passes == 3 ? 2 : 1;
+      uint32_t job = 0;
+      for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
+        const int rem = item % per_mt;
+        const int grp = rem / g.npass, ps = rem % g.npass;
+        const int b0 = grp * g.G;
+        const int qy0 = (ps * g.v_cnt) / g.Wp;                 // first padded-image row the item touches
+        const int nimg = min(g.G, P.B - b0);
+        for (int c = 0; c < g.nchunk; ++c, ++job) {
+          const int buf = job % g.nbuf;
+          mbar_wait(&a_empty[buf], ((job / g.nbuf) & 1) ^ 1);
+          const CUtensorMap* tm = c < g.nchunk0 ? &P.tmap0 : &P.tmap1;
+          const int c0 = (c < g.nchunk0 ? c : c - g.nchunk0) * g.ch;
+          mbar_expect_tx(&a_full[buf], (uint32_t)(nimg * nplanes * g.box_bytes));
+          for (int im = 0; im < nimg; ++im)
+            for (int pl = 0; pl < nplanes; ++pl)
+              tma_load_5d(act_base + (uint32_t)((buf * 2 + pl) * g.plane_bytes + im * g.img_pix * g.row_bytes), tm, c0, -g.pad,
+                          qy0 - g.pad, b0 + im, pl, &a_full[buf]);
         }
-        fence_proxy_async();                        // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(&a_full[buf]);
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -496,13 +463,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
         const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.pad;
         const float scale = g.out_scale;
         const bool sigm = P.act == ACT_SIGMOID;
-        const bool vec4 = ((g.Cout | P.out.ch_off | ps) & 3) == 0 && (P.out.sample_stride & 3) == 0;
+        const bool vec4 = ((g.Cout | P.out.ch_off | ps) & 3) == 0 && (P.out.sample_stride & 3) == 0 && (P.out.lo_off & 3) == 0;
+        const bool split = P.out.lo_off != 0;                  // split-half output (feeds another convolution)
         for (int u = half; u < g.units; u += 2) {
           const int v = v_lo + u * 128 + row;
           const int oy = v / Wp, ox = v - oy * Wp;
           const bool valid = b < P.B && ox < W && oy < H;
           const float* sb = nullptr;
           float* op = nullptr;
+          long long oo = 0;
           if (valid) {
             if (P.sabias) {
               const int cls = border_class(oy, H, pad) * g.k + border_class(ox, W, pad);
@@ -510,7 +479,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
             } else {
               sb = P.bias;
             }
-            op = P.out.p + (long long)b * P.out.sample_stride + (long long)(oy * W + ox) * ps + P.out.ch_off;
+            oo = (long long)b * P.out.sample_stride + (long long)(oy * W + ox) * ps + P.out.ch_off;
+            op = P.out.p + oo;
           }
           for (int c16 = 0; c16 < g.np; c16 += 16) {
             float4 bbv[4];
@@ -536,7 +506,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
                     o.x = __fdividef(1.f, 1.f + __expf(-o.x)); o.y = __fdividef(1.f, 1.f + __expf(-o.y));
                     o.z = __fdividef(1.f, 1.f + __expf(-o.z)); o.w = __fdividef(1.f, 1.f + __expf(-o.w));
                   }
-                  *reinterpret_cast<float4*>(op + c16 + j) = o;
+                  if (split) vst4(P.out, oo + c16 + j, o);
+                  else *reinterpret_cast<float4*>(op + c16 + j) = o;
                 }
               }
             } else {
@@ -545,7 +516,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const Params P) {
                 if (c16 + j < g.Cout) {
                   float o = fmaf(__uint_as_float(r[j]), scale, sb ? __ldg(sb + c16 + j) : 0.f);
                   if (sigm) o = __fdividef(1.f, 1.f + __expf(-o));
-                  op[c16 + j] = o;
+                  if (split) vst1(P.out, oo + c16 + j, o);
+                  else op[c16 + j] = o;
                 }
               }
             }
@@ -631,11 +603,22 @@ void current_mode(int* layout, int* bo) {
   if (s_layout < 0) {
     const char* e = getenv("VF_MMA_LAYOUT");
     s_layout = e ? atoi(e) : 1;     // SWIZZLE_64B: verified correct with tap-shifted descriptors on B200
-    if (s_layout < 0 || s_layout > 2) s_layout = 0;
+    if (s_layout < 1 || s_layout > 2) s_layout = 1;
     const char* b = getenv("VF_MMA_BO");
     s_bo = b ? atoi(b) : 0;
   }
   *layout = s_layout; *bo = s_bo;
+}
+
+// TMA box rows: every pass starts its box at the padded-image row holding its first virtual pixel and must cover
+// (offset inside that row) + v_cnt + the k-1 halo rows + k-1 pixels.
+bool box_rows(Geometry& g) {
+  int need = 0;
+  for (int ps = 0; ps < g.npass; ++ps) need = std::max(need, (ps * g.v_cnt) % g.Wp + g.v_cnt + (g.k - 1) * g.Wp + (g.k - 1));
+  g.R = (need + g.Wp - 1) / g.Wp;
+  g.img_pix = (g.R * g.Wp + 7) / 8 * 8;
+  g.box_bytes = g.R * g.Wp * g.row_bytes;
+  return g.R <= 256 && g.Wp <= 256;
 }
 
 bool plan_geometry(int layout, int bo_mode, int k, int Cin, int Cout, int H, int W, int B, int passes, Geometry* out) {
@@ -644,11 +627,12 @@ bool plan_geometry(int layout, int bo_mode, int k, int Cin, int Cout, int H, int
   g.layout = layout; g.bo_mode = bo_mode;
   g.ch = layout == 2 ? 64 : 32;
   if (Cin % 8) return false;                            // 16-byte staging units; channels/cout beyond the real extent are zero-padded
-  g.kc = g.ch / 8; g.ksteps = g.ch / 16; g.row_bytes = g.ch * 2; g.swz_mask = layout == 2 ? 7 : (layout == 1 ? 3 : 0);
+  g.kc = g.ch / 8; g.ksteps = g.ch / 16; g.row_bytes = g.ch * 2; g.swz_mask = layout == 2 ? 7 : 3;
   g.half_bytes = MT * g.ch * 2; g.stage_bytes = 2 * g.half_bytes;
   g.H = H; g.W = W; g.k = k; g.pad = k / 2; g.Wp = W + k - 1; g.Cin = Cin; g.Cout = Cout;
   g.nchunk = (Cin + g.ch - 1) / g.ch; g.ntap = k * k; g.n_mt = (Cout + MT - 1) / MT; g.passes = passes;
-  if (Cout <= 64 && layout >= 1) {
+  g.nchunk0 = g.nchunk;
+  if (Cout <= 64) {
     // ---- swapped orientation (thin layers): pixels on M in 128-row units, np = Cout padded to 16 on N ----
     g.swap = 1;
     g.np = (Cout + 15) / 16 * 16;
@@ -660,9 +644,8 @@ bool plan_geometry(int layout, int bo_mode, int k, int Cin, int Cout, int H, int
       g.npass = (Vs + 128 * units - 1) / (128 * units);
       g.units = ((Vs + g.npass - 1) / g.npass + 127) / 128;
       g.v_cnt = g.units * 128;
-      g.img_pix = (g.v_cnt + (k - 1) * g.Wp + (k - 1) + 7) / 8 * 8;
-      g.npix = g.img_pix;
-      g.plane_bytes = (g.npix * g.ch * 2 + 1023) / 1024 * 1024;
+      if (!box_rows(g)) return false;
+      g.plane_bytes = (g.img_pix * g.row_bytes + 1023) / 1024 * 1024;
       bool fit = false;
       for (g.nbuf = 2; g.nbuf >= 1; --g.nbuf) {
         const size_t act = (size_t)g.nbuf * 2 * g.plane_bytes;
@@ -709,15 +692,11 @@ bool plan_geometry(int layout, int bo_mode, int k, int Cin, int Cout, int H, int
     g.seg_n[g.nseg] = n; g.seg_off[g.nseg] = off; ++g.nseg;
     off += n; left -= n;
   }
-  g.img_pix = g.v_cnt + (k - 1) * g.Wp + (k - 1);
-  g.img_pix = (g.img_pix + 7) / 8 * 8;
+  if (!box_rows(g)) return false;
   // buffers: prefer double-buffered activations + as many weight stages as fit (>= 2)
   bool ok = false;
   for (; g.G >= 1 && !ok; --g.G) {
-    int npix = g.G * g.img_pix;
-    if (layout == 0) while (npix % 8 != 2) ++npix;      // conflict-free 16-byte stores across k-chunks
-    g.npix = npix;
-    g.plane_bytes = (npix * g.ch * 2 + 1023) / 1024 * 1024;
+    g.plane_bytes = (g.G * g.img_pix * g.row_bytes + 1023) / 1024 * 1024;
     for (g.nbuf = 2; g.nbuf >= 1; --g.nbuf) {
       const size_t act = (size_t)g.nbuf * 2 * g.plane_bytes;
       if (act + 2 * (size_t)g.stage_bytes + SMEM_SLACK > SMEM_LIMIT) continue;
@@ -756,10 +735,10 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaCon
   current_mode(&layout, &bo);
   const int ch = layout == 2 ? 64 : 32;
   if (cin % 8) { if (err) *err = "cin % 8"; return -1; }
-  const bool swap = cout <= 64 && layout >= 1;
+  const bool swap = cout <= 64;
   const int rows = swap ? (cout + 15) / 16 * 16 : MT;                 // operand tile rows (output channels)
   const int kk = k * k, nchunk = (cin + ch - 1) / ch, n_mt = swap ? 1 : (cout + MT - 1) / MT, kc = ch / 8, rb = ch * 2;
-  const int swz = layout == 2 ? 7 : (layout == 1 ? 3 : 0);
+  const int swz = layout == 2 ? 7 : 3;
   float amax = 0.f;
   for (size_t i = 0; i < (size_t)kk * cin * cout; ++i) amax = std::max(amax, fabsf(w_sp[i]));
   int sl = 0;
@@ -781,8 +760,7 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaCon
               const __half h = __float2half_rn(v);
               const __half l = __float2half_rn(v - __half2float(h));
               size_t pos;                                              // element index inside the 128-row operand tile
-              if (layout == 0) pos = ((size_t)kc8 * rows + r) * 8 + e;
-              else pos = ((size_t)r * rb + (size_t)((kc8 ^ ((r * rb >> 7) & swz)) << 4)) / 2 + e;
+              pos = ((size_t)r * rb + (size_t)((kc8 ^ ((r * rb >> 7) & swz)) << 4)) / 2 + e;
               packed[blk + pos] = h;
               packed[blk + half_elems + pos] = l;
             }
@@ -799,17 +777,80 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaCon
   return 0;
 }
 
+// ---- tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link dependency) -------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* base;
+  long long sample_stride, lo_off;
+  int C, pix_stride, H, W, B, ch, Wp, R, layout;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapEntry { MapKey key; CUtensorMap map; };
+std::vector<MapEntry> g_maps;      // a handful of (buffer, layer geometry) pairs per engine; engines are not thread-safe
+
+// 5-D view of a split-half activation tensor: (channel, x, y, sample, plane); box = ch x Wp x R x 1 x 1
+int activation_map(const View& v, const Geometry& g, int B, CUtensorMap* out) {
+  if (!v.lo_off || !v.p) return -10;                                  // the tensor-core path needs split-half storage
+  if ((v.pix_stride % 8) || (v.ch_off % 8) || (v.sample_stride % 8) || (v.lo_off % 8) || (v.C % 8)) return -11;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = reinterpret_cast<const __half*>(v.p) + v.ch_off;
+  key.sample_stride = v.sample_stride; key.lo_off = v.lo_off; key.C = v.C; key.pix_stride = v.pix_stride;
+  key.H = g.H; key.W = g.W; key.B = B; key.ch = g.ch; key.Wp = g.Wp; key.R = g.R; key.layout = g.layout;
+  for (const MapEntry& e : g_maps)
+    if (e.key == key) { *out = e.map; return 0; }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return -12;
+  const cuuint64_t gdim[5] = {(cuuint64_t)v.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)B, 2};
+  const cuuint64_t gstride[4] = {(cuuint64_t)v.pix_stride * 2, (cuuint64_t)g.W * v.pix_stride * 2,
+                                 (cuuint64_t)(B > 1 ? v.sample_stride : (long long)g.H * g.W * v.pix_stride) * 2, (cuuint64_t)v.lo_off * 2};
+  const cuuint32_t box[5] = {(cuuint32_t)g.ch, (cuuint32_t)g.Wp, (cuuint32_t)g.R, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  MapEntry e;
+  e.key = key;
+  const CUresult r = enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(key.base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, g.layout == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return -13;
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.push_back(e);
+  *out = e.map;
+  return 0;
+}
+
 int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaStream_t s) {
   Params P;
   int layout, bo;
   current_mode(&layout, &bo);
+  if (c.src.C + c.src1.C != w.cin) return -5;
   if (!plan_geometry(layout, bo, w.k, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
   P.g.out_scale = ldexpf(1.0f, -w.scale_log2);
-  P.src = c.src; P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B; P.act = c.act;
+  P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B; P.act = c.act;
   P.stats_partial = nullptr; P.stats_S = 0;
   if (c.stats_partial && !P.g.swap) { P.stats_partial = c.stats_partial; P.stats_S = P.g.npass * 2; }
   if (c.stats_slots) *c.stats_slots = P.stats_S;
-  if ((c.src.pix_stride % 4) || (c.src.ch_off % 4) || (c.src.sample_stride % 4)) return -2;      // float4 loads
+  if (!P.g.swap && c.out.lo_off) return -6;                           // the wide epilogue writes float32 (pre-norm) outputs
+  int r = activation_map(c.src, P.g, B, &P.tmap0);
+  if (r) return r;
+  P.tmap1 = P.tmap0;
+  if (c.src1.C > 0) {
+    if (c.src.C % P.g.ch) return -7;                                  // the second source starts on a chunk boundary
+    P.g.nchunk0 = c.src.C / P.g.ch;
+    if ((r = activation_map(c.src1, P.g, B, &P.tmap1))) return r;
+  }
   const size_t smem = smem_bytes(P.g);
   static bool attr_set = false;
   if (!attr_set) {

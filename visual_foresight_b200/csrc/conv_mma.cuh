@@ -17,7 +17,8 @@ struct MmaConvWeights {
 };
 
 struct MmaConvCall {
-  View src, out;
+  View src, out;     // src: split-half storage (vf_common.cuh); channels [0, src.C)
+  View src1 = make_view(nullptr, 0, 0, 0, 0);   // optional second source: channels [src.C, src.C + src1.C), src.C % 32 == 0
   const float* sabias;
   const float* bias;
   int H, W;

@@ -14,13 +14,9 @@ long long g_launch_counter = 0;
 namespace {
 
 __device__ __forceinline__ float load_src(const ConvArgs& a, int b, int y, int x, int c) {
-  if (c < a.src0.C) {
-    return __ldg(a.src0.p + (long long)b * a.src0.sample_stride + (long long)(y * a.W + x) * a.src0.pix_stride +
-                 a.src0.ch_off + c);
-  }
+  if (c < a.src0.C) return vld1(a.src0, voff(a.src0, b, (long long)(y * a.W + x)) + c);
   c -= a.src0.C;
-  return __ldg(a.src1.p + (long long)b * a.src1.sample_stride + (long long)(y * a.W + x) * a.src1.pix_stride +
-               a.src1.ch_off + c);
+  return vld1(a.src1, voff(a.src1, b, (long long)(y * a.W + x)) + c);
 }
 
 // Tile kernel: block = TH x TW output pixels x TN output channels of one sample; 256 threads, each
@@ -113,11 +109,10 @@ __global__ void __launch_bounds__(256) k_conv_tile(ConvArgs a) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) add[q] = (n + q < a.Cout) ? a.bias[n + q] : 0.f;
     }
-    float* o = a.out.p + (long long)b * a.out.sample_stride + (long long)(y * a.W + x) * a.out.pix_stride +
-               a.out.ch_off + n;
+    const long long o = voff(a.out, b, (long long)(y * a.W + x)) + n;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (n + q < a.Cout) o[q] = acc[p][q] + add[q];
+      if (n + q < a.Cout) vst1(a.out, o + q, acc[p][q] + add[q]);
   }
 }
 
@@ -153,11 +148,11 @@ __global__ void __launch_bounds__(128) k_conv_small(ConvArgs a) {
       }
     }
   }
-  float* o = a.out.p + (long long)b * a.out.sample_stride + (long long)pix * a.out.pix_stride + a.out.ch_off;
+  const long long o = voff(a.out, b, pix);
   for (int q = 0; q < a.Cout; ++q) {
     float v = acc[q] + (a.bias ? a.bias[q] : 0.f);
     if (a.act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
-    o[q] = v;
+    vst1(a.out, o + q, v);
   }
 }
 

@@ -7,7 +7,11 @@
 //   gen_distrib f32 [B][P][ncam][H][W][nd]    (vpred_model_interface.py:75-88)
 //   per view / rnn layer: lstm_in [B][h][w][2F]  = [x | h_prev] conv input, c [B][h][w][F]
 //   raw         f32 [B][H*W*Cout max]         conv output scratch (pre-norm)
-//   mask_in     f32 [B][H][W][ngf+3*(nt+3)]   [h_masks | T_0..T_nt-1 | prev | first | scratch]
+//   mask_h      [B][H][W][ngf]                h_masks (first source of the mask-logit conv)
+//   layers      [B][H][W][cl = 3*(nt+3) -> 8]  T_0..T_nt-1 | prev | first | scratch | 0   (second source, and the composite's layers)
+// On the tensor-core path every convolution INPUT buffer (lstm_in, pack0, dec_in, act_*, scr_h, mask_h, layers) is kept
+// in split-half storage (two fp16 planes, vf_common.cuh) so the convolution can fetch it with TMA; conv OUTPUTS (raw,
+// logits), the cell state and the predicted frames stay float32.
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -88,8 +92,12 @@ struct vf_engine {
   double* stats_partial = nullptr;
   std::vector<float*> act_enc, act_dec;
   float* pack0 = nullptr;    // [B][H][W][8] packed (image, first) input of enc0 (tensor-core path)
-  float *scr_h = nullptr, *mask_in = nullptr, *logits = nullptr, *kern = nullptr, *partial = nullptr;
-  int nblk = 0;
+  float *scr_h = nullptr, *mask_h = nullptr, *layers = nullptr, *logits = nullptr, *kern = nullptr, *partial = nullptr;
+  float* cdna_part = nullptr;   // split-K partial products of the CDNA dense head
+  int nblk = 0, cl = 0;
+  bool split = false;           // conv inputs in split-half storage (tensor-core path)
+  int conv_error = 0;           // first failed tensor-core conv launch (reported by rollout)
+  char conv_error_layer[64] = {0};
 
   // context / outputs
   uint8_t* ctx_u8 = nullptr;
@@ -335,7 +343,7 @@ int build_net(vf_engine* h) {
     net.scratch1 = mk("scratch.conv1", 3, h->H, h->W, g, 0, 3, false);
     net.masks0 = mk("masks.conv0", 3, h->H, h->W, g, 0, g, false);
     net.masks1 = mk("masks.conv1", 3, h->H, h->W, h->cm, 0, h->nm, false);
-    net.masks1.cin_w = g + 3 * h->nm;        // mask_in rows are padded to a multiple of 8 channels (16-byte staging units)
+    net.masks1.cin_w = g + 3 * h->nm;        // the layers buffer is padded to a multiple of 8 channels (16-byte units)
     upd(net.scratch0);
   }
   // shared scratch (first view's shapes == all views' shapes)
@@ -360,10 +368,12 @@ int build_net(vf_engine* h) {
   const size_t px = (size_t)h->H * h->W;
   DA(h->scr_h, (size_t)B * px * h->ngf);
   if (c.precision != VF_PREC_FP32_SIMT) DA(h->pack0, (size_t)B * px * 8);
-  DA(h->mask_in, (size_t)B * px * h->cm);
-  if (cudaMemset(h->mask_in, 0, (size_t)B * px * h->cm * sizeof(float)) != cudaSuccess) return fail(h, VF_ERR_CUDA, "memset mask_in");
+  DA(h->mask_h, (size_t)B * px * h->ngf);
+  DA(h->layers, (size_t)B * px * h->cl);
+  if (cudaMemset(h->layers, 0, (size_t)B * px * h->cl * sizeof(float)) != cudaSuccess) return fail(h, VF_ERR_CUDA, "memset layers");
   DA(h->logits, (size_t)B * px * h->nm);
   DA(h->kern, (size_t)B * h->nt * h->kc * h->kc);
+  DA(h->cdna_part, cdna_partial_floats((h->H >> c.n_enc) * (h->W >> c.n_enc) * c.enc_channels[c.n_enc - 1], B));
   h->nblk = composite_blocks(h->H, h->W);
   DA(h->partial, (size_t)B * h->nd * h->nblk);
   return VF_OK;
@@ -411,6 +421,10 @@ int finalize_weights(vf_engine* h) {
 }
 
 View dense_view(float* p, int hw, int C) { return make_view(p, (long long)hw * C, C, 0, C); }
+// view of a convolution-input buffer [B][hw][ps] (split-half storage on the tensor-core path: lo plane after B*hw*ps halfs)
+View cview(const vf_engine* h, float* p, int hw, int ps, int ch_off, int C) {
+  return make_view(p, (long long)hw * ps, ps, ch_off, C, h->split ? (long long)h->B * hw * ps : 0);
+}
 
 void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act, double* stats_partial, int* stats_slots);
 
@@ -436,14 +450,18 @@ void run_conv(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int 
 }
 
 void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act, double* stats_partial, int* stats_slots) {
-  if (h->cfg.precision != VF_PREC_FP32_SIMT && L.mma.ready && s1.C == 0) {
+  if (h->cfg.precision != VF_PREC_FP32_SIMT && L.mma.ready) {
     MmaConvCall c;
-    c.src = s0; c.out = out; c.sabias = L.sabias; c.bias = L.bias; c.H = L.H; c.W = L.W;
+    c.src = s0; c.src1 = s1; c.out = out; c.sabias = L.sabias; c.bias = L.bias; c.H = L.H; c.W = L.W;
     c.passes = (h->cfg.precision == VF_PREC_F16X3) ? 3 : 1;
     c.act = act;
     c.stats_partial = stats_partial;
     c.stats_slots = stats_slots;
-    mma_conv_launch(L.mma, c, B, h->stream);
+    const int rc = mma_conv_launch(L.mma, c, B, h->stream);
+    if (rc && !h->conv_error) {
+      h->conv_error = rc;
+      snprintf(h->conv_error_layer, sizeof(h->conv_error_layer), "%s", L.name.c_str());
+    }
     return;
   }
   ConvArgs a;
@@ -454,7 +472,7 @@ void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out,
 
 void run_lstm(vf_engine* h, int v, const ConvLayer& L, RnnState& r, int B, const std::string& dbg) {
   const int hw = r.h * r.w, F = r.F;
-  View in = dense_view(r.lstm_in, hw, 2 * F);
+  View in = cview(h, r.lstm_in, hw, 2 * F, 0, 2 * F);
   View gates = dense_view(h->raw, hw, 4 * F);
   View none = make_view(nullptr, 0, 0, 0, 0);
   int slots = 0;
@@ -468,7 +486,7 @@ void run_lstm(vf_engine* h, int v, const ConvLayer& L, RnnState& r, int B, const
     launch_lstm_gates_generic(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->stream);
     launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cfg.norm_eps, h->cstats, h->stats_partial, h->stream);
   }
-  View hv = make_view(r.lstm_in, (long long)hw * 2 * F, 2 * F, F, F);
+  View hv = cview(h, r.lstm_in, hw, 2 * F, F, F);
   launch_lstm_out(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cstats, L.cgamma, L.cbeta, r.c, hv, h->stream);
   h->debug[v][dbg + ".h"] = DebugEntry{hv, r.h, r.w};
   h->debug[v][dbg + ".c"] = DebugEntry{dense_view(r.c, hw, F), r.h, r.w};
@@ -505,8 +523,8 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   std::vector<int> enc_h(n), enc_w(n);
   View x0 = image, x1 = first;
   if (h->pack0) {
-    launch_pack_rgb2(image, first, B, H * W, h->pack0, h->stream);
-    x0 = dense_view(h->pack0, H * W, 8);
+    x0 = cview(h, h->pack0, H * W, 8, 0, 8);
+    launch_pack_rgb2(image, first, B, H * W, x0, h->stream);
     x1 = none;
   }
   int hh = H, ww = W;
@@ -517,14 +535,14 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     run_conv(h, L, x0, x1, rawv, B);
     hh /= 2; ww /= 2;
     launch_plane_stats(rawv, B, hh, ww, 1, c.norm_eps, h->stats, h->stats_partial, h->stream);
-    View dst = c.enc_rnn[i] ? make_view(net.enc_rnn[i].lstm_in, (long long)hh * ww * 2 * oc, 2 * oc, 0, oc)
-                            : dense_view(h->act_enc[i], hh * ww, oc);
+    View dst = c.enc_rnn[i] ? cview(h, net.enc_rnn[i].lstm_in, hh * ww, 2 * oc, 0, oc)
+                            : cview(h, h->act_enc[i], hh * ww, oc, 0, oc);
     launch_norm_act(rawv, B, hh, ww, 1, h->stats, L.gamma, L.beta, ACT_RELU, dst, h->stream);
     h->debug[v][L.name] = DebugEntry{dst, hh, ww};
     View out = dst;
     if (c.enc_rnn[i]) {
       run_lstm(h, v, net.enc_lstm[i], net.enc_rnn[i], B, net.enc_lstm[i].name);
-      out = make_view(net.enc_rnn[i].lstm_in, (long long)hh * ww * 2 * oc, 2 * oc, oc, oc);
+      out = cview(h, net.enc_rnn[i].lstm_in, hh * ww, 2 * oc, oc, oc);
     }
     enc_out[i] = out; enc_h[i] = hh; enc_w[i] = ww;
     x0 = out; x1 = none;
@@ -535,48 +553,49 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     ConvLayer& L = net.dec_conv[i];
     const int oc = L.cout;
     View skip = i > 0 ? enc_out[n - 1 - i] : none;
-    View din = dense_view(h->dec_in, 4 * hh * ww, x.C + skip.C);
+    View din = cview(h, h->dec_in, 4 * hh * ww, x.C + skip.C, 0, x.C + skip.C);
     launch_upsample2x(x, skip, B, hh, ww, din, h->stream);
     hh *= 2; ww *= 2;
     View rawv = dense_view(h->raw, hh * ww, oc);
     run_conv(h, L, din, none, rawv, B);
     launch_plane_stats(rawv, B, hh, ww, 0, c.norm_eps, h->stats, h->stats_partial, h->stream);
-    View dst = c.dec_rnn[i] ? make_view(net.dec_rnn[i].lstm_in, (long long)hh * ww * 2 * oc, 2 * oc, 0, oc)
-                            : dense_view(h->act_dec[i], hh * ww, oc);
+    View dst = c.dec_rnn[i] ? cview(h, net.dec_rnn[i].lstm_in, hh * ww, 2 * oc, 0, oc)
+                            : cview(h, h->act_dec[i], hh * ww, oc, 0, oc);
     launch_norm_act(rawv, B, hh, ww, 0, h->stats, L.gamma, L.beta, ACT_RELU, dst, h->stream);
     h->debug[v][L.name] = DebugEntry{dst, hh, ww};
     x = dst;
     if (c.dec_rnn[i]) {
       run_lstm(h, v, net.dec_lstm[i], net.dec_rnn[i], B, net.dec_lstm[i].name);
-      x = make_view(net.dec_rnn[i].lstm_in, (long long)hh * ww * 2 * oc, 2 * oc, oc, oc);
+      x = cview(h, net.dec_rnn[i].lstm_in, hh * ww, 2 * oc, oc, oc);
     }
   }
   if (tau < h->C - 1) return;   // warm-up step: its prediction is never consumed
   const int t_out = tau - (h->C - 1);
-  const int g = h->ngf, nm = h->nm, cm = h->cm;
+  const int g = h->ngf, nm = h->nm, cl = h->cl;
   View h_last = x;
   // P5/P6
-  launch_cdna_kernels(enc_out[n - 1], enc_h[n - 1] * enc_w[n - 1], net.cdna_w, net.cdna_b, h->kc, h->nt, B, h->kern, h->stream);
-  View mask_in = dense_view(h->mask_in, (int)px, cm);
-  launch_cdna_apply(image, first, h->kern, h->kc, h->nt, B, H, W, mask_in, g, h->stream);
+  const int featK = enc_h[n - 1] * enc_w[n - 1] * enc_out[n - 1].C;
+  launch_cdna_kernels(enc_out[n - 1], enc_h[n - 1] * enc_w[n - 1], net.cdna_w, h->kc, h->nt, B, h->cdna_part, h->stream);
+  View layers = cview(h, h->layers, (int)px, cl, 0, cl);
+  launch_cdna_apply(image, first, h->cdna_part, featK, net.cdna_b, h->kern, h->kc, h->nt, B, H, W, layers, h->stream);
   // P7 scratch image
   View rawg = dense_view(h->raw, (int)px, g);
   run_conv(h, net.scratch0, h_last, none, rawg, B);
   launch_plane_stats(rawg, B, H, W, 0, c.norm_eps, h->stats, h->stats_partial, h->stream);
-  View scr = dense_view(h->scr_h, (int)px, g);
+  View scr = cview(h, h->scr_h, (int)px, g, 0, g);
   launch_norm_act(rawg, B, H, W, 0, h->stats, net.scratch0.gamma, net.scratch0.beta, ACT_RELU, scr, h->stream);
-  View scratch_out = make_view(h->mask_in, px * cm, cm, g + 3 * (h->nt + 2), 3);
+  View scratch_out = cview(h, h->layers, (int)px, cl, 3 * (h->nt + 2), 3);
   run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
   // P8 masks
   run_conv(h, net.masks0, h_last, none, rawg, B);
   launch_plane_stats(rawg, B, H, W, 0, c.norm_eps, h->stats, h->stats_partial, h->stream);
-  View hm = make_view(h->mask_in, px * cm, cm, 0, g);
+  View hm = cview(h, h->mask_h, (int)px, g, 0, g);
   launch_norm_act(rawg, B, H, W, 0, h->stats, net.masks0.gamma, net.masks0.beta, ACT_RELU, hm, h->stream);
   View lg = dense_view(h->logits, (int)px, nm);
-  run_conv(h, net.masks1, mask_in, none, lg, B);
+  run_conv(h, net.masks1, hm, layers, lg, B);
   CompositeArgs ca;
   ca.logits = lg;
-  ca.layers = make_view(h->mask_in, px * cm, cm, g, 3 * nm);
+  ca.layers = layers;
   ca.prev_d = distrib; ca.first_d = first_d; ca.kern = h->kern;
   ca.gen_image = make_view(h->gen_images + ((long long)t_out * h->ncam + v) * px * 3, (long long)h->P * h->ncam * px * 3, 3, 0, 3);
   ca.gen_distrib = make_view(h->gen_distrib + ((long long)t_out * h->ncam + v) * px * nd, (long long)h->P * h->ncam * px * nd, nd, 0, nd);
@@ -594,13 +613,15 @@ void run_step(vf_engine* h, int v, int tau, int B) {
 // rolls S-1 cell steps for M samples whose actions are in h->actions [M][T][adim]
 int rollout_body(vf_engine* h, int M, int T) {
   for (auto& net : h->views) {
+    // lstm_in holds two B-strided fp16 planes on the tensor-core path: clear the whole buffer
+    const size_t Bz = h->split ? (size_t)h->B : (size_t)M;
     for (auto& r : net.enc_rnn) if (r.c) {
       CU(cudaMemsetAsync(r.c, 0, (size_t)M * r.h * r.w * r.F * sizeof(float), h->stream));
-      CU(cudaMemsetAsync(r.lstm_in, 0, (size_t)M * r.h * r.w * 2 * r.F * sizeof(float), h->stream));
+      CU(cudaMemsetAsync(r.lstm_in, 0, Bz * r.h * r.w * 2 * r.F * sizeof(float), h->stream));
     }
     for (auto& r : net.dec_rnn) if (r.c) {
       CU(cudaMemsetAsync(r.c, 0, (size_t)M * r.h * r.w * r.F * sizeof(float), h->stream));
-      CU(cudaMemsetAsync(r.lstm_in, 0, (size_t)M * r.h * r.w * 2 * r.F * sizeof(float), h->stream));
+      CU(cudaMemsetAsync(r.lstm_in, 0, Bz * r.h * r.w * 2 * r.F * sizeof(float), h->stream));
     }
   }
   SaArgs sa;
@@ -657,6 +678,11 @@ int rollout(vf_engine* h, int M, int T) {
     CU(cudaGraphLaunch(h->graph_exec, h->stream));
   }
   if (r) return r;
+  if (h->conv_error) {
+    const int ce = h->conv_error;
+    h->conv_error = 0;
+    return fail(h, VF_ERR_CUDA, "tensor-core convolution %s could not be launched (code %d)", h->conv_error_layer, ce);
+  }
   CU(cudaGetLastError());
   h->predicted = true;
   h->last_M = M;
@@ -717,7 +743,9 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
   h->adim = cfg->adim; h->sdim = cfg->sdim; h->nz = cfg->nz; h->A = cfg->adim + cfg->sdim + cfg->nz;
   h->S = cfg->seq_len; h->C = cfg->context_frames; h->P = h->S - h->C; h->ngf = cfg->ngf;
   h->nt = cfg->num_transformed; h->kc = cfg->cdna_ksize; h->nm = h->nt + 3; h->n_enc = cfg->n_enc;
-  h->cm = (cfg->ngf + 3 * h->nm + 7) / 8 * 8;
+  h->cl = (3 * h->nm + 7) / 8 * 8;
+  h->cm = cfg->ngf + h->cl;
+  h->split = cfg->precision != VF_PREC_FP32_SIMT;
   { const char* e = getenv("VF_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
   if (h->B < 1 || h->H < 8 || h->W < 8 || h->ncam < 1 || h->ncam > 4 || h->nd < 1 || h->nd > 4 || h->ncam * h->nd > VF_MAX_TASKS)
     return fail(h, VF_ERR_INVALID, "bad sizes (max_samples %d, %dx%d, ncam %d, ndesig %d)", h->B, h->H, h->W, h->ncam, h->nd);
@@ -1141,9 +1169,14 @@ int vf_debug_conv2d(vf_engine* h, int32_t impl, const float* x, const float* w, 
     std::string e;
     std::vector<float> wh(w, w + nw);
     if (mma_conv_prepare_weights(wh.data(), k, Cin, Cout, &mw, &h->allocs, &e)) return fail(h, VF_ERR_CUDA, "mma weight prep: %s", e.c_str());
+    float* dxs;                                                        // split-half copy of x (what a producer kernel would write)
+    DA(dxs, nx);
+    View vxs = make_view(dxs, (long long)H * W * Cin, Cin, 0, Cin, (long long)B * H * W * Cin);
+    launch_dense_to_view(dx, B, H * W, vxs, h->stream);
     MmaConvCall c;
-    c.src = vx; c.out = vy; c.sabias = nullptr; c.bias = db; c.H = H; c.W = W; c.passes = impl == VF_PREC_F16X3 ? 3 : 1;
-    if (mma_conv_launch(mw, c, B, h->stream)) return fail(h, VF_ERR_CUDA, "mma conv launch failed");
+    c.src = vxs; c.out = vy; c.sabias = nullptr; c.bias = db; c.H = H; c.W = W; c.passes = impl == VF_PREC_F16X3 ? 3 : 1;
+    const int rc = mma_conv_launch(mw, c, B, h->stream);
+    if (rc) return fail(h, VF_ERR_CUDA, "mma conv launch failed (code %d)", rc);
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(y, dy, ny * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -1160,13 +1193,17 @@ int64_t vf_debug_fetch(vf_engine* h, const char* name, int32_t view, float* out,
   const int64_t n = (int64_t)M * d.H * d.W * d.v.C;
   if (!out) return n;
   if (cap < n) return fail(h, VF_ERR_INVALID, "capacity %lld < %lld", (long long)cap, (long long)n);
-  const size_t rowbytes = (size_t)d.v.C * sizeof(float);
-  for (int b = 0; b < M; ++b) {
-    cudaError_t e = cudaMemcpy2DAsync(out + (size_t)b * d.H * d.W * d.v.C, rowbytes,
-                                      d.v.p + (size_t)b * d.v.sample_stride + d.v.ch_off, (size_t)d.v.pix_stride * sizeof(float),
-                                      rowbytes, (size_t)d.H * d.W, cudaMemcpyDeviceToHost, h->stream);
-    if (e != cudaSuccess) return fail(h, VF_ERR_CUDA, "debug fetch: %s", cudaGetErrorString(e));
+  float* tmp;                                                          // gather through a dense float32 copy (either storage format)
+  {
+    void* q = nullptr;
+    if (cudaMalloc(&q, (size_t)n * sizeof(float)) != cudaSuccess) return fail(h, VF_ERR_NOMEM, "debug fetch scratch");
+    tmp = (float*)q;
   }
+  launch_view_to_dense(d.v, M, d.H * d.W, tmp, h->stream);
+  cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(h, VF_ERR_CUDA, "debug fetch: %s", cudaGetErrorString(e));
   CU(cudaStreamSynchronize(h->stream));
   return n;
 }

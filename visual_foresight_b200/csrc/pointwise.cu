@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k_norm_act(View x, int H, int W, int pool
     const int pix = i / C4;
     float4 v;
     if (!pool) {
-      v = __ldg(reinterpret_cast<const float4*>(vptr(x, b, pix) + c));
+      v = vld4(x, voff(x, b, pix) + c);
     } else {
       const int py = pix / W, px = pix - py * W, Wi = 2 * W;
       const float* p00 = vptr(x, b, (long long)(2 * py) * Wi + 2 * px) + c;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) k_norm_act(View x, int H, int W, int pool
     o.x = (v.x - s0.x) * s0.y * g4.x + b4.x; o.y = (v.y - s0.z) * s0.w * g4.y + b4.y;
     o.z = (v.z - s1.x) * s1.y * g4.z + b4.z; o.w = (v.w - s1.z) * s1.w * g4.w + b4.w;
     if (act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    *reinterpret_cast<float4*>(y.p + (long long)b * y.sample_stride + (long long)pix * y.pix_stride + y.ch_off + c) = o;
+    vst4(y, voff(y, b, pix) + c, o);
   }
 }
 
@@ -166,14 +166,13 @@ __global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, con
   const int b = blockIdx.y;
   const int total = HW * F;
   float* cb_ = c + (long long)b * total;
-  float* hb = h.p + (long long)b * h.sample_stride + h.ch_off;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int f = i % F, pix = i / F;
     const float* st = cstats + ((long long)b * F + f) * 2;
     const float cn = (cb_[i] - st[0]) * st[1] * cg[f] + cb[f];
     cb_[i] = cn;
     const float go = gate_norm(gates, b, pix, 3 * F + f, gstats, gg, gb);
-    hb[(long long)pix * h.pix_stride + f] = tanhf(cn) * sigmoidf_(go);
+    vst1(h, voff(h, b, pix) + f, tanhf(cn) * sigmoidf_(go));
   }
 }
 
@@ -203,16 +202,16 @@ __global__ void __launch_bounds__(256) k_upsample2x(View s0, View s1, int H, int
     bil_idx(X, W, x0, x1, wl0, wl1);
     const View& s = (c < s0.C) ? s0 : s1;
     const int cc = (c < s0.C) ? c : c - s0.C;
-    const float4 v00 = __ldg(reinterpret_cast<const float4*>(vptr(s, b, y0 * W + x0) + cc));
-    const float4 v01 = __ldg(reinterpret_cast<const float4*>(vptr(s, b, y0 * W + x1) + cc));
-    const float4 v10 = __ldg(reinterpret_cast<const float4*>(vptr(s, b, y1 * W + x0) + cc));
-    const float4 v11 = __ldg(reinterpret_cast<const float4*>(vptr(s, b, y1 * W + x1) + cc));
+    const float4 v00 = vld4(s, voff(s, b, y0 * W + x0) + cc);
+    const float4 v01 = vld4(s, voff(s, b, y0 * W + x1) + cc);
+    const float4 v10 = vld4(s, voff(s, b, y1 * W + x0) + cc);
+    const float4 v11 = vld4(s, voff(s, b, y1 * W + x1) + cc);
     float4 o;
     o.x = hl0 * (wl0 * v00.x + wl1 * v01.x) + hl1 * (wl0 * v10.x + wl1 * v11.x);
     o.y = hl0 * (wl0 * v00.y + wl1 * v01.y) + hl1 * (wl0 * v10.y + wl1 * v11.y);
     o.z = hl0 * (wl0 * v00.z + wl1 * v01.z) + hl1 * (wl0 * v10.z + wl1 * v11.z);
     o.w = hl0 * (wl0 * v00.w + wl1 * v01.w) + hl1 * (wl0 * v10.w + wl1 * v11.w);
-    *reinterpret_cast<float4*>(out.p + (long long)b * out.sample_stride + (long long)pix * out.pix_stride + out.ch_off + c) = o;
+    vst4(out, voff(out, b, pix) + c, o);
   }
 }
 
@@ -260,15 +259,27 @@ __global__ void k_sabias(const float* __restrict__ sa, int A, const float* __res
 }
 
 // out[b, pix, 0..7] = (image rgb, first rgb, 0, 0): 8-channel (16-byte-unit) input of the first encoder conv
-__global__ void k_pack_rgb2(View image, View first, int HW, float* out) {
+__global__ void k_pack_rgb2(View image, View first, int HW, View out) {
   const int b = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= HW) return;
   const float* ip = vptr(image, b, pix);
   const float* fp = vptr(first, b, pix);
-  float4* o = reinterpret_cast<float4*>(out + ((long long)b * HW + pix) * 8);
-  o[0] = make_float4(__ldg(ip), __ldg(ip + 1), __ldg(ip + 2), __ldg(fp));
-  o[1] = make_float4(__ldg(fp + 1), __ldg(fp + 2), 0.f, 0.f);
+  const long long o = voff(out, b, pix);
+  vst4(out, o, make_float4(__ldg(ip), __ldg(ip + 1), __ldg(ip + 2), __ldg(fp)));
+  vst4(out, o + 4, make_float4(__ldg(fp + 1), __ldg(fp + 2), 0.f, 0.f));
+}
+__global__ void k_view_to_dense(View v, int HW, float* dst) {
+  const int b = blockIdx.y;
+  const long long total = (long long)HW * v.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    dst[(long long)b * total + i] = vld1(v, voff(v, b, i / v.C) + (i % v.C));
+}
+__global__ void k_dense_to_view(const float* src, int HW, View v) {
+  const int b = blockIdx.y;
+  const long long total = (long long)HW * v.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    vst1(v, voff(v, b, i / v.C) + (i % v.C), src[(long long)b * total + i]);
 }
 __global__ void k_u8_to_f32(const uint8_t* in, float* out, long long n, float scale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -356,7 +367,17 @@ void launch_sabias(const float* sa, int A, const float* wcls, const float* bias,
   ++g_launch_counter;
   k_sabias<<<grid_for((long long)B * ncls * Cout), 256, 0, s>>>(sa, A, wcls, bias, ncls, Cout, B, out);
 }
-void launch_pack_rgb2(View image, View first, int B, int HW, float* out, cudaStream_t s) {
+void launch_view_to_dense(View v, int B, int HW, float* dst, cudaStream_t s) {
+  ++g_launch_counter;
+  dim3 grid(grid_for((long long)HW * v.C, 256, 64), B);
+  k_view_to_dense<<<grid, 256, 0, s>>>(v, HW, dst);
+}
+void launch_dense_to_view(const float* src, int B, int HW, View v, cudaStream_t s) {
+  ++g_launch_counter;
+  dim3 grid(grid_for((long long)HW * v.C, 256, 64), B);
+  k_dense_to_view<<<grid, 256, 0, s>>>(src, HW, v);
+}
+void launch_pack_rgb2(View image, View first, int B, int HW, View out, cudaStream_t s) {
   ++g_launch_counter;
   dim3 grid((HW + 255) / 256, B);
   k_pack_rgb2<<<grid, 256, 0, s>>>(image, first, HW, out);

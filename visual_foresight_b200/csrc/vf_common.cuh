@@ -10,17 +10,76 @@ namespace vf {
 //   p[b * sample_stride + (y * W + x) * pix_stride + ch_off + c]
 // sample_stride == 0 broadcasts one image to every sample (context frames are shared by all
 // action samples — the reference tf.tile()s them per tower, setup_predictor.py:40-44).
+//
+// Storage format.  lo_off == 0: float32 elements.  lo_off > 0: "split-half" storage — the buffer holds two fp16
+// planes with the same element indexing, hi = rn16(x) at [i] and lo = rn16(x - hi) at [i + lo_off] (p reinterpreted
+// as __half*; same bytes as float32).  Every tensor that feeds a convolution is kept split on the tensor-core
+// path: the producer kernel performs the fp32 -> (hi, lo) split once, and the tcgen05 convolution fetches both planes
+// with TMA straight into its swizzled shared-memory operand buffers (no conversion pass, no register staging).
 struct View {
   float* p;
   long long sample_stride;
   int pix_stride;
   int ch_off;
   int C;
+  long long lo_off;
 };
 
-__host__ __device__ inline View make_view(float* p, long long ss, int ps, int co, int C) {
-  View v; v.p = p; v.sample_stride = ss; v.pix_stride = ps; v.ch_off = co; v.C = C; return v;
+__host__ __device__ inline View make_view(float* p, long long ss, int ps, int co, int C, long long lo_off = 0) {
+  View v; v.p = p; v.sample_stride = ss; v.pix_stride = ps; v.ch_off = co; v.C = C; v.lo_off = lo_off; return v;
 }
+
+#ifdef __CUDACC__
+// element offset of (b, pix, channel 0 of the view)
+__device__ __forceinline__ long long voff(const View& v, int b, long long pix) {
+  return (long long)b * v.sample_stride + pix * v.pix_stride + v.ch_off;
+}
+__device__ __forceinline__ void split_half(float x, __half& h, __half& l) {
+  h = __float2half_rn(x);
+  l = __float2half_rn(x - __half2float(h));
+}
+__device__ __forceinline__ float vld1(const View& v, long long off) {
+  if (v.lo_off) {
+    const __half* hp = reinterpret_cast<const __half*>(v.p);
+    return __half2float(__ldg(hp + off)) + __half2float(__ldg(hp + off + v.lo_off));
+  }
+  return __ldg(v.p + off);
+}
+// 4 consecutive channels, off % 4 == 0 (and lo_off % 4 == 0)
+__device__ __forceinline__ float4 vld4(const View& v, long long off) {
+  if (v.lo_off) {
+    const __half* hp = reinterpret_cast<const __half*>(v.p);
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(hp + off));
+    const uint2 b = __ldg(reinterpret_cast<const uint2*>(hp + off + v.lo_off));
+    const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+    const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+    return make_float4(a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y);
+  }
+  return __ldg(reinterpret_cast<const float4*>(v.p + off));
+}
+__device__ __forceinline__ void vst1(const View& v, long long off, float x) {
+  if (v.lo_off) {
+    __half* hp = reinterpret_cast<__half*>(v.p);
+    __half h, l;
+    split_half(x, h, l);
+    hp[off] = h;
+    hp[off + v.lo_off] = l;
+  } else {
+    v.p[off] = x;
+  }
+}
+__device__ __forceinline__ void vst4(const View& v, long long off, float4 x) {
+  if (v.lo_off) {
+    __half* hp = reinterpret_cast<__half*>(v.p);
+    __half h[4], l[4];
+    split_half(x.x, h[0], l[0]); split_half(x.y, h[1], l[1]); split_half(x.z, h[2], l[2]); split_half(x.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hp + off) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(hp + off + v.lo_off) = *reinterpret_cast<const uint2*>(l);
+  } else {
+    *reinterpret_cast<float4*>(v.p + off) = x;
+  }
+}
+#endif
 
 // border class of pixel coordinate y for a SAME zero-padded k-tap filter (k odd): which taps fall
 // inside the image.  Classes 0..pad-1 = first rows, pad = interior, pad+1..k-1 = last rows.
@@ -87,15 +146,16 @@ void launch_sabias(const float* sa, int A, const float* wcls, const float* bias,
                    int B, float* out, cudaStream_t s);
 
 // ---- CDNA ------------------------------------------------------------------------------------
-// kern[b][n][k*k]: dense(feat) + identity, relu-shift, L1 normalise   (spec P5)
-void launch_cdna_kernels(View feat, int npix, const float* w, const float* bias, int ksize, int nt,
-                         int B, float* kern, cudaStream_t s);
-// mask_in[.., base + 3n + c] = T_n(image)[c]; then prev image, first image   (spec P6)
-void launch_cdna_apply(View image, View first, const float* kern, int ksize, int nt, int B, int H, int W,
-                       View mask_in, int base, cudaStream_t s);
+// CDNA head (spec P5): split-K partial products part[ks][b][128] of dense(feat); the consumers combine them, add the
+// identity tap, relu-shift and L1-normalise in their prologue (cdna_finalize)
+size_t cdna_partial_floats(int K, int B);
+void launch_cdna_kernels(View feat, int npix, const float* w, int ksize, int nt, int B, float* part, cudaStream_t s);
+// layers[.., 3n + c] = T_n(image)[c]; then prev image, first image   (spec P6); also writes kern[b][n][k*k]
+void launch_cdna_apply(View image, View first, const float* part, int K, const float* bias, float* kern, int ksize, int nt,
+                       int B, int H, int W, View layers, cudaStream_t s);
 struct CompositeArgs {
   View logits;            // [B,H,W,n_masks]
-  View layers;            // mask_in view positioned at the first transformed image, C = 3*n_masks
+  View layers;            // [B,H,W,>= 3*n_masks]: T_0..T_nt-1, prev, first, scratch (rgb each)
   View prev_d, first_d;   // distributions [.,H,W,nd]
   const float* kern;      // [B][nt][k*k]
   View gen_image;         // out [B,H,W,3]
@@ -142,7 +202,10 @@ int topk_padded(int n);
 // mean[D], factor[D][K] = Xc^T / sqrt(K-1), cov[D][D] (unbiased)
 void launch_refit(const double* elites_nr, int K, int D, double* mean, double* factor, double* cov, cudaStream_t s);
 
-void launch_pack_rgb2(View image, View first, int B, int HW, float* out, cudaStream_t s);
+void launch_pack_rgb2(View image, View first, int B, int HW, View out, cudaStream_t s);
+// dst[b][pix][c] (dense float32) = view element (either storage format)
+void launch_view_to_dense(View v, int B, int HW, float* dst, cudaStream_t s);
+void launch_dense_to_view(const float* src, int B, int HW, View v, cudaStream_t s);
 
 // ---- misc --------------------------------------------------------------------------------------
 void launch_u8_to_f32(const uint8_t* in, float* out, long long n, float scale, cudaStream_t s);
