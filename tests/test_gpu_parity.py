@@ -308,7 +308,11 @@ MMA_SHAPES = [(3, 32, 32, 64, 128, 5), (2, 16, 16, 128, 256, 5), (5, 8, 8, 256, 
               (4, 6, 8, 64, 128, 5), (7, 8, 8, 32, 128, 5), (2, 12, 16, 32, 128, 5), (1, 24, 32, 32, 128, 3),
               # zero-padded channel chunks / output tiles (thin layers: Cout 3, 7, 32, 64; Cin 40, 56)
               (2, 16, 16, 56, 7, 3), (3, 16, 16, 32, 3, 3), (2, 32, 32, 40, 32, 3), (1, 64, 64, 64, 32, 3),
-              (2, 16, 16, 128, 64, 3), (1, 32, 32, 128, 160, 3)]
+              (2, 16, 16, 128, 64, 3), (1, 32, 32, 128, 160, 3),
+              # row-stacked thin path: 5x5 with an 8-channel input (first encoder conv), 48x64 frames, many samples, Cout 64
+              (2, 64, 64, 8, 32, 5), (3, 48, 64, 8, 32, 5), (9, 32, 32, 32, 64, 3), (5, 24, 32, 64, 32, 3), (2, 8, 8, 16, 16, 5),
+              # thin layer whose k*np exceeds 256 columns: one MMA per tap
+              (2, 16, 16, 32, 64, 5)]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k", MMA_SHAPES)

@@ -66,9 +66,15 @@ struct Geometry {
   int ngroups, nitems;
   int passes;       // 1 or 3 MMA passes
   int nacc;         // TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs)
-  int swap;         // 1: pixels on the MMA M dimension (TMEM lanes), output channels on N — thin layers (Cout <= 64)
-  int np;           // swap: output channels padded to a multiple of 16 (MMA N, TMEM columns per 128-pixel unit)
+  int swap;         // thin layers (Cout <= 64): pixels on the MMA M dimension (TMEM lanes), output channels on N.
+                    //   2 = row-stacked: the k taps of one filter ROW sit side by side on N (N = k*np), so one MMA serves k
+                    //       taps; the dx shifts are undone in the epilogue (lane shuffles).  1 = one MMA per tap (k*np > 256).
+  int np;           // swap: output channels padded to a multiple of 16
   int units;        // swap: 128-pixel units per item
+  int ncols;        // swap: TMEM columns per unit (np, or k*np when row-stacked)
+  int ustride;      // swap: output pixels per unit (128, or 128-(k-1) when row-stacked: units overlap by the dx halo)
+  int nst;          // weight stages per channel chunk (k*k taps, or k filter rows when row-stacked)
+  int ksteps_last;  // K=16 steps of the last channel chunk (its zero-padded tail is not multiplied)
   float out_scale;  // 2^-scale_log2
 };
 
@@ -165,6 +171,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // Shared-memory matrix descriptor (K-major).  version = 1 (sm_100).  layout_type: 0 none, 4 = 64B, 2 = 128B swizzle.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type,
@@ -322,6 +339,146 @@ __device__ __forceinline__ void issuer_loop_swap(const Geometry& g, const IssueC
   }
 }
 
+// Row-stacked thin layers: one weight stage = the k taps of filter row dy side by side on N (ncols = k*np); the activation
+// descriptor advances by one padded image row (Wp pixel rows) per stage.  k MMAs-rows instead of k*k taps.
+template <int PASSES, int U>
+__device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const IssueCtx& cx, int acc_cols) {
+  const uint64_t unit_step = (uint64_t)(((uint32_t)g.ustride * cx.pix_b) >> 4);
+  const uint32_t idesc_b = make_idesc(g.ncols), ncols = (uint32_t)g.ncols;
+  const int nitems = g.nitems, nchunk = g.nchunk, kk = g.k, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
+  const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
+  const uint64_t row16 = (uint64_t)(((uint32_t)g.Wp * cx.pix_b) >> 4);
+  const uint64_t dw_base = cx.da_zero + (uint64_t)(cx.wst_base >> 4), dx_base = cx.db_zero + (uint64_t)(cx.act_base >> 4);
+  int s = 0;
+  uint32_t ph = 0, job = 0, it = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+    const int a = it % nacc;
+    mbar_wait(&cx.acc_empty[a], ((it / nacc) & 1) ^ 1);
+    tc_fence_after();
+    const uint32_t tacc = cx.tmem_base + (uint32_t)(a * acc_cols);
+    const uint64_t item_off16 = (uint64_t)(((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
+    uint32_t acc = 0;
+    for (int c = 0; c < nchunk; ++c, ++job) {
+      const int buf = job % nbuf;
+      const int ksteps = c == nchunk - 1 ? g.ksteps_last : g.ksteps;
+      mbar_wait(&cx.a_full[buf], (job / nbuf) & 1);
+      tc_fence_after();
+      uint64_t da_row = dx_base + (uint64_t)(buf * buf16) + item_off16;
+      for (int dy = 0; dy < kk; ++dy) {
+        mbar_wait(&cx.w_full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_tap_swap<PASSES, U>(da_row, dw_base + (uint64_t)(s * stage16), cx.b_plane, cx.a_half, cx.kstep_b, ksteps, unit_step,
+                                    tacc, ncols, idesc_b, acc);
+          tc_commit(&cx.w_empty[s]);
+        }
+        acc = 1;
+        if (++s == nstage) { s = 0; ph ^= 1; }
+        da_row += row16;
+      }
+      if (elect_one()) tc_commit(&cx.a_empty[buf]);
+    }
+    if (elect_one()) tc_commit(&cx.acc_full[a]);
+  }
+}
+
+// Epilogue of the row-stacked thin path.  TMEM holds, for lane l (pixel row r0 + l of the flat padded image) and filter
+// column dx, D[l][dx*np + c] = sum_{dy,cin} W[dy,dx][cin][c] * F[r0 + l + dy*Wp]; the output of home lane l0 is
+// sum_dx D[l0 + dx][dx*np + c].  Lanes of the same warp exchange by shuffle, the first KS-1 lanes of every warp publish their
+// blocks in shared memory for the previous warp (double-buffered, one 128-thread named barrier per 16-channel block).
+// Only home lanes < 128-(KS-1) produce outputs: consecutive units overlap by KS-1 rows.
+template <int KS>
+__device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& g, uint32_t tmem_base, int a, int acc_cols, int q4,
+                                               int lane, int half, int b, int v_lo, float* xch_half, const float* tab) {
+  const int row = q4 * 32 + lane;
+  const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.pad;
+  const float scale = g.out_scale;
+  const bool sigm = P.act == ACT_SIGMOID;
+  const bool vec4 = ((g.Cout | P.out.ch_off | ps) & 3) == 0 && (P.out.sample_stride & 3) == 0 && (P.out.lo_off & 3) == 0;
+  const bool split = P.out.lo_off != 0;
+  uint32_t par = 0;
+  // work items = (unit, 16-channel block), dealt alternately to the two halves of the epilogue (4 warps each)
+  const int ncb = g.np >> 4;
+  for (int idx = half; idx < g.units * ncb; idx += 2) {
+    const int u = idx / ncb, c16 = (idx - u * ncb) << 4;
+    const int v = v_lo + u * g.ustride + row;
+    const int oy = v / Wp, ox = v - oy * Wp;
+    const bool valid = row < g.ustride && b < P.B && ox < W && oy < H;
+    const float* sb = tab;                    // this sample's (border class, channel) bias table, staged in shared memory
+    float* op = nullptr;
+    long long oo = 0;
+    if (valid) {
+      if (P.sabias) sb = tab + (border_class(oy, H, pad) * g.k + border_class(ox, W, pad)) * g.np;
+      oo = (long long)b * P.out.sample_stride + (long long)(oy * W + ox) * ps + P.out.ch_off;
+      op = P.out.p + oo;
+    }
+    {
+      uint32_t r[KS][16];
+      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + u * g.ncols + c16);
+#pragma unroll
+      for (int dx = 0; dx < KS; ++dx) tmem_ld16_nowait(t0 + (uint32_t)(dx * g.np), r[dx]);
+      tmem_wait_ld();
+      float* xw = xch_half + (size_t)par * (4 * (KS - 1) * (KS - 1) * 16);
+      if (lane < KS - 1) {
+#pragma unroll
+        for (int dx = 1; dx < KS; ++dx) {
+          float4* d = reinterpret_cast<float4*>(xw + (((q4 * (KS - 1) + (dx - 1)) * (KS - 1) + lane) * 16));
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            d[j] = make_float4(__uint_as_float(r[dx][4 * j]), __uint_as_float(r[dx][4 * j + 1]), __uint_as_float(r[dx][4 * j + 2]),
+                               __uint_as_float(r[dx][4 * j + 3]));
+        }
+      }
+      named_bar_sync(1 + half, 128);
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[0][j]);
+#pragma unroll
+      for (int dx = 1; dx < KS; ++dx) {
+        const bool from_next = lane + dx >= 32;
+        const float* xs = xw + ((((q4 + 1) * (KS - 1) + (dx - 1)) * (KS - 1) + (lane + dx - 32)) * 16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float t = __shfl_down_sync(0xffffffffu, __uint_as_float(r[dx][j]), dx);
+          if (from_next) t = q4 < 3 ? xs[j] : 0.f;
+          acc[j] += t;
+        }
+      }
+      par ^= 1;
+      if (!valid) continue;
+      if (vec4) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          if (c16 + j < g.Cout) {
+            const float4 bb = *reinterpret_cast<const float4*>(sb + c16 + j);
+            float4 o;
+            o.x = fmaf(acc[j], scale, bb.x);
+            o.y = fmaf(acc[j + 1], scale, bb.y);
+            o.z = fmaf(acc[j + 2], scale, bb.z);
+            o.w = fmaf(acc[j + 3], scale, bb.w);
+            if (sigm) {
+              o.x = __fdividef(1.f, 1.f + __expf(-o.x)); o.y = __fdividef(1.f, 1.f + __expf(-o.y));
+              o.z = __fdividef(1.f, 1.f + __expf(-o.z)); o.w = __fdividef(1.f, 1.f + __expf(-o.w));
+            }
+            if (split) vst4(P.out, oo + c16 + j, o);
+            else *reinterpret_cast<float4*>(op + c16 + j) = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c16 + j < g.Cout) {
+            float o = fmaf(acc[j], scale, sb[c16 + j]);
+            if (sigm) o = __fdividef(1.f, 1.f + __expf(-o));
+            if (split) vst1(P.out, oo + c16 + j, o);
+            else op[c16 + j] = o;
+          }
+        }
+      }
+    }
+  }
+}
+
 // thread layout: warp 0 weight producer, warp 1 MMA issuer (+TMEM alloc), warp 2 activation producer (tensor TMA),
 // warp 3 idle, warps 4..11 epilogue (warp % 4 = TMEM lane quarter, two warps per quarter split the columns / units)
 constexpr int EPI_WARP0 = 4, NEPI = 256;
@@ -360,7 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
 
   const int per_mt = g.ngroups * g.npass;
   const uint32_t ltype = g.layout == 1 ? 4u : 2u;
-  const int acc_cols = g.swap ? g.units * g.np : g.G * g.v_cnt;   // TMEM columns of one accumulator set
+  const int acc_cols = g.swap ? g.units * g.ncols : g.G * g.v_cnt;   // TMEM columns of one accumulator set
   const int nacc = g.nacc;                               // 2 when two sets fit in the 512 columns
 
   if (warp == 0) {
@@ -371,8 +528,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
       const uint32_t bytes = g.passes == 3 ? (uint32_t)g.stage_bytes : (uint32_t)g.half_bytes;
       for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
         const int mt = item / per_mt;
-        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.w) + (size_t)mt * g.nchunk * g.ntap * g.stage_bytes;
-        for (int ct = 0; ct < g.nchunk * g.ntap; ++ct) {
+        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.w) + (size_t)mt * g.nchunk * g.nst * g.stage_bytes;
+        for (int ct = 0; ct < g.nchunk * g.nst; ++ct) {
           mbar_wait(&w_empty[s], ph ^ 1);
           mbar_expect_tx(&w_full[s], bytes);
           bulk_g2s(wst_base + s * g.stage_bytes, wbase + (size_t)ct * g.stage_bytes, bytes, &w_full[s]);
@@ -391,7 +548,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
     cx.a_half = (uint64_t)(g.half_bytes >> 4); cx.b_plane = (uint64_t)(g.plane_bytes >> 4);
     cx.act_base = act_base; cx.wst_base = wst_base; cx.tmem_base = tmem_base;
     cx.w_full = w_full; cx.w_empty = w_empty; cx.a_full = a_full; cx.a_empty = a_empty; cx.acc_full = acc_full; cx.acc_empty = acc_empty;
-    if (g.swap) {
+    if (g.swap == 2) {
+#define VF_S2(PA, UU) issuer_loop_swap2<PA, UU>(g, cx, acc_cols)
+      if (g.passes == 3) {
+        switch (g.units) {
+          case 1: VF_S2(3, 1); break; case 2: VF_S2(3, 2); break; case 3: VF_S2(3, 3); break; case 4: VF_S2(3, 4); break;
+          default: VF_S2(3, 5); break;
+        }
+      } else {
+        switch (g.units) {
+          case 1: VF_S2(1, 1); break; case 2: VF_S2(1, 2); break; case 3: VF_S2(1, 3); break; case 4: VF_S2(1, 4); break;
+          default: VF_S2(1, 5); break;
+        }
+      }
+#undef VF_S2
+    } else if (g.swap) {
 #define VF_SW(PA, UU) issuer_loop_swap<PA, UU>(g, cx, acc_cols)
       if (g.passes == 3) {
         switch (g.units) {
@@ -455,9 +626,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
       const int b0 = grp * g.G, v_lo = ps_ * g.v_cnt;
       const int n = mt * MT + row;
       const int a = it % nacc;
+      float* tab = nullptr;
+      if (g.swap == 2) {
+        // stage this sample's bias table [border class][channel] in shared memory while the MMAs run (the L1 is carved out
+        // to almost nothing by the operand buffers: a global bias load per output vector costs an L2 round trip)
+        tab = s_sab_all + 4096 + (it & 1) * (g.ntap * g.np);
+        const int ncls = P.sabias ? g.ntap : 1;
+        for (int i = (int)threadIdx.x - EPI_WARP0 * 32; i < ncls * g.np; i += NEPI) {
+          const int cls = i / g.np, c = i - cls * g.np;
+          float bv = 0.f;
+          if (c < g.Cout) bv = P.sabias ? __ldg(P.sabias + ((long long)b0 * g.ntap + cls) * g.Cout + c) : (P.bias ? __ldg(P.bias + c) : 0.f);
+          tab[i] = bv;
+        }
+        named_bar_sync(3, NEPI);
+      }
       mbar_wait(&acc_full[a], (it / nacc) & 1);
       tc_fence_after();
-      if (g.swap) {
+      if (g.swap == 2) {
+        float* xch_half = s_sab_all + half * 2048;               // lane-exchange scratch (the wide path's bias tables live here)
+        if (g.k == 3) epilogue_swap2<3>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, tab);
+        else epilogue_swap2<5>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, tab);
+      } else if (g.swap) {
         // pixels on lanes: this thread owns pixel row `row` of every 128-pixel unit and all output channels of it
         const int b = b0;
         const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.pad;
@@ -613,8 +802,10 @@ void current_mode(int* layout, int* bo) {
 // TMA box rows: every pass starts its box at the padded-image row holding its first virtual pixel and must cover
 // (offset inside that row) + v_cnt + the k-1 halo rows + k-1 pixels.
 bool box_rows(Geometry& g) {
+  // pixel rows one item reads past its first one: its v_cnt outputs + k-1 taps along x (row-stacked: the last unit's 128 lanes)
+  const int span = g.swap == 2 ? (g.units - 1) * g.ustride + 128 : g.v_cnt + (g.k - 1);
   int need = 0;
-  for (int ps = 0; ps < g.npass; ++ps) need = std::max(need, (ps * g.v_cnt) % g.Wp + g.v_cnt + (g.k - 1) * g.Wp + (g.k - 1));
+  for (int ps = 0; ps < g.npass; ++ps) need = std::max(need, (ps * g.v_cnt) % g.Wp + span + (g.k - 1) * g.Wp);
   g.R = (need + g.Wp - 1) / g.Wp;
   g.img_pix = (g.R * g.Wp + 7) / 8 * 8;
   g.box_bytes = g.R * g.Wp * g.row_bytes;
@@ -632,10 +823,43 @@ bool plan_geometry(int layout, int bo_mode, int k, int Cin, int Cout, int H, int
   g.H = H; g.W = W; g.k = k; g.pad = k / 2; g.Wp = W + k - 1; g.Cin = Cin; g.Cout = Cout;
   g.nchunk = (Cin + g.ch - 1) / g.ch; g.ntap = k * k; g.n_mt = (Cout + MT - 1) / MT; g.passes = passes;
   g.nchunk0 = g.nchunk;
+  g.nst = g.ntap;
+  g.ksteps_last = (std::min(g.ch, Cin - (g.nchunk - 1) * g.ch) + 15) / 16;
+  const int np_thin = (Cout + 15) / 16 * 16;
+  if (Cout <= 64 && k * np_thin <= 256) {
+    // ---- row-stacked thin path: pixels on M, the k taps of a filter row side by side on N (k*np columns) ----
+    g.swap = 2;
+    g.np = np_thin; g.ncols = k * g.np; g.ustride = 128 - (k - 1); g.nst = k;
+    g.half_bytes = g.ncols * g.row_bytes; g.stage_bytes = 2 * g.half_bytes;
+    g.n_mt = 1; g.G = 1;
+    const int Vs = H * g.Wp;
+    const int umax = std::max(1, std::min(5, 256 / g.ncols));            // two accumulator sets in the 512 TMEM columns
+    bool found = false;
+    for (int units = umax; units >= 1 && !found; --units) {
+      g.npass = (Vs + g.ustride * units - 1) / (g.ustride * units);
+      g.units = ((Vs + g.npass - 1) / g.npass + g.ustride - 1) / g.ustride;
+      g.v_cnt = g.units * g.ustride;
+      if (!box_rows(g)) return false;
+      g.plane_bytes = (g.img_pix * g.row_bytes + 1023) / 1024 * 1024;
+      for (g.nbuf = 2; g.nbuf >= 1; --g.nbuf) {
+        const size_t act = (size_t)g.nbuf * 2 * g.plane_bytes;
+        if (act + 2 * (size_t)g.stage_bytes + SMEM_SLACK > SMEM_LIMIT) continue;
+        g.nstage = (int)std::min<size_t>(MAX_STAGE, (SMEM_LIMIT - SMEM_SLACK - act) / g.stage_bytes);
+        if (g.nbuf == 2 || units == 1) found = true;
+        break;
+      }
+    }
+    if (!found) return false;
+    g.nacc = (2 * g.units * g.ncols <= 512) ? 2 : 1;
+    g.ngroups = B;
+    g.nitems = g.ngroups * g.npass;
+    *out = g;
+    return true;
+  }
   if (Cout <= 64) {
     // ---- swapped orientation (thin layers): pixels on M in 128-row units, np = Cout padded to 16 on N ----
     g.swap = 1;
-    g.np = (Cout + 15) / 16 * 16;
+    g.np = (Cout + 15) / 16 * 16; g.ncols = g.np; g.ustride = 128;
     g.half_bytes = g.np * g.row_bytes; g.stage_bytes = 2 * g.half_bytes;
     g.n_mt = 1; g.G = 1;
     const int Vs = H * g.Wp;
@@ -736,11 +960,14 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaCon
   const int ch = layout == 2 ? 64 : 32;
   if (cin % 8) { if (err) *err = "cin % 8"; return -1; }
   const bool swap = cout <= 64;
-  const int rows = swap ? (cout + 15) / 16 * 16 : MT;                 // operand tile rows (output channels)
-  const int kk = k * k, nchunk = (cin + ch - 1) / ch, n_mt = swap ? 1 : (cout + MT - 1) / MT, kc = ch / 8, rb = ch * 2;
+  const int np = (cout + 15) / 16 * 16;
+  const bool stacked = swap && k * np <= 256;                         // one stage = a filter ROW: rows = (dx, output channel)
+  const int rows = stacked ? k * np : (swap ? np : MT);               // operand tile rows
+  const int kk = stacked ? k : k * k;                                 // stages per channel chunk
+  const int nchunk = (cin + ch - 1) / ch, n_mt = swap ? 1 : (cout + MT - 1) / MT, kc = ch / 8, rb = ch * 2;
   const int swz = layout == 2 ? 7 : 3;
   float amax = 0.f;
-  for (size_t i = 0; i < (size_t)kk * cin * cout; ++i) amax = std::max(amax, fabsf(w_sp[i]));
+  for (size_t i = 0; i < (size_t)k * k * cin * cout; ++i) amax = std::max(amax, fabsf(w_sp[i]));
   int sl = 0;
   if (amax > 0.f) sl = (int)floorf(log2f(16384.0f / amax));           // max |w| * 2^sl in [8192, 16384]
   sl = std::max(-24, std::min(sl, 24));
@@ -755,8 +982,10 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaCon
         for (int kc8 = 0; kc8 < kc; ++kc8)
           for (int r = 0; r < rows; ++r)
             for (int e = 0; e < 8; ++e) {
-              const int ci = c * ch + kc8 * 8 + e, n = mt * rows + r;
-              const float v = (ci < cin && n < cout) ? w_sp[((size_t)t * cin + ci) * cout + n] * scale : 0.f;
+              const int ci = c * ch + kc8 * 8 + e;
+              const int n = stacked ? r % np : mt * rows + r;            // output channel
+              const int tap = stacked ? t * k + r / np : t;              // stacked: stage t = filter row dy, r / np = dx
+              const float v = (ci < cin && n < cout) ? w_sp[((size_t)tap * cin + ci) * cout + n] * scale : 0.f;
               const __half h = __float2half_rn(v);
               const __half l = __float2half_rn(v - __half2float(h));
               size_t pos;                                              // element index inside the 128-row operand tile

@@ -186,15 +186,25 @@ __device__ __forceinline__ void bil_idx(int d, int n, int& i0, int& i1, float& l
   l0 = 1.f - l1;
 }
 
-// one thread = 4 consecutive channels of one output pixel (both sources have C % 4 == 0); grid.y = sample
+__device__ __forceinline__ float4 bil4(float hl0, float hl1, float wl0, float wl1, float4 v00, float4 v01, float4 v10, float4 v11) {
+  float4 o;
+  o.x = hl0 * (wl0 * v00.x + wl1 * v01.x) + hl1 * (wl0 * v10.x + wl1 * v11.x);
+  o.y = hl0 * (wl0 * v00.y + wl1 * v01.y) + hl1 * (wl0 * v10.y + wl1 * v11.y);
+  o.z = hl0 * (wl0 * v00.z + wl1 * v01.z) + hl1 * (wl0 * v10.z + wl1 * v11.z);
+  o.w = hl0 * (wl0 * v00.w + wl1 * v01.w) + hl1 * (wl0 * v10.w + wl1 * v11.w);
+  return o;
+}
+
+// one thread = V (4 or 8) consecutive channels of one output pixel (both sources have C % V == 0); grid.y = sample
+template <int V>
 __global__ void __launch_bounds__(256) k_upsample2x(View s0, View s1, int H, int W, View out) {
   const int b = blockIdx.y;
-  const int C = s0.C + s1.C, C4 = C >> 2;
+  const int C = s0.C + s1.C, CV = C / V;
   const int Ho = 2 * H, Wo = 2 * W;
-  const int total = Ho * Wo * C4;
+  const int total = Ho * Wo * CV;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = (i % C4) << 2;
-    const int pix = i / C4;
+    const int c = (i % CV) * V;
+    const int pix = i / CV;
     const int Y = pix / Wo, X = pix - Y * Wo;
     int y0, y1, x0, x1;
     float hl0, hl1, wl0, wl1;
@@ -202,16 +212,18 @@ __global__ void __launch_bounds__(256) k_upsample2x(View s0, View s1, int H, int
     bil_idx(X, W, x0, x1, wl0, wl1);
     const View& s = (c < s0.C) ? s0 : s1;
     const int cc = (c < s0.C) ? c : c - s0.C;
-    const float4 v00 = vld4(s, voff(s, b, y0 * W + x0) + cc);
-    const float4 v01 = vld4(s, voff(s, b, y0 * W + x1) + cc);
-    const float4 v10 = vld4(s, voff(s, b, y1 * W + x0) + cc);
-    const float4 v11 = vld4(s, voff(s, b, y1 * W + x1) + cc);
-    float4 o;
-    o.x = hl0 * (wl0 * v00.x + wl1 * v01.x) + hl1 * (wl0 * v10.x + wl1 * v11.x);
-    o.y = hl0 * (wl0 * v00.y + wl1 * v01.y) + hl1 * (wl0 * v10.y + wl1 * v11.y);
-    o.z = hl0 * (wl0 * v00.z + wl1 * v01.z) + hl1 * (wl0 * v10.z + wl1 * v11.z);
-    o.w = hl0 * (wl0 * v00.w + wl1 * v01.w) + hl1 * (wl0 * v10.w + wl1 * v11.w);
-    vst4(out, voff(out, b, pix) + c, o);
+    if (V == 8) {
+      const float8 v00 = vld8(s, voff(s, b, y0 * W + x0) + cc), v01 = vld8(s, voff(s, b, y0 * W + x1) + cc);
+      const float8 v10 = vld8(s, voff(s, b, y1 * W + x0) + cc), v11 = vld8(s, voff(s, b, y1 * W + x1) + cc);
+      float8 o;
+      o.a = bil4(hl0, hl1, wl0, wl1, v00.a, v01.a, v10.a, v11.a);
+      o.b = bil4(hl0, hl1, wl0, wl1, v00.b, v01.b, v10.b, v11.b);
+      vst8(out, voff(out, b, pix) + c, o);
+    } else {
+      const float4 v00 = vld4(s, voff(s, b, y0 * W + x0) + cc), v01 = vld4(s, voff(s, b, y0 * W + x1) + cc);
+      const float4 v10 = vld4(s, voff(s, b, y1 * W + x0) + cc), v11 = vld4(s, voff(s, b, y1 * W + x1) + cc);
+      vst4(out, voff(out, b, pix) + c, bil4(hl0, hl1, wl0, wl1, v00, v01, v10, v11));
+    }
   }
 }
 
@@ -355,8 +367,14 @@ void launch_lstm_out(View gates, int B, int HW, int F, const float* gstats, cons
 }
 void launch_upsample2x(View s0, View s1, int B, int H, int W, View out, cudaStream_t s) {
   ++g_launch_counter;
-  dim3 grid(grid_for((long long)4 * H * W * ((s0.C + s1.C) >> 2), 256, 64), B);
-  k_upsample2x<<<grid, 256, 0, s>>>(s0, s1, H, W, out);
+  auto al8 = [](const View& v) { return v.C == 0 || ((v.C | v.ch_off | v.pix_stride) % 8 == 0 && v.sample_stride % 8 == 0 && v.lo_off % 8 == 0); };
+  if (al8(s0) && al8(s1) && al8(out)) {
+    dim3 grid(grid_for((long long)4 * H * W * ((s0.C + s1.C) >> 3), 256, 64), B);
+    k_upsample2x<8><<<grid, 256, 0, s>>>(s0, s1, H, W, out);
+  } else {
+    dim3 grid(grid_for((long long)4 * H * W * ((s0.C + s1.C) >> 2), 256, 64), B);
+    k_upsample2x<4><<<grid, 256, 0, s>>>(s0, s1, H, W, out);
+  }
 }
 void launch_build_sa(const SaArgs& a, int M, int tau, cudaStream_t s) {
   ++g_launch_counter;

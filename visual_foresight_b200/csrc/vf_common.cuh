@@ -57,6 +57,39 @@ __device__ __forceinline__ float4 vld4(const View& v, long long off) {
   }
   return __ldg(reinterpret_cast<const float4*>(v.p + off));
 }
+// 8 consecutive channels, off % 8 == 0 (one 16-byte access per fp16 plane)
+struct float8 { float4 a, b; };
+__device__ __forceinline__ float8 vld8(const View& v, long long off) {
+  float8 r;
+  if (v.lo_off) {
+    const __half* hp = reinterpret_cast<const __half*>(v.p);
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(hp + off));
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(hp + off + v.lo_off));
+    const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&h.z)), h3 = __half22float2(*reinterpret_cast<const __half2*>(&h.w));
+    const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+    const float2 l2 = __half22float2(*reinterpret_cast<const __half2*>(&l.z)), l3 = __half22float2(*reinterpret_cast<const __half2*>(&l.w));
+    r.a = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+    r.b = make_float4(h2.x + l2.x, h2.y + l2.y, h3.x + l3.x, h3.y + l3.y);
+  } else {
+    r.a = __ldg(reinterpret_cast<const float4*>(v.p + off));
+    r.b = __ldg(reinterpret_cast<const float4*>(v.p + off + 4));
+  }
+  return r;
+}
+__device__ __forceinline__ void vst8(const View& v, long long off, const float8& x) {
+  if (v.lo_off) {
+    __half* hp = reinterpret_cast<__half*>(v.p);
+    __align__(16) __half h[8], l[8];
+    split_half(x.a.x, h[0], l[0]); split_half(x.a.y, h[1], l[1]); split_half(x.a.z, h[2], l[2]); split_half(x.a.w, h[3], l[3]);
+    split_half(x.b.x, h[4], l[4]); split_half(x.b.y, h[5], l[5]); split_half(x.b.z, h[6], l[6]); split_half(x.b.w, h[7], l[7]);
+    *reinterpret_cast<uint4*>(hp + off) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(hp + off + v.lo_off) = *reinterpret_cast<const uint4*>(l);
+  } else {
+    *reinterpret_cast<float4*>(v.p + off) = x.a;
+    *reinterpret_cast<float4*>(v.p + off + 4) = x.b;
+  }
+}
 __device__ __forceinline__ void vst1(const View& v, long long off, float x) {
   if (v.lo_off) {
     __half* hp = reinterpret_cast<__half*>(v.p);
