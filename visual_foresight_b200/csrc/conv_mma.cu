@@ -50,7 +50,9 @@ constexpr int MAX_UNIT_B = 8;          // swapped orientation: 128-pixel units p
 struct Geometry {
   int layout, bo_mode;
   int ch, kc, ksteps, row_bytes, swz_mask, half_bytes, stage_bytes, nstage, nbuf, plane_bytes;
-  int H, W, k, pad, Wp;
+  int H, W, k, pad, Wp;   // k = filter rows, pad = k/2
+  int kw, padx;           // filter columns actually multiplied (== k, or 1 when the producer folded the dx taps into channels)
+  int kcl, padc;          // kernel size of the border classes of the tiled action/state bias (the layer's nominal k)
   int Cin, Cout;
   int nchunk, ntap, n_mt;
   int G;            // images per item
@@ -181,6 +183,20 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// explicit shared-space accesses on 32-bit shared addresses (generic pointers cost a cvta sequence per access)
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // Shared-memory matrix descriptor (K-major).  version = 1 (sm_100).  layout_type: 0 none, 4 = 64B, 2 = 128B swizzle.
@@ -256,9 +272,9 @@ __device__ __forceinline__ void issuer_loop(const Geometry& g, const IssueCtx& c
     uoff[u] = (uint64_t)(((uint32_t)(im * g.img_pix + g.seg_off[sg]) * cx.pix_b) >> 4);
     uidesc[u] = make_idesc(g.seg_n[sg]);
   }
-  const int nitems = g.nitems, nchunk = g.nchunk, ntap = g.ntap, kk = g.k, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
+  const int nitems = g.nitems, nchunk = g.nchunk, ntap = g.nst, kk = g.kw, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
   const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
-  const uint64_t pix16 = (uint64_t)(cx.pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.k) * cx.pix_b) >> 4);
+  const uint64_t pix16 = (uint64_t)(cx.pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.kw) * cx.pix_b) >> 4);
   const uint64_t da_base = cx.da_zero + (uint64_t)(cx.wst_base >> 4), db_base = cx.db_zero + (uint64_t)(cx.act_base >> 4);
   int s = 0;
   uint32_t ph = 0, job = 0, it = 0;
@@ -300,10 +316,10 @@ template <int PASSES, int U>
 __device__ __forceinline__ void issuer_loop_swap(const Geometry& g, const IssueCtx& cx, int acc_cols) {
   const uint64_t unit_step = (uint64_t)((128u * cx.pix_b) >> 4);
   const uint32_t idesc_b = make_idesc(g.np), np = (uint32_t)g.np;
-  const int nitems = g.nitems, nchunk = g.nchunk, ntap = g.ntap, kk = g.k, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
+  const int nitems = g.nitems, nchunk = g.nchunk, ntap = g.nst, kk = g.kw, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
   const int ksteps = g.ksteps;
   const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
-  const uint64_t pix16 = (uint64_t)(cx.pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.k) * cx.pix_b) >> 4);
+  const uint64_t pix16 = (uint64_t)(cx.pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.kw) * cx.pix_b) >> 4);
   const uint64_t dw_base = cx.da_zero + (uint64_t)(cx.wst_base >> 4), dx_base = cx.db_zero + (uint64_t)(cx.act_base >> 4);
   int s = 0;
   uint32_t ph = 0, job = 0, it = 0;
@@ -389,9 +405,9 @@ __device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const Issue
 // Only home lanes < 128-(KS-1) produce outputs: consecutive units overlap by KS-1 rows.
 template <int KS>
 __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& g, uint32_t tmem_base, int a, int acc_cols, int q4,
-                                               int lane, int half, int b, int v_lo, float* xch_half, const float* tab) {
+                                               int lane, int half, int b, int v_lo, uint32_t xch_half, uint32_t tab) {
   const int row = q4 * 32 + lane;
-  const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.pad;
+  const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.padc;
   const float scale = g.out_scale;
   const bool sigm = P.act == ACT_SIGMOID;
   const bool vec4 = ((g.Cout | P.out.ch_off | ps) & 3) == 0 && (P.out.sample_stride & 3) == 0 && (P.out.lo_off & 3) == 0;
@@ -404,11 +420,11 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
     const int v = v_lo + u * g.ustride + row;
     const int oy = v / Wp, ox = v - oy * Wp;
     const bool valid = row < g.ustride && b < P.B && ox < W && oy < H;
-    const float* sb = tab;                    // this sample's (border class, channel) bias table, staged in shared memory
+    uint32_t sb = tab;                        // this sample's (border class, channel) bias table, staged in shared memory (address)
     float* op = nullptr;
     long long oo = 0;
     if (valid) {
-      if (P.sabias) sb = tab + (border_class(oy, H, pad) * g.k + border_class(ox, W, pad)) * g.np;
+      if (P.sabias) sb = tab + (uint32_t)((border_class(oy, H, pad) * g.kcl + border_class(ox, W, pad)) * g.np) * 4u;
       oo = (long long)b * P.out.sample_stride + (long long)(oy * W + ox) * ps + P.out.ch_off;
       op = P.out.p + oo;
     }
@@ -418,15 +434,15 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
 #pragma unroll
       for (int dx = 0; dx < KS; ++dx) tmem_ld16_nowait(t0 + (uint32_t)(dx * g.np), r[dx]);
       tmem_wait_ld();
-      float* xw = xch_half + (size_t)par * (4 * (KS - 1) * (KS - 1) * 16);
+      const uint32_t xw = xch_half + par * (uint32_t)(4 * (KS - 1) * (KS - 1) * 16 * 4);
       if (lane < KS - 1) {
 #pragma unroll
         for (int dx = 1; dx < KS; ++dx) {
-          float4* d = reinterpret_cast<float4*>(xw + (((q4 * (KS - 1) + (dx - 1)) * (KS - 1) + lane) * 16));
+          const uint32_t d = xw + (uint32_t)((((q4 * (KS - 1) + (dx - 1)) * (KS - 1) + lane) * 16) * 4);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            d[j] = make_float4(__uint_as_float(r[dx][4 * j]), __uint_as_float(r[dx][4 * j + 1]), __uint_as_float(r[dx][4 * j + 2]),
-                               __uint_as_float(r[dx][4 * j + 3]));
+            sts128(d + 16 * j, make_float4(__uint_as_float(r[dx][4 * j]), __uint_as_float(r[dx][4 * j + 1]),
+                                           __uint_as_float(r[dx][4 * j + 2]), __uint_as_float(r[dx][4 * j + 3])));
         }
       }
       named_bar_sync(1 + half, 128);
@@ -436,11 +452,20 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
 #pragma unroll
       for (int dx = 1; dx < KS; ++dx) {
         const bool from_next = lane + dx >= 32;
-        const float* xs = xw + ((((q4 + 1) * (KS - 1) + (dx - 1)) * (KS - 1) + (lane + dx - 32)) * 16);
+        const bool use_x = from_next && q4 < 3;          // the last warp's trailing lanes are not home lanes
+        const uint32_t xs = xw + (uint32_t)(((((q4 + 1) * (KS - 1) + (dx - 1)) * (KS - 1) + (use_x ? lane + dx - 32 : 0)) * 16) * 4);
+        float4 x4[4];
+        if (use_x) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x4[j] = lds128(xs + 16 * j);
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float t = __shfl_down_sync(0xffffffffu, __uint_as_float(r[dx][j]), dx);
-          if (from_next) t = q4 < 3 ? xs[j] : 0.f;
+          if (from_next) {
+            const float4 q = x4[j >> 2];
+            t = use_x ? ((j & 3) == 0 ? q.x : ((j & 3) == 1 ? q.y : ((j & 3) == 2 ? q.z : q.w))) : 0.f;
+          }
           acc[j] += t;
         }
       }
@@ -450,7 +475,7 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           if (c16 + j < g.Cout) {
-            const float4 bb = *reinterpret_cast<const float4*>(sb + c16 + j);
+            const float4 bb = lds128(sb + (uint32_t)(c16 + j) * 4u);
             float4 o;
             o.x = fmaf(acc[j], scale, bb.x);
             o.y = fmaf(acc[j + 1], scale, bb.y);
@@ -468,7 +493,7 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (c16 + j < g.Cout) {
-            float o = fmaf(acc[j], scale, sb[c16 + j]);
+            float o = fmaf(acc[j], scale, lds32(sb + (uint32_t)(c16 + j) * 4u));
             if (sigm) o = __fdividef(1.f, 1.f + __expf(-o));
             if (split) vst1(P.out, oo + c16 + j, o);
             else op[c16 + j] = o;
@@ -607,7 +632,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
           mbar_expect_tx(&a_full[buf], (uint32_t)(nimg * nplanes * g.box_bytes));
           for (int im = 0; im < nimg; ++im)
             for (int pl = 0; pl < nplanes; ++pl)
-              tma_load_5d(act_base + (uint32_t)((buf * 2 + pl) * g.plane_bytes + im * g.img_pix * g.row_bytes), tm, c0, -g.pad,
+              tma_load_5d(act_base + (uint32_t)((buf * 2 + pl) * g.plane_bytes + im * g.img_pix * g.row_bytes), tm, c0, -g.padx,
                           qy0 - g.pad, b0 + im, pl, &a_full[buf]);
         }
       }
@@ -643,13 +668,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
       mbar_wait(&acc_full[a], (it / nacc) & 1);
       tc_fence_after();
       if (g.swap == 2) {
-        float* xch_half = s_sab_all + half * 2048;               // lane-exchange scratch (the wide path's bias tables live here)
-        if (g.k == 3) epilogue_swap2<3>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, tab);
-        else epilogue_swap2<5>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, tab);
+        const uint32_t xch_half = smem_u32(s_sab_all + half * 2048);   // lane-exchange scratch (the wide path's bias tables live here)
+        if (g.k == 3) epilogue_swap2<3>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab));
+        else epilogue_swap2<5>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab));
       } else if (g.swap) {
         // pixels on lanes: this thread owns pixel row `row` of every 128-pixel unit and all output channels of it
         const int b = b0;
-        const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.pad;
+        const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.padc;
         const float scale = g.out_scale;
         const bool sigm = P.act == ACT_SIGMOID;
         const bool vec4 = ((g.Cout | P.out.ch_off | ps) & 3) == 0 && (P.out.sample_stride & 3) == 0 && (P.out.lo_off & 3) == 0;
@@ -663,7 +688,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
           long long oo = 0;
           if (valid) {
             if (P.sabias) {
-              const int cls = border_class(oy, H, pad) * g.k + border_class(ox, W, pad);
+              const int cls = border_class(oy, H, pad) * g.kcl + border_class(ox, W, pad);
               sb = P.sabias + ((long long)b * g.ntap + cls) * g.Cout;
             } else {
               sb = P.bias;
@@ -726,7 +751,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
           }
         }
         float* op = P.out.p + (long long)b * P.out.sample_stride + P.out.ch_off + n;
-        const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.pad, kk = g.k;
+        const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.padc, kk = g.kcl;
         const float scale = g.out_scale;
         const bool sigm = P.act == ACT_SIGMOID;
         double st_s = 0.0, st_q = 0.0;              // instance-norm statistics of this thread's channel (fused: no extra pass)
@@ -803,7 +828,7 @@ void current_mode(int* layout, int* bo) {
 // (offset inside that row) + v_cnt + the k-1 halo rows + k-1 pixels.
 bool box_rows(Geometry& g) {
   // pixel rows one item reads past its first one: its v_cnt outputs + k-1 taps along x (row-stacked: the last unit's 128 lanes)
-  const int span = g.swap == 2 ? (g.units - 1) * g.ustride + 128 : g.v_cnt + (g.k - 1);
+  const int span = g.swap == 2 ? (g.units - 1) * g.ustride + 128 : g.v_cnt + (g.kw - 1);
   int need = 0;
   for (int ps = 0; ps < g.npass; ++ps) need = std::max(need, (ps * g.v_cnt) % g.Wp + span + (g.k - 1) * g.Wp);
   g.R = (need + g.Wp - 1) / g.Wp;
@@ -812,7 +837,7 @@ bool box_rows(Geometry& g) {
   return g.R <= 256 && g.Wp <= 256;
 }
 
-bool plan_geometry(int layout, int bo_mode, int k, int Cin, int Cout, int H, int W, int B, int passes, Geometry* out) {
+bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int Cout, int H, int W, int B, int passes, Geometry* out) {
   Geometry g;
   memset(&g, 0, sizeof(g));
   g.layout = layout; g.bo_mode = bo_mode;
@@ -820,13 +845,14 @@ bool plan_geometry(int layout, int bo_mode, int k, int Cin, int Cout, int H, int
   if (Cin % 8) return false;                            // 16-byte staging units; channels/cout beyond the real extent are zero-padded
   g.kc = g.ch / 8; g.ksteps = g.ch / 16; g.row_bytes = g.ch * 2; g.swz_mask = layout == 2 ? 7 : 3;
   g.half_bytes = MT * g.ch * 2; g.stage_bytes = 2 * g.half_bytes;
-  g.H = H; g.W = W; g.k = k; g.pad = k / 2; g.Wp = W + k - 1; g.Cin = Cin; g.Cout = Cout;
-  g.nchunk = (Cin + g.ch - 1) / g.ch; g.ntap = k * k; g.n_mt = (Cout + MT - 1) / MT; g.passes = passes;
+  g.H = H; g.W = W; g.k = k; g.pad = k / 2; g.kw = kw; g.padx = kw / 2; g.kcl = kcl; g.padc = kcl / 2;
+  g.Wp = W + kw - 1; g.Cin = Cin; g.Cout = Cout;
+  g.nchunk = (Cin + g.ch - 1) / g.ch; g.ntap = kcl * kcl; g.n_mt = (Cout + MT - 1) / MT; g.passes = passes;
   g.nchunk0 = g.nchunk;
-  g.nst = g.ntap;
+  g.nst = k * kw;
   g.ksteps_last = (std::min(g.ch, Cin - (g.nchunk - 1) * g.ch) + 15) / 16;
   const int np_thin = (Cout + 15) / 16 * 16;
-  if (Cout <= 64 && k * np_thin <= 256) {
+  if (Cout <= 64 && kw == k && k * np_thin <= 256) {
     // ---- row-stacked thin path: pixels on M, the k taps of a filter row side by side on N (k*np columns) ----
     g.swap = 2;
     g.np = np_thin; g.ncols = k * g.np; g.ustride = 128 - (k - 1); g.nst = k;
@@ -950,24 +976,24 @@ bool mma_conv_supported(int k, int cin, int cout, int H, int W) {
   int layout, bo;
   current_mode(&layout, &bo);
   Geometry g;
-  return plan_geometry(layout, bo, k, cin, cout, H, W, 1, 3, &g);
+  return plan_geometry(layout, bo, k, k, k, cin, cout, H, W, 1, 3, &g);
 }
 
-int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaConvWeights* out, std::vector<void*>* allocs,
-                             std::string* err) {
+int mma_conv_prepare_weights(const float* w_sp, int k, int kw, int kcl, int cin, int cout, MmaConvWeights* out,
+                             std::vector<void*>* allocs, std::string* err) {
   int layout, bo;
   current_mode(&layout, &bo);
   const int ch = layout == 2 ? 64 : 32;
   if (cin % 8) { if (err) *err = "cin % 8"; return -1; }
   const bool swap = cout <= 64;
   const int np = (cout + 15) / 16 * 16;
-  const bool stacked = swap && k * np <= 256;                         // one stage = a filter ROW: rows = (dx, output channel)
+  const bool stacked = swap && kw == k && k * np <= 256;              // one stage = a filter ROW: rows = (dx, output channel)
   const int rows = stacked ? k * np : (swap ? np : MT);               // operand tile rows
-  const int kk = stacked ? k : k * k;                                 // stages per channel chunk
+  const int kk = stacked ? k : k * kw;                                // stages per channel chunk
   const int nchunk = (cin + ch - 1) / ch, n_mt = swap ? 1 : (cout + MT - 1) / MT, kc = ch / 8, rb = ch * 2;
   const int swz = layout == 2 ? 7 : 3;
   float amax = 0.f;
-  for (size_t i = 0; i < (size_t)k * k * cin * cout; ++i) amax = std::max(amax, fabsf(w_sp[i]));
+  for (size_t i = 0; i < (size_t)k * kw * cin * cout; ++i) amax = std::max(amax, fabsf(w_sp[i]));
   int sl = 0;
   if (amax > 0.f) sl = (int)floorf(log2f(16384.0f / amax));           // max |w| * 2^sl in [8192, 16384]
   sl = std::max(-24, std::min(sl, 24));
@@ -1002,7 +1028,7 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaCon
   if (e != cudaSuccess) { if (err) *err = cudaGetErrorString(e); return -1; }
   out->w_hi = reinterpret_cast<__half*>(d);
   out->w_lo = nullptr;
-  out->k = k; out->cin = cin; out->cout = cout; out->scale_log2 = sl; out->ready = true;
+  out->k = k; out->kw = kw; out->kcl = kcl; out->cin = cin; out->cout = cout; out->scale_log2 = sl; out->ready = true;
   return 0;
 }
 
@@ -1065,7 +1091,7 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   int layout, bo;
   current_mode(&layout, &bo);
   if (c.src.C + c.src1.C != w.cin) return -5;
-  if (!plan_geometry(layout, bo, w.k, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
+  if (!plan_geometry(layout, bo, w.k, w.kw, w.kcl, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
   P.g.out_scale = ldexpf(1.0f, -w.scale_log2);
   P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B; P.act = c.act;
   P.stats_partial = nullptr; P.stats_S = 0;

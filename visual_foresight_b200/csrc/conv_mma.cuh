@@ -11,6 +11,8 @@ namespace vf {
 struct MmaConvWeights {
   bool ready = false;
   int k = 0, cin = 0, cout = 0;
+  int kw = 0;    // filter columns multiplied by the MMAs: k, or 1 when the dx taps are folded into the input channels
+  int kcl = 0;   // nominal kernel size (border classes of the action/state bias)
   __half* w_hi = nullptr;   // [k*k][cout][cin]  (K-major rows), scaled by 2^scale_log2
   __half* w_lo = nullptr;
   int scale_log2 = 0;
@@ -30,7 +32,8 @@ struct MmaConvCall {
 
 bool mma_conv_supported(int k, int cin, int cout, int H, int W);
 // returns 0 on success; device allocations are appended to *allocs (owned by the engine handle)
-int mma_conv_prepare_weights(const float* w_sp, int k, int cin, int cout, MmaConvWeights* out,
+// w_sp: [k * kw][cin][cout]
+int mma_conv_prepare_weights(const float* w_sp, int k, int kw, int kcl, int cin, int cout, MmaConvWeights* out,
                              std::vector<void*>* allocs, std::string* err);
 int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaStream_t s);
 

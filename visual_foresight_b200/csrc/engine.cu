@@ -41,6 +41,8 @@ struct ConvLayer {
   int k = 0, H = 0, W = 0, cin_sp = 0, cin_const = 0, cout = 0;
   int cin_w = 0;            // spatial channels present in the weight tensor (cin_sp may be zero-padded beyond it)
   bool lstm = false;
+  bool fold = false;        // tensor-core path: the k dx taps are folded into the input channels by the producer (k x 1 conv over
+                            // k*cin_sp channels) — used for the first encoder conv, whose 8 input channels would waste the K=16 MMAs
   float* w_sp = nullptr;    // [k*k][cin_sp][cout]
   float* wcls = nullptr;    // [k*k][A][cout]
   float* bias = nullptr;
@@ -89,7 +91,7 @@ struct vf_engine {
 
   // shared scratch
   float *raw = nullptr, *dec_in = nullptr, *stats = nullptr, *cstats = nullptr;
-  double* stats_partial = nullptr;
+  double *stats_partial = nullptr, *cstats_partial = nullptr;
   std::vector<float*> act_enc, act_dec;
   float* pack0 = nullptr;    // [B][H][W][8] packed (image, first) input of enc0 (tensor-core path)
   float *scr_h = nullptr, *mask_h = nullptr, *layers = nullptr, *logits = nullptr, *kern = nullptr, *partial = nullptr;
@@ -265,9 +267,19 @@ int prepare_conv(vf_engine* h, int view, ConvLayer& L) {
       if ((r = opt(".beta", &L.beta, L.cout))) return r;
     }
   }
-  if (h->cfg.precision != VF_PREC_FP32_SIMT && mma_conv_supported(L.k, L.cin_sp, L.cout, L.H, L.W)) {
+  if (h->cfg.precision != VF_PREC_FP32_SIMT && L.fold) {
+    // folded[dy][dx*cin_sp + c][n] = w[dy][dx][c][n]
+    std::vector<float> wf((size_t)k * k * L.cin_sp * L.cout);
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx)
+        memcpy(&wf[((size_t)dy * k * L.cin_sp + (size_t)dx * L.cin_sp) * L.cout], &wsp[((size_t)(dy * k + dx) * L.cin_sp) * L.cout],
+               (size_t)L.cin_sp * L.cout * sizeof(float));
     std::string e;
-    if (mma_conv_prepare_weights(wsp.data(), L.k, L.cin_sp, L.cout, &L.mma, &h->allocs, &e))
+    if (mma_conv_prepare_weights(wf.data(), k, 1, k, k * L.cin_sp, L.cout, &L.mma, &h->allocs, &e))
+      return fail(h, VF_ERR_CUDA, "mma weight prep %s: %s", L.name.c_str(), e.c_str());
+  } else if (h->cfg.precision != VF_PREC_FP32_SIMT && mma_conv_supported(L.k, L.cin_sp, L.cout, L.H, L.W)) {
+    std::string e;
+    if (mma_conv_prepare_weights(wsp.data(), L.k, L.k, L.k, L.cin_sp, L.cout, &L.mma, &h->allocs, &e))
       return fail(h, VF_ERR_CUDA, "mma weight prep %s: %s", L.name.c_str(), e.c_str());
   }
   return VF_OK;
@@ -301,6 +313,7 @@ int build_net(vf_engine* h) {
       if (i == 0 && c.precision != VF_PREC_FP32_SIMT) {      // (image, first) packed to 8 channels for the tensor-core path
         net.enc_conv.back().cin_sp = 8;
         net.enc_conv.back().cin_w = 6;
+        net.enc_conv.back().fold = true;
       }
       upd(net.enc_conv.back());
       hh /= 2; ww /= 2;
@@ -351,6 +364,7 @@ int build_net(vf_engine* h) {
   DA(h->dec_in, (size_t)B * decin_max);
   DA(h->stats, (size_t)B * cmax * 2);
   DA(h->stats_partial, plane_stats_partial_doubles(B, (int)cmax));
+  DA(h->cstats_partial, plane_stats_partial_doubles(B, (int)std::max(fmax_, (size_t)1)));
   DA(h->cstats, (size_t)B * std::max(fmax_, (size_t)1) * 2);
   h->act_enc.assign(n, nullptr);
   h->act_dec.assign(n, nullptr);
@@ -367,7 +381,7 @@ int build_net(vf_engine* h) {
   }
   const size_t px = (size_t)h->H * h->W;
   DA(h->scr_h, (size_t)B * px * h->ngf);
-  if (c.precision != VF_PREC_FP32_SIMT) DA(h->pack0, (size_t)B * px * 8);
+  if (c.precision != VF_PREC_FP32_SIMT) DA(h->pack0, (size_t)B * px * 8 * 5);   // (image, first) x 5 dx taps, 8 channels each
   DA(h->mask_h, (size_t)B * px * h->ngf);
   DA(h->layers, (size_t)B * px * h->cl);
   if (cudaMemset(h->layers, 0, (size_t)B * px * h->cl * sizeof(float)) != cudaSuccess) return fail(h, VF_ERR_CUDA, "memset layers");
@@ -420,6 +434,11 @@ int finalize_weights(vf_engine* h) {
   return VF_OK;
 }
 
+// finalise the S partial sums of n planes into (mean, rstd) pairs and hand both to the consumer
+StatsRef fin_stats(vf_engine* h, const double* partial, int S, int n, int npix, float* dst) {
+  launch_stats_finalize(partial, n, S, npix, h->cfg.norm_eps, dst, h->stream);
+  return stats_ref(partial, S, npix, h->cfg.norm_eps, dst);
+}
 View dense_view(float* p, int hw, int C) { return make_view(p, (long long)hw * C, C, 0, C); }
 // view of a convolution-input buffer [B][hw][ps] (split-half storage on the tensor-core path: lo plane after B*hw*ps halfs)
 View cview(const vf_engine* h, float* p, int hw, int ps, int ch_off, int C) {
@@ -475,19 +494,21 @@ void run_lstm(vf_engine* h, int v, const ConvLayer& L, RnnState& r, int B, const
   View in = cview(h, r.lstm_in, hw, 2 * F, 0, 2 * F);
   View gates = dense_view(h->raw, hw, 4 * F);
   View none = make_view(nullptr, 0, 0, 0, 0);
+  const float eps = h->cfg.norm_eps;
   int slots = 0;
-  run_conv(h, L, in, none, gates, B, ACT_NONE, h->stats_partial, &slots);
-  if (slots > 0) launch_stats_finalize(h->stats_partial, B * 4 * F, slots, hw, h->cfg.norm_eps, h->stats, h->stream);
-  else launch_plane_stats(gates, B, r.h, r.w, 0, h->cfg.norm_eps, h->stats, h->stats_partial, h->stream);
+  run_conv(h, L, in, none, gates, B, ACT_NONE, h->stats_partial, &slots);            // gate statistics fused into the epilogue
+  if (slots == 0) slots = launch_plane_stats(gates, B, r.h, r.w, 0, h->stats_partial, h->stream);
+  const StatsRef gsr = fin_stats(h, h->stats_partial, slots, B * 4 * F, hw, h->stats);
+  int cslots;
   if (256 % F == 0) {     // cell-state statistics fused into the pointwise kernel
-    const int S = launch_lstm_gates(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->stats_partial, h->stream);
-    launch_stats_finalize(h->stats_partial, B * F, S, hw, h->cfg.norm_eps, h->cstats, h->stream);
+    cslots = launch_lstm_gates(gates, B, hw, F, gsr, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->cstats_partial, h->stream);
   } else {
     launch_lstm_gates_generic(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->stream);
-    launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cfg.norm_eps, h->cstats, h->stats_partial, h->stream);
+    cslots = launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cstats_partial, h->stream);
   }
   View hv = cview(h, r.lstm_in, hw, 2 * F, F, F);
-  launch_lstm_out(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cstats, L.cgamma, L.cbeta, r.c, hv, h->stream);
+  launch_lstm_out(gates, B, hw, F, gsr, L.gamma, L.beta, fin_stats(h, h->cstats_partial, cslots, B * F, hw, h->cstats), L.cgamma,
+                  L.cbeta, r.c, hv, h->stream);
   h->debug[v][dbg + ".h"] = DebugEntry{hv, r.h, r.w};
   h->debug[v][dbg + ".c"] = DebugEntry{dense_view(r.c, hw, F), r.h, r.w};
 }
@@ -513,18 +534,25 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   View first_d = make_view(h->ctx_distrib + (long long)v * px * nd, 0, nd, 0, nd);
 
   // per-layer border-class bias of the tiled action/state vector
+  SabiasBatch sbb;
+  sbb.n = 0; sbb.A = h->A; sbb.B = B; sbb.sa = h->sa;
   auto sab = [&](ConvLayer& L) {
-    if (L.k && L.wcls) launch_sabias(h->sa, h->A, L.wcls, L.bias, L.k * L.k, L.cout, B, L.sabias, h->stream);
+    if (!(L.k && L.wcls)) return;
+    if (sbb.n == 24) { launch_sabias_batch(sbb, h->stream); sbb.n = 0; }
+    SabiasBatch::Layer& e = sbb.L[sbb.n++];
+    e.wcls = L.wcls; e.bias = L.bias; e.out = L.sabias; e.ncls = L.k * L.k; e.Cout = L.cout;
   };
   for (int i = 0; i < n; ++i) { sab(net.enc_conv[i]); sab(net.enc_lstm[i]); sab(net.dec_conv[i]); sab(net.dec_lstm[i]); }
+  launch_sabias_batch(sbb, h->stream);
 
   // P2 encoder
   std::vector<View> enc_out(n);
   std::vector<int> enc_h(n), enc_w(n);
   View x0 = image, x1 = first;
   if (h->pack0) {
-    x0 = cview(h, h->pack0, H * W, 8, 0, 8);
-    launch_pack_rgb2(image, first, B, H * W, x0, h->stream);
+    const int kf = net.enc_conv[0].k;                       // dx taps folded into channels: [dx][image rgb, first rgb, 0, 0]
+    x0 = cview(h, h->pack0, H * W, 8 * kf, 0, 8 * kf);
+    launch_pack_fold(image, first, B, H, W, kf, x0, h->stream);
     x1 = none;
   }
   int hh = H, ww = W;
@@ -534,10 +562,10 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     View rawv = dense_view(h->raw, hh * ww, oc);
     run_conv(h, L, x0, x1, rawv, B);
     hh /= 2; ww /= 2;
-    launch_plane_stats(rawv, B, hh, ww, 1, c.norm_eps, h->stats, h->stats_partial, h->stream);
+    const int S_e = launch_plane_stats(rawv, B, hh, ww, 1, h->stats_partial, h->stream);
     View dst = c.enc_rnn[i] ? cview(h, net.enc_rnn[i].lstm_in, hh * ww, 2 * oc, 0, oc)
                             : cview(h, h->act_enc[i], hh * ww, oc, 0, oc);
-    launch_norm_act(rawv, B, hh, ww, 1, h->stats, L.gamma, L.beta, ACT_RELU, dst, h->stream);
+    launch_norm_act(rawv, B, hh, ww, 1, fin_stats(h, h->stats_partial, S_e, B * oc, hh * ww, h->stats), L.gamma, L.beta, ACT_RELU, dst, h->stream);
     h->debug[v][L.name] = DebugEntry{dst, hh, ww};
     View out = dst;
     if (c.enc_rnn[i]) {
@@ -558,10 +586,10 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     hh *= 2; ww *= 2;
     View rawv = dense_view(h->raw, hh * ww, oc);
     run_conv(h, L, din, none, rawv, B);
-    launch_plane_stats(rawv, B, hh, ww, 0, c.norm_eps, h->stats, h->stats_partial, h->stream);
+    const int S_d = launch_plane_stats(rawv, B, hh, ww, 0, h->stats_partial, h->stream);
     View dst = c.dec_rnn[i] ? cview(h, net.dec_rnn[i].lstm_in, hh * ww, 2 * oc, 0, oc)
                             : cview(h, h->act_dec[i], hh * ww, oc, 0, oc);
-    launch_norm_act(rawv, B, hh, ww, 0, h->stats, L.gamma, L.beta, ACT_RELU, dst, h->stream);
+    launch_norm_act(rawv, B, hh, ww, 0, fin_stats(h, h->stats_partial, S_d, B * oc, hh * ww, h->stats), L.gamma, L.beta, ACT_RELU, dst, h->stream);
     h->debug[v][L.name] = DebugEntry{dst, hh, ww};
     x = dst;
     if (c.dec_rnn[i]) {
@@ -581,16 +609,16 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   // P7 scratch image
   View rawg = dense_view(h->raw, (int)px, g);
   run_conv(h, net.scratch0, h_last, none, rawg, B);
-  launch_plane_stats(rawg, B, H, W, 0, c.norm_eps, h->stats, h->stats_partial, h->stream);
+  const int S_s = launch_plane_stats(rawg, B, H, W, 0, h->stats_partial, h->stream);
   View scr = cview(h, h->scr_h, (int)px, g, 0, g);
-  launch_norm_act(rawg, B, H, W, 0, h->stats, net.scratch0.gamma, net.scratch0.beta, ACT_RELU, scr, h->stream);
+  launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_s, B * g, (int)px, h->stats), net.scratch0.gamma, net.scratch0.beta, ACT_RELU, scr, h->stream);
   View scratch_out = cview(h, h->layers, (int)px, cl, 3 * (h->nt + 2), 3);
   run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
   // P8 masks
   run_conv(h, net.masks0, h_last, none, rawg, B);
-  launch_plane_stats(rawg, B, H, W, 0, c.norm_eps, h->stats, h->stats_partial, h->stream);
+  const int S_m = launch_plane_stats(rawg, B, H, W, 0, h->stats_partial, h->stream);
   View hm = cview(h, h->mask_h, (int)px, g, 0, g);
-  launch_norm_act(rawg, B, H, W, 0, h->stats, net.masks0.gamma, net.masks0.beta, ACT_RELU, hm, h->stream);
+  launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_m, B * g, (int)px, h->stats), net.masks0.gamma, net.masks0.beta, ACT_RELU, hm, h->stream);
   View lg = dense_view(h->logits, (int)px, nm);
   run_conv(h, net.masks1, hm, layers, lg, B);
   CompositeArgs ca;
@@ -755,6 +783,9 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
   if ((h->H % (1 << cfg->n_enc)) || (h->W % (1 << cfg->n_enc))) return fail(h, VF_ERR_INVALID, "H, W must be divisible by 2^n_enc");
   if ((h->H >> cfg->n_enc) < 4 || (h->W >> cfg->n_enc) < 4) return fail(h, VF_ERR_INVALID, "coarsest feature map must be at least 4x4");
   if (cfg->dec_channels[cfg->n_dec - 1] != cfg->ngf) return fail(h, VF_ERR_INVALID, "last decoder layer must have ngf channels");
+  for (int i = 0; i < cfg->n_enc; ++i)
+    if ((cfg->enc_channels[i] % 4) || (cfg->dec_channels[i] % 4) || cfg->enc_channels[i] > 256 || cfg->dec_channels[i] > 256 || (cfg->ngf % 4))
+      return fail(h, VF_ERR_INVALID, "layer widths must be multiples of 4 and at most 256 (vectorised statistics / conv-LSTM kernels)");
   if (!cfg->enc_rnn[cfg->n_enc - 1]) return fail(h, VF_ERR_INVALID, "the last encoder layer must be recurrent (CDNA feature)");
   if (h->nt < 1 || h->nt > 8 || h->kc * h->kc * h->nt > 128 || (h->kc % 2) == 0 || (cfg->lstm_ksize != 5 && cfg->lstm_ksize != 3))
     return fail(h, VF_ERR_INVALID, "unsupported CDNA/LSTM kernel configuration");
@@ -1168,7 +1199,7 @@ int vf_debug_conv2d(vf_engine* h, int32_t impl, const float* x, const float* w, 
     MmaConvWeights mw;
     std::string e;
     std::vector<float> wh(w, w + nw);
-    if (mma_conv_prepare_weights(wh.data(), k, Cin, Cout, &mw, &h->allocs, &e)) return fail(h, VF_ERR_CUDA, "mma weight prep: %s", e.c_str());
+    if (mma_conv_prepare_weights(wh.data(), k, k, k, Cin, Cout, &mw, &h->allocs, &e)) return fail(h, VF_ERR_CUDA, "mma weight prep: %s", e.c_str());
     float* dxs;                                                        // split-half copy of x (what a producer kernel would write)
     DA(dxs, nx);
     View vxs = make_view(dxs, (long long)H * W * Cin, Cin, 0, Cin, (long long)B * H * W * Cin);

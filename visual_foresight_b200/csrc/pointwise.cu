@@ -1,6 +1,8 @@
 // pointwise.cu — instance-norm statistics, normalise+activation, conv-LSTM pointwise, bilinear x2
 // upsample, and the action/state vector with its per-layer border-class bias.  All HBM/L2-bound:
 // threads run along the channel dimension (NHWC innermost) so every warp access is contiguous.
+#include <algorithm>
+
 #include "vf_common.cuh"
 
 namespace vf {
@@ -10,42 +12,58 @@ __device__ __forceinline__ const float* vptr(const View& v, int b, long long pix
   return v.p + (long long)b * v.sample_stride + pix * v.pix_stride + v.ch_off;
 }
 
-__device__ __forceinline__ float pooled(const View& x, int b, int W, int pool, int y, int xx, int c) {
-  if (!pool) return __ldg(vptr(x, b, (long long)y * W + xx) + c);
-  const int Wi = W * 2;
-  const float* p00 = vptr(x, b, (long long)(2 * y) * Wi + 2 * xx) + c;
-  const float a = __ldg(p00), bq = __ldg(p00 + x.pix_stride);
-  const float cq = __ldg(p00 + (long long)Wi * x.pix_stride), d = __ldg(p00 + (long long)(Wi + 1) * x.pix_stride);
-  return ((a + bq) + (cq + d)) * 0.25f;
-}
-
-// Instance-norm statistics, one pass: grid (B, ceil(C/32), S pixel splits), block (32, 8).  Every thread accumulates
-// sum and sum-of-squares of its pixels in float64 (no cancellation in E[x^2]-mean^2 at fp32 data precision), the 8
-// rows are combined in a fixed order, and the S partials of a (sample, channel) are combined in a fixed order by
-// k_stats_finalize: bit-reproducible, independent of sample count and GPU count.
+// Instance-norm statistics, one pass: grid (B, ceil(C/32), S pixel splits), block 256 = 8 channel quads x 32 pixel lanes.
+// Every thread accumulates sum and sum-of-squares of 4 channels in float64 (no cancellation in E[x^2]-mean^2 at fp32 data
+// precision) over its pixels, 4 pixels (16-byte loads) in flight per thread; the 32 pixel lanes are combined in a fixed
+// order, and the S partials of a (sample, channel) are combined in a fixed order by the consumer (stat_of):
+// bit-reproducible, independent of sample count and GPU count.
 constexpr int STATS_MAX_SPLIT = 8;
-__global__ void k_plane_stats(View x, int H, int W, int pool, double* partial) {
+__device__ __forceinline__ float4 pooled4(const View& x, int b, int W, int pool, int p, int c) {
+  if (!pool) return vld4(x, voff(x, b, p) + c);
+  const int y = p / W, xx = p - y * W, Wi = W * 2;
+  const long long o = voff(x, b, (long long)(2 * y) * Wi + 2 * xx) + c;
+  const float4 a0 = vld4(x, o), a1 = vld4(x, o + x.pix_stride);
+  const float4 a2 = vld4(x, o + (long long)Wi * x.pix_stride), a3 = vld4(x, o + (long long)(Wi + 1) * x.pix_stride);
+  return make_float4(((a0.x + a1.x) + (a2.x + a3.x)) * 0.25f, ((a0.y + a1.y) + (a2.y + a3.y)) * 0.25f,
+                     ((a0.z + a1.z) + (a2.z + a3.z)) * 0.25f, ((a0.w + a1.w) + (a2.w + a3.w)) * 0.25f);
+}
+__global__ void __launch_bounds__(256) k_plane_stats(View x, int H, int W, int pool, double* partial) {
   const int b = blockIdx.x;
-  const int c = blockIdx.y * 32 + threadIdx.x;
+  const int cq = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = blockIdx.y * 32 + cq * 4;
   const int S = gridDim.z, sp = blockIdx.z;
   const int npix = H * W;
   const int p0 = (int)((long long)npix * sp / S), p1 = (int)((long long)npix * (sp + 1) / S);
-  __shared__ double red[2][8][33];
-  double s = 0.0, q = 0.0;
-  if (c < x.C)
-    for (int p = p0 + threadIdx.y; p < p1; p += 8) {
-      const double v = (double)pooled(x, b, W, pool, p / W, p % W, c);
-      s += v;
-      q = fma(v, v, q);
-    }
-  red[0][threadIdx.y][threadIdx.x] = s;
-  red[1][threadIdx.y][threadIdx.x] = q;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < x.C) {
-    double ts = 0.0, tq = 0.0;
+  __shared__ double red[32][8][9];
+  double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < x.C) {
+    int p = p0 + pl;
+    for (; p + 96 < p1; p += 128) {                 // 4 independent loads in flight
+      const float4 v0 = pooled4(x, b, W, pool, p, c), v1 = pooled4(x, b, W, pool, p + 32, c);
+      const float4 v2 = pooled4(x, b, W, pool, p + 64, c), v3 = pooled4(x, b, W, pool, p + 96, c);
+      const float4 vv[4] = {v0, v1, v2, v3};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { ts += red[0][i][threadIdx.x]; tq += red[1][i][threadIdx.x]; }
-    double* o = partial + (((long long)b * x.C + c) * S + sp) * 2;
+      for (int u = 0; u < 4; ++u) {
+        const double d0 = vv[u].x, d1 = vv[u].y, d2 = vv[u].z, d3 = vv[u].w;
+        s[0] += d0; q[0] = fma(d0, d0, q[0]); s[1] += d1; q[1] = fma(d1, d1, q[1]);
+        s[2] += d2; q[2] = fma(d2, d2, q[2]); s[3] += d3; q[3] = fma(d3, d3, q[3]);
+      }
+    }
+    for (; p < p1; p += 32) {
+      const float4 v = pooled4(x, b, W, pool, p, c);
+      const double d0 = v.x, d1 = v.y, d2 = v.z, d3 = v.w;
+      s[0] += d0; q[0] = fma(d0, d0, q[0]); s[1] += d1; q[1] = fma(d1, d1, q[1]);
+      s[2] += d2; q[2] = fma(d2, d2, q[2]); s[3] += d3; q[3] = fma(d3, d3, q[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[pl][cq][j] = s[j]; red[pl][cq][4 + j] = q[j]; }
+  __syncthreads();
+  if (threadIdx.x < 32 && blockIdx.y * 32 + threadIdx.x < x.C) {
+    const int cc = threadIdx.x;
+    double ts = 0.0, tq = 0.0;
+    for (int i = 0; i < 32; ++i) { ts += red[i][cc >> 2][cc & 3]; tq += red[i][cc >> 2][4 + (cc & 3)]; }
+    double* o = partial + (((long long)b * x.C + blockIdx.y * 32 + cc) * S + sp) * 2;
     o[0] = ts;
     o[1] = tq;
   }
@@ -63,13 +81,31 @@ __global__ void k_stats_finalize(const double* __restrict__ partial, int n, int 
   stats[(long long)i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// (mean, rstd) of plane `idx` from its S float64 partial sums: the same arithmetic as k_stats_finalize, run by the
+// consumer in its prologue so that no separate finalize launch is needed
+__device__ __forceinline__ float2 stat_of(const StatsRef& r, long long idx) {
+  if (r.fin) return __ldg(reinterpret_cast<const float2*>(r.fin) + idx);
+  double ts = 0.0, tq = 0.0;
+  for (int k = 0; k < r.S; ++k) { ts += r.partial[(idx * r.S + k) * 2]; tq += r.partial[(idx * r.S + k) * 2 + 1]; }
+  const double mean = ts / r.npix;
+  double var = tq / r.npix - mean * mean;
+  if (var < 0.0) var = 0.0;
+  return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)r.eps)));
+}
+
 // one thread = 4 consecutive channels of one output pixel; grid.y = sample
-__global__ void __launch_bounds__(256) k_norm_act(View x, int H, int W, int pool, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256) k_norm_act(View x, int H, int W, int pool, StatsRef sr,
                                                   const float* __restrict__ gamma, const float* __restrict__ beta, int act, View y) {
   const int b = blockIdx.y;
   const int C4 = x.C >> 2;
   const int total = H * W * C4;
-  const float* st = stats + (long long)b * x.C * 2;
+  __shared__ __align__(16) float st[2 * 512];
+  for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
+    const float2 v = stat_of(sr, (long long)b * x.C + c);
+    st[2 * c] = v.x;
+    st[2 * c + 1] = v.y;
+  }
+  __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = (i % C4) << 2;
     const int pix = i / C4;
@@ -107,7 +143,7 @@ __device__ __forceinline__ float gate_norm(const View& g, int b, long long pix, 
 // gate order along channels: i, j, f, o   (spec P3).  grid (pixel blocks, sample); 256 threads = (256/F) pixel lanes x F
 // channels (F in {32, 64, 128}: each thread keeps ONE channel).  The instance-norm statistics of the new cell state
 // are accumulated on the fly (float64 per thread, lanes combined in a fixed order) -> partial[(b*F+f)*S + block].
-__global__ void __launch_bounds__(256) k_lstm_gates(View gates, int HW, int F, const float* __restrict__ gstats,
+__global__ void __launch_bounds__(256) k_lstm_gates(View gates, int HW, int F, StatsRef gsr,
                                                     const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c,
                                                     double* partial) {
   const int b = blockIdx.y;
@@ -116,9 +152,9 @@ __global__ void __launch_bounds__(256) k_lstm_gates(View gates, int HW, int F, c
   const int per = (HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
   float* cb_ = c + (long long)b * HW * F;
-  const float* st = gstats + (long long)b * gates.C * 2;
-  const float mi = st[2 * f], ri = st[2 * f + 1], mj = st[2 * (F + f)], rj = st[2 * (F + f) + 1];
-  const float mf = st[2 * (2 * F + f)], rf = st[2 * (2 * F + f) + 1];
+  const float2 si = stat_of(gsr, (long long)b * gates.C + f), sj = stat_of(gsr, (long long)b * gates.C + F + f);
+  const float2 sf = stat_of(gsr, (long long)b * gates.C + 2 * F + f);
+  const float mi = si.x, ri = si.y, mj = sj.x, rj = sj.y, mf = sf.x, rf = sf.y;
   const float gi_g = gg[f], gi_b = gb[f], gj_g = gg[F + f], gj_b = gb[F + f], gf_g = gg[2 * F + f], gf_b = gb[2 * F + f];
   double s = 0.0, q = 0.0;
   for (int pix = p0 + pl; pix < p1; pix += lanes) {
@@ -159,19 +195,26 @@ __global__ void __launch_bounds__(256) k_lstm_gates_generic(View gates, int HW, 
   }
 }
 
-__global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, const float* __restrict__ gstats,
+__global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, StatsRef gsr,
                                                   const float* __restrict__ gg, const float* __restrict__ gb,
-                                                  const float* __restrict__ cstats, const float* __restrict__ cg,
+                                                  StatsRef csr, const float* __restrict__ cg,
                                                   const float* __restrict__ cb, float* c, View h) {
   const int b = blockIdx.y;
   const int total = HW * F;
   float* cb_ = c + (long long)b * total;
+  // per-channel affine forms of both instance norms: y = x * a + d
+  __shared__ float ca[512], cd[512], oa[512], od[512];
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    const float2 cs = stat_of(csr, (long long)b * F + f);
+    const float2 os = stat_of(gsr, (long long)b * gates.C + 3 * F + f);
+    ca[f] = cs.x; cd[f] = cs.y; oa[f] = os.x; od[f] = os.y;
+  }
+  __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int f = i % F, pix = i / F;
-    const float* st = cstats + ((long long)b * F + f) * 2;
-    const float cn = (cb_[i] - st[0]) * st[1] * cg[f] + cb[f];
+    const float cn = (cb_[i] - ca[f]) * cd[f] * cg[f] + cb[f];
     cb_[i] = cn;
-    const float go = gate_norm(gates, b, pix, 3 * F + f, gstats, gg, gb);
+    const float go = (__ldg(vptr(gates, b, pix) + 3 * F + f) - oa[f]) * od[f] * gg[3 * F + f] + gb[3 * F + f];
     vst1(h, voff(h, b, pix) + f, tanhf(cn) * sigmoidf_(go));
   }
 }
@@ -270,6 +313,20 @@ __global__ void k_sabias(const float* __restrict__ sa, int A, const float* __res
   }
 }
 
+// every layer's border-class bias of one cell step in ONE launch: grid.y = layer
+__global__ void k_sabias_batch(SabiasBatch a) {
+  const SabiasBatch::Layer L = a.L[blockIdx.y];
+  const long long total = (long long)a.B * L.ncls * L.Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % L.Cout);
+    const int cls = (int)((i / L.Cout) % L.ncls);
+    const int b = (int)(i / ((long long)L.Cout * L.ncls));
+    float acc = 0.f;
+    for (int k = 0; k < a.A; ++k) acc = fmaf(a.sa[(long long)b * a.A + k], __ldg(L.wcls + ((long long)cls * a.A + k) * L.Cout + n), acc);
+    L.out[i] = acc + (L.bias ? L.bias[n] : 0.f);
+  }
+}
+
 // out[b, pix, 0..7] = (image rgb, first rgb, 0, 0): 8-channel (16-byte-unit) input of the first encoder conv
 __global__ void k_pack_rgb2(View image, View first, int HW, View out) {
   const int b = blockIdx.y;
@@ -280,6 +337,23 @@ __global__ void k_pack_rgb2(View image, View first, int HW, View out) {
   const long long o = voff(out, b, pix);
   vst4(out, o, make_float4(__ldg(ip), __ldg(ip + 1), __ldg(ip + 2), __ldg(fp)));
   vst4(out, o + 4, make_float4(__ldg(fp + 1), __ldg(fp + 2), 0.f, 0.f));
+}
+__global__ void k_pack_fold(View image, View first, int H, int W, int kf, View out) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W * kf) return;
+  const int dx = i % kf, pix = i / kf;
+  const int y = pix / W, x = pix - y * W, xs = x + dx - kf / 2;
+  float8 v;
+  v.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  v.b = v.a;
+  if (xs >= 0 && xs < W) {
+    const float* ip = vptr(image, b, (long long)y * W + xs);
+    const float* fp = vptr(first, b, (long long)y * W + xs);
+    v.a = make_float4(__ldg(ip), __ldg(ip + 1), __ldg(ip + 2), __ldg(fp));
+    v.b = make_float4(__ldg(fp + 1), __ldg(fp + 2), 0.f, 0.f);
+  }
+  vst8(out, voff(out, b, pix) + dx * 8, v);
 }
 __global__ void k_view_to_dense(View v, int HW, float* dst) {
   const int b = blockIdx.y;
@@ -324,24 +398,23 @@ inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
 
 }  // namespace
 
-void launch_plane_stats(View x, int B, int H, int W, int pool, float eps, float* stats, double* partial, cudaStream_t s) {
-  g_launch_counter += 2;
+int launch_plane_stats(View x, int B, int H, int W, int pool, double* partial, cudaStream_t s) {
+  ++g_launch_counter;
   const int npix = H * W;
   int S = npix >= 2048 ? 8 : (npix >= 512 ? 4 : (npix >= 128 ? 2 : 1));
   while (S < STATS_MAX_SPLIT && (long long)B * ((x.C + 31) / 32) * S < 296 && npix / (2 * S) >= 16) S *= 2;   // fill the 148 SMs
-  dim3 grid(B, (x.C + 31) / 32, S), block(32, 8);
-  k_plane_stats<<<grid, block, 0, s>>>(x, H, W, pool, partial);
-  const int n = B * x.C;
-  k_stats_finalize<<<(n + 255) / 256, 256, 0, s>>>(partial, n, S, npix, eps, stats);
+  dim3 grid(B, (x.C + 31) / 32, S);                 // requires C % 4 == 0 and 16-byte aligned pixel rows (all conv outputs)
+  k_plane_stats<<<grid, 256, 0, s>>>(x, H, W, pool, partial);
+  return S;
 }
 size_t plane_stats_partial_doubles(int B, int C) { return (size_t)B * C * 16 * 2; }   // up to 16 slots per (sample, channel)
-void launch_norm_act(View x, int B, int H, int W, int pool, const float* stats, const float* gamma,
+void launch_norm_act(View x, int B, int H, int W, int pool, StatsRef stats, const float* gamma,
                      const float* beta, int act, View y, cudaStream_t s) {
   ++g_launch_counter;
   dim3 grid(grid_for((long long)H * W * (x.C >> 2), 256, 64), B);
   k_norm_act<<<grid, 256, 0, s>>>(x, H, W, pool, stats, gamma, beta, act, y);
 }
-int launch_lstm_gates(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
+int launch_lstm_gates(View gates, int B, int HW, int F, StatsRef gstats, const float* gg, const float* gb,
                       float fb, float* c, double* partial, cudaStream_t s) {
   ++g_launch_counter;
   int S = HW >= 1024 ? 8 : (HW >= 256 ? 4 : (HW >= 64 ? 2 : 1));      // pixel blocks per sample = stats partial slots
@@ -359,8 +432,8 @@ void launch_stats_finalize(const double* partial, int n, int S, int npix, float 
   ++g_launch_counter;
   k_stats_finalize<<<(n + 255) / 256, 256, 0, s>>>(partial, n, S, npix, eps, stats);
 }
-void launch_lstm_out(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
-                     const float* cstats, const float* cg, const float* cb, float* c, View h, cudaStream_t s) {
+void launch_lstm_out(View gates, int B, int HW, int F, StatsRef gstats, const float* gg, const float* gb,
+                     StatsRef cstats, const float* cg, const float* cb, float* c, View h, cudaStream_t s) {
   ++g_launch_counter;
   dim3 grid(grid_for((long long)HW * F, 256, 64), B);
   k_lstm_out<<<grid, 256, 0, s>>>(gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h);
@@ -380,6 +453,14 @@ void launch_build_sa(const SaArgs& a, int M, int tau, cudaStream_t s) {
   ++g_launch_counter;
   k_build_sa<<<(M + 127) / 128, 128, 0, s>>>(a, M, tau);
 }
+void launch_sabias_batch(const SabiasBatch& a, cudaStream_t s) {
+  if (a.n == 0) return;
+  ++g_launch_counter;
+  long long mx = 1;
+  for (int i = 0; i < a.n; ++i) mx = std::max(mx, (long long)a.B * a.L[i].ncls * a.L[i].Cout);
+  dim3 grid(grid_for(mx, 256, 148 * 8), a.n);
+  k_sabias_batch<<<grid, 256, 0, s>>>(a);
+}
 void launch_sabias(const float* sa, int A, const float* wcls, const float* bias, int ncls, int Cout, int B,
                    float* out, cudaStream_t s) {
   ++g_launch_counter;
@@ -394,6 +475,11 @@ void launch_dense_to_view(const float* src, int B, int HW, View v, cudaStream_t 
   ++g_launch_counter;
   dim3 grid(grid_for((long long)HW * v.C, 256, 64), B);
   k_dense_to_view<<<grid, 256, 0, s>>>(src, HW, v);
+}
+void launch_pack_fold(View image, View first, int B, int H, int W, int kf, View out, cudaStream_t s) {
+  ++g_launch_counter;
+  dim3 grid((H * W * kf + 255) / 256, B);
+  k_pack_fold<<<grid, 256, 0, s>>>(image, first, H, W, kf, out);
 }
 void launch_pack_rgb2(View image, View first, int B, int HW, View out, cudaStream_t s) {
   ++g_launch_counter;

@@ -138,23 +138,35 @@ enum { ACT_NONE = 0, ACT_SIGMOID = 1, ACT_RELU = 2 };
 void launch_conv_simt(const ConvArgs& a, int B, cudaStream_t s);
 
 // ---- normalisation / pointwise --------------------------------------------------------------
-// stats[(b*C + c)*2 + {0,1}] = mean, rstd of (optionally 2x2 avg-pooled) x over the plane
-// (partial: scratch of plane_stats_partial_doubles(B, C) float64)
-void launch_plane_stats(View x, int B, int H, int W, int pool, float eps, float* stats, double* partial, cudaStream_t s);
+// Instance-norm statistics are kept as float64 partial sums partial[((b*C + c)*S + k)*2 + {sum, sumsq}] (k < S slots,
+// written by k_plane_stats, by the tensor-core conv epilogue or by k_lstm_gates); every consumer finalises
+// (mean, rstd) of the planes it needs in its prologue, in a fixed order (bit-reproducible).
+struct StatsRef {
+  const float* fin;       // finalised (mean, rstd) pairs (k_stats_finalize), or null: finalise from the partials on the fly
+  const double* partial;
+  int S;        // partial slots per (sample, channel)
+  int npix;     // pixels per plane
+  float eps;
+};
+inline StatsRef stats_ref(const double* partial, int S, int npix, float eps, const float* fin = nullptr) {
+  StatsRef r; r.fin = fin; r.partial = partial; r.S = S; r.npix = npix; r.eps = eps; return r;
+}
+// partial sums of the (optionally 2x2 avg-pooled) planes of x; returns the slot count S
+int launch_plane_stats(View x, int B, int H, int W, int pool, double* partial, cudaStream_t s);
 size_t plane_stats_partial_doubles(int B, int C);
 // y = act((pool(x) - mean) * rstd * gamma + beta)
-void launch_norm_act(View x, int B, int H, int W, int pool, const float* stats, const float* gamma,
+void launch_norm_act(View x, int B, int H, int W, int pool, StatsRef stats, const float* gamma,
                      const float* beta, int act, View y, cudaStream_t s);
 // conv-LSTM pointwise, part 1: c <- c*sigmoid(f+fb) + sigmoid(i)*tanh(j) with gates instance-normalised
 // also accumulates the instance-norm partial sums of the new cell state; returns the partial slots per (sample, channel)
-int launch_lstm_gates(View gates, int B, int HW, int F, const float* gstats, const float* ggamma,
+int launch_lstm_gates(View gates, int B, int HW, int F, StatsRef gstats, const float* ggamma,
                       const float* gbeta, float forget_bias, float* c, double* partial, cudaStream_t s);
 void launch_lstm_gates_generic(View gates, int B, int HW, int F, const float* gstats, const float* ggamma,
                                const float* gbeta, float forget_bias, float* c, cudaStream_t s);
 void launch_stats_finalize(const double* partial, int n, int S, int npix, float eps, float* stats, cudaStream_t s);
 // part 2: c <- IN(c);  h <- tanh(c) * sigmoid(IN(o))
-void launch_lstm_out(View gates, int B, int HW, int F, const float* gstats, const float* ggamma,
-                     const float* gbeta, const float* cstats, const float* cgamma, const float* cbeta,
+void launch_lstm_out(View gates, int B, int HW, int F, StatsRef gstats, const float* ggamma,
+                     const float* gbeta, StatsRef cstats, const float* cgamma, const float* cbeta,
                      float* c, View h, cudaStream_t s);
 // out[b, 2H, 2W, C0+C1] = bilinear_x2(concat(src0, src1))   (half-pixel centres, edge clamp)
 void launch_upsample2x(View src0, View src1, int B, int H, int W, View out, cudaStream_t s);
@@ -174,6 +186,13 @@ struct SaArgs {
   int P;
 };
 void launch_build_sa(const SaArgs& a, int M, int tau, cudaStream_t s);
+struct SabiasBatch {
+  struct Layer { const float* wcls; const float* bias; float* out; int ncls, Cout; };
+  Layer L[24];
+  int n, A, B;
+  const float* sa;
+};
+void launch_sabias_batch(const SabiasBatch& a, cudaStream_t s);
 // sabias[b][cls][n] = bias[n] + sum_a sa[b][a] * wcls[cls][a][n]
 void launch_sabias(const float* sa, int A, const float* wcls, const float* bias, int ncls, int Cout,
                    int B, float* out, cudaStream_t s);
@@ -236,6 +255,9 @@ int topk_padded(int n);
 void launch_refit(const double* elites_nr, int K, int D, double* mean, double* factor, double* cov, cudaStream_t s);
 
 void launch_pack_rgb2(View image, View first, int B, int HW, View out, cudaStream_t s);
+// out[b, (y,x), dx*8 + 0..7] = (image rgb, first rgb, 0, 0) at (y, x + dx - kf/2), zeros outside the image: the kf dx taps of
+// the first encoder conv folded into channels (its tensor-core form is then a kf x 1 convolution over 8*kf channels)
+void launch_pack_fold(View image, View first, int B, int H, int W, int kf, View out, cudaStream_t s);
 // dst[b][pix][c] (dense float32) = view element (either storage format)
 void launch_view_to_dense(View v, int B, int HW, float* dst, cudaStream_t s);
 void launch_dense_to_view(const float* src, int B, int HW, View v, cudaStream_t s);
