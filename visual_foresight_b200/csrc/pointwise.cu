@@ -411,7 +411,8 @@ size_t plane_stats_partial_doubles(int B, int C) { return (size_t)B * C * 16 * 2
 void launch_norm_act(View x, int B, int H, int W, int pool, StatsRef stats, const float* gamma,
                      const float* beta, int act, View y, cudaStream_t s) {
   ++g_launch_counter;
-  dim3 grid(grid_for((long long)H * W * (x.C >> 2), 256, 64), B);
+  // few, long-lived blocks per sample: every block stages the sample's statistics in shared memory first
+  dim3 grid(grid_for((long long)H * W * (x.C >> 2), 256, B >= 64 ? 16 : 64), B);
   k_norm_act<<<grid, 256, 0, s>>>(x, H, W, pool, stats, gamma, beta, act, y);
 }
 int launch_lstm_gates(View gates, int B, int HW, int F, StatsRef gstats, const float* gg, const float* gb,
@@ -435,7 +436,7 @@ void launch_stats_finalize(const double* partial, int n, int S, int npix, float 
 void launch_lstm_out(View gates, int B, int HW, int F, StatsRef gstats, const float* gg, const float* gb,
                      StatsRef cstats, const float* cg, const float* cb, float* c, View h, cudaStream_t s) {
   ++g_launch_counter;
-  dim3 grid(grid_for((long long)HW * F, 256, 64), B);
+  dim3 grid(grid_for((long long)HW * F, 256, B >= 64 ? 16 : 64), B);
   k_lstm_out<<<grid, 256, 0, s>>>(gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h);
 }
 void launch_upsample2x(View s0, View s1, int B, int H, int W, View out, cudaStream_t s) {
