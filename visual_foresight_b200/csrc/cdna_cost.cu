@@ -20,6 +20,8 @@ __device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -1 - i : (i
 constexpr int CK_S = 8, CK_KC = 512;
 __global__ void __launch_bounds__(256) k_cdna_partial(View feat, int npix, const float* __restrict__ w, int nout, int B,
                                                       float* __restrict__ part) {
+  pdl_wait();
+  pdl_trigger();
   const int ks = blockIdx.x, k0 = ks * CK_KC, b0 = blockIdx.y * CK_S;
   const int K = npix * feat.C;
   __shared__ float sf[CK_S][CK_KC];
@@ -84,6 +86,8 @@ __device__ __forceinline__ void cdna_finalize(const float* __restrict__ part, in
 __global__ void __launch_bounds__(256) k_cdna_apply4(View image, View first, const float* __restrict__ part, int nks,
                                                      const float* __restrict__ bias, int B, int H, int W, int TR, View layers,
                                                      float* __restrict__ kern_out) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float4 sm4[];
   float4* sk4 = sm4;                       // [25]
   float* tmp = reinterpret_cast<float*>(sm4 + 25);    // [128] + sums [8]
@@ -187,6 +191,8 @@ constexpr int COMP_THREADS = 256;
 // memory; kernels as [tap][nt].  Per-thread sums of the raw distribution are combined by a fixed shuffle tree + fixed
 // warp order -> partial[b][p][band].
 __global__ void __launch_bounds__(COMP_THREADS) k_composite(CompositeArgs a, int TR) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float smc[];
   __shared__ float red[COMP_THREADS / 32];
   const int b = blockIdx.y, y0 = blockIdx.x * TR;
@@ -274,6 +280,8 @@ __global__ void __launch_bounds__(COMP_THREADS) k_composite(CompositeArgs a, int
 }
 
 __global__ void k_distrib_normalize(View d, const float* __restrict__ partial, int nblk, int H, int W, int nd) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   __shared__ float inv[4];
   if (threadIdx.x < nd) {
@@ -375,7 +383,7 @@ void launch_cdna_kernels(View feat, int npix, const float* w, int ksize, int nt,
   ++g_launch_counter;
   const int K = npix * feat.C;
   dim3 grid((K + CK_KC - 1) / CK_KC, (B + CK_S - 1) / CK_S);
-  k_cdna_partial<<<grid, 256, 0, s>>>(feat, npix, w, ksize * ksize * nt, B, part);
+  launch_k(k_cdna_partial, dim3(grid), dim3(256), 0, s, feat, npix, w, ksize * ksize * nt, B, part);
 }
 void launch_cdna_apply(View image, View first, const float* part, int K, const float* bias, float* kern, int ksize, int nt,
                        int B, int H, int W, View layers, cudaStream_t s) {
@@ -385,7 +393,7 @@ void launch_cdna_apply(View image, View first, const float* part, int K, const f
     const int TR = band_rows(H, W);
     dim3 grid((H + TR - 1) / TR, B);
     const size_t smem = (size_t)(25 + 34 + (TR + 4) * W) * sizeof(float4);
-    k_cdna_apply4<<<grid, 256, smem, s>>>(image, first, part, nks, bias, B, H, W, TR, layers, kern);
+    launch_k(k_cdna_apply4, dim3(grid), dim3(256), smem, s, image, first, part, nks, bias, B, H, W, TR, layers, kern);
   } else {
     dim3 grid((H * W + 127) / 128, B);
     k_cdna_apply<<<grid, 128, 0, s>>>(image, first, part, nks, bias, ksize, nt, B, H, W, layers, kern);
@@ -397,12 +405,12 @@ void launch_composite(const CompositeArgs& a, int B, cudaStream_t s) {
   const int TR = band_rows(a.H, a.W);
   dim3 grid((a.H + TR - 1) / TR, B);
   const size_t smem = (size_t)(((a.nt * a.ksize * a.ksize + 3) & ~3) + a.nd * (TR + a.ksize - 1) * a.W) * sizeof(float);
-  k_composite<<<grid, COMP_THREADS, smem, s>>>(a, TR);
+  launch_k(k_composite, dim3(grid), dim3(COMP_THREADS), smem, s, a, TR);
 }
 void launch_distrib_normalize(View d, const float* partial, int nblk, int B, int H, int W, int nd, cudaStream_t s) {
   ++g_launch_counter;
   dim3 grid((H * W * nd + 255) / 256, B);
-  k_distrib_normalize<<<grid, 256, 0, s>>>(d, partial, nblk, H, W, nd);
+  launch_k(k_distrib_normalize, dim3(grid), dim3(256), 0, s, d, partial, nblk, H, W, nd);
 }
 void launch_pixel_cost(const float* distrib, int M, int P, int ncam, int H, int W, int nd, const double* goal,
                        float* cost, cudaStream_t s) {

@@ -539,6 +539,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barrier init and the TMEM allocation above overlap the tail of the previous kernel (programmatic dependent launch);
+  // nothing before this point touches global memory
+  pdl_wait();
+  pdl_trigger();
 
   const int per_mt = g.ngroups * g.npass;
   const uint32_t ltype = g.layout == 1 ? 4u : 2u;
@@ -1117,8 +1121,7 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   }
   const int grid = std::min(P.g.nitems, g_num_sms > 0 ? g_num_sms : 148);
   ++g_launch_counter;
-  k_conv_mma<<<grid, NTHREADS, smem, s>>>(P);
-  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+  return launch_k(k_conv_mma, dim3(grid), dim3(NTHREADS), smem, s, P) == cudaSuccess ? 0 : -4;
 }
 
 }  // namespace vf

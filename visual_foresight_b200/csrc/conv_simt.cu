@@ -10,6 +10,7 @@
 namespace vf {
 
 long long g_launch_counter = 0;
+bool g_use_pdl = false;   // set by vf_create from VF_PDL=1 (off by default: see engine.cu)
 
 namespace {
 

@@ -775,6 +775,8 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
   h->cm = cfg->ngf + h->cl;
   h->split = cfg->precision != VF_PREC_FP32_SIMT;
   { const char* e = getenv("VF_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
+  // programmatic dependent launch: measured SLOWER on B200 inside the replayed graph (131.4 vs 124.7 ms per plan), so opt-in
+  { const char* e = getenv("VF_PDL"); g_use_pdl = e && e[0] == '1'; }
   if (h->B < 1 || h->H < 8 || h->W < 8 || h->ncam < 1 || h->ncam > 4 || h->nd < 1 || h->nd > 4 || h->ncam * h->nd > VF_MAX_TASKS)
     return fail(h, VF_ERR_INVALID, "bad sizes (max_samples %d, %dx%d, ncam %d, ndesig %d)", h->B, h->H, h->W, h->ncam, h->nd);
   if (h->adim < 1 || h->adim > 8 || h->sdim < 0 || h->sdim > 16 || h->nz < 0) return fail(h, VF_ERR_INVALID, "bad adim/sdim/nz");

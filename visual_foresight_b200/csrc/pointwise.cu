@@ -28,6 +28,8 @@ __device__ __forceinline__ float4 pooled4(const View& x, int b, int W, int pool,
                      ((a0.z + a1.z) + (a2.z + a3.z)) * 0.25f, ((a0.w + a1.w) + (a2.w + a3.w)) * 0.25f);
 }
 __global__ void __launch_bounds__(256) k_plane_stats(View x, int H, int W, int pool, double* partial) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
   const int cq = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int c = blockIdx.y * 32 + cq * 4;
@@ -70,6 +72,8 @@ __global__ void __launch_bounds__(256) k_plane_stats(View x, int H, int W, int p
 }
 
 __global__ void k_stats_finalize(const double* __restrict__ partial, int n, int S, int npix, float eps, float* stats) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double ts = 0.0, tq = 0.0;
@@ -96,6 +100,8 @@ __device__ __forceinline__ float2 stat_of(const StatsRef& r, long long idx) {
 // one thread = 4 consecutive channels of one output pixel; grid.y = sample
 __global__ void __launch_bounds__(256) k_norm_act(View x, int H, int W, int pool, StatsRef sr,
                                                   const float* __restrict__ gamma, const float* __restrict__ beta, int act, View y) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   const int C4 = x.C >> 2;
   const int total = H * W * C4;
@@ -146,6 +152,8 @@ __device__ __forceinline__ float gate_norm(const View& g, int b, long long pix, 
 __global__ void __launch_bounds__(256) k_lstm_gates(View gates, int HW, int F, StatsRef gsr,
                                                     const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c,
                                                     double* partial) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   const int lanes = 256 / F;
   const int f = threadIdx.x % F, pl = threadIdx.x / F;
@@ -157,7 +165,22 @@ __global__ void __launch_bounds__(256) k_lstm_gates(View gates, int HW, int F, S
   const float mi = si.x, ri = si.y, mj = sj.x, rj = sj.y, mf = sf.x, rf = sf.y;
   const float gi_g = gg[f], gi_b = gb[f], gj_g = gg[F + f], gj_b = gb[F + f], gf_g = gg[2 * F + f], gf_b = gb[2 * F + f];
   double s = 0.0, q = 0.0;
-  for (int pix = p0 + pl; pix < p1; pix += lanes) {
+  int pix = p0 + pl;
+  for (; pix + lanes < p1; pix += 2 * lanes) {              // two pixels in flight per thread
+    const float* gp = vptr(gates, b, pix);
+    const float* gq = vptr(gates, b, pix + lanes);
+    const float a0 = __ldg(gp + f), a1 = __ldg(gp + F + f), a2 = __ldg(gp + 2 * F + f);
+    const float e0 = __ldg(gq + f), e1 = __ldg(gq + F + f), e2 = __ldg(gq + 2 * F + f);
+    const int i0 = pix * F + f, i1 = (pix + lanes) * F + f;
+    const float c0 = cb_[i0], c1 = cb_[i1];
+    const float cn0 = c0 * sigmoidf_((a2 - mf) * rf * gf_g + gf_b + fb) + sigmoidf_((a0 - mi) * ri * gi_g + gi_b) * tanhf((a1 - mj) * rj * gj_g + gj_b);
+    const float cn1 = c1 * sigmoidf_((e2 - mf) * rf * gf_g + gf_b + fb) + sigmoidf_((e0 - mi) * ri * gi_g + gi_b) * tanhf((e1 - mj) * rj * gj_g + gj_b);
+    cb_[i0] = cn0;
+    cb_[i1] = cn1;
+    s += (double)cn0; q = fma((double)cn0, (double)cn0, q);
+    s += (double)cn1; q = fma((double)cn1, (double)cn1, q);
+  }
+  for (; pix < p1; pix += lanes) {
     const float* gp = vptr(gates, b, pix);
     const float gi = (__ldg(gp + f) - mi) * ri * gi_g + gi_b;
     const float gj = (__ldg(gp + F + f) - mj) * rj * gj_g + gj_b;
@@ -199,6 +222,8 @@ __global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, Sta
                                                   const float* __restrict__ gg, const float* __restrict__ gb,
                                                   StatsRef csr, const float* __restrict__ cg,
                                                   const float* __restrict__ cb, float* c, View h) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   const int total = HW * F;
   float* cb_ = c + (long long)b * total;
@@ -210,12 +235,24 @@ __global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, Sta
     ca[f] = cs.x; cd[f] = cs.y; oa[f] = os.x; od[f] = os.y;
   }
   __syncthreads();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int f = i % F, pix = i / F;
-    const float cn = (cb_[i] - ca[f]) * cd[f] * cg[f] + cb[f];
-    cb_[i] = cn;
-    const float go = (__ldg(vptr(gates, b, pix) + 3 * F + f) - oa[f]) * od[f] * gg[3 * F + f] + gb[3 * F + f];
-    vst1(h, voff(h, b, pix) + f, tanhf(cn) * sigmoidf_(go));
+  // one thread = 4 consecutive channels of one pixel (16-byte accesses)
+  const int F4 = F >> 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (total >> 2); i += gridDim.x * blockDim.x) {
+    const int f = (i % F4) << 2, pix = i / F4;
+    float4* cp = reinterpret_cast<float4*>(cb_ + (long long)pix * F + f);
+    const float4 cv = *cp;
+    const float4 ov = __ldg(reinterpret_cast<const float4*>(vptr(gates, b, pix) + 3 * F + f));
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(cg + f)), b4 = __ldg(reinterpret_cast<const float4*>(cb + f));
+    const float4 og = __ldg(reinterpret_cast<const float4*>(gg + 3 * F + f)), ob = __ldg(reinterpret_cast<const float4*>(gb + 3 * F + f));
+    float4 cn, hv;
+    cn.x = (cv.x - ca[f]) * cd[f] * g4.x + b4.x;             cn.y = (cv.y - ca[f + 1]) * cd[f + 1] * g4.y + b4.y;
+    cn.z = (cv.z - ca[f + 2]) * cd[f + 2] * g4.z + b4.z;     cn.w = (cv.w - ca[f + 3]) * cd[f + 3] * g4.w + b4.w;
+    *cp = cn;
+    hv.x = tanhf(cn.x) * sigmoidf_((ov.x - oa[f]) * od[f] * og.x + ob.x);
+    hv.y = tanhf(cn.y) * sigmoidf_((ov.y - oa[f + 1]) * od[f + 1] * og.y + ob.y);
+    hv.z = tanhf(cn.z) * sigmoidf_((ov.z - oa[f + 2]) * od[f + 2] * og.z + ob.z);
+    hv.w = tanhf(cn.w) * sigmoidf_((ov.w - oa[f + 3]) * od[f + 3] * og.w + ob.w);
+    vst4(h, voff(h, b, pix) + f, hv);
   }
 }
 
@@ -241,6 +278,8 @@ __device__ __forceinline__ float4 bil4(float hl0, float hl1, float wl0, float wl
 // one thread = V (4 or 8) consecutive channels of one output pixel (both sources have C % V == 0); grid.y = sample
 template <int V>
 __global__ void __launch_bounds__(256) k_upsample2x(View s0, View s1, int H, int W, View out) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   const int C = s0.C + s1.C, CV = C / V;
   const int Ho = 2 * H, Wo = 2 * W;
@@ -272,6 +311,8 @@ __global__ void __launch_bounds__(256) k_upsample2x(View s0, View s1, int H, int
 
 // sa[m] = concat(action_tau, state_tau[, z_tau]);  gen_state = dense(concat(action, state))   (P1, P9)
 __global__ void k_build_sa(SaArgs a, int M, int tau) {
+  pdl_wait();
+  pdl_trigger();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const int A = a.adim + a.sdim + a.nz;
@@ -315,6 +356,8 @@ __global__ void k_sabias(const float* __restrict__ sa, int A, const float* __res
 
 // every layer's border-class bias of one cell step in ONE launch: grid.y = layer
 __global__ void k_sabias_batch(SabiasBatch a) {
+  pdl_wait();
+  pdl_trigger();
   const SabiasBatch::Layer L = a.L[blockIdx.y];
   const long long total = (long long)a.B * L.ncls * L.Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -339,6 +382,8 @@ __global__ void k_pack_rgb2(View image, View first, int HW, View out) {
   vst4(out, o + 4, make_float4(__ldg(fp + 1), __ldg(fp + 2), 0.f, 0.f));
 }
 __global__ void k_pack_fold(View image, View first, int H, int W, int kf, View out) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * W * kf) return;
@@ -404,7 +449,7 @@ int launch_plane_stats(View x, int B, int H, int W, int pool, double* partial, c
   int S = npix >= 2048 ? 8 : (npix >= 512 ? 4 : (npix >= 128 ? 2 : 1));
   while (S < STATS_MAX_SPLIT && (long long)B * ((x.C + 31) / 32) * S < 296 && npix / (2 * S) >= 16) S *= 2;   // fill the 148 SMs
   dim3 grid(B, (x.C + 31) / 32, S);                 // requires C % 4 == 0 and 16-byte aligned pixel rows (all conv outputs)
-  k_plane_stats<<<grid, 256, 0, s>>>(x, H, W, pool, partial);
+  launch_k(k_plane_stats, dim3(grid), dim3(256), 0, s, x, H, W, pool, partial);
   return S;
 }
 size_t plane_stats_partial_doubles(int B, int C) { return (size_t)B * C * 16 * 2; }   // up to 16 slots per (sample, channel)
@@ -413,14 +458,14 @@ void launch_norm_act(View x, int B, int H, int W, int pool, StatsRef stats, cons
   ++g_launch_counter;
   // few, long-lived blocks per sample: every block stages the sample's statistics in shared memory first
   dim3 grid(grid_for((long long)H * W * (x.C >> 2), 256, B >= 64 ? 16 : 64), B);
-  k_norm_act<<<grid, 256, 0, s>>>(x, H, W, pool, stats, gamma, beta, act, y);
+  launch_k(k_norm_act, dim3(grid), dim3(256), 0, s, x, H, W, pool, stats, gamma, beta, act, y);
 }
 int launch_lstm_gates(View gates, int B, int HW, int F, StatsRef gstats, const float* gg, const float* gb,
                       float fb, float* c, double* partial, cudaStream_t s) {
   ++g_launch_counter;
   int S = HW >= 1024 ? 8 : (HW >= 256 ? 4 : (HW >= 64 ? 2 : 1));      // pixel blocks per sample = stats partial slots
   dim3 grid(S, B);
-  k_lstm_gates<<<grid, 256, 0, s>>>(gates, HW, F, gstats, gg, gb, fb, c, partial);
+  launch_k(k_lstm_gates, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, fb, c, partial);
   return S;
 }
 void launch_lstm_gates_generic(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
@@ -431,28 +476,28 @@ void launch_lstm_gates_generic(View gates, int B, int HW, int F, const float* gs
 }
 void launch_stats_finalize(const double* partial, int n, int S, int npix, float eps, float* stats, cudaStream_t s) {
   ++g_launch_counter;
-  k_stats_finalize<<<(n + 255) / 256, 256, 0, s>>>(partial, n, S, npix, eps, stats);
+  launch_k(k_stats_finalize, dim3((n + 255) / 256), dim3(256), 0, s, partial, n, S, npix, eps, stats);
 }
 void launch_lstm_out(View gates, int B, int HW, int F, StatsRef gstats, const float* gg, const float* gb,
                      StatsRef cstats, const float* cg, const float* cb, float* c, View h, cudaStream_t s) {
   ++g_launch_counter;
-  dim3 grid(grid_for((long long)HW * F, 256, B >= 64 ? 16 : 64), B);
-  k_lstm_out<<<grid, 256, 0, s>>>(gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h);
+  dim3 grid(grid_for((long long)HW * F / 4, 256, B >= 64 ? 16 : 64), B);
+  launch_k(k_lstm_out, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h);
 }
 void launch_upsample2x(View s0, View s1, int B, int H, int W, View out, cudaStream_t s) {
   ++g_launch_counter;
   auto al8 = [](const View& v) { return v.C == 0 || ((v.C | v.ch_off | v.pix_stride) % 8 == 0 && v.sample_stride % 8 == 0 && v.lo_off % 8 == 0); };
   if (al8(s0) && al8(s1) && al8(out)) {
     dim3 grid(grid_for((long long)4 * H * W * ((s0.C + s1.C) >> 3), 256, 64), B);
-    k_upsample2x<8><<<grid, 256, 0, s>>>(s0, s1, H, W, out);
+    launch_k(k_upsample2x<8>, dim3(grid), dim3(256), 0, s, s0, s1, H, W, out);
   } else {
     dim3 grid(grid_for((long long)4 * H * W * ((s0.C + s1.C) >> 2), 256, 64), B);
-    k_upsample2x<4><<<grid, 256, 0, s>>>(s0, s1, H, W, out);
+    launch_k(k_upsample2x<4>, dim3(grid), dim3(256), 0, s, s0, s1, H, W, out);
   }
 }
 void launch_build_sa(const SaArgs& a, int M, int tau, cudaStream_t s) {
   ++g_launch_counter;
-  k_build_sa<<<(M + 127) / 128, 128, 0, s>>>(a, M, tau);
+  launch_k(k_build_sa, dim3((M + 127) / 128), dim3(128), 0, s, a, M, tau);
 }
 void launch_sabias_batch(const SabiasBatch& a, cudaStream_t s) {
   if (a.n == 0) return;
@@ -460,7 +505,7 @@ void launch_sabias_batch(const SabiasBatch& a, cudaStream_t s) {
   long long mx = 1;
   for (int i = 0; i < a.n; ++i) mx = std::max(mx, (long long)a.B * a.L[i].ncls * a.L[i].Cout);
   dim3 grid(grid_for(mx, 256, 148 * 8), a.n);
-  k_sabias_batch<<<grid, 256, 0, s>>>(a);
+  launch_k(k_sabias_batch, dim3(grid), dim3(256), 0, s, a);
 }
 void launch_sabias(const float* sa, int A, const float* wcls, const float* bias, int ncls, int Cout, int B,
                    float* out, cudaStream_t s) {
@@ -480,7 +525,7 @@ void launch_dense_to_view(const float* src, int B, int HW, View v, cudaStream_t 
 void launch_pack_fold(View image, View first, int B, int H, int W, int kf, View out, cudaStream_t s) {
   ++g_launch_counter;
   dim3 grid((H * W * kf + 255) / 256, B);
-  k_pack_fold<<<grid, 256, 0, s>>>(image, first, H, W, kf, out);
+  launch_k(k_pack_fold, dim3(grid), dim3(256), 0, s, image, first, H, W, kf, out);
 }
 void launch_pack_rgb2(View image, View first, int B, int HW, View out, cudaStream_t s) {
   ++g_launch_counter;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace vf {
 
@@ -30,6 +31,24 @@ __host__ __device__ inline View make_view(float* p, long long ss, int ps, int co
 }
 
 #ifdef __CUDACC__
+// Programmatic dependent launch: every rollout kernel starts with pdl_wait() (blocks until the kernels it depends on have
+// completed and flushed) and pdl_trigger() (lets the next kernel's launch + prologue overlap this kernel).  Without the launch
+// attribute both are no-ops, so the kernels behave identically under plain stream ordering.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+extern bool g_use_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 // element offset of (b, pix, channel 0 of the view)
 __device__ __forceinline__ long long voff(const View& v, int b, long long pix) {
   return (long long)b * v.sample_stride + pix * v.pix_stride + v.ch_off;
