@@ -243,6 +243,10 @@ def run_ours(args, rank, world, local_rank):
     prof = be.engine.profile_read()
     be.engine.profile_enable(False)
     peak_tf, peak_hbm, peak_src = measured_peaks()
+    traffic = None                                   # DRAM bytes per gate-conv launch from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     fl = S.flops_per_sample_step(spec)
     alg_lstm = fl["conv_lstm"] * spec.n_steps * M_local * CFG["iters"]          # algorithmic flops of the profiled plan's LSTM convs
     lstm_ms = prof["lstm_conv"]["ms"]
@@ -250,7 +254,9 @@ def run_ours(args, rank, world, local_rank):
     plan_ms_prof = None
     roofline = {"bound": "tensor", "kernel": "conv-LSTM gate convolution (%s)" % args.precision,
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": peak_src + " bf16 sustained",
-                "traffic": None, "launches": prof["lstm_conv"]["launches"], "ms_per_launch": lstm_ms / max(prof["lstm_conv"]["launches"], 1),
+                "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read+write, mean of the 5 gate convs)",
+                "effective_peak_x3": peak_tf / 3.0, "frac_of_x3_peak": ach / (peak_tf / 3.0),
+                "launches": prof["lstm_conv"]["launches"], "ms_per_launch": lstm_ms / max(prof["lstm_conv"]["launches"], 1),
                 "share_of_step": lstm_ms / (ms / args.steps), "other_conv_ms": prof["other_conv"]["ms"],
                 "algorithmic_flops_per_launch": alg_lstm / max(prof["lstm_conv"]["launches"], 1),
                 "whole_plan_frac": (S.flops_per_plan(spec, M_local, CFG["iters"]) / (ms / args.steps * 1e-3) / 1e12) / peak_tf}
