@@ -111,7 +111,14 @@ typedef struct vf_cem_params {
   double task_weights[VF_MAX_TASKS];/* per (cam, desig); 1/n reproduces np.mean, pixel_cost_controller.py:153 */
   uint64_t seed;                    /* Philox key */
   uint32_t plan_index;              /* Philox counter word: MPC step */
-  int32_t reserved[8];
+  /* Stochastic planning (nz > 0, BASELINE config c5): every action sequence is rolled k_futures times with independent
+   * latents z ~ N(0, I) (consecutive copies, the order of np.repeat(actions, K, 0) in samplers/gaussian_sampler.py:139-141)
+   * and scored by mean_k + lambda_variance * var_k (variants/ensemble_vidpred.py:56-58).  0 or 1 = one future.
+   * num_samples * k_futures <= max_samples.  Latents are Philox draws keyed by the GLOBAL rollout index, so sharded plans
+   * stay bit-identical. */
+  int32_t k_futures;
+  float lambda_variance;
+  int32_t reserved[6];
 } vf_cem_params;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */

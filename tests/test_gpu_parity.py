@@ -161,6 +161,85 @@ def test_rollout_c1_config_vs_oracle():
     e.close()
 
 
+def test_rollout_128px_spec_tensor_core_vs_oracle():
+    """BASELINE c5 geometry family: 128x128 frames, 4-level encoder whose first layer is not recurrent, 256-channel
+    conv-LSTMs (gate convs with 1024 output channels) on the tensor-core path — frames within 1e-4 of the fp32 oracle."""
+    sp = S.spec_128(seq_len=4)
+    w = Hh.make_weights(sp, seed=2)
+    inp = Hh.synth_inputs(sp, seed=4)
+    acts = Hh.gaussian_actions(sp, 2, 15, seed=6)
+    e, (gi, gd, gs) = _engine_rollout(sp, w, inp, acts, precision="f16x3")
+    oi, od, os_ = Hh.oracle_rollout(sp, w, inp, acts)
+    assert np.abs(gi - oi).max() <= FRAME_TOL
+    assert np.abs(gd - od).max() <= 1e-5
+    np.testing.assert_allclose(gs, os_, atol=1e-5)
+    e.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "f16x3"])
+def test_rollout_with_latents_vs_oracle(precision):
+    """stochastic predictor input (nz > 0): the per-step latent z is tiled into every conv like the action/state vector
+    (spec P1); identical z on both sides -> frames within 1e-4."""
+    import torch
+    from oracle.predictor import OracleMultiViewPredictor
+    from visual_foresight_b200.engine import Engine
+    sp = S.spec_64(height=32, width=32, seq_len=5, nz=8)
+    w = Hh.make_weights(sp, seed=11)
+    inp = Hh.synth_inputs(sp, seed=12)
+    M = 3
+    acts = Hh.gaussian_actions(sp, M, 15, seed=13)
+    zs = np.random.default_rng(14).standard_normal((M, sp.seq_len - 1, sp.nz)).astype(np.float32)
+    e = Engine(sp, M, precision=precision)
+    e.load_weights(w)
+    e.set_context(inp["frames"], inp["states"], inp["ctx_actions"])
+    e.set_desig(inp["desig"])
+    gi, gd, gs = e.predict(acts, zs=zs)
+    onehot = OC.switch_on_pix(inp["desig"], sp.context_frames, sp.ncam, sp.height, sp.width, sp.ndesig)
+    oi, od, os_ = OracleMultiViewPredictor(sp, w, torch.float32).rollout(
+        inp["frames"].astype(np.float32) / 255.0, inp["states"], onehot, Hh.step_actions(sp, inp["ctx_actions"], acts), zs)
+    assert np.abs(gi - oi).max() <= FRAME_TOL
+    assert np.abs(gd - od).max() <= 1e-5
+    z2 = zs.copy()
+    z2[1] += 1.0                                             # the latent really is an input: changing it changes the frames
+    gi2 = e.predict(acts, zs=z2)[0]
+    assert np.abs(gi2[1] - gi[1]).max() > 1e-4 and np.abs(gi2[0] - gi[0]).max() == 0.0
+    e.close()
+
+
+@pytest.mark.parametrize("name,kw,M", [
+    ("c3", dict(height=48, width=64, seq_len=13, ncam=2, ndesig=2, adim=4, sdim=5), 600),      # Sawyer two-view, full size
+    ("c4-shard", dict(height=64, width=64, seq_len=15), 512),                                  # M=4096 / 8 GPUs
+])
+def test_full_size_configs_batch_invariance(name, kw, M):
+    """BASELINE c3 / one c4 shard at FULL sample count on the tensor-core path: the oracle only rolls three of the samples
+    (first, middle, last); every sample's distributions stay normalised, scores are finite, equal action rows give equal
+    frames (batch-position invariance), and the elite set equals the stable argsort of the device scores."""
+    from visual_foresight_b200.engine import Engine
+    sp = S.spec_64(**kw)
+    w = Hh.make_weights(sp, seed=21)
+    inp = Hh.synth_inputs(sp, seed=22)
+    acts = Hh.gaussian_actions(sp, M, 15, seed=23)
+    acts[M - 2] = acts[1]                                    # duplicate action row at another batch position
+    e = Engine(sp, M, precision="f16x3")
+    e.load_weights(w)
+    e.set_context(inp["frames"], inp["states"] if sp.sdim else None, inp["ctx_actions"])
+    e.set_desig(inp["desig"])
+    e.predict(acts, fetch=False)
+    pick = [0, M // 2, M - 1, 1, M - 2]
+    gi, gd = e.fetch(pick)
+    oi, od, _ = Hh.oracle_rollout(sp, w, inp, acts[pick[:3]])
+    assert np.abs(gi[:3] - oi).max() <= FRAME_TOL, name
+    assert np.abs(gd[:3] - od).max() <= 1e-5
+    np.testing.assert_array_equal(gi[3], gi[4])
+    np.testing.assert_array_equal(gd[3], gd[4])
+    sc = e.score(inp["goal"], M=M)
+    assert sc.shape == (M,) and np.all(np.isfinite(sc))
+    np.testing.assert_allclose(sc[pick[:3]], OC.eval_pixel_cost(od, inp["goal"]), rtol=1e-5)
+    K = max(10, M // 20)
+    np.testing.assert_array_equal(e.topk(sc, K), np.argsort(sc, kind="stable")[:K])
+    e.close()
+
+
 # ---- CEM ------------------------------------------------------------------------------------------------
 def _plan_kwargs(sp, M, K, iters, seed=0):
     from visual_foresight_b200.samplers import GaussianCEMSampler, action_bounds, per_dim_variance
@@ -196,6 +275,47 @@ def test_cem_plan_vs_oracle_explicit_noise():
     np.testing.assert_array_equal(res["elite_idx"], idx)
     np.testing.assert_allclose(res["best_actions"], best, rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(be.engine.cem_actions(), all_actions[-1], rtol=1e-12, atol=1e-15)
+    be.engine.close()
+
+
+def test_stochastic_plan_futures_vs_oracle():
+    """Stochastic planning (BASELINE c5 family: nz = 8, K futures per action sequence): the device plan equals the oracle
+    plan that rolls np.repeat(actions, K, 0) with the restated Philox latents and scores mean_k + lambda * var_k —
+    per-sequence scores within tolerance, elite sets bit-exact, best actions equal."""
+    import torch
+    from oracle.predictor import OracleMultiViewPredictor
+    from visual_foresight_b200.predictor import EngineBackend
+    sp = S.spec_64(height=32, width=32, seq_len=6, nz=8)
+    w = Hh.make_weights(sp, seed=31)
+    inp = Hh.synth_inputs(sp, seed=32)
+    M, K, iters, KF, LAM, SEED, PLAN = 6, 2, 2, 3, 0.5, 77, 4
+    kw = _plan_kwargs(sp, M, K, iters, seed=SEED)
+    kw["plan_index"] = PLAN
+    noise = np.random.default_rng(33).standard_normal((iters, M, 20)).astype(np.float32)
+    be = EngineBackend(sp, w, M * KF, precision="fp32_simt")
+    onehot = OC.switch_on_pix(inp["desig"], 2, 1, 32, 32, 1)
+    ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"],
+           "context_pixel_distributions": onehot}
+    res = be.plan(ctx, goal_pix=inp["goal"], noise=noise, k_futures=KF, lambda_variance=LAM, **kw)
+    oracle = OracleMultiViewPredictor(sp, w, torch.float32)
+    it = [0]
+
+    def evaluate(actions):
+        rep = np.repeat(actions.astype(np.float32), KF, axis=0)
+        zs = OC.philox_latents(SEED, PLAN, it[0], M * KF, sp.seq_len - 1, sp.nz)
+        it[0] += 1
+        _, od, _ = oracle.rollout(inp["frames"].astype(np.float32) / 255.0, inp["states"], onehot,
+                                  Hh.step_actions(sp, inp["ctx_actions"], rep), zs)
+        return OC.reduce_futures(OC.eval_pixel_cost(od, inp["goal"]), KF, LAM)
+    best, idx, scores, all_actions = OC.cem_plan(evaluate, num_samples=M, iterations=iters, num_elites_k=K, nactions=5,
+                                                 repeat=3, adim=4, std=kw["std"], noise=noise, clip=kw["clip"])
+    np.testing.assert_allclose(res["scores"], scores, rtol=1e-5)
+    np.testing.assert_array_equal(res["elite_idx"], idx)
+    np.testing.assert_allclose(res["best_actions"], best, rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(be.engine.cem_actions(), all_actions[-1], rtol=1e-12, atol=1e-15)
+    # the futures of one action sequence really differ (the latent reaches the frames)
+    gi, _ = be.engine.fetch([0, 1])
+    assert np.abs(gi[0] - gi[1]).max() > 1e-5
     be.engine.close()
 
 

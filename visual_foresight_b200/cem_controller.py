@@ -198,7 +198,10 @@ class PixelCostController(CEMBaseController):
                          verbose_img_height=128, predictor_propagation=False, only_take_first_view=False,
                          state_append=None, finalweight=10., use_predictor_ncam=False, device_cem=True,
                          cem_seed=0, task_weights=None, log_to_stdout=False, model_spec=None, model_seed=0,
-                         precision="f16x3").items():
+                         precision="f16x3",
+                         # stochastic planning (samplers/gaussian_sampler.py:139-141 repeats every action sequence K times;
+                         # variants/ensemble_vidpred.py:56-58 scores mean + lambda * var): futures per action sequence
+                         num_futures=1, lambda_variance=0.0).items():
             hp.add_hparam(k, v)
         return hp
 
@@ -289,13 +292,13 @@ class PixelCostController(CEMBaseController):
             clip=(lo, hi) if hp.action_bound else None, mean0=mean0,
             reduce_std_scale=(hp.reduce_std_dev if (self._t is not None and self._t >= 2) else 1.0),
             goal_pix=self._goal_pix, finalweight=hp.finalweight, task_weights=self._task_weights(),
-            seed=hp.cem_seed, plan_index=self._plan_counter)
+            seed=hp.cem_seed, plan_index=self._plan_counter, k_futures=hp.num_futures, lambda_variance=hp.lambda_variance)
         self._plan_counter += 1
         self._best_actions, self._best_indices = res["best_actions"], res["elite_idx"]
         for i in range(self._n_iter):
             self.plan_stat["scores_itr{}".format(i)] = res["scores"][i]
         if hp.predictor_propagation:
-            self._chosen_distrib = self._backend.fetch_distrib(int(self._best_indices[0]))
+            self._chosen_distrib = self._backend.fetch_distrib(int(self._best_indices[0]) * max(int(hp.num_futures), 1))
         if self._verbose_condition(self._n_iter - 1):
             self._export_verbose(res["scores"][-1])
         self._t_since_replan = 0

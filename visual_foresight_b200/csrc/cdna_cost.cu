@@ -17,7 +17,7 @@ __device__ __forceinline__ int mirror(int i, int n) { return i < 0 ? -1 - i : (i
 // Split-K partial products: grid (K slices of CK_KC, sample groups of CK_S) fills the 148 SMs (c2: 16 x 25 blocks); every
 // weight element fetched from L2 feeds CK_S FMAs.  part[ks][b][128] is combined in a fixed order by cdna_finalize(), which
 // the consumers (CDNA apply) run in their prologue: no separate finalize launch.
-constexpr int CK_S = 8, CK_KC = 512;
+constexpr int CK_S = 8, CK_KC = 256;
 __global__ void __launch_bounds__(256) k_cdna_partial(View feat, int npix, const float* __restrict__ w, int nout, int B,
                                                       float* __restrict__ part) {
   pdl_wait();
@@ -65,7 +65,13 @@ __device__ __forceinline__ void cdna_finalize(const float* __restrict__ part, in
   const int kk = ksize * ksize, nout = kk * nt, j = threadIdx.x;
   if (j < nout) {
     float v = bias[j];
-    for (int ks = 0; ks < nks; ++ks) v += part[((long long)ks * B + b) * 128 + j];       // fixed order
+    for (int k0 = 0; k0 < nks; k0 += 8) {                    // 8 independent loads in flight, summed in a fixed order
+      float pv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pv[u] = k0 + u < nks ? __ldg(part + ((long long)(k0 + u) * B + b) * 128 + j) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += pv[u];
+    }
     if (j / nt == (ksize / 2) * ksize + ksize / 2) v += 1.0f;
     tmp[j] = fmaxf(v - 1e-12f, 0.f) + 1e-12f;
   }
@@ -190,19 +196,22 @@ constexpr int COMP_THREADS = 256;
 // Block = (band of TR rows, sample); the previous distribution's band (+halo, SYMMETRIC-mirrored) is staged in shared
 // memory; kernels as [tap][nt].  Per-thread sums of the raw distribution are combined by a fixed shuffle tree + fixed
 // warp order -> partial[b][p][band].
+// NTT > 0: compile-time transformed-image count (the mask / kernel arrays live in registers); NTT == 0: generic
+template <int NTT>
 __global__ void __launch_bounds__(COMP_THREADS) k_composite(CompositeArgs a, int TR) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float smc[];
   __shared__ float red[COMP_THREADS / 32];
   const int b = blockIdx.y, y0 = blockIdx.x * TR;
-  const int kk = a.ksize * a.ksize, nm = a.nt + 3, pad = a.ksize / 2, W = a.W, H = a.H;
+  const int nt = NTT > 0 ? NTT : a.nt;
+  const int kk = a.ksize * a.ksize, nm = nt + 3, pad = a.ksize / 2, W = a.W, H = a.H;
   const int BR = TR + 2 * pad;
   float* sk = smc;                         // [kk][nt]
-  float* band = smc + ((kk * a.nt + 3) & ~3);   // [nd][BR][W]
-  for (int i = threadIdx.x; i < a.nt * kk; i += COMP_THREADS) {
-    const int t = i / a.nt, n = i - t * a.nt;
-    sk[i] = a.kern[((long long)b * a.nt + n) * kk + t];
+  float* band = smc + ((kk * nt + 3) & ~3);   // [nd][BR][W]
+  for (int i = threadIdx.x; i < nt * kk; i += COMP_THREADS) {
+    const int t = i / nt, n = i - t * nt;
+    sk[i] = a.kern[((long long)b * nt + n) * kk + t];
   }
   for (int i = threadIdx.x; i < a.nd * BR * W; i += COMP_THREADS) {
     const int p = i / (BR * W), rem = i - p * BR * W, r = rem / W, x = rem - r * W;
@@ -218,10 +227,10 @@ __global__ void __launch_bounds__(COMP_THREADS) k_composite(CompositeArgs a, int
     float m[16];
     const float* lg = vptr(a.logits, b, pix);
     float mx = -3.4e38f;
-    for (int n = 0; n < nm; ++n) { m[n] = __ldg(lg + n); mx = fmaxf(mx, m[n]); }
+    _Pragma("unroll") for (int n = 0; n < nm; ++n) { m[n] = __ldg(lg + n); mx = fmaxf(mx, m[n]); }
     float se = 0.f;
-    for (int n = 0; n < nm; ++n) { m[n] = expf(m[n] - mx); se += m[n]; }
-    for (int n = 0; n < nm; ++n) m[n] = m[n] / se;
+    _Pragma("unroll") for (int n = 0; n < nm; ++n) { m[n] = expf(m[n] - mx); se += m[n]; }
+    _Pragma("unroll") for (int n = 0; n < nm; ++n) m[n] = m[n] / se;
     const long long lo = voff(a.layers, b, pix);
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
     if (nm == 7) {                           // 21 channels = 6 vector loads (the buffer is padded to 24 channels)
@@ -234,7 +243,7 @@ __global__ void __launch_bounds__(COMP_THREADS) k_composite(CompositeArgs a, int
 #pragma unroll
       for (int n = 0; n < 7; ++n) { g0 += m[n] * l[3 * n]; g1 += m[n] * l[3 * n + 1]; g2 += m[n] * l[3 * n + 2]; }
     } else {
-      for (int n = 0; n < nm; ++n) {
+      _Pragma("unroll") for (int n = 0; n < nm; ++n) {
         g0 += m[n] * vld1(a.layers, lo + 3 * n);
         g1 += m[n] * vld1(a.layers, lo + 3 * n + 1);
         g2 += m[n] * vld1(a.layers, lo + 3 * n + 2);
@@ -246,19 +255,20 @@ __global__ void __launch_bounds__(COMP_THREADS) k_composite(CompositeArgs a, int
     for (int p = 0; p < a.nd; ++p) {
       const float* bp = band + p * BR * W;
       float t[8];
-      for (int n = 0; n < a.nt; ++n) t[n] = 0.f;
-      for (int u = 0; u < a.ksize; ++u)
-        for (int v = 0; v < a.ksize; ++v) {
+      _Pragma("unroll") for (int n = 0; n < nt; ++n) t[n] = 0.f;
+      const int ks = NTT > 0 ? 5 : a.ksize;        // the specialised instance is the 5x5 CDNA kernel
+      _Pragma("unroll") for (int u = 0; u < ks; ++u)
+        _Pragma("unroll") for (int v = 0; v < ks; ++v) {
           const float d = bp[(r + u) * W + mirror(x + v - pad, W)];
-          const float* kp = sk + (u * a.ksize + v) * a.nt;
-          for (int n = 0; n < a.nt; ++n) t[n] = fmaf(d, kp[n], t[n]);
+          const float* kp = sk + (u * a.ksize + v) * nt;
+          _Pragma("unroll") for (int n = 0; n < nt; ++n) t[n] = fmaf(d, kp[n], t[n]);
         }
       const float pd = bp[(r + pad) * W + x], fd = __ldg(vptr(a.first_d, b, pix) + p);
       float v = 0.f;
-      for (int n = 0; n < a.nt; ++n) v += m[n] * t[n];
-      v += m[a.nt] * pd;
-      v += m[a.nt + 1] * fd;
-      v += m[a.nt + 2] * pd;
+      _Pragma("unroll") for (int n = 0; n < nt; ++n) v += m[n] * t[n];
+      v += m[nt] * pd;
+      v += m[nt + 1] * fd;
+      v += m[nt + 2] * pd;
       gd[p] = v;
       dsum[p] += v;
     }
@@ -373,9 +383,14 @@ __global__ void __launch_bounds__(256) k_goal_image_cost(const float* __restrict
 
 }  // namespace
 
-inline int band_rows(int H, int W) {                 // rows per block of the banded CDNA / composite kernels
-  int tr = 16;
-  while (tr > 4 && (long long)(tr + 4) * W * 16 > 40 * 1024) tr /= 2;
+inline int band_rows(int H, int W) {                 // rows per block of the banded CDNA-apply kernel (1-2 pixels per thread)
+  int tr = 8;
+  while (tr > 2 && tr * W > 512) tr /= 2;
+  return tr;
+}
+inline int comp_rows(int H, int W) {                 // rows per block of the composite kernel (one pixel per thread)
+  int tr = 8;
+  while (tr > 1 && tr * W > COMP_THREADS) tr /= 2;
   return tr;
 }
 size_t cdna_partial_floats(int K, int B) { return (size_t)((K + CK_KC - 1) / CK_KC) * B * 128; }
@@ -399,13 +414,14 @@ void launch_cdna_apply(View image, View first, const float* part, int K, const f
     k_cdna_apply<<<grid, 128, 0, s>>>(image, first, part, nks, bias, ksize, nt, B, H, W, layers, kern);
   }
 }
-int composite_blocks(int H, int W) { const int TR = band_rows(H, W); return (H + TR - 1) / TR; }
+int composite_blocks(int H, int W) { const int TR = comp_rows(H, W); return (H + TR - 1) / TR; }
 void launch_composite(const CompositeArgs& a, int B, cudaStream_t s) {
   ++g_launch_counter;
-  const int TR = band_rows(a.H, a.W);
+  const int TR = comp_rows(a.H, a.W);
   dim3 grid((a.H + TR - 1) / TR, B);
   const size_t smem = (size_t)(((a.nt * a.ksize * a.ksize + 3) & ~3) + a.nd * (TR + a.ksize - 1) * a.W) * sizeof(float);
-  launch_k(k_composite, dim3(grid), dim3(COMP_THREADS), smem, s, a, TR);
+  if (a.nt == 4 && a.ksize == 5) launch_k(k_composite<4>, dim3(grid), dim3(COMP_THREADS), smem, s, a, TR);
+  else launch_k(k_composite<0>, dim3(grid), dim3(COMP_THREADS), smem, s, a, TR);
 }
 void launch_distrib_normalize(View d, const float* partial, int nblk, int B, int H, int W, int nd, cudaStream_t s) {
   ++g_launch_counter;

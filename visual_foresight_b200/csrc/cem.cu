@@ -41,6 +41,27 @@ __device__ double philox_normal(uint64_t seed, uint32_t plan, uint32_t iter, uin
   return (j & 1) ? r * sin(th) : r * cos(th);
 }
 
+// latent z[r][step][i] ~ N(0,1) for rollout sample r (global index goff + r): the Philox stream of the action noise with
+// bit 30 of the draw-index word set, so latents never collide with action draws
+__global__ void k_sample_latents(float* zs, int n, int steps, int nz, int goff, uint64_t seed, uint32_t plan, uint32_t iter) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n * steps * nz) return;
+  const int r = tid / (steps * nz), j = tid - r * steps * nz;
+  zs[tid] = (float)philox_normal(seed, plan, iter, (uint32_t)(goff + r), 0x80000000u | (uint32_t)j);
+}
+
+// scores[m] = mean_k s[m*K + k] + lambda * var_k (population variance, np.var); fixed summation order
+__global__ void k_reduce_futures(const double* __restrict__ s, int M, int K, double lambda, double* out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double mean = 0.0;
+  for (int k = 0; k < K; ++k) mean += s[(long long)m * K + k];
+  mean /= (double)K;
+  double var = 0.0;
+  for (int k = 0; k < K; ++k) { const double d = s[(long long)m * K + k] - mean; var += d * d; }
+  out[m] = mean + lambda * (var / (double)K);
+}
+
 // thread per (row i, coordinate d)
 __global__ void k_sample_actions(SampleArgs a, int n) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,6 +155,16 @@ void launch_sample_actions(const SampleArgs& a, int n, cudaStream_t s) {
   ++g_launch_counter;
   const int total = n * a.D;
   k_sample_actions<<<(total + 127) / 128, 128, 0, s>>>(a, n);
+}
+void launch_sample_latents(float* zs, int n, int steps, int nz, int goff, uint64_t seed, uint32_t plan, uint32_t iter,
+                           cudaStream_t st) {
+  ++g_launch_counter;
+  const int total = n * steps * nz;
+  k_sample_latents<<<(total + 255) / 256, 256, 0, st>>>(zs, n, steps, nz, goff, seed, plan, iter);
+}
+void launch_reduce_futures(const double* s, int M, int K, double lambda, double* out, cudaStream_t st) {
+  ++g_launch_counter;
+  k_reduce_futures<<<(M + 127) / 128, 128, 0, st>>>(s, M, K, lambda, out);
 }
 int topk_padded(int n) {
   int p = 2;

@@ -130,6 +130,9 @@ struct vf_engine {
   bool cem_has_noise = false;
   int* cem_elite_idx = nullptr;
   double *cem_elites_nr = nullptr, *cem_best64 = nullptr, *cem_local_nr = nullptr, *cem_actions64 = nullptr;
+  int cem_Kf = 1;                   // futures per action sequence (stochastic planning)
+  int* cem_fut_idx = nullptr;       // [B] global action index of every rollout sample
+  double* cem_fut_scores = nullptr; // [B] per-rollout scores before the mean over futures
   double* topk_keys = nullptr;
   int* topk_idx = nullptr;
   size_t topk_cap = 0;
@@ -779,7 +782,8 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
   { const char* e = getenv("VF_PDL"); g_use_pdl = e && e[0] == '1'; }
   if (h->B < 1 || h->H < 8 || h->W < 8 || h->ncam < 1 || h->ncam > 4 || h->nd < 1 || h->nd > 4 || h->ncam * h->nd > VF_MAX_TASKS)
     return fail(h, VF_ERR_INVALID, "bad sizes (max_samples %d, %dx%d, ncam %d, ndesig %d)", h->B, h->H, h->W, h->ncam, h->nd);
-  if (h->adim < 1 || h->adim > 8 || h->sdim < 0 || h->sdim > 16 || h->nz < 0) return fail(h, VF_ERR_INVALID, "bad adim/sdim/nz");
+  if (h->adim < 1 || h->adim > 8 || h->sdim < 0 || h->sdim > 16 || h->nz < 0 || h->A > 24)
+    return fail(h, VF_ERR_INVALID, "bad adim/sdim/nz (adim <= 8, sdim <= 16, adim + sdim + nz <= 24)");
   if (h->C < 1 || h->S <= h->C) return fail(h, VF_ERR_INVALID, "need seq_len > context_frames >= 1");
   if (cfg->n_enc < 1 || cfg->n_enc > VF_MAX_LAYERS || cfg->n_dec != cfg->n_enc) return fail(h, VF_ERR_INVALID, "n_enc/n_dec");
   if ((h->H % (1 << cfg->n_enc)) || (h->W % (1 << cfg->n_enc))) return fail(h, VF_ERR_INVALID, "H, W must be divisible by 2^n_enc");
@@ -982,7 +986,9 @@ static void fill_sample_args(vf_engine* h, SampleArgs& a, int iteration) {
 int vf_cem_begin(vf_engine* h, const vf_cem_params* p, const float* goal, const float* noise) {
   if (!h || !p || !goal) return fail(h, VF_ERR_INVALID, "params and goal are required");
   const int M = p->num_samples, Mg = p->global_samples, K = p->num_elites;
-  if (M < 1 || M > h->B) return fail(h, VF_ERR_INVALID, "num_samples=%d outside [1, max_samples=%d]", M, h->B);
+  const int Kf = p->k_futures > 1 ? p->k_futures : 1;
+  if (M < 1 || (long long)M * Kf > h->B)
+    return fail(h, VF_ERR_INVALID, "num_samples=%d x k_futures=%d outside [1, max_samples=%d]", M, Kf, h->B);
   if (Mg < M || p->sample_offset < 0 || p->sample_offset + M > Mg) return fail(h, VF_ERR_INVALID, "bad shard (offset %d, M %d, global %d)", p->sample_offset, M, Mg);
   if (K < 1 || K > Mg) return fail(h, VF_ERR_INVALID, "num_elites=%d outside [1, %d]", K, Mg);
   if (p->iterations < 1 || p->nactions < 1 || p->repeat < 1) return fail(h, VF_ERR_INVALID, "bad iterations/nactions/repeat");
@@ -1010,6 +1016,14 @@ int vf_cem_begin(vf_engine* h, const vf_cem_params* p, const float* goal, const 
   if (!h->cem_local_nr) { DA(h->cem_local_nr, (size_t)h->B * 128); }
   if (h->cem_T > h->cem_act_cap) { DA(h->cem_actions64, (size_t)h->B * h->cem_T * h->adim); h->cem_act_cap = h->cem_T; }
   if ((size_t)K * h->cem_T * h->adim > (size_t)Mg * 128 * 8) return fail(h, VF_ERR_INVALID, "elite buffer too small");
+  h->cem_Kf = Kf;
+  if (!h->cem_fut_idx) { DA(h->cem_fut_idx, (size_t)h->B); DA(h->cem_fut_scores, (size_t)h->B); }
+  if (Kf > 1) {                                     // rollout sample r evaluates action sequence offset + r / Kf
+    std::vector<int> fi((size_t)M * Kf);
+    for (int r = 0; r < M * Kf; ++r) fi[r] = p->sample_offset + r / Kf;
+    CU(cudaMemcpyAsync(h->cem_fut_idx, fi.data(), sizeof(int) * fi.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   h->cem_has_noise = noise != nullptr;
   if (noise) {
     const size_t nn = (size_t)p->iterations * Mg * h->cem_Dmax;
@@ -1050,21 +1064,27 @@ int vf_cem_iter_rollout(vf_engine* h, int32_t it) {
   if (!h || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
   const vf_cem_params& p = h->cem;
   if (it < 0 || it >= p.iterations) return fail(h, VF_ERR_INVALID, "iteration %d out of range", it);
+  const int Kf = h->cem_Kf, nroll = p.num_samples * Kf;
   SampleArgs a;
   fill_sample_args(h, a, it);
+  if (Kf > 1) a.indices = h->cem_fut_idx;           // consecutive copies of every action sequence (np.repeat order)
   a.out_nr = h->cem_local_nr; a.out_actions = h->actions; a.out_actions64 = h->cem_actions64;
-  launch_sample_actions(a, p.num_samples, h->stream);
+  launch_sample_actions(a, nroll, h->stream);
+  if (h->nz > 0)                                    // latents of the stochastic predictor: Philox, keyed by the global rollout index
+    launch_sample_latents(h->zs, nroll, h->S - 1, h->nz, p.sample_offset * Kf, p.seed, p.plan_index, (uint32_t)it, h->stream);
   h->T = h->cem_T;
-  int r = rollout(h, p.num_samples, h->cem_T);
+  int r = rollout(h, nroll, h->cem_T);
   if (r) return r;
   double* sc = h->cem_scores + (size_t)it * p.global_samples + p.sample_offset;
+  double* raw_sc = Kf > 1 ? h->cem_fut_scores : sc;
   const int ntask = h->ncam * h->nd;
   if (p.cost_kind == VF_COST_PIXEL_DISTANCE) {
-    launch_pixel_cost(h->gen_distrib, p.num_samples, h->P, h->ncam, h->H, h->W, h->nd, h->goal_dev, h->cost, h->stream);
-    launch_score_final(h->cost, p.num_samples, h->P, ntask, h->taskw_dev, (double)p.finalweight, sc, h->stream);
+    launch_pixel_cost(h->gen_distrib, nroll, h->P, h->ncam, h->H, h->W, h->nd, h->goal_dev, h->cost, h->stream);
+    launch_score_final(h->cost, nroll, h->P, ntask, h->taskw_dev, (double)p.finalweight, raw_sc, h->stream);
   } else {
-    launch_goal_image_cost(h->gen_images, p.num_samples, h->P, h->ncam, h->H, h->W, h->goal_img, sc, h->stream);
+    launch_goal_image_cost(h->gen_images, nroll, h->P, h->ncam, h->H, h->W, h->goal_img, raw_sc, h->stream);
   }
+  if (Kf > 1) launch_reduce_futures(raw_sc, p.num_samples, Kf, (double)p.lambda_variance, sc, h->stream);
   CU(cudaGetLastError());
   return VF_OK;
 }
@@ -1127,7 +1147,9 @@ int vf_cem_scores_write(vf_engine* h, int32_t it, int32_t off, int32_t n, const 
 
 int vf_cem_actions(vf_engine* h, double* out) {
   if (!h || !out || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
-  CU(cudaMemcpyAsync(out, h->cem_actions64, sizeof(double) * (size_t)h->cem.num_samples * h->cem_T * h->adim, cudaMemcpyDeviceToHost, h->stream));
+  // with k_futures > 1 every action row appears k_futures times (rollout order); row r belongs to action r / k_futures
+  CU(cudaMemcpyAsync(out, h->cem_actions64, sizeof(double) * (size_t)h->cem.num_samples * h->cem_Kf * h->cem_T * h->adim,
+                     cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return VF_OK;
 }

@@ -354,19 +354,34 @@ __global__ void k_sabias(const float* __restrict__ sa, int A, const float* __res
   }
 }
 
-// every layer's border-class bias of one cell step in ONE launch: grid.y = layer
-__global__ void k_sabias_batch(SabiasBatch a) {
+// every layer's border-class bias of one cell step in ONE launch: grid (row blocks, layer, sample chunks).  A thread owns one
+// (class, channel) row: its A weights stay in registers while it walks SB_CHUNK samples (sa staged in shared memory),
+// stores coalesced along the row index.
+constexpr int SB_CHUNK = 25;
+__global__ void __launch_bounds__(256) k_sabias_batch(SabiasBatch a) {
   pdl_wait();
   pdl_trigger();
   const SabiasBatch::Layer L = a.L[blockIdx.y];
-  const long long total = (long long)a.B * L.ncls * L.Cout;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(i % L.Cout);
-    const int cls = (int)((i / L.Cout) % L.ncls);
-    const int b = (int)(i / ((long long)L.Cout * L.ncls));
+  const int per = L.ncls * L.Cout;
+  const int b0 = blockIdx.z * SB_CHUNK, nb = min(SB_CHUNK, a.B - b0);
+  __shared__ float ssa[SB_CHUNK][24];
+  for (int i = threadIdx.x; i < nb * a.A; i += blockDim.x) ssa[i / a.A][i % a.A] = a.sa[(long long)b0 * a.A + i];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per) return;
+  const int cls = i / L.Cout, n = i - cls * L.Cout;
+  const float* w = L.wcls + (cls * a.A) * L.Cout + n;
+  float wr[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) wr[k] = k < a.A ? __ldg(w + k * L.Cout) : 0.f;
+  const float bias = L.bias ? L.bias[n] : 0.f;
+  float* o = L.out + (long long)b0 * per + i;
+  for (int b = 0; b < nb; ++b) {
     float acc = 0.f;
-    for (int k = 0; k < a.A; ++k) acc = fmaf(a.sa[(long long)b * a.A + k], __ldg(L.wcls + ((long long)cls * a.A + k) * L.Cout + n), acc);
-    L.out[i] = acc + (L.bias ? L.bias[n] : 0.f);
+#pragma unroll
+    for (int k = 0; k < 24; ++k)
+      if (k < a.A) acc = fmaf(ssa[b][k], wr[k], acc);
+    o[(long long)b * per] = acc + bias;
   }
 }
 
@@ -502,9 +517,10 @@ void launch_build_sa(const SaArgs& a, int M, int tau, cudaStream_t s) {
 void launch_sabias_batch(const SabiasBatch& a, cudaStream_t s) {
   if (a.n == 0) return;
   ++g_launch_counter;
-  long long mx = 1;
-  for (int i = 0; i < a.n; ++i) mx = std::max(mx, (long long)a.B * a.L[i].ncls * a.L[i].Cout);
-  dim3 grid(grid_for(mx, 256, 148 * 8), a.n);
+  if (a.A > 24) return;                                      // adim + sdim + nz <= 24 (vf_create)
+  int mx = 1;
+  for (int i = 0; i < a.n; ++i) mx = std::max(mx, a.L[i].ncls * a.L[i].Cout);
+  dim3 grid((mx + 255) / 256, a.n, (a.B + SB_CHUNK - 1) / SB_CHUNK);
   launch_k(k_sabias_batch, dim3(grid), dim3(256), 0, s, a);
 }
 void launch_sabias(const float* sa, int A, const float* wcls, const float* bias, int ncls, int Cout, int B,

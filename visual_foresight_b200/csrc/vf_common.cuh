@@ -267,6 +267,11 @@ struct SampleArgs {
   double* out_actions64;   // [n][T][adim] or null
 };
 void launch_sample_actions(const SampleArgs& a, int n, cudaStream_t s);
+// zs[n][steps][nz] standard normals, Philox keyed by the global rollout index goff + r (j word: 0x80000000 | (step*nz + i))
+void launch_sample_latents(float* zs, int n, int steps, int nz, int goff, uint64_t seed, uint32_t plan, uint32_t iter,
+                           cudaStream_t st);
+// out[m] = mean_k s[m*K+k] + lambda * var_k
+void launch_reduce_futures(const double* s, int M, int K, double lambda, double* out, cudaStream_t st);
 // stable ascending top-k (ties -> lower index, NaN last) == np.argsort(kind='stable')[:k]
 void launch_topk(const double* scores, int n, int k, int* out_idx, double* work_keys, int* work_idx, cudaStream_t s);
 int topk_padded(int n);

@@ -57,7 +57,8 @@ class VfCemParams(C.Structure):
         ("initial_std", C.c_double * 8), ("clip_lo", C.c_double * 8), ("clip_hi", C.c_double * 8),
         ("mean0", C.c_double * 128), ("reduce_std_scale", C.c_double), ("finalweight", C.c_double),
         ("task_weights", C.c_double * VF_MAX_TASKS),
-        ("seed", C.c_uint64), ("plan_index", C.c_uint32), ("reserved", C.c_int32 * 8),
+        ("seed", C.c_uint64), ("plan_index", C.c_uint32),
+        ("k_futures", C.c_int32), ("lambda_variance", C.c_float), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -326,9 +327,10 @@ class Engine:
 
     def cem_actions(self):
         p = self._cem_params
-        out = np.empty((p.num_samples, p.nactions * p.repeat, self.spec.adim), np.float64)
+        kf = max(int(p.k_futures), 1)        # the device holds k_futures consecutive copies of every action row
+        out = np.empty((p.num_samples * kf, p.nactions * p.repeat, self.spec.adim), np.float64)
         self._check(self.lib.vf_cem_actions(self._h, _ptr(out)))
-        return out
+        return out[::kf]
 
     def topk(self, scores, k: int):
         s = np.ascontiguousarray(scores, dtype=np.float64)

@@ -52,7 +52,8 @@ def load_weights(path: str):
 
 def cem_params(spec: PredictorSpec, *, num_samples, iterations, num_elites, nactions, repeat, std, clip=None,
                mean0=None, reduce_std_scale=1.0, cost_kind=COST_PIXEL_DISTANCE, finalweight=10.0, task_weights=None,
-               n_ctx_actions=0, seed=0, plan_index=0, global_samples=None, sample_offset=0) -> VfCemParams:
+               n_ctx_actions=0, seed=0, plan_index=0, global_samples=None, sample_offset=0, k_futures=1,
+               lambda_variance=0.0) -> VfCemParams:
     p = VfCemParams()
     p.num_samples = int(num_samples)
     p.global_samples = int(global_samples if global_samples is not None else num_samples)
@@ -82,6 +83,7 @@ def cem_params(spec: PredictorSpec, *, num_samples, iterations, num_elites, nact
         p.task_weights[i] = float(tw[i])
     p.n_ctx_actions = int(n_ctx_actions)
     p.seed, p.plan_index = int(seed), int(plan_index)
+    p.k_futures, p.lambda_variance = int(k_futures), float(lambda_variance)
     return p
 
 
@@ -156,12 +158,13 @@ class EngineBackend:
 
     def plan(self, context, *, num_samples, iterations, num_elites, nactions, repeat, std, clip, mean0,
              reduce_std_scale, goal_pix, finalweight, task_weights, seed, plan_index, noise=None,
-             cost_kind=COST_PIXEL_DISTANCE):
+             cost_kind=COST_PIXEL_DISTANCE, k_futures=1, lambda_variance=0.0):
         self.set_context(context)
         p = cem_params(self.spec, num_samples=num_samples, iterations=iterations, num_elites=num_elites,
                        nactions=nactions, repeat=repeat, std=std, clip=clip, mean0=mean0,
                        reduce_std_scale=reduce_std_scale, cost_kind=cost_kind, finalweight=finalweight,
-                       task_weights=task_weights, n_ctx_actions=self._n_ctx_actions, seed=seed, plan_index=plan_index)
+                       task_weights=task_weights, n_ctx_actions=self._n_ctx_actions, seed=seed, plan_index=plan_index,
+                       k_futures=k_futures, lambda_variance=lambda_variance)
         best, eidx, scores = self.engine.cem_plan(p, np.asarray(goal_pix, np.float32), noise)
         return {"best_actions": best, "elite_idx": eidx, "scores": scores}
 
@@ -212,7 +215,8 @@ class B200VPredEvaluation:
         self.sequence_length = self.spec.seq_len
         self.n_cam = self.spec.ncam
         self._precision = pol.get("precision", self._hp.get("precision", "f16x3"))
-        self._max_samples = int(pol.get("num_samples", self._hp.get("run_batch_size", 200)))
+        # rollout capacity: every action sequence is rolled num_futures times under stochastic planning
+        self._max_samples = int(pol.get("num_samples", self._hp.get("run_batch_size", 200))) * max(int(pol.get("num_futures", 1) or 1), 1)
         self._state_append = pol.get("state_append")
 
     def restore(self):
