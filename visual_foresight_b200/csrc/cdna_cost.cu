@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) k_cdna_partial(View feat, int npix, const
   pdl_trigger();
   const int ks = blockIdx.x, k0 = ks * CK_KC, b0 = blockIdx.y * CK_S;
   const int K = npix * feat.C;
-  __shared__ float sf[CK_S][CK_KC];
+  __shared__ __align__(16) float sf[CK_S][CK_KC];
   __shared__ float red[CK_S][128];
   for (int i = threadIdx.x; i < CK_S * CK_KC; i += 256) {
     const int sI = i / CK_KC, kk = i - sI * CK_KC, k = k0 + kk, b = b0 + sI;
@@ -39,8 +39,18 @@ __global__ void __launch_bounds__(256) k_cdna_partial(View feat, int npix, const
     const int kb = g * (CK_KC / 2);
     const int ke = min(CK_KC / 2, max(0, K - k0 - kb));
     const float* wp = w + (long long)(k0 + kb) * nout + j;
-#pragma unroll 4
-    for (int kk = 0; kk < ke; ++kk) {
+    int kk = 0;
+    for (; kk + 4 <= ke; kk += 4) {          // 4 weights in registers, one 16-byte broadcast read per sample
+      const float w0 = __ldg(wp + (long long)kk * nout), w1 = __ldg(wp + (long long)(kk + 1) * nout);
+      const float w2 = __ldg(wp + (long long)(kk + 2) * nout), w3 = __ldg(wp + (long long)(kk + 3) * nout);
+#pragma unroll
+      for (int sI = 0; sI < CK_S; ++sI) {
+        const float4 f = *reinterpret_cast<const float4*>(&sf[sI][kb + kk]);
+        acc[sI] = fmaf(f.x, w0, acc[sI]); acc[sI] = fmaf(f.y, w1, acc[sI]);
+        acc[sI] = fmaf(f.z, w2, acc[sI]); acc[sI] = fmaf(f.w, w3, acc[sI]);
+      }
+    }
+    for (; kk < ke; ++kk) {
       const float wv = __ldg(wp + (long long)kk * nout);
 #pragma unroll
       for (int sI = 0; sI < CK_S; ++sI) acc[sI] = fmaf(sf[sI][kb + kk], wv, acc[sI]);
@@ -86,20 +96,35 @@ __device__ __forceinline__ void cdna_finalize(const float* __restrict__ part, in
   __syncthreads();
 }
 
+// kern[b][n][tap]: one block per sample finalises the split-K partials once (the appliers read the 100 finished taps)
+__global__ void __launch_bounds__(128) k_cdna_finalize(const float* __restrict__ part, int nks, int B,
+                                                       const float* __restrict__ bias, int ksize, int nt, float* __restrict__ kern) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float sk[128], tmp[128], sums[8];
+  const int b = blockIdx.x, kk = ksize * ksize;
+  cdna_finalize(part, nks, B, b, bias, ksize, nt, sk, tmp, sums);
+  if (threadIdx.x < kk * nt) {
+    const int t = threadIdx.x / nt, n = threadIdx.x % nt;
+    kern[((long long)b * nt + n) * kk + t] = sk[threadIdx.x];
+  }
+}
+
 // CDNA application (spec P6), nt = 4 transformed images, 5x5 kernels: block = (band of TR rows, sample).  The band
 // (+2 halo rows, SYMMETRIC-mirrored) is staged in shared memory as float4 pixels, the four kernels of a tap are one
 // float4: 2 LDS.128 + 12 FMA per tap.  Writes layers[.., 0..17] = T_0..T_3 (rgb each), prev image, first image.
-__global__ void __launch_bounds__(256) k_cdna_apply4(View image, View first, const float* __restrict__ part, int nks,
-                                                     const float* __restrict__ bias, int B, int H, int W, int TR, View layers,
-                                                     float* __restrict__ kern_out) {
+__global__ void __launch_bounds__(256) k_cdna_apply4(View image, View first, const float* __restrict__ kern, int B, int H, int W,
+                                                     int TR, View layers) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float4 sm4[];
-  float4* sk4 = sm4;                       // [25]
-  float* tmp = reinterpret_cast<float*>(sm4 + 25);    // [128] + sums [8]
-  float* sums = tmp + 128;
+  float4* sk4 = sm4;                       // [25] taps x 4 kernels
   float4* img = sm4 + 25 + 34;             // [(TR+4)][W]
   const int b = blockIdx.y, y0 = blockIdx.x * TR;
+  if (threadIdx.x < 100) {                 // kern[b][n][t] -> sk[t][n]
+    const int t = threadIdx.x >> 2, n = threadIdx.x & 3;
+    reinterpret_cast<float*>(sk4)[threadIdx.x] = __ldg(kern + ((long long)b * 4 + n) * 25 + t);
+  }
   for (int i = threadIdx.x; i < (TR + 4) * W; i += 256) {
     const int r = i / W, x = i - r * W;
     const int yy = mirror(y0 - 2 + r, H);
@@ -110,11 +135,7 @@ __global__ void __launch_bounds__(256) k_cdna_apply4(View image, View first, con
     }
     img[i] = v;
   }
-  cdna_finalize(part, nks, B, b, bias, 5, 4, reinterpret_cast<float*>(sk4), tmp, sums);
-  if (blockIdx.x == 0 && threadIdx.x < 100) {     // materialise kern[b][n][tap] for the composite kernel / debugging
-    const int t = threadIdx.x >> 2, n = threadIdx.x & 3;
-    kern_out[((long long)b * 4 + n) * 25 + t] = reinterpret_cast<const float*>(sk4)[threadIdx.x];
-  }
+  __syncthreads();
   for (int p = threadIdx.x; p < TR * W; p += 256) {
     const int r = p / W, x = p - r * W, y = y0 + r;
     if (y >= H) break;
@@ -148,17 +169,16 @@ __global__ void __launch_bounds__(256) k_cdna_apply4(View image, View first, con
 }
 
 // generic (any nt <= 8, odd ksize): one thread per pixel, global loads
-__global__ void __launch_bounds__(128) k_cdna_apply(View image, View first, const float* __restrict__ part, int nks,
-                                                    const float* __restrict__ bias, int ksize, int nt, int B, int H, int W,
-                                                    View layers, float* __restrict__ kern_out) {
-  __shared__ float sk[128], tmp[128], sums[8];
+__global__ void __launch_bounds__(128) k_cdna_apply(View image, View first, const float* __restrict__ kern, int ksize, int nt,
+                                                    int B, int H, int W, View layers) {
+  __shared__ float sk[128];
   const int b = blockIdx.y;
   const int kk = ksize * ksize;
-  cdna_finalize(part, nks, B, b, bias, ksize, nt, sk, tmp, sums);
-  if (blockIdx.x == 0 && threadIdx.x < kk * nt) {
+  if (threadIdx.x < kk * nt) {
     const int t = threadIdx.x / nt, n = threadIdx.x % nt;
-    kern_out[((long long)b * nt + n) * kk + t] = sk[threadIdx.x];
+    sk[threadIdx.x] = __ldg(kern + ((long long)b * nt + n) * kk + t);
   }
+  __syncthreads();
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= H * W) return;
   const int y = pix / W, x = pix % W, pad = ksize / 2;
@@ -402,16 +422,17 @@ void launch_cdna_kernels(View feat, int npix, const float* w, int ksize, int nt,
 }
 void launch_cdna_apply(View image, View first, const float* part, int K, const float* bias, float* kern, int ksize, int nt,
                        int B, int H, int W, View layers, cudaStream_t s) {
-  ++g_launch_counter;
+  g_launch_counter += 2;
   const int nks = (K + CK_KC - 1) / CK_KC;
+  launch_k(k_cdna_finalize, dim3(B), dim3(128), 0, s, part, nks, B, bias, ksize, nt, kern);
   if (nt == 4 && ksize == 5 && W >= 8) {
     const int TR = band_rows(H, W);
     dim3 grid((H + TR - 1) / TR, B);
     const size_t smem = (size_t)(25 + 34 + (TR + 4) * W) * sizeof(float4);
-    launch_k(k_cdna_apply4, dim3(grid), dim3(256), smem, s, image, first, part, nks, bias, B, H, W, TR, layers, kern);
+    launch_k(k_cdna_apply4, dim3(grid), dim3(256), smem, s, image, first, (const float*)kern, B, H, W, TR, layers);
   } else {
     dim3 grid((H * W + 127) / 128, B);
-    k_cdna_apply<<<grid, 128, 0, s>>>(image, first, part, nks, bias, ksize, nt, B, H, W, layers, kern);
+    k_cdna_apply<<<grid, 128, 0, s>>>(image, first, (const float*)kern, ksize, nt, B, H, W, layers);
   }
 }
 int composite_blocks(int H, int W) { const int TR = comp_rows(H, W); return (H + TR - 1) / TR; }
