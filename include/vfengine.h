@@ -78,7 +78,8 @@ typedef struct vf_config {
   int32_t max_samples;              /* capacity in action samples held by THIS handle (per rank) */
   int32_t device;                   /* CUDA ordinal (policy ctor gpu_id, sim/simulator.py:19-21) */
   int32_t precision;                /* enum vf_precision */
-  int32_t reserved[8];
+  int32_t rnn_z;                    /* use_rnn_z: latent z -> dense LSTM(nz) -> tiled (weights zrnn.w [(z,h), 4nz] i,j,f,o; zrnn.b) */
+  int32_t reserved[7];
 } vf_config;
 
 typedef struct vf_tensor {

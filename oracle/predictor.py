@@ -205,6 +205,7 @@ class OraclePredictor:
         first_d = None if dist is None else dist[0:1].expand(M, -1, -1, -1)
         states: List = [None] * (2 * len(spec.encoder))
         gen_image = gen_distrib = gen_state = None
+        zc = zh = torch.zeros(M, spec.nz, dtype=self.dtype) if spec.rnn_z else None   # dense LSTM over the latent (use_rnn_z)
         out_i, out_d, out_s = [], [], []
         for tau in range(S - 1):
             if tau < C:
@@ -217,7 +218,14 @@ class OraclePredictor:
             if state is not None:
                 parts.append(state)
             if spec.nz > 0:
-                parts.append(_t(zs[:, tau], self.dtype))
+                z = _t(zs[:, tau], self.dtype)
+                if spec.rnn_z:                                                       # BasicLSTMCell, forget_bias 1.0, gates i, j, f, o
+                    g = torch.cat([z, zh], dim=1) @ self.w["zrnn.w"] + self.w["zrnn.b"]
+                    gi_, gj_, gf_, go_ = torch.chunk(g, 4, dim=1)
+                    zc = zc * torch.sigmoid(gf_ + 1.0) + torch.sigmoid(gi_) * torch.tanh(gj_)
+                    zh = torch.tanh(zc) * torch.sigmoid(go_)
+                    z = zh
+                parts.append(z)
             sa = torch.cat(parts, dim=1)
             dbg = None
             if debug_steps is not None and tau in debug_steps:

@@ -37,7 +37,7 @@ def test_spec_from_hparams():
     assert len(CK.spec_from_hparams({}, None, {"orig_size": [128, 128]}).encoder) == 4     # 128-px family
 
 
-@pytest.mark.parametrize("family,kw", [("64", dict(height=48, width=64, sdim=5)), ("128", dict(seq_len=6, nz=8))])
+@pytest.mark.parametrize("family,kw", [("64", dict(height=48, width=64, sdim=5)), ("128", dict(seq_len=6, nz=8, rnn_z=True))])
 def test_round_trip_and_shape_checks(family, kw):
     sp = (S.spec_128 if family == "128" else S.spec_64)(**kw)
     w = S.init_weights(sp, seed=3)

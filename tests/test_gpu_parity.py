@@ -176,14 +176,14 @@ def test_rollout_128px_spec_tensor_core_vs_oracle():
     e.close()
 
 
-@pytest.mark.parametrize("precision", ["fp32_simt", "f16x3"])
-def test_rollout_with_latents_vs_oracle(precision):
+@pytest.mark.parametrize("precision,rnn_z", [("fp32_simt", False), ("f16x3", False), ("f16x3", True)])
+def test_rollout_with_latents_vs_oracle(precision, rnn_z):
     """stochastic predictor input (nz > 0): the per-step latent z is tiled into every conv like the action/state vector
     (spec P1); identical z on both sides -> frames within 1e-4."""
     import torch
     from oracle.predictor import OracleMultiViewPredictor
     from visual_foresight_b200.engine import Engine
-    sp = S.spec_64(height=32, width=32, seq_len=5, nz=8)
+    sp = S.spec_64(height=32, width=32, seq_len=5, nz=8, rnn_z=rnn_z)   # rnn_z: the latent passes through a dense LSTM first
     w = Hh.make_weights(sp, seed=11)
     inp = Hh.synth_inputs(sp, seed=12)
     M = 3

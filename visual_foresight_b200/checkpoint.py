@@ -76,7 +76,7 @@ def spec_from_hparams(model_hparams: Mapping, dataset_hparams: Optional[Mapping]
               seq_len=int(mh.get("sequence_length", conf.get("sequence_length", 15))),
               context_frames=int(mh.get("context_frames", conf.get("context_frames", 2))),
               ngf=int(mh.get("ngf", 32)), num_transformed=int(mh.get("num_transformed_images", 4)),
-              nz=int(mh.get("nz", 0)))
+              nz=int(mh.get("nz", 0)), rnn_z=bool(mh.get("use_rnn_z", False)) and int(mh.get("nz", 0)) > 0)
     ks = mh.get("kernel_size", (5, 5))
     kw["cdna_ksize"] = int(ks[0] if isinstance(ks, (list, tuple)) else ks)
     family = specmod.spec_128 if int(H) >= 128 else specmod.spec_64
@@ -117,6 +117,8 @@ def default_tf_names(spec: PredictorSpec) -> Dict[str, str]:
     t["masks.conv1.w"], t["masks.conv1.b"] = "masks/conv2d/kernel", "masks/conv2d/bias"
     if spec.sdim > 0:
         t["state.dense.w"], t["state.dense.b"] = "state_pred/dense/kernel", "state_pred/dense/bias"
+    if spec.rnn_z:
+        t["zrnn.w"], t["zrnn.b"] = "rnn_z/basic_lstm_cell/kernel", "rnn_z/basic_lstm_cell/bias"
     return t
 
 

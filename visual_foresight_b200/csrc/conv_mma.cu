@@ -987,6 +987,7 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int kw, int kcl, int cin,
                              std::vector<void*>* allocs, std::string* err) {
   int layout, bo;
   current_mode(&layout, &bo);
+  if (layout == 2 && !(cin % 64 == 0 && cout >= 128)) layout = 1;      // SWIZZLE_128B only for the wide gate convolutions
   const int ch = layout == 2 ? 64 : 32;
   if (cin % 8) { if (err) *err = "cin % 8"; return -1; }
   const bool swap = cout <= 64;
@@ -1094,6 +1095,7 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   Params P;
   int layout, bo;
   current_mode(&layout, &bo);
+  if (layout == 2 && !(w.cin % 64 == 0 && w.cout >= 128)) layout = 1;   // must agree with mma_conv_prepare_weights
   if (c.src.C + c.src1.C != w.cin) return -5;
   if (!plan_geometry(layout, bo, w.k, w.kw, w.kcl, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
   P.g.out_scale = ldexpf(1.0f, -w.scale_log2);

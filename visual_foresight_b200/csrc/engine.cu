@@ -65,6 +65,8 @@ struct ViewNet {
   ConvLayer scratch0, scratch1, masks0, masks1;
   float *cdna_w = nullptr, *cdna_b = nullptr;
   float *w_state = nullptr, *b_state = nullptr;   // per-view state head (IndepMultiSAVP: independent weight sets)
+  float *w_z = nullptr, *b_z = nullptr;           // dense LSTM over the latent (use_rnn_z)
+  float* zstate = nullptr;                        // [B][2*nz] its (c, h)
   float* state_cur = nullptr;                      // [B][sdim] this view's predicted state
 };
 
@@ -432,6 +434,17 @@ int finalize_weights(vf_engine* h) {
     if ((r = upload(h, &h->views[v].b_state, sb->data))) return r;
     DA(h->views[v].state_cur, (size_t)h->B * h->sdim);
   }
+  for (int v = 0; v < h->ncam && h->cfg.rnn_z; ++v) {
+    const HostTensor* zw = find_w(h, v, "zrnn.w");
+    const HostTensor* zb = find_w(h, v, "zrnn.b");
+    if (!zw || !zb) return fail(h, VF_ERR_STATE, "missing weight view%d.zrnn.{w,b}", v);
+    if ((int)zw->data.size() != 2 * h->nz * 4 * h->nz || (int)zb->data.size() != 4 * h->nz)
+      return fail(h, VF_ERR_INVALID, "zrnn has wrong shape");
+    int r;
+    if ((r = upload(h, &h->views[v].w_z, zw->data))) return r;
+    if ((r = upload(h, &h->views[v].b_z, zb->data))) return r;
+    DA(h->views[v].zstate, (size_t)h->B * 2 * h->nz);
+  }
   h->host_w.clear();
   h->weights_ready = true;
   return VF_OK;
@@ -644,6 +657,7 @@ void run_step(vf_engine* h, int v, int tau, int B) {
 // rolls S-1 cell steps for M samples whose actions are in h->actions [M][T][adim]
 int rollout_body(vf_engine* h, int M, int T) {
   for (auto& net : h->views) {
+    if (net.zstate) CU(cudaMemsetAsync(net.zstate, 0, (size_t)M * 2 * h->nz * sizeof(float), h->stream));
     // lstm_in holds two B-strided fp16 planes on the tensor-core path: clear the whole buffer
     const size_t Bz = h->split ? (size_t)h->B : (size_t)M;
     for (auto& r : net.enc_rnn) if (r.c) {
@@ -664,6 +678,7 @@ int rollout_body(vf_engine* h, int M, int T) {
       // every view runs its own state recurrence with its own state head; the states returned to the
       // caller are view 0's (vpred_model_interface.py:80-82 reads outputs['gen_states'] of the first model)
       sa.w_state = h->views[v].w_state; sa.b_state = h->views[v].b_state;
+      sa.w_z = h->views[v].w_z; sa.b_z = h->views[v].b_z; sa.zstate = h->views[v].zstate;
       sa.state_cur = h->sdim ? h->views[v].state_cur : h->state_cur;
       sa.gen_states_all = (h->sdim && v == 0) ? h->gen_states : nullptr;
       launch_build_sa(sa, M, tau, h->stream);
@@ -796,6 +811,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
   if (h->nt < 1 || h->nt > 8 || h->kc * h->kc * h->nt > 128 || (h->kc % 2) == 0 || (cfg->lstm_ksize != 5 && cfg->lstm_ksize != 3))
     return fail(h, VF_ERR_INVALID, "unsupported CDNA/LSTM kernel configuration");
   if (cfg->precision < 0 || cfg->precision > VF_PREC_F16X1) return fail(h, VF_ERR_INVALID, "bad precision");
+  if (cfg->rnn_z && (h->nz < 1 || h->nz > 16)) return fail(h, VF_ERR_INVALID, "rnn_z needs 1 <= nz <= 16");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)

@@ -330,7 +330,27 @@ __global__ void k_build_sa(SaArgs a, int M, int tau) {
     st[i] = v;
     sa[a.adim + i] = v;
   }
-  for (int i = 0; i < a.nz; ++i) sa[a.adim + a.sdim + i] = a.zs ? a.zs[((long long)m * (a.P + a.C - 1) + tau) * a.nz + i] : 0.f;
+  if (a.w_z && a.zs && a.nz <= 16) {          // latent through a BasicLSTMCell(nz): forget bias 1, gate order i, j, f, o
+    const int nz = a.nz;
+    float in[32], g[64];
+    float* zc = a.zstate + (long long)m * 2 * nz;
+    float* zh = zc + nz;
+    for (int i = 0; i < nz; ++i) { in[i] = a.zs[((long long)m * (a.P + a.C - 1) + tau) * nz + i]; in[nz + i] = zh[i]; }
+    for (int j = 0; j < 4 * nz; ++j) {
+      float acc = 0.f;
+      for (int i = 0; i < 2 * nz; ++i) acc = fmaf(in[i], a.w_z[i * 4 * nz + j], acc);
+      g[j] = acc + a.b_z[j];
+    }
+    for (int i = 0; i < nz; ++i) {
+      const float cn = zc[i] * sigmoidf_(g[2 * nz + i] + 1.0f) + sigmoidf_(g[i]) * tanhf(g[nz + i]);
+      const float hn = tanhf(cn) * sigmoidf_(g[3 * nz + i]);
+      zc[i] = cn;
+      zh[i] = hn;
+      sa[a.adim + a.sdim + i] = hn;
+    }
+  } else {
+    for (int i = 0; i < a.nz; ++i) sa[a.adim + a.sdim + i] = a.zs ? a.zs[((long long)m * (a.P + a.C - 1) + tau) * a.nz + i] : 0.f;
+  }
   for (int j = 0; j < a.sdim; ++j) {
     float acc = 0.f;
     for (int i = 0; i < a.adim; ++i) acc = fmaf(act[i], a.w_state[i * a.sdim + j], acc);

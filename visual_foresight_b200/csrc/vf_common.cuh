@@ -197,6 +197,9 @@ struct SaArgs {
   const float* ctx_actions;  // [n_ctx_actions][adim]
   const float* ctx_states;   // [C][sdim]
   const float* zs;           // [M][S-1][nz] or null
+  const float* w_z;          // [(2*nz)][4*nz] dense LSTM over the latent (use_rnn_z) or null: z is tiled directly
+  const float* b_z;          // [4*nz]
+  float* zstate;             // [M][2*nz] (c, h), zero at the start of a rollout
   const float* w_state;      // [(adim+sdim)][sdim]
   const float* b_state;      // [sdim]
   float* state_cur;          // [M][sdim]  (gen_state of the previous step, in/out)

@@ -39,7 +39,7 @@ class VfConfig(C.Structure):
         ("num_transformed", C.c_int32), ("cdna_ksize", C.c_int32), ("lstm_ksize", C.c_int32),
         ("norm_eps", C.c_float), ("forget_bias", C.c_float),
         ("max_samples", C.c_int32), ("device", C.c_int32), ("precision", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("rnn_z", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -148,6 +148,7 @@ def spec_to_config(spec: PredictorSpec, max_samples: int, device: int = 0, preci
     cfg.num_transformed, cfg.cdna_ksize, cfg.lstm_ksize = spec.num_transformed, spec.cdna_ksize, spec.lstm_ksize
     cfg.norm_eps, cfg.forget_bias = spec.norm_eps, spec.forget_bias
     cfg.max_samples, cfg.device, cfg.precision = int(max_samples), int(device), int(precision)
+    cfg.rnn_z = int(spec.rnn_z)
     return cfg
 
 

@@ -32,6 +32,7 @@ class PredictorSpec:
     adim: int = 4
     sdim: int = 4               # state dims fed to the net (0 = use_state False)
     nz: int = 0
+    rnn_z: bool = False         # use_rnn_z: the latent passes through a dense LSTM(nz) before being tiled into the convs
     seq_len: int = 15           # S  (BASELINE "H")
     context_frames: int = 2     # C
     ngf: int = 32
@@ -78,6 +79,7 @@ class PredictorSpec:
         assert self.decoder[-1][0] == self.ngf
         assert self.context_frames >= 1 and self.seq_len > self.context_frames
         assert self.cdna_ksize % 2 == 1 and self.lstm_ksize % 2 == 1
+        assert not self.rnn_z or self.nz > 0, "rnn_z needs nz > 0"
 
 
 def spec_64(**kw) -> PredictorSpec:
@@ -176,6 +178,9 @@ def weight_shapes(spec: PredictorSpec) -> "OrderedDict[str, Tuple[int, ...]]":
     if spec.sdim > 0:
         s["state.dense.w"] = (spec.adim + spec.sdim, spec.sdim)
         s["state.dense.b"] = (spec.sdim,)
+    if spec.rnn_z:                       # BasicLSTMCell(nz): kernel [(z, h), 4*nz] with gate order i, j, f, o
+        s["zrnn.w"] = (2 * spec.nz, 4 * spec.nz)
+        s["zrnn.b"] = (4 * spec.nz,)
     return s
 
 
