@@ -240,6 +240,45 @@ def test_full_size_configs_batch_invariance(name, kw, M):
     e.close()
 
 
+@pytest.mark.parametrize("precision", ["fp32_simt", "f16x3"])
+def test_ragged_batches_and_call_order_errors(precision):
+    """Ragged sample counts (M = 1, an odd M that leaves a partly filled tile group, M = capacity) give bit-identical
+    per-sample results — a sample never depends on its batch — and the C-ABI reports misuse as errors (negative status +
+    vf_last_error) instead of computing on stale state: the Python layer raises, like the reference's asserts."""
+    from visual_foresight_b200.engine import Engine, EngineError
+    sp = S.spec_64(height=32, width=32, seq_len=5)
+    w = Hh.make_weights(sp, seed=41)
+    inp = Hh.synth_inputs(sp, seed=42)
+    acts = Hh.gaussian_actions(sp, 9, 15, seed=43)
+    e = Engine(sp, 9, precision=precision)
+    with pytest.raises(EngineError, match="weight"):
+        e.set_context(inp["frames"], inp["states"], inp["ctx_actions"])
+        e.set_desig(inp["desig"])
+        e.predict(acts[:1])                                  # no weights loaded
+    e.close()
+    e = Engine(sp, 9, precision=precision)
+    e.load_weights(w)
+    with pytest.raises(EngineError, match="vf_set_context"):
+        e.predict(acts[:1])                                  # rollout before the context
+    e.set_context(inp["frames"], inp["states"], inp["ctx_actions"])
+    with pytest.raises(EngineError, match="designated-pixel"):
+        e.predict(acts[:1])                                  # context without a designated-pixel distribution
+    e.set_desig(inp["desig"])
+    with pytest.raises(EngineError, match="max_samples"):
+        e.predict(np.concatenate([acts, acts]))              # beyond the handle's capacity
+    with pytest.raises(EngineError, match="actions per sample"):
+        e.predict(acts[:, :1])                               # too few actions for the horizon
+    full = e.predict(acts)
+    for m in (1, 7):
+        part = e.predict(acts[:m])
+        for a_, b_ in zip(part, full):
+            np.testing.assert_array_equal(a_, b_[:m])
+    sc = e.score(inp["goal"], M=7)
+    assert sc.shape == (7,) and np.all(np.isfinite(sc))
+    np.testing.assert_array_equal(e.topk(sc, 7), np.argsort(sc, kind="stable"))      # K == M
+    e.close()
+
+
 # ---- CEM ------------------------------------------------------------------------------------------------
 def _plan_kwargs(sp, M, K, iters, seed=0):
     from visual_foresight_b200.samplers import GaussianCEMSampler, action_bounds, per_dim_variance
