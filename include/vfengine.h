@@ -214,7 +214,8 @@ VF_API int vf_debug_conv2d(vf_engine* h, int32_t impl, const float* x, const flo
 /* copy a named internal activation of the LAST cell step to host (tests): returns element count */
 VF_API int64_t vf_debug_fetch(vf_engine* h, const char* name, int32_t view, float* out, int64_t capacity);
 /* per-kernel-class timing with CUDA events on the handle's stream (bench roofline): enable, run, read.
- * classes: 0 = conv-LSTM gate convolutions, 1 = all other convolutions.  ms / flops / launches are
+ * classes: 0 = conv-LSTM gate convolutions, 1 = all other convolutions, 2 (optional, nclass >= 3) = convolutions of the
+ * shared-prefix cell steps that run once on one sample instead of on all M.  ms / flops / launches are
  * accumulated since the last enable; flops are the EXECUTED 2*MAC of the launches (sa channels folded). */
 VF_API int vf_profile_enable(vf_engine* h, int32_t on);
 VF_API int vf_profile_read(vf_engine* h, double* out_ms, double* out_flops, int64_t* out_launches, int32_t nclass);

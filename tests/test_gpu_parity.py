@@ -358,6 +358,43 @@ def test_stochastic_plan_futures_vs_oracle():
     be.engine.close()
 
 
+@pytest.mark.timeout(900)
+def test_c5_shard_stochastic_128px_full_size():
+    """BASELINE c5 at the shape ONE of its 8 GPUs sees: 128x128 frames, S = 15, nz = 8 with the recurrent latent, 25 action
+    sequences x 10 futures = 250 rollouts on the tensor-core path.  The oracle rolls the first two futures of action
+    sequence 0 with the restated Philox latents (frames within 1e-4); the per-sequence plan scores equal
+    mean + lambda * var of the device's own per-rollout scores; elites = stable argsort."""
+    import torch
+    from oracle.predictor import OracleMultiViewPredictor
+    from visual_foresight_b200.predictor import EngineBackend
+    sp = S.spec_128(seq_len=15, nz=8, rnn_z=True)
+    w = Hh.make_weights(sp, seed=51)
+    inp = Hh.synth_inputs(sp, seed=52)
+    M, KF, K, LAM, SEED, PLAN = 25, 10, 5, 0.25, 5, 2
+    kw = _plan_kwargs(sp, M, K, 1, seed=SEED)
+    kw["plan_index"] = PLAN
+    noise = np.random.default_rng(53).standard_normal((1, M, 20)).astype(np.float32)
+    be = EngineBackend(sp, w, M * KF, precision="f16x3")
+    onehot = OC.switch_on_pix(inp["desig"], 2, 1, sp.height, sp.width, 1)
+    ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"],
+           "context_pixel_distributions": onehot}
+    res = be.plan(ctx, goal_pix=inp["goal"], noise=noise, k_futures=KF, lambda_variance=LAM, **kw)
+    per_rollout = be.engine.score(inp["goal"], M=M * KF)
+    assert np.all(np.isfinite(per_rollout))
+    np.testing.assert_allclose(res["scores"][0], OC.reduce_futures(per_rollout, KF, LAM), rtol=1e-12)
+    np.testing.assert_array_equal(res["elite_idx"], np.argsort(res["scores"][0], kind="stable")[:K])
+    acts = be.engine.cem_actions()                                         # (M, T, adim) float64
+    zs = OC.philox_latents(SEED, PLAN, 0, 2, sp.seq_len - 1, sp.nz)         # rollouts 0, 1 = futures 0, 1 of sequence 0
+    rep = np.repeat(acts[:1].astype(np.float32), 2, axis=0)
+    oi, od, _ = OracleMultiViewPredictor(sp, w, torch.float32).rollout(
+        inp["frames"].astype(np.float32) / 255.0, inp["states"], onehot, Hh.step_actions(sp, inp["ctx_actions"], rep), zs)
+    gi, gd = be.engine.fetch([0, 1])
+    assert np.abs(gi - oi).max() <= FRAME_TOL
+    assert np.abs(gd - od).max() <= 1e-5
+    np.testing.assert_allclose(per_rollout[:2], OC.eval_pixel_cost(od, inp["goal"]), rtol=1e-5)
+    be.engine.close()
+
+
 @pytest.mark.parametrize("PREC", ["fp32_simt", "f16x3"])
 def test_philox_sampling_matches_restatement_and_shards_are_invariant(PREC):
     """Device Philox normals == numpy restatement; a plan split into two shards (run back to back on one
@@ -532,6 +569,36 @@ def test_rollout_tensor_core_path_vs_oracle(precision, tol):
     print("precision %s: frames max-abs err %.3g, distrib %.3g" % (precision, err, float(np.abs(gd - od).max())))
     assert err <= tol
     e.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "f16x3"])
+def test_shared_prefix_steps_are_bit_identical(precision, monkeypatch):
+    """The cell steps fed only by context (frame, state AND action: tau < min(n_ctx_actions, C-1)) are the same for every
+    sample, so the engine runs them once on one sample and replicates the recurrent state (engine.cu: rollout_body).
+    With three context frames (two shared steps) the predicted frames, distributions and states equal, bit for bit, the
+    rollout that recomputes the prefix for every sample (VF_SHARED_PREFIX=0), and both stay within tolerance of the oracle."""
+    from visual_foresight_b200.engine import Engine
+    sp = S.spec_64(height=32, width=32, seq_len=7, context_frames=3)
+    w = Hh.make_weights(sp, seed=21)
+    inp = Hh.synth_inputs(sp, seed=22)
+    assert np.asarray(inp["ctx_actions"]).shape[0] == 2
+    acts = Hh.gaussian_actions(sp, 5, 6, seed=23)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("VF_SHARED_PREFIX", flag)
+        e = Engine(sp, 5, precision=precision)
+        e.load_weights(w)
+        e.set_context(inp["frames"], inp["states"], inp["ctx_actions"])
+        e.set_desig(inp["desig"])
+        outs.append(e.predict(acts))
+        outs.append(e.predict(acts))          # second call replays the captured graph
+        e.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            np.testing.assert_array_equal(a, b)
+    oi, od, os_ = Hh.oracle_rollout(sp, w, inp, acts)
+    assert np.abs(outs[0][0] - oi).max() <= FRAME_TOL
+    assert np.abs(outs[0][1] - od).max() <= 1e-5
 
 
 # ---- multi-GPU (only when the box has >= 2 GPUs; the 1-GPU round-end run skips it) ------------------------------

@@ -403,7 +403,7 @@ __device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const Issue
 // sum_dx D[l0 + dx][dx*np + c].  Lanes of the same warp exchange by shuffle, the first KS-1 lanes of every warp publish their
 // blocks in shared memory for the previous warp (double-buffered, one 128-thread named barrier per 16-channel block).
 // Only home lanes < 128-(KS-1) produce outputs: consecutive units overlap by KS-1 rows.
-template <int KS>
+template <int KS, int NG>
 __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& g, uint32_t tmem_base, int a, int acc_cols, int q4,
                                                int lane, int half, int b, int v_lo, uint32_t xch_half, uint32_t tab) {
   const int row = q4 * 32 + lane;
@@ -413,9 +413,9 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
   const bool vec4 = ((g.Cout | P.out.ch_off | ps) & 3) == 0 && (P.out.sample_stride & 3) == 0 && (P.out.lo_off & 3) == 0;
   const bool split = P.out.lo_off != 0;
   uint32_t par = 0;
-  // work items = (unit, 16-channel block), dealt alternately to the two halves of the epilogue (4 warps each)
+  // work items = (unit, 16-channel block), dealt round-robin to the NG groups of the epilogue (4 warps each)
   const int ncb = g.np >> 4;
-  for (int idx = half; idx < g.units * ncb; idx += 2) {
+  for (int idx = half; idx < g.units * ncb; idx += NG) {
     const int u = idx / ncb, c16 = (idx - u * ncb) << 4;
     const int v = v_lo + u * g.ustride + row;
     const int oy = v / Wp, ox = v - oy * Wp;
@@ -505,10 +505,17 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
 }
 
 // thread layout: warp 0 weight producer, warp 1 MMA issuer (+TMEM alloc), warp 2 activation producer (tensor TMA),
-// warp 3 idle, warps 4..11 epilogue (warp % 4 = TMEM lane quarter, two warps per quarter split the columns / units)
-constexpr int EPI_WARP0 = 4, NEPI = 256;
+// warp 3 idle, warps 4.. epilogue in NG groups of 4 warps (warp % 4 = TMEM lane quarter; the groups split the columns /
+// units).  NG = 2 serves every tiling; NG = 3 / 4 (512 / 640 threads, <= 128 / 96 registers) are the row-stacked 3x3 thin path
+// only, whose epilogue is latency-bound (TMEM load -> exchange -> barrier -> shuffles -> stores per work item): an item of
+// 2 units x 2 channel blocks is 4 work items, one per group with NG = 4.
+constexpr int EPI_WARP0 = 4;
+constexpr int TAB_BAR = 7;             // named barrier of the bias-table hand-over (ids 1..NG: the groups' exchange barriers)
+constexpr int NPRE = 5;                // bias-table entries prefetched per epilogue thread (ntap * np <= 25 * 48 = 1200)
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant__ Params P) {
+template <int NG>
+__global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_constant__ Params P) {
+  constexpr int NEPI = 128 * NG;
   extern __shared__ uint8_t smem_raw[];
   const Geometry& g = P.g;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;        // 1024-aligned: swizzle phases are address based
@@ -577,7 +584,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
     cx.a_half = (uint64_t)(g.half_bytes >> 4); cx.b_plane = (uint64_t)(g.plane_bytes >> 4);
     cx.act_base = act_base; cx.wst_base = wst_base; cx.tmem_base = tmem_base;
     cx.w_full = w_full; cx.w_empty = w_empty; cx.a_full = a_full; cx.a_empty = a_empty; cx.acc_full = acc_full; cx.acc_empty = acc_empty;
-    if (g.swap == 2) {
+    if (NG >= 3 || g.swap == 2) {
 #define VF_S2(PA, UU) issuer_loop_swap2<PA, UU>(g, cx, acc_cols)
       if (g.passes == 3) {
         switch (g.units) {
@@ -591,6 +598,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
         }
       }
 #undef VF_S2
+    } else if constexpr (NG != 2) {
     } else if (g.swap) {
 #define VF_SW(PA, UU) issuer_loop_swap<PA, UU>(g, cx, acc_cols)
       if (g.passes == 3) {
@@ -646,7 +654,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
     const int q4 = warp & 3;                        // TMEM lane quarter this warp may read
     const int row = q4 * 32 + lane;                 // output channel within the cout tile
     const int half = (warp - EPI_WARP0) >> 2;       // the two warps of a quarter take alternate column chunks / units
-    float* s_sab = s_sab_all + half * 25 * MT;
+    float* s_sab = s_sab_all + (half & 1) * 25 * MT;
+    // Row-stacked path: the sample's bias table [border class][channel] is staged in shared memory (the L1 is carved out to
+    // almost nothing by the operand buffers: a global bias load per output vector costs an L2 round trip).  The table of
+    // item i+1 is fetched into registers BEFORE the epilogue of item i and handed over after it, so the L2 latency of the
+    // fetch never sits on the epilogue's critical path.
+    const int etid = (int)threadIdx.x - EPI_WARP0 * 32;
+    const int tabn = (P.sabias ? g.ntap : 1) * g.np;
+    float pre[NPRE];
+    auto tab_fetch = [&](int item_) {
+      const int b_ = ((item_ % per_mt) / g.npass) * g.G;
+#pragma unroll
+      for (int j = 0; j < NPRE; ++j) {
+        const int i = etid + j * NEPI;
+        float bv = 0.f;
+        if (i < tabn) {
+          const int cls = i / g.np, c = i - cls * g.np;
+          if (c < g.Cout) bv = P.sabias ? __ldg(P.sabias + ((long long)b_ * g.ntap + cls) * g.Cout + c) : (P.bias ? __ldg(P.bias + c) : 0.f);
+        }
+        pre[j] = bv;
+      }
+    };
+    auto tab_store = [&](float* t) {
+#pragma unroll
+      for (int j = 0; j < NPRE; ++j) {
+        const int i = etid + j * NEPI;
+        if (i < tabn) t[i] = pre[j];
+      }
+    };
+    const bool stacked = NG >= 3 || g.swap == 2;
+    float* const tab0 = s_sab_all + 4096;
+    if (stacked && (int)blockIdx.x < g.nitems) {
+      tab_fetch(blockIdx.x);
+      tab_store(tab0);
+      named_bar_sync(TAB_BAR, NEPI);
+    }
     uint32_t it = 0;
     for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
       const int mt = item / per_mt;
@@ -655,26 +697,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_mma(const __grid_constant_
       const int b0 = grp * g.G, v_lo = ps_ * g.v_cnt;
       const int n = mt * MT + row;
       const int a = it % nacc;
-      float* tab = nullptr;
-      if (g.swap == 2) {
-        // stage this sample's bias table [border class][channel] in shared memory while the MMAs run (the L1 is carved out
-        // to almost nothing by the operand buffers: a global bias load per output vector costs an L2 round trip)
-        tab = s_sab_all + 4096 + (it & 1) * (g.ntap * g.np);
-        const int ncls = P.sabias ? g.ntap : 1;
-        for (int i = (int)threadIdx.x - EPI_WARP0 * 32; i < ncls * g.np; i += NEPI) {
-          const int cls = i / g.np, c = i - cls * g.np;
-          float bv = 0.f;
-          if (c < g.Cout) bv = P.sabias ? __ldg(P.sabias + ((long long)b0 * g.ntap + cls) * g.Cout + c) : (P.bias ? __ldg(P.bias + c) : 0.f);
-          tab[i] = bv;
-        }
-        named_bar_sync(3, NEPI);
-      }
+      const int next = item + (int)gridDim.x;
+      if (stacked && next < g.nitems) tab_fetch(next);
       mbar_wait(&acc_full[a], (it / nacc) & 1);
       tc_fence_after();
-      if (g.swap == 2) {
-        const uint32_t xch_half = smem_u32(s_sab_all + half * 2048);   // lane-exchange scratch (the wide path's bias tables live here)
-        if (g.k == 3) epilogue_swap2<3>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab));
-        else epilogue_swap2<5>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab));
+      if (stacked) {
+        float* tab = tab0 + (it & 1) * (g.ntap * g.np);
+        // lane-exchange scratch (the wide path's bias tables live here): 2 parities x 4 quarters x (KS-1)^2 rows x 16 floats
+        if constexpr (NG >= 3) {
+          epilogue_swap2<3, NG>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, smem_u32(s_sab_all + half * 512), smem_u32(tab));
+        } else {
+          const uint32_t xch_half = smem_u32(s_sab_all + half * 2048);
+          if (g.k == 3) epilogue_swap2<3, 2>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab));
+          else epilogue_swap2<5, 2>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab));
+        }
+        if (next < g.nitems) {               // every reader of the other table finished one item ago
+          tab_store(tab0 + ((it + 1) & 1) * (g.ntap * g.np));
+          named_bar_sync(TAB_BAR, NEPI);
+        }
+      } else if constexpr (NG != 2) {
       } else if (g.swap) {
         // pixels on lanes: this thread owns pixel row `row` of every 128-pixel unit and all output channels of it
         const int b = b0;
@@ -856,14 +897,15 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
   g.nst = k * kw;
   g.ksteps_last = (std::min(g.ch, Cin - (g.nchunk - 1) * g.ch) + 15) / 16;
   const int np_thin = (Cout + 15) / 16 * 16;
-  if (Cout <= 64 && kw == k && k * np_thin <= 256) {
+  if (Cout <= 64 && kw == k && k * np_thin <= 256 && 2 * kcl * kcl * np_thin <= 2304) {   // 2 bias tables behind the exchange scratch
     // ---- row-stacked thin path: pixels on M, the k taps of a filter row side by side on N (k*np columns) ----
     g.swap = 2;
     g.np = np_thin; g.ncols = k * g.np; g.ustride = 128 - (k - 1); g.nst = k;
     g.half_bytes = g.ncols * g.row_bytes; g.stage_bytes = 2 * g.half_bytes;
     g.n_mt = 1; g.G = 1;
     const int Vs = H * g.Wp;
-    const int umax = std::max(1, std::min(5, 256 / g.ncols));            // two accumulator sets in the 512 TMEM columns
+    const int umax = std::max(1, std::min(4, 256 / g.ncols));            // two accumulator sets in the 512 TMEM columns; <= 4 units
+                                                                          // of one channel block = one work item per epilogue group
     bool found = false;
     for (int units = umax; units >= 1 && !found; --units) {
       g.npass = (Vs + g.ustride * units - 1) / (g.ustride * units);
@@ -992,7 +1034,7 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int kw, int kcl, int cin,
   if (cin % 8) { if (err) *err = "cin % 8"; return -1; }
   const bool swap = cout <= 64;
   const int np = (cout + 15) / 16 * 16;
-  const bool stacked = swap && kw == k && k * np <= 256;              // one stage = a filter ROW: rows = (dx, output channel)
+  const bool stacked = swap && kw == k && k * np <= 256 && 2 * kcl * kcl * np <= 2304;   // one stage = a filter ROW: rows = (dx, output channel); must agree with plan_geometry
   const int rows = stacked ? k * np : (swap ? np : MT);               // operand tile rows
   const int kk = stacked ? k : k * kw;                                // stages per channel chunk
   const int nchunk = (cin + ch - 1) / ch, n_mt = swap ? 1 : (cout + MT - 1) / MT, kc = ch / 8, rb = ch * 2;
@@ -1114,16 +1156,25 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   }
   const size_t smem = smem_bytes(P.g);
   static bool attr_set = false;
+  static int epi_groups = 4;          // epilogue warp groups of the 3x3 row-stacked layers (VF_EPI_GROUPS=2|3|4: A/B switch)
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_conv_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) != cudaSuccess) return -3;
+    if (cudaFuncSetAttribute(k_conv_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) != cudaSuccess) return -3;
+    if (cudaFuncSetAttribute(k_conv_mma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) != cudaSuccess) return -3;
+    if (cudaFuncSetAttribute(k_conv_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) != cudaSuccess) return -3;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("VF_EPI_GROUPS");
+    if (e && atoi(e) >= 2 && atoi(e) <= 4) epi_groups = atoi(e);
     attr_set = true;
   }
   const int grid = std::min(P.g.nitems, g_num_sms > 0 ? g_num_sms : 148);
   ++g_launch_counter;
-  return launch_k(k_conv_mma, dim3(grid), dim3(NTHREADS), smem, s, P) == cudaSuccess ? 0 : -4;
+  if (epi_groups == 4 && P.g.swap == 2 && P.g.k == 3)
+    return launch_k(k_conv_mma<4>, dim3(grid), dim3(128 + 128 * 4), smem, s, P) == cudaSuccess ? 0 : -4;
+  if (epi_groups == 3 && P.g.swap == 2 && P.g.k == 3)
+    return launch_k(k_conv_mma<3>, dim3(grid), dim3(128 + 128 * 3), smem, s, P) == cudaSuccess ? 0 : -4;
+  return launch_k(k_conv_mma<2>, dim3(grid), dim3(NTHREADS), smem, s, P) == cudaSuccess ? 0 : -4;
 }
 
 }  // namespace vf

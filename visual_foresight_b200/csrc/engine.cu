@@ -43,6 +43,10 @@ struct ConvLayer {
   bool lstm = false;
   bool fold = false;        // tensor-core path: the k dx taps are folded into the input channels by the producer (k x 1 conv over
                             // k*cin_sp channels) — used for the first encoder conv, whose 8 input channels would waste the K=16 MMAs
+  bool s2d = false;         // tensor-core path, first encoder conv: conv k x k + 2x2 average pool evaluated as ONE 3x3 conv over the
+                            // space-to-depth input (2x2 pixel blocks -> 4*cin_sp channels) with pre-averaged weights; the conv
+                            // output is already pooled (see prepare_conv)
+  int kcls = 0;             // kernel size of the border classes of sabias (0 = k; 3 for s2d)
   float* w_sp = nullptr;    // [k*k][cin_sp][cout]
   float* wcls = nullptr;    // [k*k][A][cout]
   float* bias = nullptr;
@@ -147,6 +151,7 @@ struct vf_engine {
   long long graph_key = -1, graph_seen_key = -1;
   long long graph_launches = 0;
   bool use_graph = true;
+  int cur_M = 0;               // samples of the rollout being launched (convs on fewer samples = shared-prefix steps)
 
   // profiling (vf_profile_*)
   bool prof_on = false;
@@ -272,7 +277,49 @@ int prepare_conv(vf_engine* h, int view, ConvLayer& L) {
       if ((r = opt(".beta", &L.beta, L.cout))) return r;
     }
   }
-  if (h->cfg.precision != VF_PREC_FP32_SIMT && L.fold) {
+  if (h->cfg.precision != VF_PREC_FP32_SIMT && L.s2d) {
+    // pooled(Y,X) = 1/4 sum_{py,px in {0,1}} sum_{dy,dx} w[dy][dx][c] in(2Y+py+dy-pad, 2X+px+dx-pad, c).  With input pixel
+    // (2(Y+by-1)+sy, 2(X+bx-1)+sx) = block (Y+by-1, X+bx-1), sub-position (sy,sx):  dy = 2by+sy-py+pad-2, dx likewise, so
+    //   w'[by][bx][(sy*2+sx)*cin_sp + c][n] = 1/4 sum_{py,px} w[2by+sy-py+pad-2][2bx+sx-px+pad-2][c][n]   (taps outside 0..k-1 drop).
+    // SAME zero padding of pad <= 2 pixels is exactly the one zero BLOCK of the 3x3 block conv (H, W even).
+    const int pad = k / 2, C4 = 4 * L.cin_sp;
+    std::vector<float> w2((size_t)9 * C4 * L.cout, 0.f);
+    for (int by = 0; by < 3; ++by)
+      for (int bx = 0; bx < 3; ++bx)
+        for (int sy = 0; sy < 2; ++sy)
+          for (int sx = 0; sx < 2; ++sx)
+            for (int c = 0; c < L.cin_sp; ++c)
+              for (int n = 0; n < L.cout; ++n) {
+                double acc = 0.0;
+                for (int py = 0; py < 2; ++py)
+                  for (int px_ = 0; px_ < 2; ++px_) {
+                    const int dy = 2 * by + sy - py + pad - 2, dx = 2 * bx + sx - px_ + pad - 2;
+                    if (dy < 0 || dy >= k || dx < 0 || dx >= k) continue;
+                    acc += (double)wsp[((size_t)(dy * k + dx) * L.cin_sp + c) * L.cout + n];
+                  }
+                w2[((size_t)(by * 3 + bx) * C4 + (sy * 2 + sx) * L.cin_sp + c) * L.cout + n] = (float)(0.25 * acc);
+              }
+    if (A > 0) {
+      // border classes of the pooled output: pooled row 0 averages pixel rows 0,1 (classes 0,1 of the k x k conv), the last
+      // pooled row the classes k-2,k-1, every other row the interior class (needs H/2 >= 3 rows: checked in build_net)
+      std::vector<float> wc_full((size_t)kk * A * L.cout), wc9((size_t)9 * A * L.cout);
+      CU(cudaMemcpy(wc_full.data(), L.wcls, wc_full.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      auto cls_of = [&](int c3, int p) { return c3 == 0 ? p : (c3 == 2 ? k - 2 + p : pad); };
+      for (int cy = 0; cy < 3; ++cy)
+        for (int cx = 0; cx < 3; ++cx)
+          for (size_t i = 0; i < (size_t)A * L.cout; ++i) {
+            double acc = 0.0;
+            for (int py = 0; py < 2; ++py)
+              for (int px_ = 0; px_ < 2; ++px_) acc += (double)wc_full[((size_t)(cls_of(cy, py) * k + cls_of(cx, px_))) * A * L.cout + i];
+            wc9[(size_t)(cy * 3 + cx) * A * L.cout + i] = (float)(0.25 * acc);
+          }
+      CU(cudaMemcpy(L.wcls, wc9.data(), wc9.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    L.kcls = 3;
+    std::string e;
+    if (mma_conv_prepare_weights(w2.data(), 3, 3, 3, C4, L.cout, &L.mma, &h->allocs, &e))
+      return fail(h, VF_ERR_CUDA, "mma weight prep %s: %s", L.name.c_str(), e.c_str());
+  } else if (h->cfg.precision != VF_PREC_FP32_SIMT && L.fold) {
     // folded[dy][dx*cin_sp + c][n] = w[dy][dx][c][n]
     std::vector<float> wf((size_t)k * k * L.cin_sp * L.cout);
     for (int dy = 0; dy < k; ++dy)
@@ -318,7 +365,14 @@ int build_net(vf_engine* h) {
       if (i == 0 && c.precision != VF_PREC_FP32_SIMT) {      // (image, first) packed to 8 channels for the tensor-core path
         net.enc_conv.back().cin_sp = 8;
         net.enc_conv.back().cin_w = 6;
-        net.enc_conv.back().fold = true;
+        // default: conv + pool as one 3x3 conv over 2x2 pixel blocks (s2d); VF_ENC0=fold keeps the full-resolution k x 1 conv
+        // over the dx-folded input (A/B switch and fallback for shapes the block conv does not cover)
+        const char* e0 = getenv("VF_ENC0");
+        const bool want_fold = e0 && !strcmp(e0, "fold");
+        if (!want_fold && hh % 2 == 0 && ww % 2 == 0 && hh >= 6 && ww >= 6 && mma_conv_supported(3, 32, oc, hh / 2, ww / 2))
+          net.enc_conv.back().s2d = true;
+        else
+          net.enc_conv.back().fold = true;
       }
       upd(net.enc_conv.back());
       hh /= 2; ww /= 2;
@@ -476,7 +530,7 @@ void run_conv(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int 
   if (!h->prof_on) { run_conv_impl(h, L, s0, s1, out, B, act, stats_partial, stats_slots); return; }
   vf_engine::ProfRec r;
   r.a = prof_event(h); r.b = prof_event(h);
-  r.cls = L.lstm ? 0 : 1;
+  r.cls = (B < h->cur_M) ? 2 : (L.lstm ? 0 : 1);           // class 2: shared-prefix steps (run on one sample)
   r.flops = 2.0 * B * L.H * L.W * L.k * L.k * (double)L.cin_sp * L.cout;
   cudaEventRecord(r.a, h->stream);
   run_conv_impl(h, L, s0, s1, out, B, act, stats_partial, stats_slots);
@@ -487,7 +541,8 @@ void run_conv(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int 
 void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act, double* stats_partial, int* stats_slots) {
   if (h->cfg.precision != VF_PREC_FP32_SIMT && L.mma.ready) {
     MmaConvCall c;
-    c.src = s0; c.src1 = s1; c.out = out; c.sabias = L.sabias; c.bias = L.bias; c.H = L.H; c.W = L.W;
+    c.src = s0; c.src1 = s1; c.out = out; c.sabias = L.sabias; c.bias = L.bias;
+    c.H = L.s2d ? L.H / 2 : L.H; c.W = L.s2d ? L.W / 2 : L.W;
     c.passes = (h->cfg.precision == VF_PREC_F16X3) ? 3 : 1;
     c.act = act;
     c.stats_partial = stats_partial;
@@ -556,7 +611,8 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     if (!(L.k && L.wcls)) return;
     if (sbb.n == 24) { launch_sabias_batch(sbb, h->stream); sbb.n = 0; }
     SabiasBatch::Layer& e = sbb.L[sbb.n++];
-    e.wcls = L.wcls; e.bias = L.bias; e.out = L.sabias; e.ncls = L.k * L.k; e.Cout = L.cout;
+    const int kc_ = L.kcls ? L.kcls : L.k;
+    e.wcls = L.wcls; e.bias = L.bias; e.out = L.sabias; e.ncls = kc_ * kc_; e.Cout = L.cout;
   };
   for (int i = 0; i < n; ++i) { sab(net.enc_conv[i]); sab(net.enc_lstm[i]); sab(net.dec_conv[i]); sab(net.dec_lstm[i]); }
   launch_sabias_batch(sbb, h->stream);
@@ -565,7 +621,11 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   std::vector<View> enc_out(n);
   std::vector<int> enc_h(n), enc_w(n);
   View x0 = image, x1 = first;
-  if (h->pack0) {
+  if (h->pack0 && net.enc_conv[0].s2d) {                    // 2x2 pixel blocks -> channels: [sub-position][image rgb, first rgb, 0, 0]
+    x0 = cview(h, h->pack0, (H / 2) * (W / 2), 32, 0, 32);
+    launch_pack_s2d(image, first, B, H, W, x0, h->stream);
+    x1 = none;
+  } else if (h->pack0) {
     const int kf = net.enc_conv[0].k;                       // dx taps folded into channels: [dx][image rgb, first rgb, 0, 0]
     x0 = cview(h, h->pack0, H * W, 8 * kf, 0, 8 * kf);
     launch_pack_fold(image, first, B, H, W, kf, x0, h->stream);
@@ -575,13 +635,14 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   for (int i = 0; i < n; ++i) {
     ConvLayer& L = net.enc_conv[i];
     const int oc = L.cout;
-    View rawv = dense_view(h->raw, hh * ww, oc);
+    const int pooled = L.s2d ? 0 : 1;                       // s2d: the conv output is the pooled map already
+    View rawv = dense_view(h->raw, L.s2d ? (hh / 2) * (ww / 2) : hh * ww, oc);
     run_conv(h, L, x0, x1, rawv, B);
     hh /= 2; ww /= 2;
-    const int S_e = launch_plane_stats(rawv, B, hh, ww, 1, h->stats_partial, h->stream);
+    const int S_e = launch_plane_stats(rawv, B, hh, ww, pooled, h->stats_partial, h->stream);
     View dst = c.enc_rnn[i] ? cview(h, net.enc_rnn[i].lstm_in, hh * ww, 2 * oc, 0, oc)
                             : cview(h, h->act_enc[i], hh * ww, oc, 0, oc);
-    launch_norm_act(rawv, B, hh, ww, 1, fin_stats(h, h->stats_partial, S_e, B * oc, hh * ww, h->stats), L.gamma, L.beta, ACT_RELU, dst, h->stream);
+    launch_norm_act(rawv, B, hh, ww, pooled, fin_stats(h, h->stats_partial, S_e, B * oc, hh * ww, h->stats), L.gamma, L.beta, ACT_RELU, dst, h->stream);
     h->debug[v][L.name] = DebugEntry{dst, hh, ww};
     View out = dst;
     if (c.enc_rnn[i]) {
@@ -654,6 +715,12 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   h->debug[v]["dec_last"] = DebugEntry{h_last, H, W};
 }
 
+int shared_prefix_steps(const vf_engine* h, int M) {
+  const char* e = getenv("VF_SHARED_PREFIX");            // read per rollout (tests flip it); part of the graph key
+  if (e && atoi(e) == 0) return 0;
+  return (h->nz == 0 && M > 1) ? std::max(0, std::min(h->n_ctx_actions, h->C - 1)) : 0;
+}
+
 // rolls S-1 cell steps for M samples whose actions are in h->actions [M][T][adim]
 int rollout_body(vf_engine* h, int M, int T) {
   for (auto& net : h->views) {
@@ -673,7 +740,15 @@ int rollout_body(vf_engine* h, int M, int T) {
   sa.actions = h->actions; sa.T = T; sa.adim = h->adim; sa.sdim = h->sdim; sa.nz = h->nz;
   sa.n_ctx_actions = h->n_ctx_actions; sa.C = h->C; sa.ctx_actions = h->ctx_actions; sa.ctx_states = h->ctx_states;
   sa.zs = h->nz ? h->zs : nullptr; sa.sa = h->sa; sa.P = h->P;
+  // Shared prefix: while the cell is still fed context frames, context states AND context actions (tau < n_ctx_actions,
+  // tau < C-1 so that no prediction is emitted) and there is no per-sample latent, every one of the M samples computes
+  // exactly the same thing from the same zero state (the reference tiles the context per tower and recomputes it,
+  // setup_predictor.py:40-44).  Those steps run once, on sample 0, and the recurrent state is replicated to the other
+  // samples before the first per-sample step.  VF_SHARED_PREFIX=0 switches it off (A/B, tests).
+  const int n_shared = shared_prefix_steps(h, M);
+  h->cur_M = M;
   for (int tau = 0; tau < h->S - 1; ++tau) {
+    const bool shared = tau < n_shared;
     for (int v = 0; v < h->ncam; ++v) {
       // every view runs its own state recurrence with its own state head; the states returned to the
       // caller are view 0's (vpred_model_interface.py:80-82 reads outputs['gen_states'] of the first model)
@@ -682,7 +757,26 @@ int rollout_body(vf_engine* h, int M, int T) {
       sa.state_cur = h->sdim ? h->views[v].state_cur : h->state_cur;
       sa.gen_states_all = (h->sdim && v == 0) ? h->gen_states : nullptr;
       launch_build_sa(sa, M, tau, h->stream);
-      run_step(h, v, tau, M);
+      run_step(h, v, tau, shared ? 1 : M);
+      if (shared && tau == n_shared - 1) {
+        BroadcastBatch bb;
+        bb.n = 0;
+        auto add = [&](RnnState& r) {
+          if (!r.c) return;
+          const long long hw = (long long)r.h * r.w;
+          bb.b[bb.n++] = {r.c, hw * r.F * (long long)sizeof(float)};
+          if (h->split) {                                   // two fp16 planes, the lo plane h->B samples after the hi plane
+            bb.b[bb.n++] = {r.lstm_in, hw * 2 * r.F * 2};
+            bb.b[bb.n++] = {reinterpret_cast<__half*>(r.lstm_in) + (long long)h->B * hw * 2 * r.F, hw * 2 * r.F * 2};
+          } else {
+            bb.b[bb.n++] = {r.lstm_in, hw * 2 * r.F * (long long)sizeof(float)};
+          }
+          if (bb.n > 21) { launch_broadcast_rows(bb, M, h->stream); bb.n = 0; }
+        };
+        for (auto& r : h->views[v].enc_rnn) add(r);
+        for (auto& r : h->views[v].dec_rnn) add(r);
+        launch_broadcast_rows(bb, M, h->stream);
+      }
     }
   }
   return VF_OK;
@@ -697,7 +791,7 @@ int rollout(vf_engine* h, int M, int T) {
   if (!h->distrib_set) return fail(h, VF_ERR_STATE, "no designated-pixel distribution: pass pix_distrib to vf_set_context or call vf_set_desig");
   const int need = h->S - 1 - h->n_ctx_actions;
   if (T < need) return fail(h, VF_ERR_INVALID, "need %d actions per sample (S-1-n_ctx_actions), got T=%d", need, T);
-  const long long key = ((long long)M << 24) | ((long long)T << 8) | (long long)h->n_ctx_actions;
+  const long long key = ((long long)shared_prefix_steps(h, M) << 56) | ((long long)M << 24) | ((long long)T << 8) | (long long)h->n_ctx_actions;
   int r = VF_OK;
   if (!h->use_graph || h->prof_on) {
     r = rollout_body(h, M, T);
@@ -1295,6 +1389,7 @@ int vf_profile_read(vf_engine* h, double* ms, double* flops, int64_t* launches, 
   for (auto& r : h->prof) {
     float t = 0.f;
     CU(cudaEventElapsedTime(&t, r.a, r.b));
+    if (r.cls >= nclass) continue;
     ms[r.cls] += t; flops[r.cls] += r.flops; launches[r.cls] += 1;
   }
   return VF_OK;

@@ -435,6 +435,39 @@ __global__ void k_pack_fold(View image, View first, int H, int W, int kf, View o
   }
   vst8(out, voff(out, b, pix) + dx * 8, v);
 }
+// Space-to-depth pack of (image, first) for the first encoder conv: out[b][Y][X][(sy*2+sx)*8 + c] = (image rgb, first rgb, 0, 0)
+// at pixel (2Y+sy, 2X+sx).  A k x k SAME convolution followed by the 2x2 average pool is a 3x3 SAME convolution over these
+// 2x2 blocks (k <= 5) with pre-averaged weights (engine.cu: prepare_conv), so the full-resolution conv output never exists.
+__global__ void k_pack_s2d(View image, View first, int H, int W, View out) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int H2 = H >> 1, W2 = W >> 1;
+  if (i >= H2 * W2 * 4) return;
+  const int sub = i & 3, blk = i >> 2;
+  const int Y = blk / W2, X = blk - Y * W2;
+  const long long pix = (long long)(2 * Y + (sub >> 1)) * W + (2 * X + (sub & 1));
+  const float* ip = vptr(image, b, pix);
+  const float* fp = vptr(first, b, pix);
+  float8 v;
+  v.a = make_float4(__ldg(ip), __ldg(ip + 1), __ldg(ip + 2), __ldg(fp));
+  v.b = make_float4(__ldg(fp + 1), __ldg(fp + 2), 0.f, 0.f);
+  vst8(out, voff(out, b, blk) + sub * 8, v);
+}
+// grid (chunks, buffers, row groups): every thread reads 16 bytes of row 0 once and stores them to its group's rows
+__global__ void k_broadcast_rows(BroadcastBatch a, int M, int rows_per_group) {
+  pdl_wait();
+  pdl_trigger();
+  const BroadcastBatch::Buf buf = a.b[blockIdx.y];
+  const long long n16 = buf.row_bytes >> 4;
+  const int m0 = 1 + blockIdx.z * rows_per_group, m1 = min(M, m0 + rows_per_group);
+  uint4* base = reinterpret_cast<uint4*>(buf.p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = base[i];
+    for (int m = m0; m < m1; ++m) base[(long long)m * n16 + i] = v;
+  }
+}
 __global__ void k_view_to_dense(View v, int HW, float* dst) {
   const int b = blockIdx.y;
   const long long total = (long long)HW * v.C;
@@ -562,6 +595,20 @@ void launch_pack_fold(View image, View first, int B, int H, int W, int kf, View 
   ++g_launch_counter;
   dim3 grid((H * W * kf + 255) / 256, B);
   launch_k(k_pack_fold, dim3(grid), dim3(256), 0, s, image, first, H, W, kf, out);
+}
+void launch_pack_s2d(View image, View first, int B, int H, int W, View out, cudaStream_t s) {
+  ++g_launch_counter;
+  dim3 grid(((H / 2) * (W / 2) * 4 + 255) / 256, B);
+  launch_k(k_pack_s2d, dim3(grid), dim3(256), 0, s, image, first, H, W, out);
+}
+void launch_broadcast_rows(const BroadcastBatch& a, int M, cudaStream_t s) {
+  if (a.n == 0 || M <= 1) return;
+  ++g_launch_counter;
+  long long mx = 16;
+  for (int i = 0; i < a.n; ++i) mx = std::max(mx, a.b[i].row_bytes);
+  const int rows_per_group = 8;
+  dim3 grid((unsigned)std::min<long long>((mx / 16 + 255) / 256, 64), a.n, (M - 1 + rows_per_group - 1) / rows_per_group);
+  launch_k(k_broadcast_rows, dim3(grid), dim3(256), 0, s, a, M, rows_per_group);
 }
 void launch_pack_rgb2(View image, View first, int B, int HW, View out, cudaStream_t s) {
   ++g_launch_counter;

@@ -215,6 +215,13 @@ struct SabiasBatch {
   const float* sa;
 };
 void launch_sabias_batch(const SabiasBatch& a, cudaStream_t s);
+// rows[m] = rows[0] for m in [1, M): replicates the recurrent state of sample 0 after the shared-prefix cell steps (engine.cu)
+struct BroadcastBatch {
+  struct Buf { void* p; long long row_bytes; };     // row_bytes % 16 == 0, rows contiguous
+  Buf b[24];
+  int n;
+};
+void launch_broadcast_rows(const BroadcastBatch& a, int M, cudaStream_t s);
 // sabias[b][cls][n] = bias[n] + sum_a sa[b][a] * wcls[cls][a][n]
 void launch_sabias(const float* sa, int A, const float* wcls, const float* bias, int ncls, int Cout,
                    int B, float* out, cudaStream_t s);
@@ -285,6 +292,7 @@ void launch_pack_rgb2(View image, View first, int B, int HW, View out, cudaStrea
 // out[b, (y,x), dx*8 + 0..7] = (image rgb, first rgb, 0, 0) at (y, x + dx - kf/2), zeros outside the image: the kf dx taps of
 // the first encoder conv folded into channels (its tensor-core form is then a kf x 1 convolution over 8*kf channels)
 void launch_pack_fold(View image, View first, int B, int H, int W, int kf, View out, cudaStream_t s);
+void launch_pack_s2d(View image, View first, int B, int H, int W, View out, cudaStream_t s);
 // dst[b][pix][c] (dense float32) = view element (either storage format)
 void launch_view_to_dense(View v, int B, int HW, float* dst, cudaStream_t s);
 void launch_dense_to_view(const float* src, int B, int HW, View v, cudaStream_t s);

@@ -352,10 +352,11 @@ class Engine:
         self._check(self.lib.vf_profile_enable(self._h, int(on)))
 
     def profile_read(self):
-        ms, fl, n = np.zeros(2), np.zeros(2), np.zeros(2, np.int64)
-        self._check(self.lib.vf_profile_read(self._h, _ptr(ms), _ptr(fl), _ptr(n), 2))
+        ms, fl, n = np.zeros(3), np.zeros(3), np.zeros(3, np.int64)
+        self._check(self.lib.vf_profile_read(self._h, _ptr(ms), _ptr(fl), _ptr(n), 3))
         return {"lstm_conv": {"ms": ms[0], "flops": fl[0], "launches": int(n[0])},
-                "other_conv": {"ms": ms[1], "flops": fl[1], "launches": int(n[1])}}
+                "other_conv": {"ms": ms[1], "flops": fl[1], "launches": int(n[1])},
+                "shared_prefix_conv": {"ms": ms[2], "flops": fl[2], "launches": int(n[2])}}
 
     # -- debug ---------------------------------------------------------------------------------------
     def debug_conv2d(self, x, w, bias=None, impl=PREC_FP32_SIMT):
