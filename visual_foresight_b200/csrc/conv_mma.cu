@@ -405,13 +405,17 @@ __device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const Issue
 // Only home lanes < 128-(KS-1) produce outputs: consecutive units overlap by KS-1 rows.
 template <int KS, int NG>
 __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& g, uint32_t tmem_base, int a, int acc_cols, int q4,
-                                               int lane, int half, int b, int v_lo, uint32_t xch_half, uint32_t tab) {
+                                               int lane, int half, int b, int v_lo, uint32_t xch_half, uint32_t tab, uint32_t stg) {
   const int row = q4 * 32 + lane;
   const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.padc;
   const float scale = g.out_scale;
   const bool sigm = P.act == ACT_SIGMOID;
   const bool vec4 = ((g.Cout | P.out.ch_off | ps) & 3) == 0 && (P.out.sample_stride & 3) == 0 && (P.out.lo_off & 3) == 0;
   const bool split = P.out.lo_off != 0;
+  // float32 outputs with whole 16-channel blocks leave through a per-warp shared-memory tile (stg: 32 pixels x 64 bytes,
+  // XOR-swizzled 16-byte chunks): a store instruction then covers 8 pixels x 64 contiguous bytes (full sectors) instead of
+  // 16 bytes in each of 32 different lines — the uncoalesced form kept the store queue full (STG operand-release stalls).
+  const bool tiled = vec4 && !split && !sigm && (g.Cout & 15) == 0;
   uint32_t par = 0;
   // work items = (unit, 16-channel block), dealt round-robin to the NG groups of the epilogue (4 warps each)
   const int ncb = g.np >> 4;
@@ -470,6 +474,26 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
         }
       }
       par ^= 1;
+      if (tiled) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bb = lds128(sb + (uint32_t)(c16 + j) * 4u);
+          sts128(stg + (uint32_t)(lane * 64 + ((((j >> 2) ^ (lane >> 1)) & 3) << 4)),
+                 make_float4(fmaf(acc[j], scale, bb.x), fmaf(acc[j + 1], scale, bb.y), fmaf(acc[j + 2], scale, bb.z), fmaf(acc[j + 3], scale, bb.w)));
+        }
+        __syncwarp();
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const int q = lane & 3;
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int pp = 8 * s4 + (lane >> 2);
+          const float4 v4 = lds128(stg + (uint32_t)(pp * 64 + (((q ^ (pp >> 1)) & 3) << 4)));
+          const long long oo_p = __shfl_sync(0xffffffffu, oo, pp);
+          if ((vmask >> pp) & 1u) *reinterpret_cast<float4*>(P.out.p + oo_p + c16 + 4 * q) = v4;
+        }
+        __syncwarp();
+        continue;
+      }
       if (!valid) continue;
       if (vec4) {
 #pragma unroll
@@ -512,6 +536,8 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
 constexpr int EPI_WARP0 = 4;
 constexpr int TAB_BAR = 7;             // named barrier of the bias-table hand-over (ids 1..NG: the groups' exchange barriers)
 constexpr int NPRE = 5;                // bias-table entries prefetched per epilogue thread (ntap * np <= 25 * 48 = 1200)
+constexpr uint32_t STG_OFF = 2 * 25 * MT * 4 + 256;   // output tiles of the row-stacked epilogue: behind the bias tables + barriers
+constexpr size_t STG_BYTES = 16 * 2048;               // 2 KB per epilogue warp, up to 16 warps (NG = 4)
 
 template <int NG>
 __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_constant__ Params P) {
@@ -704,12 +730,13 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
       if (stacked) {
         float* tab = tab0 + (it & 1) * (g.ntap * g.np);
         // lane-exchange scratch (the wide path's bias tables live here): 2 parities x 4 quarters x (KS-1)^2 rows x 16 floats
+        const uint32_t stg = smem_u32(tail) + STG_OFF + (uint32_t)(warp - EPI_WARP0) * 2048u;   // this warp's output tile
         if constexpr (NG >= 3) {
-          epilogue_swap2<3, NG>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, smem_u32(s_sab_all + half * 512), smem_u32(tab));
+          epilogue_swap2<3, NG>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, smem_u32(s_sab_all + half * 512), smem_u32(tab), stg);
         } else {
           const uint32_t xch_half = smem_u32(s_sab_all + half * 2048);
-          if (g.k == 3) epilogue_swap2<3, 2>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab));
-          else epilogue_swap2<5, 2>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab));
+          if (g.k == 3) epilogue_swap2<3, 2>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab), stg);
+          else epilogue_swap2<5, 2>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab), stg);
         }
         if (next < g.nitems) {               // every reader of the other table finished one item ago
           tab_store(tab0 + ((it + 1) & 1) * (g.ntap * g.np));
@@ -869,6 +896,9 @@ void current_mode(int* layout, int* bo) {
   *layout = s_layout; *bo = s_bo;
 }
 
+// output tiles of the row-stacked epilogue: only layers whose epilogue can take the tiled path (whole 16-channel blocks)
+size_t stg_bytes(const Geometry& g) { return (g.swap == 2 && (g.Cout & 15) == 0) ? STG_BYTES : 0; }
+
 // TMA box rows: every pass starts its box at the padded-image row holding its first virtual pixel and must cover
 // (offset inside that row) + v_cnt + the k-1 halo rows + k-1 pixels.
 bool box_rows(Geometry& g) {
@@ -914,7 +944,7 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
       if (!box_rows(g)) return false;
       g.plane_bytes = (g.img_pix * g.row_bytes + 1023) / 1024 * 1024;
       for (g.nbuf = 2; g.nbuf >= 1; --g.nbuf) {
-        const size_t act = (size_t)g.nbuf * 2 * g.plane_bytes;
+        const size_t act = (size_t)g.nbuf * 2 * g.plane_bytes + stg_bytes(g);  // + the epilogue's output tiles
         if (act + 2 * (size_t)g.stage_bytes + SMEM_SLACK > SMEM_LIMIT) continue;
         g.nstage = (int)std::min<size_t>(MAX_STAGE, (SMEM_LIMIT - SMEM_SLACK - act) / g.stage_bytes);
         if (g.nbuf == 2 || units == 1) found = true;
@@ -1012,7 +1042,8 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
 
 // >= 116 KB so that exactly one CTA is resident per SM: every CTA allocates all 512 TMEM columns
 size_t smem_bytes(const Geometry& g) {
-  return std::max((size_t)g.nbuf * 2 * g.plane_bytes + (size_t)g.nstage * g.stage_bytes + SMEM_SLACK, (size_t)116 * 1024);
+  return std::max((size_t)g.nbuf * 2 * g.plane_bytes + (size_t)g.nstage * g.stage_bytes + SMEM_SLACK + stg_bytes(g),
+                  (size_t)116 * 1024);
 }
 
 }  // namespace
