@@ -77,6 +77,13 @@ struct Geometry {
   int ustride;      // swap: output pixels per unit (128, or 128-(k-1) when row-stacked: units overlap by the dx halo)
   int nst;          // weight stages per channel chunk (k*k taps, or k filter rows when row-stacked)
   int ksteps_last;  // K=16 steps of the last channel chunk (its zero-padded tail is not multiplied)
+  int rg;           // wide path, W == 8 ("row groups"): an image row is exactly one 8-pixel core-matrix group of the pixel operand, so
+                    //   the descriptor's group stride (SBO) is the PADDED row pitch Wp and the k-1 wrap columns are never multiplied;
+                    //   the G images of an item are stacked pad rows apart (the zero halo rows between two images are shared) and
+                    //   ONE MMA of N = ((G-1)(H+pad)+H)*8 columns spans all of them.
+  int col_stride;   // rg: TMEM columns between consecutive images of an item ((H+pad)*8)
+  int ncols_item;   // rg: TMEM columns of one accumulator set (the MMA's N)
+  int We;           // row pitch of the epilogue's column -> pixel map (Wp, or W when rg)
   float out_scale;  // 2^-scale_log2
 };
 
@@ -579,7 +586,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
 
   const int per_mt = g.ngroups * g.npass;
   const uint32_t ltype = g.layout == 1 ? 4u : 2u;
-  const int acc_cols = g.swap ? g.units * g.ncols : g.G * g.v_cnt;   // TMEM columns of one accumulator set
+  const int acc_cols = g.swap ? g.units * g.ncols : (g.rg ? g.ncols_item : g.G * g.v_cnt);   // TMEM columns of one accumulator set
   const int nacc = g.nacc;                               // 2 when two sets fit in the 512 columns
 
   if (warp == 0) {
@@ -606,7 +613,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
     cx.kstep_a = cx.kstep_b = 32u >> 4;                                   // start-address advance per K=16 step (16-byte units)
     cx.pix_b = (uint32_t)g.row_bytes;
     cx.da_zero = make_desc(0, 16u, sbo_b, ltype, 0);
-    cx.db_zero = make_desc(0, 16u, sbo_b, ltype, 0);
+    cx.db_zero = make_desc(0, 16u, g.rg ? (uint32_t)(g.Wp * g.row_bytes) : sbo_b, ltype, 0);   // rg: group pitch = padded image row
     cx.a_half = (uint64_t)(g.half_bytes >> 4); cx.b_plane = (uint64_t)(g.plane_bytes >> 4);
     cx.act_base = act_base; cx.wst_base = wst_base; cx.tmem_base = tmem_base;
     cx.w_full = w_full; cx.w_empty = w_empty; cx.a_full = a_full; cx.a_empty = a_empty; cx.acc_full = acc_full; cx.acc_empty = acc_empty;
@@ -640,7 +647,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
       }
 #undef VF_SW
     } else {
-      const int U = g.G * g.nseg;
+      const int U = g.rg ? 1 : g.G * g.nseg;
 #define VF_IS(PA, UU)                                       \
   if (g.ksteps == 2) issuer_loop<PA, 2, UU>(g, cx, acc_cols); \
   else issuer_loop<PA, 4, UU>(g, cx, acc_cols)
@@ -823,13 +830,14 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
           }
         }
         float* op = P.out.p + (long long)b * P.out.sample_stride + P.out.ch_off + n;
-        const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.padc, kk = g.kcl;
+        const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.We, pad = g.padc, kk = g.kcl;
+        const int im_cols = g.rg ? g.col_stride : g.v_cnt;
         const float scale = g.out_scale;
         const bool sigm = P.act == ACT_SIGMOID;
         double st_s = 0.0, st_q = 0.0;              // instance-norm statistics of this thread's channel (fused: no extra pass)
         for (int cc = half * 32; cc < g.v_cnt; cc += 64) {
           uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + im * g.v_cnt + cc), r);
+          tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + im * im_cols + cc), r);
           if (!live) continue;
           // Every lane handles the SAME pixel (a different channel).  Branch-free and without loop-carried state so the
           // 32 elements overlap: a 32-column chunk spans at most 4 image rows (Wp >= 10), selected by compare-and-add.
@@ -993,6 +1001,46 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
   const int V = H * g.Wp;                               // virtual pixels per image (incl. k-1 wrap columns per row)
   // (G, v_cnt, npass): several whole small images per item, or an (almost) even slice of one large image.
   // v_cnt is rounded up to 32 columns; the overshoot reads zero-filled staging rows and is masked in the epilogue.
+  g.We = g.Wp;
+  static const bool rg_env = !(getenv("VF_ROWGROUPS") && atoi(getenv("VF_ROWGROUPS")) == 0);
+  if (rg_env && W == 8 && kw == k && layout == 1 && H >= 2 && H * 8 <= 128) {
+    // ---- row-group mode (see Geometry::rg) ----
+    const int pitch = H + g.pad;
+    int G = 1;
+    for (int c = 2; c <= 4; ++c) {
+      const int rows = (c - 1) * pitch + H;
+      if (rows * 8 <= 256 && rows % 2 == 0) G = c;
+    }
+    if ((H % 2) == 0 || G > 1) {
+      const int rows = (G - 1) * pitch + H;
+      if (rows % 2 == 0) {
+        g.rg = 1; g.G = G; g.npass = 1; g.We = W;
+        g.v_cnt = (H * 8 + 31) / 32 * 32;
+        g.col_stride = pitch * 8; g.ncols_item = rows * 8;
+        g.nseg = 1; g.seg_n[0] = g.ncols_item; g.seg_off[0] = 0;
+        g.R = H + 2 * g.pad;
+        g.img_pix = pitch * g.Wp;
+        g.box_bytes = g.R * g.Wp * g.row_bytes;
+        g.plane_bytes = (((G - 1) * g.img_pix + g.R * g.Wp) * g.row_bytes + 1023) / 1024 * 1024;
+        bool ok_rg = false;
+        for (g.nbuf = 2; g.nbuf >= 1; --g.nbuf) {
+          const size_t act = (size_t)g.nbuf * 2 * g.plane_bytes;
+          if (act + 2 * (size_t)g.stage_bytes + SMEM_SLACK > SMEM_LIMIT) continue;
+          g.nstage = (int)std::min<size_t>(MAX_STAGE, (SMEM_LIMIT - SMEM_SLACK - act) / g.stage_bytes);
+          ok_rg = true;
+          break;
+        }
+        if (ok_rg) {
+          g.nacc = (2 * g.ncols_item <= 512) ? 2 : 1;
+          g.ngroups = (B + g.G - 1) / g.G;
+          g.nitems = g.n_mt * g.ngroups * g.npass;
+          *out = g;
+          return true;
+        }
+        g.rg = 0; g.We = g.Wp;
+      }
+    }
+  }
   if (V <= 128) {
     g.v_cnt = (V + 31) / 32 * 32;
     g.G = std::max(1, std::min(256 / g.v_cnt, 3));
