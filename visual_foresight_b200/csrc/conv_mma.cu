@@ -64,7 +64,8 @@ struct Geometry {
   int nchunk0;      // channel chunks taken from the first source (the rest come from the second)
   int nseg;         // MMA column segments per image
   int seg_n[MAX_SEG];
-  int seg_off[MAX_SEG];
+  int seg_off[MAX_SEG];   // first accumulator column of the segment
+  int seg_px[MAX_SEG];    // first shared-memory pixel row of the segment (== seg_off except in row-group mode 2)
   int ngroups, nitems;
   int passes;       // 1 or 3 MMA passes
   int nacc;         // TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs)
@@ -81,6 +82,9 @@ struct Geometry {
                     //   the descriptor's group stride (SBO) is the PADDED row pitch Wp and the k-1 wrap columns are never multiplied;
                     //   the G images of an item are stacked pad rows apart (the zero halo rows between two images are shared) and
                     //   ONE MMA of N = ((G-1)(H+pad)+H)*8 columns spans all of them.
+                    //   rg == 2 (W == 16): one image per item, two MMAs per K step — the left and the right 8-pixel group of every
+                    //   row (N = 8*H each, group stride Wp, the right one starting 8 pixels later) -> columns [0, 8H) and [8H, 16H).
+  int half_cols;    // rg == 2: accumulator columns per 8-pixel column group (8*H)
   int col_stride;   // rg: TMEM columns between consecutive images of an item ((H+pad)*8)
   int ncols_item;   // rg: TMEM columns of one accumulator set (the MMA's N)
   int We;           // row pitch of the epilogue's column -> pixel map (Wp, or W when rg)
@@ -276,7 +280,7 @@ __device__ __forceinline__ void issuer_loop(const Geometry& g, const IssueCtx& c
   for (int u = 0; u < MAX_UNIT; ++u) {
     const int im = u / g.nseg, sg = u % g.nseg;
     ucol0[u] = cx.tmem_base + (uint32_t)(im * g.v_cnt + g.seg_off[sg]);
-    uoff[u] = (uint64_t)(((uint32_t)(im * g.img_pix + g.seg_off[sg]) * cx.pix_b) >> 4);
+    uoff[u] = (uint64_t)(((uint32_t)(im * g.img_pix + g.seg_px[sg]) * cx.pix_b) >> 4);
     uidesc[u] = make_idesc(g.seg_n[sg]);
   }
   const int nitems = g.nitems, nchunk = g.nchunk, ntap = g.nst, kk = g.kw, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
@@ -647,7 +651,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
       }
 #undef VF_SW
     } else {
-      const int U = g.rg ? 1 : g.G * g.nseg;
+      const int U = g.rg == 1 ? 1 : g.G * g.nseg;
 #define VF_IS(PA, UU)                                       \
   if (g.ksteps == 2) issuer_loop<PA, 2, UU>(g, cx, acc_cols); \
   else issuer_loop<PA, 4, UU>(g, cx, acc_cols)
@@ -841,7 +845,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
           if (!live) continue;
           // Every lane handles the SAME pixel (a different channel).  Branch-free and without loop-carried state so the
           // 32 elements overlap: a 32-column chunk spans at most 4 image rows (Wp >= 10), selected by compare-and-add.
-          const int v = v_lo + cc;
+          const int xoff = g.rg == 2 ? (cc / g.half_cols) * 8 : 0;       // rg 2: second column group of the rows
+          const int v = v_lo + (g.rg == 2 ? cc % g.half_cols : cc);
           const int oy0 = v / Wp, ox0 = v - oy0 * Wp;
           int cyk[4], rbase[4];
 #pragma unroll
@@ -854,7 +859,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
           for (int j = 0; j < 32; ++j) {
             const int x0 = ox0 + j;
             const int wr = (x0 >= Wp) + (x0 >= 2 * Wp) + (x0 >= 3 * Wp);
-            const int x = x0 - wr * Wp;
+            const int x = x0 - wr * Wp + xoff;
             const bool valid = (x < W) & (oy0 + wr < H);
             const int cx = x < pad ? x : (x >= W - pad ? x - (W - 1 - 2 * pad) : pad);
             const int cyw = wr == 0 ? cyk[0] : (wr == 1 ? cyk[1] : (wr == 2 ? cyk[2] : cyk[3]));
@@ -1003,6 +1008,35 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
   // v_cnt is rounded up to 32 columns; the overshoot reads zero-filled staging rows and is masked in the epilogue.
   g.We = g.Wp;
   static const bool rg_env = !(getenv("VF_ROWGROUPS") && atoi(getenv("VF_ROWGROUPS")) == 0);
+  if (rg_env && W == 16 && H == 16 && kw == k && layout == 1) {
+    // ---- row-group mode 2 (see Geometry::rg) ----
+    g.rg = 2; g.G = 1; g.npass = 1; g.We = 8;
+    g.half_cols = H * 8; g.v_cnt = 2 * g.half_cols; g.col_stride = g.v_cnt; g.ncols_item = g.v_cnt;
+    g.nseg = 2;
+    g.seg_n[0] = g.seg_n[1] = g.half_cols;
+    g.seg_off[0] = 0; g.seg_off[1] = g.half_cols;
+    g.seg_px[0] = 0; g.seg_px[1] = 8;
+    g.R = H + 2 * g.pad;
+    g.img_pix = (g.R * g.Wp + 7) / 8 * 8;
+    g.box_bytes = g.R * g.Wp * g.row_bytes;
+    g.plane_bytes = ((g.img_pix + 16) * g.row_bytes + 1023) / 1024 * 1024;    // + the right group's reach past the last row
+    bool ok_rg = false;
+    for (g.nbuf = 2; g.nbuf >= 1; --g.nbuf) {
+      const size_t act = (size_t)g.nbuf * 2 * g.plane_bytes;
+      if (act + 2 * (size_t)g.stage_bytes + SMEM_SLACK > SMEM_LIMIT) continue;
+      g.nstage = (int)std::min<size_t>(MAX_STAGE, (SMEM_LIMIT - SMEM_SLACK - act) / g.stage_bytes);
+      ok_rg = true;
+      break;
+    }
+    if (ok_rg) {
+      g.nacc = (2 * g.ncols_item <= 512) ? 2 : 1;
+      g.ngroups = B;
+      g.nitems = g.n_mt * g.ngroups;
+      *out = g;
+      return true;
+    }
+    g.rg = 0; g.We = g.Wp;
+  }
   if (rg_env && W == 8 && kw == k && layout == 1 && H >= 2 && H * 8 <= 128) {
     // ---- row-group mode (see Geometry::rg) ----
     const int pitch = H + g.pad;
@@ -1017,7 +1051,7 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
         g.rg = 1; g.G = G; g.npass = 1; g.We = W;
         g.v_cnt = (H * 8 + 31) / 32 * 32;
         g.col_stride = pitch * 8; g.ncols_item = rows * 8;
-        g.nseg = 1; g.seg_n[0] = g.ncols_item; g.seg_off[0] = 0;
+        g.nseg = 1; g.seg_n[0] = g.ncols_item; g.seg_off[0] = 0; g.seg_px[0] = 0;
         g.R = H + 2 * g.pad;
         g.img_pix = pitch * g.Wp;
         g.box_bytes = g.R * g.Wp * g.row_bytes;
@@ -1063,7 +1097,7 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
   while (left > 0) {
     const int n = std::min(base, left);
     if (n % 16 || g.nseg >= MAX_SEG) return false;
-    g.seg_n[g.nseg] = n; g.seg_off[g.nseg] = off; ++g.nseg;
+    g.seg_n[g.nseg] = n; g.seg_off[g.nseg] = off; g.seg_px[g.nseg] = off; ++g.nseg;
     off += n; left -= n;
   }
   if (!box_rows(g)) return false;
