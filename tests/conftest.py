@@ -34,3 +34,9 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "ref_cem_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def sampler_golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_samplers_golden.npz"))

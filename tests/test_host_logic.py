@@ -108,6 +108,67 @@ def test_correlated_noise_sampler(golden):
                                golden["corr_next_seed6"], rtol=1e-12, atol=1e-15)
 
 
+def test_autograsp_sampler_matches_reference(sampler_golden):
+    """AutograspSampler (reference samplers/autograsp_sampler.py) draws the same np.random stream and applies the same
+    gripper rule as the unmodified reference: initial batches bit-identical for the default, reopen + deviation-noise and
+    scaled-threshold settings (fixtures: tests/golden/make_sampler_golden.py)."""
+    g = sampler_golden
+    assert int(g["ag_next_raises"]) == 1          # the reference's sample_next_actions is broken (missing argument)
+    for tag, over in (("default", {}), ("reopen_dev", {"reopen": True, "deviation_prob": 0.3}),
+                      ("scaled", {"action_norm_factor": 2.5, "z_thresh": 0.05, "deviation_prob": 0.1})):
+        d = S.AutograspSampler.get_default_hparams()
+        d.update(rejection_sampling=False, **over)
+        smp = S.AutograspSampler(HParams(**d), 5, 5)
+        np.random.seed(21)
+        a = smp.sample_initial_actions(1, 12, g["ag_state"])
+        np.testing.assert_array_equal(a, g["ag_init_" + tag])
+        assert set(np.unique(a[:, :, -1])) <= {-1.0, 1.0}
+    # the repaired sample_next_actions: arm dimensions refit like the Gaussian sampler, gripper by rule or by elite frequency
+    d = S.AutograspSampler.get_default_hparams()
+    d.update(rejection_sampling=False)
+    smp = S.AutograspSampler(HParams(**d), 5, 5)
+    np.random.seed(21)
+    first = smp.sample_initial_actions(1, 12, g["ag_state"])
+    nxt = smp.sample_next_actions(12, first[:6], np.arange(6.0))
+    assert nxt.shape == (12, 15, 5)
+    z = np.cumsum(nxt[:, :, 2], axis=1) + g["ag_state"][2] < 0.15
+    for row in range(12):                                            # closes at the first crossing and stays closed
+        want = np.zeros(15, bool)
+        if z[row].any():
+            want[int(np.argmax(z[row])):] = True
+        np.testing.assert_array_equal(nxt[row, :, 4] == 1, want)
+    d.update(no_refit=False)
+    smp = S.AutograspSampler(HParams(**d), 5, 5)
+    np.random.seed(21)
+    first = smp.sample_initial_actions(1, 12, g["ag_state"])
+    elites = first[:6].copy()
+    elites[:, :5, 4], elites[:, 5:, 4] = -1, 1                       # elites all open for 5 steps, then all closed
+    nxt = smp.sample_next_actions(12, elites, np.arange(6.0))
+    assert np.all(nxt[:, :5, 4] == -1) and np.all(nxt[:, 5:, 4] == 1)
+
+
+def test_folding_sampler_matches_reference(sampler_golden):
+    """FoldingCEMSampler (reference samplers/folding_sampler.py) reproduces the unmodified reference's action tensors under
+    the same np.random seed: initial proposal, refit proposal, and a 6-step / repeat-2 / split 0.9 configuration."""
+    g = sampler_golden
+    fs = S.FoldingCEMSampler(HParams(**S.FoldingCEMSampler.get_default_hparams()), 4, 4)
+    np.random.seed(31)
+    np.testing.assert_array_equal(fs.sample_initial_actions(1, 24, g["fold_state"]), g["fold_init_seed31"])
+    np.random.seed(32)
+    np.testing.assert_allclose(fs.sample_next_actions(24, g["fold_elites"], np.arange(8.0)), g["fold_next_seed32"],
+                               rtol=1e-10, atol=1e-13)
+    fs2 = S.FoldingCEMSampler(HParams(**dict(S.FoldingCEMSampler.get_default_hparams(), split_frac=0.9, nactions=6, repeat=2)), 4, 4)
+    np.random.seed(33)
+    a = fs2.sample_initial_actions(0, 12, g["fold_state"])
+    np.testing.assert_array_equal(a, g["fold_init6_seed33"])
+    lim = np.array([1. / 5, 1. / 5, 1. / 3])
+    assert np.all(np.abs(a[:, :, :3]) <= lim + 1e-15)
+    with pytest.raises(AssertionError):
+        fs.sample_initial_actions(0, 10, g["fold_state"])            # sample count must split three ways
+    with pytest.raises(AssertionError):
+        S.FoldingCEMSampler(HParams(**S.FoldingCEMSampler.get_default_hparams()), 5, 4)
+
+
 def test_policy_arg_resolution():
     pol = NullPolicy({"adim": 4}, {})
     assert get_policy_args(pol, {}, 0, 0) == {}

@@ -279,3 +279,125 @@ class CorrelatedNoiseSampler(CEMSampler):
         mean = (best_actions * weight[:, None, None]).sum(0) / (weight.sum() + 1e-4)
         cov = np.cov(best_actions.reshape(best_actions.shape[0], -1).T) if hp.refit_cov else None
         return self._noise(n_samples, cov) + mean.reshape(1, best_actions.shape[1], self._adim)
+
+
+class AutograspSampler(GaussianCEMSampler):
+    """Gaussian CEM over the arm dimensions with a rule-based gripper command appended as the last action dimension
+    (reference samplers/autograsp_sampler.py:5-58): the gripper closes from the first step at which the integrated
+    z displacement (times ``action_norm_factor``) brings the arm below ``z_thresh`` and, unless ``reopen``, stays closed;
+    ``deviation_prob`` flips single steps.  With ``no_refit`` (default) the rule is re-applied to every resampled batch,
+    otherwise the gripper column is drawn per step from the elites' closing frequency.
+
+    Deviation: the reference's ``sample_next_actions`` calls the parent without the ``scores`` argument and raises
+    ``TypeError`` (autograsp_sampler.py:26); here the call is well-formed."""
+
+    def __init__(self, hp, adim, sdim, **kwargs):
+        super().__init__(hp, adim - 1, sdim, **kwargs)
+        self._current_state = None
+
+    @staticmethod
+    def get_default_hparams():
+        hp = GaussianCEMSampler.get_default_hparams()
+        hp.update(deviation_prob=0, reopen=False, action_norm_factor=1.0, z_thresh=0.15, gripper_close_cmd=1,
+                  gripper_open_cmd=-1, no_refit=True)
+        return hp
+
+    def sample_initial_actions(self, t, nsamples, current_state):
+        self._current_state = current_state
+        return self._with_gripper_rule(super().sample_initial_actions(t, nsamples, current_state))
+
+    def sample_next_actions(self, n_samples, best_actions, scores):
+        hp = self._hp
+        arm = super().sample_next_actions(n_samples, best_actions[:, :, :-1], scores)
+        if hp.no_refit:
+            return self._with_gripper_rule(arm)
+        p_close = (best_actions[:, :, -1] == hp.gripper_close_cmd).astype(np.float32).mean(axis=0)
+        grip = np.zeros((arm.shape[0], arm.shape[1], 1), dtype=np.float32)
+        for step in range(arm.shape[1]):                       # one uniform vector per step, like the reference
+            close = np.random.uniform(size=arm.shape[0]) < p_close[step]
+            grip[:, step, 0] = np.where(close, hp.gripper_close_cmd, hp.gripper_open_cmd)
+        return np.concatenate((arm, grip), axis=-1)
+
+    def _with_gripper_rule(self, arm):
+        hp = self._hp
+        z0 = self._current_state[2]
+        closed = np.cumsum(arm[:, :, 2] * hp.action_norm_factor, axis=1) + z0 < hp.z_thresh
+        grip = np.zeros((arm.shape[0], arm.shape[1], 1))
+        for row in range(arm.shape[0]):                        # row order matters: deviation noise is drawn per sample
+            mask = closed[row].copy()
+            if not hp.reopen and mask.any():
+                mask[int(np.argmax(mask)):] = True
+            if hp.deviation_prob:
+                flip = np.random.uniform(size=mask.shape[0]) < hp.deviation_prob
+                mask = np.logical_xor(mask, flip)
+            grip[row, :, 0] = np.where(mask, hp.gripper_close_cmd, hp.gripper_open_cmd)
+        return np.concatenate((arm, grip), axis=-1)
+
+
+class FoldingCEMSampler(CEMSampler):
+    """Cloth-folding proposal distribution (reference samplers/folding_sampler.py:7-132).  A ``split_frac`` share of the
+    samples (halved on the first iteration) follows two scripted motion templates built from uniformly drawn way-points —
+    (reach, lower, lift, carry, lower) and (lift, carry, lower, hold) with tight covariance on the vertical moves — and the
+    rest is drawn from the fitted Gaussian; xyz are clipped to ``max_shift``.  The ``np.random`` draw order is the
+    reference's, so a seeded run reproduces its action tensors."""
+
+    _REACH_CARRY = ((+1.0, "wide", 0), (-1.0, "tight", None), (+1.0, "tight", None), (+1.0, "wide", 1), (-1.0, "tight", None))
+
+    def __init__(self, hp, adim, sdim, **kwargs):
+        super().__init__(hp, adim, sdim, **kwargs)
+        assert adim == 4, "Requires base action dimension of 4"
+        assert hp.nactions >= 5, "Requires at least 5 steps"
+        self._xy = None
+        self._mean = self._cov = None
+
+    @staticmethod
+    def get_default_hparams():
+        return dict(action_order=None, initial_std=0.05, initial_std_lift=0.15, initial_std_rot=np.pi / 18,
+                    initial_std_grasp=2, nactions=5, repeat=3, max_shift=[1. / 5, 1. / 5, 1. / 3], split_frac=0.5)
+
+    def sample_initial_actions(self, t, n_samples, current_state):
+        self._xy = np.asarray(current_state)[:2]
+        return self._propose(n_samples, np.zeros(self._hp.nactions * self._adim), initial_covariance(self._hp, self._adim, t))
+
+    def sample_next_actions(self, n_samples, best_actions, scores):
+        hp = self._hp
+        last = best_actions.reshape(-1, hp.nactions, hp.repeat, self._adim)[:, :, -1]
+        flat = last.reshape(last.shape[0], hp.nactions * self._adim)
+        return self._propose(n_samples, flat.mean(axis=0), np.cov(flat, rowvar=False, bias=False))
+
+    def _propose(self, count, mean, cov):
+        hp, steps, rep = self._hp, self._hp.nactions, self._hp.repeat
+        assert count % 3 == 0, "splits samples into setting with 3 means"
+        self._mean, self._cov = np.array(mean, copy=True), np.array(cov, copy=True)
+        wide = self._cov[:4, :4]
+        tight = wide.copy()
+        tight[:2, :2] /= 10
+        tight[3, 3] /= 2
+        covs = {"wide": wide, "tight": tight}
+        n_tpl = max(int(int(count * hp.split_frac / 2) / 2), 1)     # both public entry points are "first iteration" calls
+
+        def draw(mu, which):
+            return np.random.multivariate_normal(np.asarray(mu, dtype=np.float64), covs[which], 1).reshape(-1)
+
+        out = np.zeros((count, steps, self._adim))
+        for row in range(n_tpl):                                 # template 1: reach, lower, lift, carry, lower
+            p1, p2 = np.random.uniform(size=2), np.random.uniform(size=2)
+            legs = ((p1 - self._xy) / rep, (p2 - p1) / rep)
+            for step, (dz, which, leg) in enumerate(self._REACH_CARRY):
+                dxy = legs[leg] if leg is not None else (0.0, 0.0)
+                out[row, step] = draw([dxy[0], dxy[1], dz, 0.0], which)
+            if steps > 5:                                        # the reference assigns these draws to an empty slice
+                np.random.multivariate_normal(np.zeros(4), wide, steps - 5)
+        for row in range(n_tpl, 2 * n_tpl):                      # template 2: lift, carry, lower, hold
+            carry = (np.random.uniform(size=2) - self._xy) / rep
+            out[row, 0] = draw([0.0, 0.0, 1.0, 0.0], "tight")
+            out[row, 1] = draw([carry[0], carry[1], 1.0, 0.0], "wide")
+            out[row, 2] = draw([0.0, 0.0, -1.0, 0.0], "tight")
+            out[row, 3:] = draw([0.0, 0.0, 0.0, 0.0], "tight")
+            if steps > 5:
+                np.random.multivariate_normal(np.zeros(4), wide, steps - 5)
+        rest = count - 2 * n_tpl
+        out[2 * n_tpl:] = np.random.multivariate_normal(self._mean, self._cov, rest).reshape(rest, steps, self._adim)
+        lim = np.asarray(hp.max_shift)
+        out[:, :, :3] = np.clip(out[:, :, :3], -lim, lim)
+        return np.repeat(out, rep, axis=1)
