@@ -571,6 +571,44 @@ def test_rollout_tensor_core_path_vs_oracle(precision, tol):
     e.close()
 
 
+def test_goal_image_cost_and_controller():
+    """SURVEY a7 (goal_im_controller.py:87-93): score = mean squared error of the final predicted frame of view 0 against
+    the goal image.  The device kernel against numpy on the fetched frames (rel 1e-5), then GoalImController.act() end to
+    end: zeros before t = n_context, a plan afterwards whose recorded scores are that cost of the sampled actions."""
+    from visual_foresight_b200.cem_controller import GoalImController
+    from visual_foresight_b200.engine import COST_GOAL_IMAGE
+    sp = S.spec_64(height=32, width=32, seq_len=6)
+    w = Hh.make_weights(sp, seed=31)
+    inp = Hh.synth_inputs(sp, seed=32)
+    acts = Hh.gaussian_actions(sp, 6, 6, seed=33)
+    e, (gi, gd, gs) = _engine_rollout(sp, w, inp, acts, precision="f16x3")
+    goal = np.random.default_rng(34).uniform(0, 1, (32, 32, 3)).astype(np.float32)
+    sc = e.score(goal, cost_kind=COST_GOAL_IMAGE, M=6)
+    want = ((gi[:, -1, 0].astype(np.float64) - goal) ** 2).mean(axis=(1, 2, 3))
+    np.testing.assert_allclose(sc, want, rtol=1e-5)
+    e.close()
+
+    ag = {"adim": 4, "sdim": 4, "image_height": 32, "image_width": 32, "gpu_id": 0}
+    pp = {"num_samples": 12, "minimum_selection": 4, "iterations": 2, "rejection_sampling": False, "verbose": False,
+          "model_spec": {"height": 32, "width": 32, "seq_len": 15}, "model_seed": 31}
+    pol = GoalImController(ag, pp, 0, 1)
+    pol.reset()
+    rng = np.random.default_rng(35)
+    images = rng.integers(0, 256, size=(4, 1, 32, 32, 3), dtype=np.uint8)
+    state = rng.uniform(-0.5, 0.5, size=(4, 4))
+    goal_u8 = rng.integers(0, 256, size=(1, 1, 32, 32, 3), dtype=np.uint8)
+    np.random.seed(3)
+    for t in range(3):
+        out = pol.act(t=t, i_tr=0, goal_image=goal_u8, images=images[:t + 1], state=state[:t + 1])
+        assert out["actions"].shape == (4,)
+        if t < 2:
+            assert np.all(out["actions"] == 0)                  # start_planning = n_context (goal_im_controller.py:35)
+    s0, s1 = out["plan_stat"]["scores_itr0"], out["plan_stat"]["scores_itr1"]
+    assert s0.shape == (12,) and np.all(np.isfinite(s0)) and np.all(s0 > 0) and np.all(s0 < 1)
+    best = pol._backend.engine.fetch([int(np.argmin(s1))])[0][0]
+    np.testing.assert_allclose(s1.min(), ((best[-1, 0].astype(np.float64) - goal_u8[0, 0] / 255.0) ** 2).mean(), rtol=1e-5)
+
+
 @pytest.mark.parametrize("precision", ["fp32_simt", "f16x3"])
 def test_shared_prefix_steps_are_bit_identical(precision, monkeypatch):
     """The cell steps fed only by context (frame, state AND action: tau < min(n_ctx_actions, C-1)) are the same for every

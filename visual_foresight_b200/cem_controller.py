@@ -309,3 +309,40 @@ class PixelCostController(CEMBaseController):
         self._images = images
         self._verbose_worker = verbose_worker
         return super().act(t, i_tr, state)
+
+
+class GoalImController(PixelCostController):
+    """Goal-image controller (reference ``goal_im_controller.py:12-93``): the cost of a rollout is the mean squared error
+    between its FINAL predicted frame of view 0 and the goal image, planning starts at ``t = n_context``
+    (:35).  Prediction and cost run on the engine; the sampler loop is the host plugin path.
+
+    Deviations: the reference reads the goal image from a hard-coded file and compares frames in [0,1] with uint8 pixels;
+    here the goal image arrives through ``act(goal_image=...)`` (the agent's ``goal_image`` entry, ``general_agent.py:142-151``)
+    and is brought to [0,1] like the frames."""
+
+    def __init__(self, ag_params, policyparams, gpu_id=0, ngpu=1):
+        super().__init__(ag_params, policyparams, gpu_id, ngpu)
+        if self._backend is None:
+            raise NotImplementedError("GoalImController needs the engine-backed predictor (the cost runs on the device)")
+        self._hp.start_planning = self._net_context
+        self._goal_image = None
+
+    def _device_path_ok(self):
+        return False                          # the device CEM loop scores pixel distance; this cost goes through the plugin path
+
+    def evaluate_rollouts(self, actions, cem_itr):
+        context = {"context_frames": self._images, "context_actions": self._sampler.chosen_actions,
+                   "context_pixel_distributions": self._make_input_distrib(cem_itr), "context_states": self._state}
+        scores = self._backend.evaluate_goal_image(context, actions, self._goal_image)
+        if self._verbose_condition(cem_itr):
+            self._export_verbose(scores)
+        return scores
+
+    def act(self, t=None, i_tr=None, goal_image=None, images=None, state=None, verbose_worker=None):
+        g = np.asarray(goal_image)
+        while g.ndim > 3:                      # (T, ncam, H, W, 3) or (ncam, H, W, 3): last time step, view 0
+            g = g[-1] if g.ndim == 5 else g[0]
+        g = g.astype(np.float32)
+        self._goal_image = g / 255.0 if g.max() > 1.5 else g
+        zeros = np.zeros((self._n_cam, self._n_desig, 2))
+        return super().act(t, i_tr, zeros, zeros, images, state, verbose_worker)

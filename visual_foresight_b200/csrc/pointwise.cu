@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) k_lstm_gates_generic(View gates, int HW, 
 __global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, StatsRef gsr,
                                                   const float* __restrict__ gg, const float* __restrict__ gb,
                                                   StatsRef csr, const float* __restrict__ cg,
-                                                  const float* __restrict__ cb, float* c, View h) {
+                                                  const float* __restrict__ cb, float* c, View h, View h2, int W) {
   pdl_wait();
   pdl_trigger();
   const int b = blockIdx.y;
@@ -253,6 +253,10 @@ __global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, Sta
     hv.z = tanhf(cn.z) * sigmoidf_((ov.z - oa[f + 2]) * od[f + 2] * og.z + ob.z);
     hv.w = tanhf(cn.w) * sigmoidf_((ov.w - oa[f + 3]) * od[f + 3] * og.w + ob.w);
     vst4(h, voff(h, b, pix) + f, hv);
+    if (h2.p) {          // space-to-depth copy for the next encoder conv (2x2 pixel blocks -> channels [sub-position][F])
+      const int y = pix / W, x = pix - y * W;
+      vst4(h2, voff(h2, b, (long long)(y >> 1) * (W >> 1) + (x >> 1)) + ((y & 1) * 2 + (x & 1)) * F + f, hv);
+    }
   }
 }
 
@@ -547,10 +551,10 @@ void launch_stats_finalize(const double* partial, int n, int S, int npix, float 
   launch_k(k_stats_finalize, dim3((n + 255) / 256), dim3(256), 0, s, partial, n, S, npix, eps, stats);
 }
 void launch_lstm_out(View gates, int B, int HW, int F, StatsRef gstats, const float* gg, const float* gb,
-                     StatsRef cstats, const float* cg, const float* cb, float* c, View h, cudaStream_t s) {
+                     StatsRef cstats, const float* cg, const float* cb, float* c, View h, cudaStream_t s, View h2, int W) {
   ++g_launch_counter;
   dim3 grid(grid_for((long long)HW * F / 4, 256, B >= 64 ? 16 : 64), B);
-  launch_k(k_lstm_out, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h);
+  launch_k(k_lstm_out, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h, h2, W);
 }
 void launch_upsample2x(View s0, View s1, int B, int H, int W, View out, cudaStream_t s) {
   ++g_launch_counter;

@@ -186,7 +186,8 @@ void launch_stats_finalize(const double* partial, int n, int S, int npix, float 
 // part 2: c <- IN(c);  h <- tanh(c) * sigmoid(IN(o))
 void launch_lstm_out(View gates, int B, int HW, int F, StatsRef gstats, const float* ggamma,
                      const float* gbeta, StatsRef cstats, const float* cgamma, const float* cbeta,
-                     float* c, View h, cudaStream_t s);
+                     float* c, View h, cudaStream_t s, View h2 = make_view(nullptr, 0, 0, 0, 0), int W = 0);   // h2: optional
+                     // space-to-depth copy of h ([B][H/2*W/2][4F]: 2x2 pixel blocks in channels) for a pool-fused encoder conv
 // out[b, 2H, 2W, C0+C1] = bilinear_x2(concat(src0, src1))   (half-pixel centres, edge clamp)
 void launch_upsample2x(View src0, View src1, int B, int H, int W, View out, cudaStream_t s);
 
