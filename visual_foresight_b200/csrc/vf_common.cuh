@@ -35,7 +35,11 @@ __host__ __device__ inline View make_view(float* p, long long ss, int ps, int co
 // completed and flushed) and pdl_trigger() (lets the next kernel's launch + prologue overlap this kernel).  Without the launch
 // attribute both are no-ops, so the kernels behave identically under plain stream ordering.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef VF_PDL_LATE   // experiment: no early trigger (dependents are released when the blocks exit)
+__device__ __forceinline__ void pdl_trigger() {}
+#else
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 extern bool g_use_pdl;
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {

@@ -17,7 +17,7 @@ PREC_FP32_SIMT, PREC_F16X3, PREC_F16X1 = 0, 1, 2
 COST_PIXEL_DISTANCE, COST_GOAL_IMAGE = 0, 1
 PRECISIONS = {"fp32_simt": PREC_FP32_SIMT, "f16x3": PREC_F16X3, "f16x1": PREC_F16X1}
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvfengine.so")
+LIB_PATH = os.environ.get("VF_ENGINE_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvfengine.so")
 
 
 class EngineUnavailable(RuntimeError):
