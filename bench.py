@@ -299,8 +299,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("VF_PRECISION", "f16x3"), choices=["fp32_simt", "f16x3", "f16x1"])
     ap.add_argument("--samples", type=int, default=0, help="override per-GPU M (debug)")
-    ap.add_argument("--cpu-samples", type=int, default=8)
-    ap.add_argument("--ref-samples", type=int, default=8)
+    ap.add_argument("--cpu-samples", type=int, default=200, help="samples of the cpu_baseline leg (one full CEM iteration by default)")
+    ap.add_argument("--ref-samples", type=int, default=50, help="samples per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = env_rank()
