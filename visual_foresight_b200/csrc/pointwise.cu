@@ -465,10 +465,12 @@ __global__ void k_broadcast_rows(BroadcastBatch a, int M, int rows_per_group) {
   pdl_trigger();
   const BroadcastBatch::Buf buf = a.b[blockIdx.y];
   const long long n16 = buf.row_bytes >> 4;
-  const int m0 = 1 + blockIdx.z * rows_per_group, m1 = min(M, m0 + rows_per_group);
+  const int first = buf.src ? 0 : 1;
+  const int m0 = first + blockIdx.z * rows_per_group, m1 = min(M, m0 + rows_per_group);
   uint4* base = reinterpret_cast<uint4*>(buf.p);
+  const uint4* src = buf.src ? reinterpret_cast<const uint4*>(buf.src) : base;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
-    const uint4 v = base[i];
+    const uint4 v = src[i];
     for (int m = m0; m < m1; ++m) base[(long long)m * n16 + i] = v;
   }
 }
@@ -606,12 +608,14 @@ void launch_pack_s2d(View image, View first, int B, int H, int W, View out, cuda
   launch_k(k_pack_s2d, dim3(grid), dim3(256), 0, s, image, first, H, W, out);
 }
 void launch_broadcast_rows(const BroadcastBatch& a, int M, cudaStream_t s) {
-  if (a.n == 0 || M <= 1) return;
-  ++g_launch_counter;
+  if (a.n == 0 || M < 1) return;
+  bool any_src = false;
   long long mx = 16;
-  for (int i = 0; i < a.n; ++i) mx = std::max(mx, a.b[i].row_bytes);
+  for (int i = 0; i < a.n; ++i) { mx = std::max(mx, a.b[i].row_bytes); any_src = any_src || a.b[i].src; }
+  if (M <= 1 && !any_src) return;
+  ++g_launch_counter;
   const int rows_per_group = 8;
-  dim3 grid((unsigned)std::min<long long>((mx / 16 + 255) / 256, 64), a.n, (M - 1 + rows_per_group - 1) / rows_per_group);
+  dim3 grid((unsigned)std::min<long long>((mx / 16 + 255) / 256, 64), a.n, (M + rows_per_group - 1) / rows_per_group);
   launch_k(k_broadcast_rows, dim3(grid), dim3(256), 0, s, a, M, rows_per_group);
 }
 void launch_pack_rgb2(View image, View first, int B, int HW, View out, cudaStream_t s) {

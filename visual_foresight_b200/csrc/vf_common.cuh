@@ -222,7 +222,8 @@ struct SabiasBatch {
 void launch_sabias_batch(const SabiasBatch& a, cudaStream_t s);
 // rows[m] = rows[0] for m in [1, M): replicates the recurrent state of sample 0 after the shared-prefix cell steps (engine.cu)
 struct BroadcastBatch {
-  struct Buf { void* p; long long row_bytes; };     // row_bytes % 16 == 0, rows contiguous
+  struct Buf { void* p; long long row_bytes; const void* src; };   // row_bytes % 16 == 0, rows contiguous; src == nullptr: rows[m] = rows[0]
+                                                                     // for m >= 1, else rows[m] = src row for every m >= 0
   Buf b[24];
   int n;
 };
