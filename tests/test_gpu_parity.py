@@ -639,6 +639,37 @@ def test_shared_prefix_steps_are_bit_identical(precision, monkeypatch):
     assert np.abs(outs[0][1] - od).max() <= 1e-5
 
 
+def test_plan_prefix_cache_is_bit_identical(monkeypatch):
+    """Within one plan the context does not change, so CEM iterations 1.. start from the recurrent state iteration 0 saved
+    after the shared-prefix steps instead of recomputing them (engine.cu: PREFIX_SAVE / PREFIX_RESTORE).  Two consecutive
+    plans (the second replays captured graphs, with a NEW context in between) give bit-identical scores, elites and actions
+    with the cache on and off."""
+    from visual_foresight_b200.predictor import EngineBackend
+    sp = S.spec_64(height=32, width=32, seq_len=6)
+    w = Hh.make_weights(sp, seed=41)
+    M, K = 12, 4
+    results = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("VF_PREFIX_CACHE", flag)
+        be = EngineBackend(sp, w, M, precision="f16x3")
+        out = []
+        for plan in range(3):
+            inp = Hh.synth_inputs(sp, seed=42 + plan % 2)                 # the context changes between plans
+            onehot = OC.switch_on_pix(inp["desig"], 2, 1, sp.height, sp.width, 1)
+            ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"],
+                   "context_pixel_distributions": onehot}
+            kw = _plan_kwargs(sp, M, K, 3, seed=7)
+            kw["plan_index"] = plan
+            res = be.plan(ctx, goal_pix=inp["goal"], **kw)
+            out.append((res["scores"].copy(), res["elite_idx"].copy(), res["best_actions"].copy()))
+        be.engine.close()
+        results.append(out)
+    for a, b in zip(*results):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+    assert not np.array_equal(results[0][0][0], results[0][1][0])       # different contexts really give different plans
+
+
 # ---- multi-GPU (only when the box has >= 2 GPUs; the 1-GPU round-end run skips it) ------------------------------
 def test_two_gpu_sharded_plan_is_bit_identical():
     """torchrun x2: contiguous shards + NCCL in-place all-gather of the float64 scores per CEM iteration give the

@@ -58,6 +58,8 @@ struct ConvLayer {
 
 struct RnnState {
   float* h_s2d = nullptr;     // [B][h/2][w/2][4F]: space-to-depth copy of h for the next (pool-fused) encoder conv, or null
+  float* snap_c = nullptr;    // [h][w][F]    sample 0's cell state after the shared-prefix steps (per-plan prefix cache)
+  float* snap_in = nullptr;   // [h][w][2F]   sample 0's lstm_in row (split-half: hi row then lo row, same bytes)
   float* lstm_in = nullptr;   // [B][h][w][2F]
   float* c = nullptr;         // [B][h][w][F]
   int h = 0, w = 0, F = 0;
@@ -148,9 +150,10 @@ struct vf_engine {
   std::map<std::string, DebugEntry> debug[4];
 
   // CUDA graph of one rollout (S-1 cell steps): captured on the second call with a given key, replayed afterwards
-  cudaGraphExec_t graph_exec = nullptr;
-  long long graph_key = -1, graph_seen_key = -1;
-  long long graph_launches = 0;
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; bool seen = false; };
+  std::map<long long, GraphSlot> graphs;      // rollout graphs by (prefix mode, shared steps, M, T, n_ctx_actions)
+  long long ctx_version = 0;                  // bumped by everything the shared-prefix state depends on (context, weights)
+  long long snap_version = -1;                // ctx_version the prefix snapshot was taken at (-1: none)
   bool use_graph = true;
   int cur_M = 0;               // samples of the rollout being launched (convs on fewer samples = shared-prefix steps)
 
@@ -396,6 +399,8 @@ int build_net(vf_engine* h) {
         r.h = hh; r.w = ww; r.F = oc;
         DA(r.lstm_in, (size_t)B * hh * ww * 2 * oc);
         DA(r.c, (size_t)B * hh * ww * oc);
+        DA(r.snap_in, (size_t)hh * ww * 2 * oc);
+        DA(r.snap_c, (size_t)hh * ww * oc);
         fmax_ = std::max(fmax_, (size_t)oc);
       }
       enc_out.push_back(oc);
@@ -418,6 +423,8 @@ int build_net(vf_engine* h) {
         r.h = hh; r.w = ww; r.F = oc;
         DA(r.lstm_in, (size_t)B * hh * ww * 2 * oc);
         DA(r.c, (size_t)B * hh * ww * oc);
+        DA(r.snap_in, (size_t)hh * ww * 2 * oc);
+        DA(r.snap_c, (size_t)hh * ww * oc);
         fmax_ = std::max(fmax_, (size_t)oc);
       }
       cprev = oc;
@@ -735,10 +742,18 @@ int shared_prefix_steps(const vf_engine* h, int M) {
   return (h->nz == 0 && M > 1) ? std::max(0, std::min(h->n_ctx_actions, h->C - 1)) : 0;
 }
 
+// prefix modes of a rollout: the recurrent state after the shared-prefix steps is the same for every rollout of one plan
+// (the context does not change between CEM iterations), so iteration 0 saves sample 0's state (PREFIX_SAVE) and the later
+// iterations start from it (PREFIX_RESTORE) instead of recomputing the prefix; vf_predict uses PREFIX_NONE.
+enum { PREFIX_NONE = 0, PREFIX_SAVE = 1, PREFIX_RESTORE = 2 };
+
 // rolls S-1 cell steps for M samples whose actions are in h->actions [M][T][adim]
-int rollout_body(vf_engine* h, int M, int T) {
+int rollout_body(vf_engine* h, int M, int T, int mode) {
+  const int n_shared = shared_prefix_steps(h, M);
+  const bool restore = mode == PREFIX_RESTORE && n_shared > 0;
   for (auto& net : h->views) {
     if (net.zstate) CU(cudaMemsetAsync(net.zstate, 0, (size_t)M * 2 * h->nz * sizeof(float), h->stream));
+    if (restore) continue;                           // every state row is overwritten from the snapshot
     // lstm_in holds two B-strided fp16 planes on the tensor-core path: clear the whole buffer
     const size_t Bz = h->split ? (size_t)h->B : (size_t)M;
     for (auto& r : net.enc_rnn) if (r.c) {
@@ -759,10 +774,39 @@ int rollout_body(vf_engine* h, int M, int T) {
   // exactly the same thing from the same zero state (the reference tiles the context per tower and recomputes it,
   // setup_predictor.py:40-44).  Those steps run once, on sample 0, and the recurrent state is replicated to the other
   // samples before the first per-sample step.  VF_SHARED_PREFIX=0 switches it off (A/B, tests).
-  const int n_shared = shared_prefix_steps(h, M);
   h->cur_M = M;
+  // the recurrent-state rows of one view as (buffer, row bytes[, snapshot]) entries
+  auto state_rows = [&](int v, bool from_snapshot, BroadcastBatch& bb, auto&& flush) {
+    auto add = [&](RnnState& r) {
+      if (!r.c) return;
+      const long long hw = (long long)r.h * r.w;
+      const long long cb = hw * r.F * (long long)sizeof(float);
+      bb.b[bb.n++] = {r.c, cb, from_snapshot ? r.snap_c : nullptr};
+      if (h->split) {                                   // two fp16 planes, the lo plane h->B samples after the hi plane
+        const long long pb = hw * 2 * r.F * 2;
+        char* snap = reinterpret_cast<char*>(r.snap_in);
+        bb.b[bb.n++] = {r.lstm_in, pb, from_snapshot ? snap : nullptr};
+        bb.b[bb.n++] = {reinterpret_cast<__half*>(r.lstm_in) + (long long)h->B * hw * 2 * r.F, pb, from_snapshot ? snap + pb : nullptr};
+      } else {
+        bb.b[bb.n++] = {r.lstm_in, hw * 2 * r.F * (long long)sizeof(float), from_snapshot ? r.snap_in : nullptr};
+      }
+      if (bb.n > 20) flush();
+    };
+    for (auto& r : h->views[v].enc_rnn) add(r);
+    for (auto& r : h->views[v].dec_rnn) add(r);
+    flush();
+  };
   for (int tau = 0; tau < h->S - 1; ++tau) {
     const bool shared = tau < n_shared;
+    if (shared && restore) {                         // prefix cached by iteration 0 of this plan
+      if (tau == n_shared - 1)
+        for (int v = 0; v < h->ncam; ++v) {
+          BroadcastBatch bb;
+          bb.n = 0;
+          state_rows(v, true, bb, [&]() { launch_broadcast_rows(bb, M, h->stream); bb.n = 0; });
+        }
+      continue;
+    }
     for (int v = 0; v < h->ncam; ++v) {
       // every view runs its own state recurrence with its own state head; the states returned to the
       // caller are view 0's (vpred_model_interface.py:80-82 reads outputs['gen_states'] of the first model)
@@ -775,21 +819,14 @@ int rollout_body(vf_engine* h, int M, int T) {
       if (shared && tau == n_shared - 1) {
         BroadcastBatch bb;
         bb.n = 0;
-        auto add = [&](RnnState& r) {
-          if (!r.c) return;
-          const long long hw = (long long)r.h * r.w;
-          bb.b[bb.n++] = {r.c, hw * r.F * (long long)sizeof(float)};
-          if (h->split) {                                   // two fp16 planes, the lo plane h->B samples after the hi plane
-            bb.b[bb.n++] = {r.lstm_in, hw * 2 * r.F * 2};
-            bb.b[bb.n++] = {reinterpret_cast<__half*>(r.lstm_in) + (long long)h->B * hw * 2 * r.F, hw * 2 * r.F * 2};
-          } else {
-            bb.b[bb.n++] = {r.lstm_in, hw * 2 * r.F * (long long)sizeof(float)};
-          }
-          if (bb.n > 21) { launch_broadcast_rows(bb, M, h->stream); bb.n = 0; }
-        };
-        for (auto& r : h->views[v].enc_rnn) add(r);
-        for (auto& r : h->views[v].dec_rnn) add(r);
-        launch_broadcast_rows(bb, M, h->stream);
+        if (mode == PREFIX_SAVE) {                     // keep sample 0's rows for the later iterations of this plan
+          state_rows(v, true, bb, [&]() {
+            for (int i = 0; i < bb.n; ++i)
+              cudaMemcpyAsync(const_cast<void*>(bb.b[i].src), bb.b[i].p, (size_t)bb.b[i].row_bytes, cudaMemcpyDeviceToDevice, h->stream);
+            bb.n = 0;
+          });
+        }
+        state_rows(v, false, bb, [&]() { launch_broadcast_rows(bb, M, h->stream); bb.n = 0; });
       }
     }
   }
@@ -799,39 +836,46 @@ int rollout_body(vf_engine* h, int M, int T) {
 // rolls S-1 cell steps for M samples whose actions are in h->actions [M][T][adim].  The launch sequence of a rollout is
 // static for a given (M, T, n_ctx_actions), so it is captured into a CUDA graph the second time a key is seen and replayed
 // afterwards (~3300 kernel launches per plan collapse into 3 graph launches).
-int rollout(vf_engine* h, int M, int T) {
+int rollout(vf_engine* h, int M, int T, int mode = PREFIX_NONE) {
   if (!h->weights_ready) { int r = finalize_weights(h); if (r) return r; }
   if (!h->context_set) return fail(h, VF_ERR_STATE, "vf_set_context must be called before predicting");
   if (!h->distrib_set) return fail(h, VF_ERR_STATE, "no designated-pixel distribution: pass pix_distrib to vf_set_context or call vf_set_desig");
   const int need = h->S - 1 - h->n_ctx_actions;
   if (T < need) return fail(h, VF_ERR_INVALID, "need %d actions per sample (S-1-n_ctx_actions), got T=%d", need, T);
-  const long long key = ((long long)shared_prefix_steps(h, M) << 56) | ((long long)M << 24) | ((long long)T << 8) | (long long)h->n_ctx_actions;
+  if (shared_prefix_steps(h, M) == 0) mode = PREFIX_NONE;
+  if (mode == PREFIX_RESTORE && h->snap_version != h->ctx_version) mode = PREFIX_SAVE;     // no snapshot of this context yet
+  const long long key = ((long long)shared_prefix_steps(h, M) << 56) | ((long long)mode << 52) | ((long long)M << 24) | ((long long)T << 8) |
+                        (long long)h->n_ctx_actions;
+  if (h->graphs.size() > 12 && !h->graphs.count(key)) {       // a handful of (mode, M, T) keys per controller: bound the cache
+    for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    h->graphs.clear();
+  }
+  vf_engine::GraphSlot& gs = h->graphs[key];
   int r = VF_OK;
   if (!h->use_graph || h->prof_on) {
-    r = rollout_body(h, M, T);
-  } else if (h->graph_exec && h->graph_key == key) {
-    CU(cudaGraphLaunch(h->graph_exec, h->stream));
-    g_launch_counter += h->graph_launches;
-  } else if (h->graph_seen_key != key) {
-    h->graph_seen_key = key;                       // first sighting: run eagerly (one-time attribute setup, JIT-free warm-up)
-    r = rollout_body(h, M, T);
+    r = rollout_body(h, M, T, mode);
+  } else if (gs.exec) {
+    CU(cudaGraphLaunch(gs.exec, h->stream));
+    g_launch_counter += gs.launches;
+  } else if (!gs.seen) {
+    gs.seen = true;                                // first sighting: run eagerly (one-time attribute setup, JIT-free warm-up)
+    r = rollout_body(h, M, T, mode);
   } else {
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; h->graph_key = -1; }
     cudaGraph_t graph = nullptr;
     const long long before = g_launch_counter;
     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    r = rollout_body(h, M, T);
+    r = rollout_body(h, M, T, mode);
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
     if (r) { if (graph) cudaGraphDestroy(graph); return r; }
     if (e != cudaSuccess) return fail(h, VF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-    h->graph_launches = g_launch_counter - before;
-    e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    gs.launches = g_launch_counter - before;
+    e = cudaGraphInstantiate(&gs.exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { h->graph_exec = nullptr; return fail(h, VF_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
-    h->graph_key = key;
-    CU(cudaGraphLaunch(h->graph_exec, h->stream));
+    if (e != cudaSuccess) { gs.exec = nullptr; return fail(h, VF_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+    CU(cudaGraphLaunch(gs.exec, h->stream));
   }
   if (r) return r;
+  if (mode == PREFIX_SAVE) h->snap_version = h->ctx_version;
   if (h->conv_error) {
     const int ce = h->conv_error;
     h->conv_error = 0;
@@ -954,7 +998,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
 int vf_destroy(vf_engine* h) {
   if (!h) return VF_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1008,6 +1052,7 @@ int vf_set_context(vf_engine* h, const uint8_t* frames, const float* states, con
   }
   CU(cudaStreamSynchronize(h->stream));   // caller buffers may be pageable / short-lived
   h->context_set = true;
+  ++h->ctx_version;                                  // invalidates the shared-prefix snapshot
   return VF_OK;
 }
 
@@ -1197,7 +1242,9 @@ int vf_cem_iter_rollout(vf_engine* h, int32_t it) {
   if (h->nz > 0)                                    // latents of the stochastic predictor: Philox, keyed by the global rollout index
     launch_sample_latents(h->zs, nroll, h->S - 1, h->nz, p.sample_offset * Kf, p.seed, p.plan_index, (uint32_t)it, h->stream);
   h->T = h->cem_T;
-  int r = rollout(h, nroll, h->cem_T);
+  const char* pc = getenv("VF_PREFIX_CACHE");         // read per call (tests flip it); the mode is part of the graph key
+  const bool cache_env = !(pc && atoi(pc) == 0);
+  int r = rollout(h, nroll, h->cem_T, !cache_env ? PREFIX_NONE : (it == 0 ? PREFIX_SAVE : PREFIX_RESTORE));
   if (r) return r;
   double* sc = h->cem_scores + (size_t)it * p.global_samples + p.sample_offset;
   double* raw_sc = Kf > 1 ? h->cem_fut_scores : sc;
