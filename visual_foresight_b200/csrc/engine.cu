@@ -834,8 +834,9 @@ int rollout_body(vf_engine* h, int M, int T, int mode) {
 }
 
 // rolls S-1 cell steps for M samples whose actions are in h->actions [M][T][adim].  The launch sequence of a rollout is
-// static for a given (M, T, n_ctx_actions), so it is captured into a CUDA graph the second time a key is seen and replayed
-// afterwards (~3300 kernel launches per plan collapse into 3 graph launches).
+// static for a given (prefix mode, shared steps, M, T, n_ctx_actions), so it is captured into a CUDA graph the second time
+// a key is seen and replayed afterwards (~2100 kernel launches per plan collapse into 3 graph launches: one PREFIX_SAVE
+// rollout and two PREFIX_RESTORE rollouts).
 int rollout(vf_engine* h, int M, int T, int mode = PREFIX_NONE) {
   if (!h->weights_ready) { int r = finalize_weights(h); if (r) return r; }
   if (!h->context_set) return fail(h, VF_ERR_STATE, "vf_set_context must be called before predicting");
