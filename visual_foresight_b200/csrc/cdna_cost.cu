@@ -168,6 +168,84 @@ __global__ void __launch_bounds__(256) k_cdna_apply4(View image, View first, con
   }
 }
 
+// Same contract, W % 4 == 0: one thread = a strip of 4 horizontally adjacent pixels.  A filter row needs 8 staged pixels for
+// the 4 outputs (instead of 4 x 5) and a tap's kernel vector is loaded once for the strip: 16 shared-memory loads per
+// pixel instead of 50, same accumulation order per output (bit-identical to k_cdna_apply4).  Every pixel of `layers` is
+// written as three 8-channel vectors (T_0..T_3, prev, first, zeros): channels 18..20 are rewritten by the scratch-image conv
+// later in the step, 21..23 are padding.
+__global__ void __launch_bounds__(256) k_cdna_apply4s(View image, View first, const float* __restrict__ kern, int B, int H, int W,
+                                                      int TR, View layers) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float4 sm4[];
+  float4* sk4 = sm4;                       // [25] taps x 4 kernels
+  float4* img = sm4 + 25 + 34;             // [(TR+4)][W]
+  const int b = blockIdx.y, y0 = blockIdx.x * TR;
+  if (threadIdx.x < 100) {                 // kern[b][n][t] -> sk[t][n]
+    const int t = threadIdx.x >> 2, n = threadIdx.x & 3;
+    reinterpret_cast<float*>(sk4)[threadIdx.x] = __ldg(kern + ((long long)b * 4 + n) * 25 + t);
+  }
+  for (int i = threadIdx.x; i < (TR + 4) * W; i += 256) {
+    const int r = i / W, x = i - r * W;
+    const int yy = mirror(y0 - 2 + r, H);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < H) {
+      const float* ip = vptr(image, b, (long long)yy * W + x);
+      v = make_float4(__ldg(ip), __ldg(ip + 1), __ldg(ip + 2), 0.f);
+    }
+    img[i] = v;
+  }
+  __syncthreads();
+  const int W4 = W >> 2;
+  for (int sidx = threadIdx.x; sidx < TR * W4; sidx += 256) {
+    const int r = sidx / W4, x0 = (sidx - r * W4) << 2, y = y0 + r;
+    if (y >= H) break;
+    int col[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) col[i] = mirror(x0 - 2 + i, W);
+    float a[4][4][3];                      // [pixel][kernel][channel]
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) a[p][n][0] = a[p][n][1] = a[p][n][2] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      float4 px[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) px[i] = img[(r + u) * W + col[i]];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        const float4 kv = sk4[u * 5 + v];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float4 q = px[p + v];
+          a[p][0][0] = fmaf(q.x, kv.x, a[p][0][0]); a[p][0][1] = fmaf(q.y, kv.x, a[p][0][1]); a[p][0][2] = fmaf(q.z, kv.x, a[p][0][2]);
+          a[p][1][0] = fmaf(q.x, kv.y, a[p][1][0]); a[p][1][1] = fmaf(q.y, kv.y, a[p][1][1]); a[p][1][2] = fmaf(q.z, kv.y, a[p][1][2]);
+          a[p][2][0] = fmaf(q.x, kv.z, a[p][2][0]); a[p][2][1] = fmaf(q.y, kv.z, a[p][2][1]); a[p][2][2] = fmaf(q.z, kv.z, a[p][2][2]);
+          a[p][3][0] = fmaf(q.x, kv.w, a[p][3][0]); a[p][3][1] = fmaf(q.y, kv.w, a[p][3][1]); a[p][3][2] = fmaf(q.z, kv.w, a[p][3][2]);
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float4 pv = img[(r + 2) * W + x0 + p];
+      const float* fp = vptr(first, b, (long long)y * W + x0 + p);
+      const float f0 = __ldg(fp), f1 = __ldg(fp + 1), f2 = __ldg(fp + 2);
+      const long long o = voff(layers, b, (long long)y * W + x0 + p);
+      float8 w0, w1, w2;
+      w0.a = make_float4(a[p][0][0], a[p][0][1], a[p][0][2], a[p][1][0]);
+      w0.b = make_float4(a[p][1][1], a[p][1][2], a[p][2][0], a[p][2][1]);
+      w1.a = make_float4(a[p][2][2], a[p][3][0], a[p][3][1], a[p][3][2]);
+      w1.b = make_float4(pv.x, pv.y, pv.z, f0);
+      w2.a = make_float4(f1, f2, 0.f, 0.f);
+      w2.b = make_float4(0.f, 0.f, 0.f, 0.f);
+      vst8(layers, o, w0);
+      vst8(layers, o + 8, w1);
+      vst8(layers, o + 16, w2);
+    }
+  }
+}
+
 // generic (any nt <= 8, odd ksize): one thread per pixel, global loads
 __global__ void __launch_bounds__(128) k_cdna_apply(View image, View first, const float* __restrict__ kern, int ksize, int nt,
                                                     int B, int H, int W, View layers) {
@@ -309,6 +387,129 @@ __global__ void __launch_bounds__(COMP_THREADS) k_composite(CompositeArgs a, int
   }
 }
 
+// nt = 4, 5x5 kernels, 7 masks, W % 4 == 0, logits dense [.,7], gen_image dense [.,3]: one thread = a strip of 4 adjacent
+// pixels.  28 logits and 12 output colours are 7 + 3 vector accesses, a filter row of the distribution stencil needs 8
+// staged values for the 4 outputs and a tap's four kernel weights are one 16-byte load (the one-pixel kernel issues 125
+// scalar shared-memory loads per pixel, this one ~17).  Accumulation order per output pixel is unchanged.
+__global__ void __launch_bounds__(COMP_THREADS) k_composite4s(CompositeArgs a, int TR) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) float smc[];
+  __shared__ float red[COMP_THREADS / 32];
+  const int b = blockIdx.y, y0 = blockIdx.x * TR;
+  const int W = a.W, H = a.H, BR = TR + 4;
+  float4* sk4 = reinterpret_cast<float4*>(smc);            // [25] taps x 4 kernels
+  float* band = smc + 100;                                 // [nd][BR][W]
+  if (threadIdx.x < 100) {
+    const int t = threadIdx.x >> 2, n = threadIdx.x & 3;
+    smc[threadIdx.x] = a.kern[((long long)b * 4 + n) * 25 + t];
+  }
+  for (int i = threadIdx.x; i < a.nd * BR * W; i += COMP_THREADS) {
+    const int p = i / (BR * W), rem = i - p * BR * W, r = rem / W, x = rem - r * W;
+    const int yy = mirror(y0 - 2 + r, H);
+    band[i] = (yy >= 0 && yy < H) ? __ldg(vptr(a.prev_d, b, (long long)yy * W + x) + p) : 0.f;
+  }
+  __syncthreads();
+  float dsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const int W4 = W >> 2;
+  for (int sidx = threadIdx.x; sidx < TR * W4; sidx += COMP_THREADS) {
+    const int r = sidx / W4, x0 = (sidx - r * W4) << 2, y = y0 + r;
+    if (y >= H) break;
+    const long long pix = (long long)y * W + x0;
+    // masks of the 4 pixels
+    float m[4][7];
+    {
+      float lg[28];
+      const float4* lp = reinterpret_cast<const float4*>(vptr(a.logits, b, pix));
+#pragma unroll
+      for (int j = 0; j < 7; ++j) { const float4 v4 = __ldg(lp + j); lg[4 * j] = v4.x; lg[4 * j + 1] = v4.y; lg[4 * j + 2] = v4.z; lg[4 * j + 3] = v4.w; }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float mx = -3.4e38f;
+#pragma unroll
+        for (int n = 0; n < 7; ++n) { m[p][n] = lg[7 * p + n]; mx = fmaxf(mx, m[p][n]); }
+        float se = 0.f;
+#pragma unroll
+        for (int n = 0; n < 7; ++n) { m[p][n] = expf(m[p][n] - mx); se += m[p][n]; }
+#pragma unroll
+        for (int n = 0; n < 7; ++n) m[p][n] = m[p][n] / se;
+      }
+    }
+    // colour composite
+    float g[12];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const long long lo = voff(a.layers, b, pix + p);
+      float l[24];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float8 v8 = vld8(a.layers, lo + 8 * j);
+        l[8 * j] = v8.a.x; l[8 * j + 1] = v8.a.y; l[8 * j + 2] = v8.a.z; l[8 * j + 3] = v8.a.w;
+        l[8 * j + 4] = v8.b.x; l[8 * j + 5] = v8.b.y; l[8 * j + 6] = v8.b.z; l[8 * j + 7] = v8.b.w;
+      }
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+      for (int n = 0; n < 7; ++n) { g0 += m[p][n] * l[3 * n]; g1 += m[p][n] * l[3 * n + 1]; g2 += m[p][n] * l[3 * n + 2]; }
+      g[3 * p] = g0; g[3 * p + 1] = g1; g[3 * p + 2] = g2;
+    }
+    float4* gi = reinterpret_cast<float4*>(a.gen_image.p + voff(a.gen_image, b, pix));
+    gi[0] = make_float4(g[0], g[1], g[2], g[3]);
+    gi[1] = make_float4(g[4], g[5], g[6], g[7]);
+    gi[2] = make_float4(g[8], g[9], g[10], g[11]);
+    // distribution: 5x5 stencil of the previous distribution with the sample's 4 kernels, then the mask mix
+    int col[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) col[i] = mirror(x0 - 2 + i, W);
+    float* gd = a.gen_distrib.p + voff(a.gen_distrib, b, pix);
+    for (int p = 0; p < a.nd; ++p) {
+      const float* bp = band + p * BR * W;
+      float t[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) t[q][0] = t[q][1] = t[q][2] = t[q][3] = 0.f;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        float d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = bp[(r + u) * W + col[i]];
+#pragma unroll
+        for (int v = 0; v < 5; ++v) {
+          const float4 kv = sk4[u * 5 + v];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            t[q][0] = fmaf(d[q + v], kv.x, t[q][0]); t[q][1] = fmaf(d[q + v], kv.y, t[q][1]);
+            t[q][2] = fmaf(d[q + v], kv.z, t[q][2]); t[q][3] = fmaf(d[q + v], kv.w, t[q][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float pd = bp[(r + 2) * W + x0 + q], fd = __ldg(vptr(a.first_d, b, pix + q) + p);
+        float v = 0.f;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) v += m[q][n] * t[q][n];
+        v += m[q][4] * pd;
+        v += m[q][5] * fd;
+        v += m[q][6] * pd;
+        gd[(long long)q * a.gen_distrib.pix_stride + p] = v;
+        dsum[p] += v;
+      }
+    }
+  }
+  for (int p = 0; p < a.nd; ++p) {
+    float v = dsum[p];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float sacc = 0.f;
+      for (int i = 0; i < COMP_THREADS / 32; ++i) sacc += red[i];
+      a.partial[((long long)b * a.nd + p) * gridDim.x + blockIdx.x] = sacc;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void k_distrib_normalize(View d, const float* __restrict__ partial, int nblk, int H, int W, int nd) {
   pdl_wait();
   pdl_trigger();
@@ -408,10 +609,19 @@ inline int band_rows(int H, int W) {                 // rows per block of the ba
   while (tr > 2 && tr * W > 512) tr /= 2;
   return tr;
 }
-inline int comp_rows(int H, int W) {                 // rows per block of the composite kernel (one pixel per thread)
-  int tr = 8;
-  while (tr > 1 && tr * W > COMP_THREADS) tr /= 2;
+inline int comp_rows(int H, int W) {                 // rows per block of the composite kernels (a 4-pixel strip per thread and pass)
+  int tr = 16;
+  while (tr > 1 && (tr * W / 4 > COMP_THREADS || tr > H)) tr /= 2;
   return tr;
+}
+inline int strip_rows(int H, int W) {                // rows per block of the strip-mined CDNA apply
+  int tr = 16;
+  while (tr > 2 && (tr * W / 4 > 256 || tr > H)) tr /= 2;
+  return tr;
+}
+bool strips_enabled() {
+  static const bool on = !(getenv("VF_STRIPS") && atoi(getenv("VF_STRIPS")) == 0);     // A/B switch: 0 = one pixel per thread
+  return on;
 }
 size_t cdna_partial_floats(int K, int B) { return (size_t)((K + CK_KC - 1) / CK_KC) * B * 128; }
 void launch_cdna_kernels(View feat, int npix, const float* w, int ksize, int nt, int B, float* part, cudaStream_t s) {
@@ -425,7 +635,14 @@ void launch_cdna_apply(View image, View first, const float* part, int K, const f
   g_launch_counter += 2;
   const int nks = (K + CK_KC - 1) / CK_KC;
   launch_k(k_cdna_finalize, dim3(B), dim3(128), 0, s, part, nks, B, bias, ksize, nt, kern);
-  if (nt == 4 && ksize == 5 && W >= 8) {
+  const bool al8 = layers.lo_off ? ((layers.pix_stride | layers.ch_off) % 8 == 0 && layers.sample_stride % 8 == 0 && layers.lo_off % 8 == 0)
+                                 : ((layers.pix_stride | layers.ch_off) % 4 == 0 && layers.sample_stride % 4 == 0);
+  if (nt == 4 && ksize == 5 && W >= 8 && W % 4 == 0 && layers.C >= 24 && al8 && strips_enabled()) {
+    const int TR = strip_rows(H, W);
+    dim3 grid((H + TR - 1) / TR, B);
+    const size_t smem = (size_t)(25 + 34 + (TR + 4) * W) * sizeof(float4);
+    launch_k(k_cdna_apply4s, dim3(grid), dim3(256), smem, s, image, first, (const float*)kern, B, H, W, TR, layers);
+  } else if (nt == 4 && ksize == 5 && W >= 8) {
     const int TR = band_rows(H, W);
     dim3 grid((H + TR - 1) / TR, B);
     const size_t smem = (size_t)(25 + 34 + (TR + 4) * W) * sizeof(float4);
@@ -441,7 +658,15 @@ void launch_composite(const CompositeArgs& a, int B, cudaStream_t s) {
   const int TR = comp_rows(a.H, a.W);
   dim3 grid((a.H + TR - 1) / TR, B);
   const size_t smem = (size_t)(((a.nt * a.ksize * a.ksize + 3) & ~3) + a.nd * (TR + a.ksize - 1) * a.W) * sizeof(float);
-  if (a.nt == 4 && a.ksize == 5) launch_k(k_composite<4>, dim3(grid), dim3(COMP_THREADS), smem, s, a, TR);
+  const bool dense = a.logits.pix_stride == 7 && a.logits.ch_off == 0 && a.logits.sample_stride % 4 == 0 && !a.logits.lo_off &&
+                     a.gen_image.pix_stride == 3 && a.gen_image.ch_off == 0 && a.gen_image.sample_stride % 4 == 0 &&
+                     ((uintptr_t)a.logits.p % 16 == 0) && ((uintptr_t)a.gen_image.p % 16 == 0) &&
+                     (a.layers.lo_off ? ((a.layers.pix_stride | a.layers.ch_off) % 8 == 0 && a.layers.sample_stride % 8 == 0 && a.layers.lo_off % 8 == 0)
+                                      : ((a.layers.pix_stride | a.layers.ch_off) % 4 == 0 && a.layers.sample_stride % 4 == 0)) && a.layers.C >= 24;
+  if (a.nt == 4 && a.ksize == 5 && a.W % 4 == 0 && a.nd <= 4 && dense && strips_enabled()) {
+    const size_t smem4 = (size_t)(100 + a.nd * (TR + 4) * a.W) * sizeof(float);
+    launch_k(k_composite4s, dim3(grid), dim3(COMP_THREADS), smem4, s, a, TR);
+  } else if (a.nt == 4 && a.ksize == 5) launch_k(k_composite<4>, dim3(grid), dim3(COMP_THREADS), smem, s, a, TR);
   else launch_k(k_composite<0>, dim3(grid), dim3(COMP_THREADS), smem, s, a, TR);
 }
 void launch_distrib_normalize(View d, const float* partial, int nblk, int B, int H, int W, int nd, cudaStream_t s) {
