@@ -169,6 +169,53 @@ def test_folding_sampler_matches_reference(sampler_golden):
         S.FoldingCEMSampler(HParams(**S.FoldingCEMSampler.get_default_hparams()), 5, 4)
 
 
+def test_pred_util_matches_reference(golden):
+    """get_context / rollout_predictions (reference video_prediction/pred_util.py:4-48): context slice with state_append,
+    chunking with a zero-padded last chunk, outputs cut back and returned per chunk."""
+    from visual_foresight_b200 import pred_util as PU
+    g = golden
+    lf, ls = PU.get_context(2, 3, g["ctx_states"], g["ctx_images"], HParams(state_append=[0.1, 0.2]))
+    np.testing.assert_array_equal(lf, g["ctx_last_frames"])
+    np.testing.assert_array_equal(ls, g["ctx_last_states"])
+    assert lf.dtype == np.float32 and lf.shape == (1, 2, 2, 8, 8, 3)
+    lf2, ls2 = PU.get_context(2, 3, g["ctx_states"], g["ctx_images"])
+    assert ls2.shape == (1, 2, 3)
+    seen = []
+
+    def pf(input_images=None, input_state=None, input_actions=None, input_one_hot_images=None):
+        seen.append(input_actions.copy())
+        s = input_actions.sum(axis=(1, 2))
+        return s[:, None] * np.ones((1, 2)), None, s[:, None] * 2.0
+    gi, gd, gs = PU.rollout_predictions(pf, 3, g["rollout_actions"], lf, ls)
+    assert len(seen) == int(g["rollout_ncalls"]) == 3 and [a.shape[0] for a in gi] == [3, 3, 1] and gd == [None] * 3
+    np.testing.assert_array_equal(np.concatenate(gi, 0), g["rollout_gen_images"])
+    np.testing.assert_array_equal(np.concatenate(gs, 0), g["rollout_gen_states"])
+    np.testing.assert_array_equal(seen[-1], g["rollout_seen_last"])          # zero-padded to the chunk size
+
+
+def test_predictor_class_chunks_oversized_batches():
+    """B200VPredEvaluation.__call__ with more action sequences than the handle's capacity: capacity-sized engine calls, ragged
+    last chunk, outputs concatenated in order (the role of rollout_predictions, pred_util.py:21-48).  Stub backend: no GPU."""
+    from visual_foresight_b200.predictor import B200VPredEvaluation
+    pred = B200VPredEvaluation("", {"run_batch_size": 4, "model_spec": {"height": 8, "width": 8, "seq_len": 4}})
+    calls = []
+
+    class Stub:
+        def predict(self, context, actions):
+            calls.append(actions.shape[0])
+            tag = actions[:, 0, 0].astype(np.float32)
+            return tag[:, None] * np.ones((1, 2), np.float32), tag[:, None] * 2 * np.ones((1, 3), np.float32), None
+    pred.backend = Stub()
+    acts = np.arange(10, dtype=np.float64)[:, None, None] * np.ones((1, 3, 4))
+    out = pred({}, {"actions": acts})
+    assert calls == [4, 4, 2]
+    np.testing.assert_array_equal(out["predicted_frames"][:, 0], np.arange(10, dtype=np.float32))
+    np.testing.assert_array_equal(out["predicted_pixel_distributions"][:, 0], 2 * np.arange(10, dtype=np.float32))
+    calls.clear()
+    pred({}, {"actions": acts[:3]})
+    assert calls == [3]
+
+
 def test_policy_arg_resolution():
     pol = NullPolicy({"adim": 4}, {})
     assert get_policy_args(pol, {}, 0, 0) == {}

@@ -230,7 +230,16 @@ class B200VPredEvaluation:
         self._weights = None
 
     def __call__(self, context, inputs):
-        frames, distrib, _ = self.backend.predict(context, inputs["actions"])
+        actions = np.asarray(inputs["actions"])
+        cap = self._max_samples
+        if actions.shape[0] <= cap:
+            frames, distrib, _ = self.backend.predict(context, actions)
+        else:
+            # more rollouts than the handle holds: run_batch_size-sized calls like the reference's rollout_predictions
+            # (pred_util.py:21-48); the engine takes a ragged last chunk, so nothing is padded
+            parts = [self.backend.predict(context, actions[i:i + cap]) for i in range(0, actions.shape[0], cap)]
+            frames = np.concatenate([p[0] for p in parts], axis=0)
+            distrib = np.concatenate([p[1] for p in parts], axis=0)
         return {"predicted_frames": frames, "predicted_pixel_distributions": distrib}
 
 
