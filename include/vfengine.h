@@ -211,6 +211,10 @@ VF_API int vf_refit(vf_engine* h, const double* elites, int32_t K, int32_t nacti
  * w (k,k,Cin,Cout) HWIO, bias (Cout) or NULL -> y (B,H,W,Cout).  impl: enum vf_precision */
 VF_API int vf_debug_conv2d(vf_engine* h, int32_t impl, const float* x, const float* w, const float* bias,
                     int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, float* y);
+/* tuning aid (profiles/conv_microbench.py): average milliseconds of `reps` back-to-back launches of ONE convolution of the
+ * given shape on data resident in HBM, CUDA events on the handle's stream.  Not part of the reference surface. */
+VF_API int vf_debug_conv_time(vf_engine* h, int32_t impl, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                       int32_t k, int32_t reps, double* out_ms);
 /* copy a named internal activation of the LAST cell step to host (tests): returns element count */
 VF_API int64_t vf_debug_fetch(vf_engine* h, const char* name, int32_t view, float* out, int64_t capacity);
 /* per-kernel-class timing with CUDA events on the handle's stream (bench roofline): enable, run, read.

@@ -1411,6 +1411,62 @@ int vf_debug_conv2d(vf_engine* h, int32_t impl, const float* x, const float* w, 
   return VF_OK;
 }
 
+int vf_debug_conv_time(vf_engine* h, int32_t impl, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
+                       int32_t reps, double* out_ms) {
+  if (!h || !out_ms || (k != 3 && k != 5) || B < 1 || reps < 1) return fail(h, VF_ERR_INVALID, "bad conv arguments");
+  const size_t nx = (size_t)B * H * W * Cin, nw = (size_t)k * k * Cin * Cout, ny = (size_t)B * H * W * Cout;
+  // device buffers of this tool are freed on return (a sweep over many shapes must not accumulate them in the handle)
+  float *dx = nullptr, *dy = nullptr, *dw = nullptr;
+  auto release = [&]() { cudaFree(dx); cudaFree(dy); cudaFree(dw); };
+  if (cudaMalloc(&dx, nx * sizeof(float)) != cudaSuccess || cudaMalloc(&dy, ny * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&dw, nw * sizeof(float)) != cudaSuccess) { release(); return fail(h, VF_ERR_NOMEM, "conv timing scratch"); }
+  std::vector<float> wh(nw);
+  uint32_t st = 12345u;
+  const float wscale = 1.0f / sqrtf((float)(k * k * Cin));
+  for (size_t i = 0; i < nw; ++i) { st = st * 1664525u + 1013904223u; wh[i] = ((float)(st >> 8) / 8388608.0f - 1.0f) * wscale; }
+  cudaMemcpyAsync(dw, wh.data(), nw * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+  launch_fill(dx, (long long)nx, 0.25f, h->stream);
+  View vy = make_view(dy, (long long)H * W * Cout, Cout, 0, Cout);
+  MmaConvWeights mw;
+  std::vector<void*> wallocs;
+  View vx = make_view(dx, (long long)H * W * Cin, Cin, 0, Cin);
+  if (impl != VF_PREC_FP32_SIMT) {
+    if (!mma_conv_supported(k, Cin, Cout, H, W)) { release(); return fail(h, VF_ERR_UNSUPPORTED, "shape not supported by the tcgen05 conv"); }
+    std::string e;
+    if (mma_conv_prepare_weights(wh.data(), k, k, k, Cin, Cout, &mw, &wallocs, &e)) { release(); return fail(h, VF_ERR_CUDA, "mma weight prep: %s", e.c_str()); }
+    // split-half view over the same bytes: hi plane = first half of dx, lo plane B*H*W*Cin halfs later (values are irrelevant)
+    vx = make_view(dx, (long long)H * W * Cin, Cin, 0, Cin, (long long)B * H * W * Cin);
+  }
+  auto one = [&]() -> int {
+    if (impl == VF_PREC_FP32_SIMT) {
+      ConvArgs a;
+      a.src0 = vx; a.src1 = make_view(nullptr, 0, 0, 0, 0); a.w = dw; a.bias = nullptr; a.sabias = nullptr; a.out = vy;
+      a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.k = k; a.act = ACT_NONE;
+      launch_conv_simt(a, B, h->stream);
+      return 0;
+    }
+    MmaConvCall c;
+    c.src = vx; c.out = vy; c.sabias = nullptr; c.bias = nullptr; c.H = H; c.W = W; c.passes = impl == VF_PREC_F16X3 ? 3 : 1;
+    return mma_conv_launch(mw, c, B, h->stream);
+  };
+  int rc = one();                                                      // warm-up (attribute setup, tensor-map cache)
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, h->stream);
+  for (int i = 0; i < reps && !rc; ++i) rc = one();
+  cudaEventRecord(e1, h->stream);
+  cudaError_t ce = cudaStreamSynchronize(h->stream);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (void* q : wallocs) cudaFree(q);
+  release();
+  if (rc) return fail(h, VF_ERR_CUDA, "conv launch failed (code %d)", rc);
+  if (ce != cudaSuccess) return fail(h, VF_ERR_CUDA, "conv timing: %s", cudaGetErrorString(ce));
+  *out_ms = (double)ms / reps;
+  return VF_OK;
+}
+
 int64_t vf_debug_fetch(vf_engine* h, const char* name, int32_t view, float* out, int64_t cap) {
   if (!h || !name || view < 0 || view >= h->ncam) return VF_ERR_INVALID;
   auto it = h->debug[view].find(name);

@@ -92,6 +92,8 @@ _SIGS = {
     "vf_refit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vf_debug_conv2d": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "vf_debug_fetch": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int64]),
+    "vf_debug_conv_time": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_void_p]),
     "vf_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "vf_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "vf_launch_count": (C.c_int64, [C.c_void_p]),
@@ -368,6 +370,12 @@ class Engine:
         y = np.empty((B, H, W, Cout), np.float32)
         self._check(self.lib.vf_debug_conv2d(self._h, impl, _ptr(x), _ptr(w), _ptr(b), B, H, W, Cin, Cout, k, _ptr(y)))
         return y
+
+    def debug_conv_time(self, B, H, W, Cin, Cout, k, impl=PREC_F16X3, reps=20) -> float:
+        """average ms per launch of one convolution of this shape (tuning aid)"""
+        ms = C.c_double(0.0)
+        self._check(self.lib.vf_debug_conv_time(self._h, impl, B, H, W, Cin, Cout, k, reps, C.byref(ms)))
+        return ms.value
 
     def debug_fetch(self, name: str, view: int = 0):
         n = self._check(self.lib.vf_debug_fetch(self._h, name.encode(), view, None, 0))
