@@ -34,6 +34,10 @@ VARIANTS = {
     "selfrac": dict(selection_frac=0.5),
     "replan3": dict(replan_interval=3),
     "reuse": dict(reuse_mean=True, reduce_std_dev=0.5, replan_interval=3, predictor_propagation=True),
+    # the `sampler` plugin point (cem_base_controller.py:52,66-76,82): class names are resolved per side by `samplers`
+    "corr": dict(sampler="CorrelatedNoiseSampler"),
+    "folding": dict(sampler="FoldingCEMSampler"),
+    "autograsp": dict(sampler="AutograspSampler", iterations=1),      # the reference's refit path raises (autograsp_sampler.py:26)
 }
 STEPS = 6
 
@@ -50,12 +54,19 @@ def inputs():
 
 
 def ag_for(name):
-    return dict(AG, adim=5) if name == "append" else dict(AG)       # the appended gripper value is part of the action
+    return dict(AG, adim=5) if name in ("append", "autograsp") else dict(AG)   # gripper value appended / drawn by rule
 
 
-def drive(ctrl_cls, predictor_cls, get_policy_args, name, over, record):
+def drive(ctrl_cls, predictor_cls, get_policy_args, name, over, record, samplers=None):
     images, state, desig, goal = inputs()
-    pol = quiet(ctrl_cls, ag_for(name), dict(BASE, predictor_class=predictor_cls, **over), 0, 1)
+    over = dict(over)
+    if isinstance(over.get("sampler"), str):
+        over["sampler"] = getattr(samplers, over["sampler"])
+        over.pop("rejection_sampling", None)
+    base = dict(BASE)
+    if "sampler" in over and "rejection_sampling" not in over["sampler"].get_default_hparams():
+        base.pop("rejection_sampling")                              # not a hyper-parameter of this sampler: overriding it raises
+    pol = quiet(ctrl_cls, ag_for(name), dict(base, predictor_class=predictor_cls, **over), 0, 1)
     if name == "append":
         pol._adim = 4                                               # the sampler draws the 4 arm dimensions (run.py passes env dims)
     quiet(pol.reset)
@@ -77,9 +88,15 @@ def main():
     ref_shim.install()
     from visual_mpc.policy.cem_controllers import PixelCostController
     from visual_mpc.policy.policy import get_policy_args
+    import types
+    from visual_mpc.policy.cem_controllers.samplers.autograsp_sampler import AutograspSampler
+    from visual_mpc.policy.cem_controllers.samplers.correlated_noise import CorrelatedNoiseSampler
+    from visual_mpc.policy.cem_controllers.samplers.folding_sampler import FoldingCEMSampler
+    ref_samplers = types.SimpleNamespace(AutograspSampler=AutograspSampler, CorrelatedNoiseSampler=CorrelatedNoiseSampler,
+                                         FoldingCEMSampler=FoldingCEMSampler)
     G = {}
     for name, over in VARIANTS.items():
-        drive(PixelCostController, BlobPredictor, get_policy_args, name, over, G.__setitem__)
+        drive(PixelCostController, BlobPredictor, get_policy_args, name, over, G.__setitem__, ref_samplers)
     out = os.path.join(HERE, "ref_act_variants_golden.npz")
     np.savez_compressed(out, **G)
     print("wrote", out, len(G), "arrays", os.path.getsize(out) // 1024, "KB")

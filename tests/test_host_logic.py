@@ -280,10 +280,12 @@ def test_full_act_matches_reference(golden):
             np.testing.assert_allclose(pol._best_actions, golden["act_t%d_best_actions" % t], rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["warm_sampler", "warm_hard", "append", "selfrac", "replan3", "reuse"])
+@pytest.mark.filterwarnings("ignore:covariance is not symmetric positive-semidefinite")
+@pytest.mark.parametrize("name", ["warm_sampler", "warm_hard", "append", "selfrac", "replan3", "reuse", "corr", "folding", "autograsp"])
 def test_act_variants_match_reference(name):
     """Six MPC steps of act() under hparam variants the default-path fixture does not reach (warm-up branches, append_action,
-    selection_frac, replan_interval, reuse_mean + reduce_std_dev + predictor_propagation): returned actions, number of
+    selection_frac, replan_interval, reuse_mean + reduce_std_dev + predictor_propagation, and the CorrelatedNoise / Folding /
+    Autograsp samplers through the `sampler` plugin point): returned actions, number of
     predictor calls, elite indices and last-iteration scores equal the unmodified reference's, step by step
     (fixtures: tests/golden/make_act_variants_golden.py)."""
     import os
@@ -291,7 +293,7 @@ def test_act_variants_match_reference(name):
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_act_variants_golden.npz"))
     got = {}
     over = dict(MG.VARIANTS[name], device_cem=False)
-    MG.drive(PixelCostController, _Injected, get_policy_args, name, over, got.__setitem__)
+    MG.drive(PixelCostController, _Injected, get_policy_args, name, over, got.__setitem__, S)
     keys = [k for k in g.files if k.startswith(name + "_")]
     assert keys and sorted(keys) == sorted(got)
     for k in keys:
