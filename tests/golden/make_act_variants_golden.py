@@ -38,6 +38,9 @@ VARIANTS = {
     "corr": dict(sampler="CorrelatedNoiseSampler"),
     "folding": dict(sampler="FoldingCEMSampler"),
     "autograsp": dict(sampler="AutograspSampler", iterations=1),      # the reference's refit path raises (autograsp_sampler.py:26)
+    # two designated pixels: per-task scores averaged (pixel_cost_controller.py:148-153).  `only_take_first_view=True` with more
+    # than one task cannot be recorded: the reference's logging loop indexes the sliced score matrix out of bounds (:158)
+    "ndesig2": dict(designated_pixel_count=2),
 }
 STEPS = 6
 
@@ -60,6 +63,8 @@ def ag_for(name):
 def drive(ctrl_cls, predictor_cls, get_policy_args, name, over, record, samplers=None):
     images, state, desig, goal = inputs()
     over = dict(over)
+    if over.get("designated_pixel_count") == 2:
+        desig, goal = np.array([[6, 8], [17, 5]]), np.array([[15, 20], [3, 27]])
     if isinstance(over.get("sampler"), str):
         over["sampler"] = getattr(samplers, over["sampler"])
         over.pop("rejection_sampling", None)

@@ -281,7 +281,8 @@ def test_full_act_matches_reference(golden):
 
 
 @pytest.mark.filterwarnings("ignore:covariance is not symmetric positive-semidefinite")
-@pytest.mark.parametrize("name", ["warm_sampler", "warm_hard", "append", "selfrac", "replan3", "reuse", "corr", "folding", "autograsp"])
+@pytest.mark.parametrize("name", ["warm_sampler", "warm_hard", "append", "selfrac", "replan3", "reuse", "corr", "folding", "autograsp",
+                                  "ndesig2"])
 def test_act_variants_match_reference(name):
     """Six MPC steps of act() under hparam variants the default-path fixture does not reach (warm-up branches, append_action,
     selection_frac, replan_interval, reuse_mean + reduce_std_dev + predictor_propagation, and the CorrelatedNoise / Folding /
