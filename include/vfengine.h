@@ -211,6 +211,14 @@ VF_API int vf_refit(vf_engine* h, const double* elites, int32_t K, int32_t nacti
  * w (k,k,Cin,Cout) HWIO, bias (Cout) or NULL -> y (B,H,W,Cout).  impl: enum vf_precision */
 VF_API int vf_debug_conv2d(vf_engine* h, int32_t impl, const float* x, const float* w, const float* bias,
                     int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, float* y);
+/* Host-only (no device, no handle): the tiling the tcgen05 convolution picks for a k x kw layer (kw = k, or 1 for a
+ * dx-folded input) with B samples, as 24 integers: {swap, rg, G, npass, v_cnt, units, ncols, max MMA N, TMEM columns per
+ * accumulator set, accumulator sets, activation buffers, weight stages, stage bytes, plane bytes, dynamic shared memory
+ * bytes, work items, TMA box rows, padded row pitch, image pitch in pixel rows, box bytes, last pixel row an item's MMAs
+ * read, pixel rows a plane holds, channel chunks, Cout tiles}.  VF_ERR_UNSUPPORTED when the shape has no plan.  Used by
+ * the CPU test suite to check the resource invariants of every layer shape. */
+VF_API int vf_debug_conv_plan(int32_t k, int32_t kw, int32_t cin, int32_t cout, int32_t H, int32_t W, int32_t B,
+                       int32_t passes, int32_t* out24);
 /* tuning aid (profiles/conv_microbench.py): average milliseconds of `reps` back-to-back launches of ONE convolution of the
  * given shape on data resident in HBM, CUDA events on the handle's stream.  Not part of the reference surface. */
 VF_API int vf_debug_conv_time(vf_engine* h, int32_t impl, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,

@@ -1138,6 +1138,34 @@ bool mma_conv_supported(int k, int cin, int cout, int H, int W) {
   return plan_geometry(layout, bo, k, k, k, cin, cout, H, W, 1, 3, &g);
 }
 
+// Host-only description of the tiling plan_geometry() picks for a layer (no device needed): lets the CPU test suite check the
+// resource invariants (shared memory, TMEM columns, MMA N, box coverage) for every layer shape of the supported specs.
+bool mma_conv_describe(int k, int kw, int cin, int cout, int H, int W, int B, int passes, int out[24]) {
+  int layout, bo;
+  current_mode(&layout, &bo);
+  if (layout == 2 && !(cin % 64 == 0 && cout >= 128)) layout = 1;
+  Geometry g;
+  if (!plan_geometry(layout, bo, k, kw, k, cin, cout, H, W, B, passes == 3 ? 3 : 1, &g)) return false;
+  const int acc_cols = g.swap ? g.units * g.ncols : (g.rg ? g.ncols_item : g.G * g.v_cnt);
+  int nmax = 0;                                       // largest MMA N
+  if (g.swap) nmax = g.ncols; else for (int i = 0; i < g.nseg; ++i) nmax = std::max(nmax, g.seg_n[i]);
+  // last shared-memory pixel row any MMA of an item reads (relative to the item's plane), and the rows the plane holds
+  int last_read, plane_rows = g.plane_bytes / g.row_bytes;
+  const int tap_reach = (g.k - 1) * g.Wp + (g.kw - 1);
+  int off = 0;                                        // largest offset of an item's first virtual pixel inside its first box row
+  for (int ps = 0; ps < g.npass; ++ps) off = std::max(off, (ps * g.v_cnt) % g.Wp);
+  if (g.swap == 2) last_read = off + (g.units - 1) * g.ustride + 127 + (g.k - 1) * g.Wp;
+  else if (g.swap) last_read = off + g.units * 128 - 1 + tap_reach;
+  else if (g.rg == 1) last_read = ((g.G - 1) * (g.H + g.pad) + g.H - 1) * g.Wp + 7 + tap_reach;
+  else if (g.rg == 2) last_read = (g.H - 1) * g.Wp + 8 + 7 + tap_reach;
+  else last_read = (g.G - 1) * g.img_pix + off + g.v_cnt - 1 + tap_reach;
+  const int v[24] = {g.swap, g.rg, g.G, g.npass, g.v_cnt, g.units, g.ncols, nmax, acc_cols, g.nacc, g.nbuf, g.nstage,
+                     g.stage_bytes, g.plane_bytes, (int)smem_bytes(g), g.nitems, g.R, g.Wp, g.img_pix, g.box_bytes,
+                     last_read, plane_rows, g.nchunk, g.n_mt};
+  for (int i = 0; i < 24; ++i) out[i] = v[i];
+  return true;
+}
+
 int mma_conv_prepare_weights(const float* w_sp, int k, int kw, int kcl, int cin, int cout, MmaConvWeights* out,
                              std::vector<void*>* allocs, std::string* err) {
   int layout, bo;

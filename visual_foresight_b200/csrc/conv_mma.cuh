@@ -31,6 +31,8 @@ struct MmaConvCall {
 };
 
 bool mma_conv_supported(int k, int cin, int cout, int H, int W);
+// host-only: the tiling picked for a layer as 24 integers (see vf_debug_conv_plan in include/vfengine.h); false = unsupported
+bool mma_conv_describe(int k, int kw, int cin, int cout, int H, int W, int B, int passes, int out[24]);
 // returns 0 on success; device allocations are appended to *allocs (owned by the engine handle)
 // w_sp: [k * kw][cin][cout]
 int mma_conv_prepare_weights(const float* w_sp, int k, int kw, int kcl, int cin, int cout, MmaConvWeights* out,

@@ -1411,6 +1411,15 @@ int vf_debug_conv2d(vf_engine* h, int32_t impl, const float* x, const float* w, 
   return VF_OK;
 }
 
+int vf_debug_conv_plan(int32_t k, int32_t kw, int32_t cin, int32_t cout, int32_t H, int32_t W, int32_t B, int32_t passes,
+                       int32_t* out24) {
+  if (!out24 || (k != 3 && k != 5) || (kw != k && kw != 1)) return VF_ERR_INVALID;
+  int v[24];
+  if (!mma_conv_describe(k, kw, cin, cout, H, W, B, passes, v)) return VF_ERR_UNSUPPORTED;
+  for (int i = 0; i < 24; ++i) out24[i] = v[i];
+  return VF_OK;
+}
+
 int vf_debug_conv_time(vf_engine* h, int32_t impl, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
                        int32_t reps, double* out_ms) {
   if (!h || !out_ms || (k != 3 && k != 5) || B < 1 || reps < 1) return fail(h, VF_ERR_INVALID, "bad conv arguments");

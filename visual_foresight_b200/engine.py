@@ -92,6 +92,7 @@ _SIGS = {
     "vf_refit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vf_debug_conv2d": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "vf_debug_fetch": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int64]),
+    "vf_debug_conv_plan": (C.c_int, [C.c_int32] * 8 + [C.c_void_p]),
     "vf_debug_conv_time": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_void_p]),
     "vf_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
