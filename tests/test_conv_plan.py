@@ -15,6 +15,12 @@ F = ["swap", "rg", "G", "npass", "v_cnt", "units", "ncols", "nmax", "acc_cols", 
      "plane_bytes", "smem", "nitems", "R", "Wp", "img_pix", "box_bytes", "last_read", "plane_rows", "nchunk", "n_mt"]
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    from visual_foresight_b200 import build
+    build.build()                                      # in-tree nvcc build if the library is missing or stale (no GPU needed)
+
+
 def plan(k, kw, cin, cout, H, W, B, passes=3):
     lib = load_library()
     out = (C.c_int32 * 24)()
