@@ -42,7 +42,7 @@ __device__ double philox_normal(uint64_t seed, uint32_t plan, uint32_t iter, uin
 }
 
 // latent z[r][step][i] ~ N(0,1) for rollout sample r (global index goff + r): the Philox stream of the action noise with
-// bit 30 of the draw-index word set, so latents never collide with action draws
+// bit 31 of the draw-index word set, so latents never collide with action draws
 __global__ void k_sample_latents(float* zs, int n, int steps, int nz, int goff, uint64_t seed, uint32_t plan, uint32_t iter) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n * steps * nz) return;
@@ -93,6 +93,8 @@ __global__ void k_sample_actions(SampleArgs a, int n) {
 
 // strict total order: (score asc, NaN last, index asc) == np.argsort(kind='stable')
 __device__ __forceinline__ bool key_less(double a, int ia, double b, int ib) {
+  const bool pa = ia == 0x7fffffff, pb = ib == 0x7fffffff;      // padding entries sort after everything, NaN scores included
+  if (pa != pb) return pb;
   const bool na = a != a, nb = b != b;
   if (na != nb) return nb;
   if (!na && a != b) return a < b;

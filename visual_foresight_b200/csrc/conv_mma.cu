@@ -416,7 +416,8 @@ __device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const Issue
 // Only home lanes < 128-(KS-1) produce outputs: consecutive units overlap by KS-1 rows.
 template <int KS, int NG>
 __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& g, uint32_t tmem_base, int a, int acc_cols, int q4,
-                                               int lane, int half, int b, int v_lo, uint32_t xch_half, uint32_t tab, uint32_t stg) {
+                                               int lane, int half, int b, int v_lo, uint32_t xch_half, uint32_t tab, uint32_t stg,
+                                               float (&stat_acc)[NG >= 3 ? 1 : 4]) {
   const int row = q4 * 32 + lane;
   const int ps = P.out.pix_stride, W = g.W, H = g.H, Wp = g.Wp, pad = g.padc;
   const float scale = g.out_scale;
@@ -495,12 +496,46 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
         __syncwarp();
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         const int q = lane & 3;
+        float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sums / sums of squares of this lane's 4 channels over its 4 pixels
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {
           const int pp = 8 * s4 + (lane >> 2);
           const float4 v4 = lds128(stg + (uint32_t)(pp * 64 + (((q ^ (pp >> 1)) & 3) << 4)));
           const long long oo_p = __shfl_sync(0xffffffffu, oo, pp);
-          if ((vmask >> pp) & 1u) *reinterpret_cast<float4*>(P.out.p + oo_p + c16 + 4 * q) = v4;
+          if ((vmask >> pp) & 1u) {
+            *reinterpret_cast<float4*>(P.out.p + oo_p + c16 + 4 * q) = v4;
+            sv[0] += v4.x; sv[1] += v4.y; sv[2] += v4.z; sv[3] += v4.w;
+            sv[4] = fmaf(v4.x, v4.x, sv[4]); sv[5] = fmaf(v4.y, v4.y, sv[5]);
+            sv[6] = fmaf(v4.z, v4.z, sv[6]); sv[7] = fmaf(v4.w, v4.w, sv[7]);
+          }
+        }
+        if (P.stats_partial) {
+          // Instance-norm statistics of the stored outputs (no separate pass over the conv output): reduce-scatter over the 8
+          // lanes that hold the same channel quad (fixed tree -> bit-reproducible).  Afterwards lane l holds ONE value:
+          // kind = l >> 4 (0 sum, 1 sum of squares) of channel c16 + 4*(l & 3) + 2*((l >> 3) & 1) + ((l >> 2) & 1),
+          // summed over the warp's 32 pixel rows.
+          const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+          float t4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float snd = b4 ? sv[i] : sv[4 + i], kp = b4 ? sv[4 + i] : sv[i];
+            t4[i] = kp + __shfl_xor_sync(0xffffffffu, snd, 16);
+          }
+          float t2[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float snd = b3 ? t4[i] : t4[2 + i], kp = b3 ? t4[2 + i] : t4[i];
+            t2[i] = kp + __shfl_xor_sync(0xffffffffu, snd, 8);
+          }
+          const float snd = b2 ? t2[0] : t2[1], kp = b2 ? t2[1] : t2[0];
+          const float tot = kp + __shfl_xor_sync(0xffffffffu, snd, 4);
+          if constexpr (NG >= 3) {
+            stat_acc[0] += tot;                 // NG % (channel blocks) == 0 (host-checked): this group always sees the same block
+          } else {
+            const int cb = c16 >> 4;
+            stat_acc[0] += cb == 0 ? tot : 0.f; stat_acc[1] += cb == 1 ? tot : 0.f;
+            stat_acc[2] += cb == 2 ? tot : 0.f; stat_acc[3] += cb == 3 ? tot : 0.f;
+          }
         }
         __syncwarp();
         continue;
@@ -548,7 +583,10 @@ constexpr int EPI_WARP0 = 4;
 constexpr int TAB_BAR = 7;             // named barrier of the bias-table hand-over (ids 1..NG: the groups' exchange barriers)
 constexpr int NPRE = 5;                // bias-table entries prefetched per epilogue thread (ntap * np <= 25 * 48 = 1200)
 constexpr uint32_t STG_OFF = 2 * 25 * MT * 4 + 256;   // output tiles of the row-stacked epilogue: behind the bias tables + barriers
-constexpr size_t STG_BYTES = 16 * 2048;               // 2 KB per epilogue warp, up to 16 warps (NG = 4)
+constexpr size_t STG_TILE_BYTES = 16 * 2048;          // 2 KB per epilogue warp, up to 16 warps (NG = 4)
+constexpr uint32_t STAT_OFF = STG_OFF + (uint32_t)STG_TILE_BYTES;   // fused instance-norm statistics: [2 buffers][16 warps][4 channel blocks][32 lanes] floats
+constexpr size_t STAT_BYTES = 2 * 16 * 4 * 32 * 4;
+constexpr size_t STG_BYTES = STG_TILE_BYTES + STAT_BYTES;
 
 template <int NG>
 __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_constant__ Params P) {
@@ -727,6 +765,10 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
       named_bar_sync(TAB_BAR, NEPI);
     }
     uint32_t it = 0;
+    constexpr int NACC = NG >= 3 ? 1 : 4;       // row-stacked path: this lane's statistic per channel block over the item (epilogue_swap2);
+    float stat_acc[NACC];                       // with NG >= 3 groups a group always handles the same block (NG % blocks == 0)
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) stat_acc[i] = 0.f;
     for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
       const int mt = item / per_mt;
       const int rem = item % per_mt;
@@ -743,15 +785,38 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
         // lane-exchange scratch (the wide path's bias tables live here): 2 parities x 4 quarters x (KS-1)^2 rows x 16 floats
         const uint32_t stg = smem_u32(tail) + STG_OFF + (uint32_t)(warp - EPI_WARP0) * 2048u;   // this warp's output tile
         if constexpr (NG >= 3) {
-          epilogue_swap2<3, NG>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, smem_u32(s_sab_all + half * 512), smem_u32(tab), stg);
+          epilogue_swap2<3, NG>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, smem_u32(s_sab_all + half * 512), smem_u32(tab), stg, stat_acc);
         } else {
           const uint32_t xch_half = smem_u32(s_sab_all + half * 2048);
-          if (g.k == 3) epilogue_swap2<3, 2>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab), stg);
-          else epilogue_swap2<5, 2>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab), stg);
+          if (g.k == 3) epilogue_swap2<3, 2>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab), stg, stat_acc);
+          else epilogue_swap2<5, 2>(P, g, tmem_base, a, acc_cols, q4, lane, half, b0, v_lo, xch_half, smem_u32(tab), stg, stat_acc);
         }
-        if (next < g.nitems) {               // every reader of the other table finished one item ago
-          tab_store(tab0 + ((it + 1) & 1) * (g.ntap * g.np));
-          named_bar_sync(TAB_BAR, NEPI);
+        const bool do_stats = P.stats_partial != nullptr;
+        const uint32_t stat_buf = smem_u32(tail) + STAT_OFF + (it & 1u) * (uint32_t)(STAT_BYTES / 2);
+        if (do_stats) {                      // publish this warp's per-channel partial sums of the item (double-buffered by item parity)
+          const uint32_t my = stat_buf + (uint32_t)(((warp - EPI_WARP0) * 4) * 32 + lane) * 4u;
+          if constexpr (NACC == 1) {
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(my + (uint32_t)((half % (g.np >> 4)) * 128)), "f"(stat_acc[0]) : "memory");
+            stat_acc[0] = 0.f;
+          } else {
+#pragma unroll
+            for (int cb = 0; cb < NACC; ++cb) {
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(my + (uint32_t)(cb * 128)), "f"(stat_acc[cb]) : "memory");
+              stat_acc[cb] = 0.f;
+            }
+          }
+        }
+        if (next < g.nitems) tab_store(tab0 + ((it + 1) & 1) * (g.ntap * g.np));   // every reader of the other table finished one item ago
+        if (next < g.nitems || do_stats) named_bar_sync(TAB_BAR, NEPI);
+        if (do_stats && etid < (g.np >> 4) * 32) {
+          // slot = pass: every (sample, channel, pass) is written exactly once; the epilogue warps are combined in a fixed order
+          const int cb = etid >> 5, l = etid & 31;
+          double tot = 0.0;
+          for (int w = 0; w < 4 * NG; ++w)
+            if (NACC > 1 || (w >> 2) % (g.np >> 4) == cb) tot += (double)lds32(stat_buf + (uint32_t)((w * 4 + cb) * 32 + l) * 4u);
+          const int ch = cb * 16 + 4 * (l & 3) + 2 * ((l >> 3) & 1) + ((l >> 2) & 1);
+          if (ch < g.Cout && b0 < P.B)
+            P.stats_partial[(((long long)b0 * g.Cout + ch) * P.stats_S + ps_) * 2 + (l >> 4)] = tot;
         }
       } else if constexpr (NG != 2) {
       } else if (g.swap) {
@@ -911,6 +976,11 @@ void current_mode(int* layout, int* bo) {
 
 // output tiles of the row-stacked epilogue: only layers whose epilogue can take the tiled path (whole 16-channel blocks)
 size_t stg_bytes(const Geometry& g) { return (g.swap == 2 && (g.Cout & 15) == 0) ? STG_BYTES : 0; }
+// host mirror of epilogue_swap2's `tiled` predicate (the path that also accumulates the instance-norm statistics)
+bool thin_epilogue_tiled(const Geometry& g, const View& out, int act) {
+  const bool vec4 = ((g.Cout | out.ch_off | out.pix_stride) & 3) == 0 && (out.sample_stride & 3) == 0 && (out.lo_off & 3) == 0;
+  return vec4 && out.lo_off == 0 && act != ACT_SIGMOID && (g.Cout & 15) == 0 && g.np <= 64;
+}
 
 // TMA box rows: every pass starts its box at the padded-image row holding its first virtual pixel and must cover
 // (offset inside that row) + v_cnt + the k-1 halo rows + k-1 pixels.
@@ -1138,6 +1208,17 @@ bool mma_conv_supported(int k, int cin, int cout, int H, int W) {
   return plan_geometry(layout, bo, k, k, k, cin, cout, H, W, 1, 3, &g);
 }
 
+// partial slots per (sample, channel) the fused instance-norm statistics of this layer shape use (0: not fused); sizes the
+// engine's partial-sum scratch
+int mma_conv_stats_slots(int k, int kw, int cin, int cout, int H, int W) {
+  int layout, bo;
+  current_mode(&layout, &bo);
+  if (layout == 2 && !(cin % 64 == 0 && cout >= 128)) layout = 1;
+  Geometry g;
+  if (!plan_geometry(layout, bo, k, kw, k, cin, cout, H, W, 1, 3, &g)) return 0;
+  return g.swap == 2 ? g.npass : (g.swap ? 0 : 2 * g.npass);
+}
+
 // Host-only description of the tiling plan_geometry() picks for a layer (no device needed): lets the CPU test suite check the
 // resource invariants (shared memory, TMEM columns, MMA N, box coverage) for every layer shape of the supported specs.
 bool mma_conv_describe(int k, int kw, int cin, int cout, int H, int W, int B, int passes, int out[24]) {
@@ -1285,7 +1366,7 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B; P.act = c.act;
   P.stats_partial = nullptr; P.stats_S = 0;
   if (c.stats_partial && !P.g.swap) { P.stats_partial = c.stats_partial; P.stats_S = P.g.npass * 2; }
-  if (c.stats_slots) *c.stats_slots = P.stats_S;
+
   if (!P.g.swap && c.out.lo_off) return -6;                           // the wide epilogue writes float32 (pre-norm) outputs
   int r = activation_map(c.src, P.g, B, &P.tmap0);
   if (r) return r;
@@ -1310,6 +1391,14 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
     attr_set = true;
   }
   const int grid = std::min(P.g.nitems, g_num_sms > 0 ? g_num_sms : 148);
+  {
+    const int ng = (P.g.swap == 2 && P.g.k == 3) ? epi_groups : 2, ncb = P.g.np >> 4;
+    if (c.stats_partial && P.g.swap == 2 && thin_epilogue_tiled(P.g, c.out, c.act) && (ng == 2 || ng % ncb == 0)) {
+      P.stats_partial = c.stats_partial;
+      P.stats_S = P.g.npass;
+    }
+  }
+  if (c.stats_slots) *c.stats_slots = P.stats_S;
   ++g_launch_counter;
   if (epi_groups == 4 && P.g.swap == 2 && P.g.k == 3)
     return launch_k(k_conv_mma<4>, dim3(grid), dim3(128 + 128 * 4), smem, s, P) == cudaSuccess ? 0 : -4;

@@ -31,6 +31,8 @@ struct MmaConvCall {
 };
 
 bool mma_conv_supported(int k, int cin, int cout, int H, int W);
+// partial slots per (sample, channel) of the fused instance-norm statistics for this layer shape (0 = not fused)
+int mma_conv_stats_slots(int k, int kw, int cin, int cout, int H, int W);
 // host-only: the tiling picked for a layer as 24 integers (see vf_debug_conv_plan in include/vfengine.h); false = unsupported
 bool mma_conv_describe(int k, int kw, int cin, int cout, int H, int W, int B, int passes, int out[24]);
 // returns 0 on success; device allocations are appended to *allocs (owned by the engine handle)

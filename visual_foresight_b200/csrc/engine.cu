@@ -70,6 +70,7 @@ struct ViewNet {
   std::vector<ConvLayer> enc_lstm, dec_lstm;     // entries with k == 0 for non-rnn layers
   std::vector<RnnState> enc_rnn, dec_rnn;
   ConvLayer scratch0, scratch1, masks0, masks1;
+  ConvLayer heads0;            // scratch.conv0 and masks.conv0 as ONE 3x3 conv ngf -> 2*ngf over the last decoder map (opt.merge_heads)
   float *cdna_w = nullptr, *cdna_b = nullptr;
   float *w_state = nullptr, *b_state = nullptr;   // per-view state head (IndepMultiSAVP: independent weight sets)
   float *w_z = nullptr, *b_z = nullptr;           // dense LSTM over the latent (use_rnn_z)
@@ -103,6 +104,7 @@ struct vf_engine {
   double *stats_partial = nullptr, *cstats_partial = nullptr;
   std::vector<float*> act_enc, act_dec;
   float* pack0 = nullptr;    // [B][H][W][8] packed (image, first) input of enc0 (tensor-core path)
+  float* heads_h = nullptr;     // [B][H][W][2*ngf] = [scratch hidden | mask hidden] (opt.merge_heads)
   float *scr_h = nullptr, *mask_h = nullptr, *layers = nullptr, *logits = nullptr, *kern = nullptr, *partial = nullptr;
   float* cdna_part = nullptr;   // split-K partial products of the CDNA dense head
   int nblk = 0, cl = 0;
@@ -145,6 +147,7 @@ struct vf_engine {
   double* topk_keys = nullptr;
   int* topk_idx = nullptr;
   size_t topk_cap = 0;
+  int cem_Mg_cap = 0;               // capacity (global samples) of the elite buffers
   float* cem_goal_host_copy = nullptr;
 
   std::map<std::string, DebugEntry> debug[4];
@@ -155,6 +158,14 @@ struct vf_engine {
   long long ctx_version = 0;                  // bumped by everything the shared-prefix state depends on (context, weights)
   long long snap_version = -1;                // ctx_version the prefix snapshot was taken at (-1: none)
   bool use_graph = true;
+  // A/B switches, read ONCE in vf_create (VF_* environment variables; defaults in brackets)
+  struct Opts {
+    bool shared_prefix = true;   // VF_SHARED_PREFIX [1]: context-only cell steps run once on one sample
+    bool prefix_cache = true;    // VF_PREFIX_CACHE [1]: CEM iterations 1.. restore the prefix state saved by iteration 0
+    bool stats_fin = false;      // VF_STATS_FIN [0]: separate k_stats_finalize launches (1) or consumers finalise on the fly (0)
+    bool epi_stats = true;       // VF_EPI_STATS [1]: instance-norm statistics of the thin convolutions come from their epilogue
+    bool merge_heads = true;     // VF_MERGE_HEADS [1]: scratch.conv0 + masks.conv0 as one convolution
+  } opt;
   int cur_M = 0;               // samples of the rollout being launched (convs on fewer samples = shared-prefix steps)
 
   // profiling (vf_profile_*)
@@ -176,11 +187,17 @@ int fail(vf_engine* h, int code, const char* fmt, ...) {
   return code;
 }
 
+// sticky device faults: a kernel of this library traps (mbar_wait in conv_mma.cu) instead of hanging when an mbarrier arrival is lost
+const char* cuda_hint(cudaError_t e) {
+  if (e == cudaErrorLaunchFailure || e == cudaErrorIllegalInstruction || e == cudaErrorIllegalAddress || e == cudaErrorAssert)
+    return " [device-side trap or fault in a vfengine kernel; the CUDA context is lost: vf_destroy the handle and restart the process]";
+  return "";
+}
 #define CU(call)                                                                                    \
   do {                                                                                              \
     cudaError_t e__ = (call);                                                                       \
     if (e__ != cudaSuccess)                                                                         \
-      return fail(h, VF_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return fail(h, VF_ERR_CUDA, "%s:%d %s -> %s%s", __FILE__, __LINE__, #call, cudaGetErrorString(e__), cuda_hint(e__)); \
   } while (0)
 
 template <typename T>
@@ -193,6 +210,30 @@ int dalloc(vf_engine* h, T** p, size_t n) {
   *p = (T*)q;
   return VF_OK;
 }
+// cudaFree a buffer that dalloc() registered in the handle (grow-only buffers release their previous copy)
+void dfree(vf_engine* h, void* p) {
+  if (!p) return;
+  auto it = std::find(h->allocs.begin(), h->allocs.end(), p);
+  if (it != h->allocs.end()) h->allocs.erase(it);
+  cudaFree(p);
+}
+void drop_graphs(vf_engine* h) {
+  for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
+}
+// device scratch of one C-ABI call, released when the call returns (after the stream has been synchronised)
+struct Scratch {
+  std::vector<void*> p;
+  ~Scratch() { for (void* q : p) cudaFree(q); }
+  template <typename T>
+  bool get(T** out, size_t n) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return false;
+    p.push_back(q);
+    *out = (T*)q;
+    return true;
+  }
+};
 #define DA(p, n)                          \
   do {                                    \
     int r__ = dalloc(h, &(p), (size_t)(n)); \
@@ -351,10 +392,18 @@ int build_net(vf_engine* h) {
   const vf_config& c = h->cfg;
   const int n = c.n_enc, A = h->A, B = h->B;
   h->views.resize(h->ncam);
-  size_t raw_max = 0, decin_max = 0, cmax = 0, fmax_ = 0;
+  size_t raw_max = 0, decin_max = 0, cmax = 0, fmax_ = 0, stat_max = 0;
   auto upd = [&](const ConvLayer& L) {
     raw_max = std::max(raw_max, (size_t)L.H * L.W * L.cout);
     cmax = std::max(cmax, (size_t)L.cout);
+    // partial-sum slots per (sample, channel): k_plane_stats / k_lstm_gates use <= 16, a conv epilogue one or two per pass
+    int slots = 16;
+    if (c.precision != VF_PREC_FP32_SIMT) {
+      const bool sd = L.s2d;
+      slots = std::max(slots, mma_conv_stats_slots(sd ? 3 : L.k, L.fold ? 1 : (sd ? 3 : L.k), L.fold ? L.k * L.cin_sp : (sd ? 4 * L.cin_sp : L.cin_sp),
+                                                   L.cout, sd ? L.H / 2 : L.H, sd ? L.W / 2 : L.W));
+    }
+    stat_max = std::max(stat_max, (size_t)L.cout * slots);
   };
   for (int v = 0; v < h->ncam; ++v) {
     ViewNet& net = h->views[v];
@@ -436,12 +485,16 @@ int build_net(vf_engine* h) {
     net.masks1 = mk("masks.conv1", 3, h->H, h->W, h->cm, 0, h->nm, false);
     net.masks1.cin_w = g + 3 * h->nm;        // the layers buffer is padded to a multiple of 8 channels (16-byte units)
     upd(net.scratch0);
+    if (h->opt.merge_heads) {
+      net.heads0 = mk("heads0", 3, h->H, h->W, g, 0, 2 * g, false);
+      upd(net.heads0);
+    }
   }
   // shared scratch (first view's shapes == all views' shapes)
   DA(h->raw, (size_t)B * raw_max);
   DA(h->dec_in, (size_t)B * decin_max);
   DA(h->stats, (size_t)B * cmax * 2);
-  DA(h->stats_partial, plane_stats_partial_doubles(B, (int)cmax));
+  DA(h->stats_partial, std::max(plane_stats_partial_doubles(B, (int)cmax), (size_t)B * stat_max * 2));
   DA(h->cstats_partial, plane_stats_partial_doubles(B, (int)std::max(fmax_, (size_t)1)));
   DA(h->cstats, (size_t)B * std::max(fmax_, (size_t)1) * 2);
   h->act_enc.assign(n, nullptr);
@@ -458,9 +511,13 @@ int build_net(vf_engine* h) {
     }
   }
   const size_t px = (size_t)h->H * h->W;
-  DA(h->scr_h, (size_t)B * px * h->ngf);
+  if (h->opt.merge_heads) {
+    DA(h->heads_h, (size_t)B * px * 2 * h->ngf);
+  } else {
+    DA(h->scr_h, (size_t)B * px * h->ngf);
+    DA(h->mask_h, (size_t)B * px * h->ngf);
+  }
   if (c.precision != VF_PREC_FP32_SIMT) DA(h->pack0, (size_t)B * px * 8 * 5);   // (image, first) x 5 dx taps, 8 channels each
-  DA(h->mask_h, (size_t)B * px * h->ngf);
   DA(h->layers, (size_t)B * px * h->cl);
   if (cudaMemset(h->layers, 0, (size_t)B * px * h->cl * sizeof(float)) != cudaSuccess) return fail(h, VF_ERR_CUDA, "memset layers");
   DA(h->logits, (size_t)B * px * h->nm);
@@ -480,9 +537,33 @@ int finalize_weights(vf_engine* h) {
     for (auto& L : net.dec_conv) if ((r = prepare_conv(h, v, L))) return r;
     for (auto& L : net.enc_lstm) if (L.k && (r = prepare_conv(h, v, L))) return r;
     for (auto& L : net.dec_lstm) if (L.k && (r = prepare_conv(h, v, L))) return r;
-    if ((r = prepare_conv(h, v, net.scratch0))) return r;
+    if (h->opt.merge_heads) {
+      // heads0 = [scratch.conv0 | masks.conv0] along the output channels (same input, same 3x3 geometry, both instance-normalised)
+      const char* parts[4] = {".w", ".b", ".gamma", ".beta"};
+      for (const char* suf : parts) {
+        const HostTensor* a = find_w(h, v, std::string("scratch.conv0") + suf);
+        const HostTensor* b = find_w(h, v, std::string("masks.conv0") + suf);
+        if (!a || !b) return fail(h, VF_ERR_STATE, "missing weight view%d.{scratch,masks}.conv0%s", v, suf);
+        if (a->shape != b->shape) return fail(h, VF_ERR_INVALID, "scratch.conv0%s and masks.conv0%s differ in shape", suf, suf);
+        const size_t inner = (size_t)a->shape.back(), outer = a->data.size() / inner;
+        HostTensor m;
+        m.shape = a->shape;
+        m.shape.back() = 2 * (int64_t)inner;
+        m.data.resize(2 * a->data.size());
+        for (size_t o = 0; o < outer; ++o) {
+          memcpy(&m.data[o * 2 * inner], &a->data[o * inner], inner * sizeof(float));
+          memcpy(&m.data[o * 2 * inner + inner], &b->data[o * inner], inner * sizeof(float));
+        }
+        char nm[64];
+        snprintf(nm, sizeof(nm), "view%d.heads0%s", v, suf);
+        h->host_w[nm] = std::move(m);
+      }
+      if ((r = prepare_conv(h, v, net.heads0))) return r;
+    } else {
+      if ((r = prepare_conv(h, v, net.scratch0))) return r;
+      if ((r = prepare_conv(h, v, net.masks0))) return r;
+    }
     if ((r = prepare_conv(h, v, net.scratch1))) return r;
-    if ((r = prepare_conv(h, v, net.masks0))) return r;
     if ((r = prepare_conv(h, v, net.masks1))) return r;
     const HostTensor* cw = find_w(h, v, "cdna.dense.w");
     const HostTensor* cb = find_w(h, v, "cdna.dense.b");
@@ -525,6 +606,7 @@ int finalize_weights(vf_engine* h) {
 
 // finalise the S partial sums of n planes into (mean, rstd) pairs and hand both to the consumer
 StatsRef fin_stats(vf_engine* h, const double* partial, int S, int n, int npix, float* dst) {
+  if (!h->opt.stats_fin) return stats_ref(partial, S, npix, h->cfg.norm_eps, nullptr);   // the consumer finalises in its prologue
   launch_stats_finalize(partial, n, S, npix, h->cfg.norm_eps, dst, h->stream);
   return stats_ref(partial, S, npix, h->cfg.norm_eps, dst);
 }
@@ -657,9 +739,10 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     const int oc = L.cout;
     const int pooled = L.s2d ? 0 : 1;                       // s2d: the conv output is the pooled map already
     View rawv = dense_view(h->raw, L.s2d ? (hh / 2) * (ww / 2) : hh * ww, oc);
-    run_conv(h, L, x0, x1, rawv, B);
+    int S_e = 0;                                             // statistics of the POOLED map: only a pool-fused conv can supply them
+    run_conv(h, L, x0, x1, rawv, B, ACT_NONE, (h->opt.epi_stats && !pooled) ? h->stats_partial : nullptr, &S_e);
     hh /= 2; ww /= 2;
-    const int S_e = launch_plane_stats(rawv, B, hh, ww, pooled, h->stats_partial, h->stream);
+    if (!S_e) S_e = launch_plane_stats(rawv, B, hh, ww, pooled, h->stats_partial, h->stream);
     View dst = c.enc_rnn[i] ? cview(h, net.enc_rnn[i].lstm_in, hh * ww, 2 * oc, 0, oc)
                             : cview(h, h->act_enc[i], hh * ww, oc, 0, oc);
     launch_norm_act(rawv, B, hh, ww, pooled, fin_stats(h, h->stats_partial, S_e, B * oc, hh * ww, h->stats), L.gamma, L.beta, ACT_RELU, dst, h->stream);
@@ -683,8 +766,9 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     launch_upsample2x(x, skip, B, hh, ww, din, h->stream);
     hh *= 2; ww *= 2;
     View rawv = dense_view(h->raw, hh * ww, oc);
-    run_conv(h, L, din, none, rawv, B);
-    const int S_d = launch_plane_stats(rawv, B, hh, ww, 0, h->stats_partial, h->stream);
+    int S_d = 0;
+    run_conv(h, L, din, none, rawv, B, ACT_NONE, h->opt.epi_stats ? h->stats_partial : nullptr, &S_d);
+    if (!S_d) S_d = launch_plane_stats(rawv, B, hh, ww, 0, h->stats_partial, h->stream);
     View dst = c.dec_rnn[i] ? cview(h, net.dec_rnn[i].lstm_in, hh * ww, 2 * oc, 0, oc)
                             : cview(h, h->act_dec[i], hh * ww, oc, 0, oc);
     launch_norm_act(rawv, B, hh, ww, 0, fin_stats(h, h->stats_partial, S_d, B * oc, hh * ww, h->stats), L.gamma, L.beta, ACT_RELU, dst, h->stream);
@@ -704,19 +788,37 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   launch_cdna_kernels(enc_out[n - 1], enc_h[n - 1] * enc_w[n - 1], net.cdna_w, h->kc, h->nt, B, h->cdna_part, h->stream);
   View layers = cview(h, h->layers, (int)px, cl, 0, cl);
   launch_cdna_apply(image, first, h->cdna_part, featK, net.cdna_b, h->kern, h->kc, h->nt, B, H, W, layers, h->stream);
-  // P7 scratch image
-  View rawg = dense_view(h->raw, (int)px, g);
-  run_conv(h, net.scratch0, h_last, none, rawg, B);
-  const int S_s = launch_plane_stats(rawg, B, H, W, 0, h->stats_partial, h->stream);
-  View scr = cview(h, h->scr_h, (int)px, g, 0, g);
-  launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_s, B * g, (int)px, h->stats), net.scratch0.gamma, net.scratch0.beta, ACT_RELU, scr, h->stream);
+  double* epi_sp = h->opt.epi_stats ? h->stats_partial : nullptr;
+  View scr, hm;
   View scratch_out = cview(h, h->layers, (int)px, cl, 3 * (h->nt + 2), 3);
-  run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
-  // P8 masks
-  run_conv(h, net.masks0, h_last, none, rawg, B);
-  const int S_m = launch_plane_stats(rawg, B, H, W, 0, h->stats_partial, h->stream);
-  View hm = cview(h, h->mask_h, (int)px, g, 0, g);
-  launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_m, B * g, (int)px, h->stats), net.masks0.gamma, net.masks0.beta, ACT_RELU, hm, h->stream);
+  if (h->opt.merge_heads) {
+    // P7 + P8 first layers: scratch.conv0 and masks.conv0 read the same map -> ONE 3x3 conv ngf -> 2*ngf, one statistics set,
+    // one normalise pass; the two hidden maps are the channel halves of heads_h
+    View raw2 = dense_view(h->raw, (int)px, 2 * g);
+    int S_h = 0;
+    run_conv(h, net.heads0, h_last, none, raw2, B, ACT_NONE, epi_sp, &S_h);
+    if (!S_h) S_h = launch_plane_stats(raw2, B, H, W, 0, h->stats_partial, h->stream);
+    View hh2 = cview(h, h->heads_h, (int)px, 2 * g, 0, 2 * g);
+    launch_norm_act(raw2, B, H, W, 0, fin_stats(h, h->stats_partial, S_h, B * 2 * g, (int)px, h->stats), net.heads0.gamma, net.heads0.beta, ACT_RELU, hh2, h->stream);
+    scr = cview(h, h->heads_h, (int)px, 2 * g, 0, g);
+    hm = cview(h, h->heads_h, (int)px, 2 * g, g, g);
+    run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
+  } else {
+    // P7 scratch image
+    View rawg = dense_view(h->raw, (int)px, g);
+    int S_s = 0;
+    run_conv(h, net.scratch0, h_last, none, rawg, B, ACT_NONE, epi_sp, &S_s);
+    if (!S_s) S_s = launch_plane_stats(rawg, B, H, W, 0, h->stats_partial, h->stream);
+    scr = cview(h, h->scr_h, (int)px, g, 0, g);
+    launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_s, B * g, (int)px, h->stats), net.scratch0.gamma, net.scratch0.beta, ACT_RELU, scr, h->stream);
+    run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
+    // P8 masks
+    int S_m = 0;
+    run_conv(h, net.masks0, h_last, none, rawg, B, ACT_NONE, epi_sp, &S_m);
+    if (!S_m) S_m = launch_plane_stats(rawg, B, H, W, 0, h->stats_partial, h->stream);
+    hm = cview(h, h->mask_h, (int)px, g, 0, g);
+    launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_m, B * g, (int)px, h->stats), net.masks0.gamma, net.masks0.beta, ACT_RELU, hm, h->stream);
+  }
   View lg = dense_view(h->logits, (int)px, nm);
   run_conv(h, net.masks1, hm, layers, lg, B);
   CompositeArgs ca;
@@ -737,8 +839,7 @@ void run_step(vf_engine* h, int v, int tau, int B) {
 }
 
 int shared_prefix_steps(const vf_engine* h, int M) {
-  const char* e = getenv("VF_SHARED_PREFIX");            // read per rollout (tests flip it); part of the graph key
-  if (e && atoi(e) == 0) return 0;
+  if (!h->opt.shared_prefix) return 0;
   return (h->nz == 0 && M > 1) ? std::max(0, std::min(h->n_ctx_actions, h->C - 1)) : 0;
 }
 
@@ -847,9 +948,9 @@ int rollout(vf_engine* h, int M, int T, int mode = PREFIX_NONE) {
   if (mode == PREFIX_RESTORE && h->snap_version != h->ctx_version) mode = PREFIX_SAVE;     // no snapshot of this context yet
   const long long key = ((long long)shared_prefix_steps(h, M) << 56) | ((long long)mode << 52) | ((long long)M << 24) | ((long long)T << 8) |
                         (long long)h->n_ctx_actions;
-  if (h->graphs.size() > 12 && !h->graphs.count(key)) {       // a handful of (mode, M, T) keys per controller: bound the cache
-    for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    h->graphs.clear();
+  if (h->graphs.size() > 24 && !h->graphs.count(key)) {       // a handful of (mode, M, T) keys per controller: bound the cache
+    CU(cudaStreamSynchronize(h->stream));
+    drop_graphs(h);
   }
   vf_engine::GraphSlot& gs = h->graphs[key];
   int r = VF_OK;
@@ -891,6 +992,11 @@ int rollout(vf_engine* h, int M, int T, int mode = PREFIX_NONE) {
 
 int ensure_actions(vf_engine* h, int T) {
   if (T > h->Tcap) {
+    // captured rollout graphs hold the old pointer by value (SaArgs): they must not survive the reallocation
+    CU(cudaStreamSynchronize(h->stream));
+    drop_graphs(h);
+    dfree(h, h->actions);
+    h->actions = nullptr;
     DA(h->actions, (size_t)h->B * T * h->adim);
     h->Tcap = T;
   }
@@ -904,15 +1010,14 @@ int score_device(vf_engine* h, int cost_kind, const float* goal, const float* ta
     double g[VF_MAX_TASKS * 2], tw[VF_MAX_TASKS];
     for (int i = 0; i < ntask * 2; ++i) g[i] = (double)goal[i];
     for (int i = 0; i < ntask; ++i) tw[i] = task_weights ? (double)task_weights[i] : 1.0 / ntask;
+    // pageable sources: cudaMemcpyAsync returns once they are staged, so the stack arrays may go out of scope (no stream sync)
     CU(cudaMemcpyAsync(h->goal_dev, g, sizeof(double) * ntask * 2, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->taskw_dev, tw, sizeof(double) * ntask, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));   // g/tw live on this stack frame
     launch_pixel_cost(distrib, M, P, h->ncam, h->H, h->W, h->nd, h->goal_dev, h->cost, h->stream);
     launch_score_final(h->cost, M, P, ntask, h->taskw_dev, (double)finalweight, scores_dev, h->stream);
   } else if (cost_kind == VF_COST_GOAL_IMAGE) {
     const size_t n = (size_t)h->ncam * h->H * h->W * 3;
     CU(cudaMemcpyAsync(h->goal_img, goal, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
     launch_goal_image_cost(h->gen_images, M, P, h->ncam, h->H, h->W, h->goal_img, scores_dev, h->stream);
   } else {
     return fail(h, VF_ERR_INVALID, "unknown cost kind %d", cost_kind);
@@ -946,6 +1051,14 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
   h->cm = cfg->ngf + h->cl;
   h->split = cfg->precision != VF_PREC_FP32_SIMT;
   { const char* e = getenv("VF_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
+  {
+    auto flag = [](const char* name, bool dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) != 0 : dflt; };
+    h->opt.shared_prefix = flag("VF_SHARED_PREFIX", true);
+    h->opt.prefix_cache = flag("VF_PREFIX_CACHE", true);
+    h->opt.stats_fin = flag("VF_STATS_FIN", false);
+    h->opt.epi_stats = flag("VF_EPI_STATS", true);
+    h->opt.merge_heads = flag("VF_MERGE_HEADS", true) && cfg->precision != VF_PREC_FP32_SIMT;
+  }
   // programmatic dependent launch: measured SLOWER on B200 inside the replayed graph (131.4 vs 124.7 ms per plan), so opt-in
   { const char* e = getenv("VF_PDL"); g_use_pdl = e && e[0] == '1'; }
   if (h->B < 1 || h->H < 8 || h->W < 8 || h->ncam < 1 || h->ncam > 4 || h->nd < 1 || h->nd > 4 || h->ncam * h->nd > VF_MAX_TASKS)
@@ -1174,30 +1287,56 @@ int vf_cem_begin(vf_engine* h, const vf_cem_params* p, const float* goal, const 
   }
   // per-call sized buffers (grow only)
   const size_t need_scores = (size_t)p->iterations * Mg;
-  if (need_scores > h->cem_scores_cap) { DA(h->cem_scores_own, need_scores); h->cem_scores_cap = need_scores; }
+  if (need_scores > h->cem_scores_cap) {
+    CU(cudaStreamSynchronize(h->stream));
+    dfree(h, h->cem_scores_own);
+    h->cem_scores_own = nullptr;
+    DA(h->cem_scores_own, need_scores);
+    h->cem_scores_cap = need_scores;
+  }
   h->cem_scores = h->cem_scores_ext ? h->cem_scores_ext : h->cem_scores_own;
   const size_t npad = (size_t)topk_padded(Mg);
   if (npad > h->topk_cap) {
+    CU(cudaStreamSynchronize(h->stream));
+    dfree(h, h->topk_keys); dfree(h, h->topk_idx);
+    h->topk_keys = nullptr; h->topk_idx = nullptr;
     DA(h->topk_keys, npad); DA(h->topk_idx, npad); h->topk_cap = npad;
+  }
+  if (Mg > h->cem_Mg_cap) {                          // elite buffers hold up to K <= Mg rows: sized by Mg itself, not by its padding
+    CU(cudaStreamSynchronize(h->stream));
+    dfree(h, h->cem_elite_idx); dfree(h, h->cem_factor); dfree(h, h->cem_elites_nr); dfree(h, h->cem_best64);
+    h->cem_elite_idx = nullptr; h->cem_factor = nullptr; h->cem_elites_nr = nullptr; h->cem_best64 = nullptr;
     DA(h->cem_elite_idx, Mg);
     DA(h->cem_factor, (size_t)128 * Mg); DA(h->cem_elites_nr, (size_t)Mg * 128);
     DA(h->cem_best64, (size_t)Mg * 128 * 8);
+    h->cem_Mg_cap = Mg;
   }
   if (!h->cem_local_nr) { DA(h->cem_local_nr, (size_t)h->B * 128); }
-  if (h->cem_T > h->cem_act_cap) { DA(h->cem_actions64, (size_t)h->B * h->cem_T * h->adim); h->cem_act_cap = h->cem_T; }
-  if ((size_t)K * h->cem_T * h->adim > (size_t)Mg * 128 * 8) return fail(h, VF_ERR_INVALID, "elite buffer too small");
+  if (h->cem_T > h->cem_act_cap) {
+    CU(cudaStreamSynchronize(h->stream));
+    dfree(h, h->cem_actions64);
+    h->cem_actions64 = nullptr;
+    DA(h->cem_actions64, (size_t)h->B * h->cem_T * h->adim);
+    h->cem_act_cap = h->cem_T;
+  }
+  if ((size_t)K * h->cem_T * h->adim > (size_t)h->cem_Mg_cap * 128 * 8) return fail(h, VF_ERR_INVALID, "elite buffer too small");
   h->cem_Kf = Kf;
   if (!h->cem_fut_idx) { DA(h->cem_fut_idx, (size_t)h->B); DA(h->cem_fut_scores, (size_t)h->B); }
   if (Kf > 1) {                                     // rollout sample r evaluates action sequence offset + r / Kf
     std::vector<int> fi((size_t)M * Kf);
     for (int r = 0; r < M * Kf; ++r) fi[r] = p->sample_offset + r / Kf;
-    CU(cudaMemcpyAsync(h->cem_fut_idx, fi.data(), sizeof(int) * fi.size(), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(h->cem_fut_idx, fi.data(), sizeof(int) * fi.size(), cudaMemcpyHostToDevice, h->stream));   // pageable: staged on return
   }
   h->cem_has_noise = noise != nullptr;
   if (noise) {
     const size_t nn = (size_t)p->iterations * Mg * h->cem_Dmax;
-    if (nn > h->cem_noise_cap) { DA(h->cem_noise, nn); h->cem_noise_cap = nn; }
+    if (nn > h->cem_noise_cap) {
+      CU(cudaStreamSynchronize(h->stream));
+      dfree(h, h->cem_noise);
+      h->cem_noise = nullptr;
+      DA(h->cem_noise, nn);
+      h->cem_noise_cap = nn;
+    }
     CU(cudaMemcpyAsync(h->cem_noise, noise, nn * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   }
   double mean[128], std0[128];
@@ -1225,7 +1364,7 @@ int vf_cem_begin(vf_engine* h, const vf_cem_params* p, const float* goal, const 
   } else {
     return fail(h, VF_ERR_INVALID, "unknown cost kind");
   }
-  CU(cudaStreamSynchronize(h->stream));   // host staging arrays above are on this stack frame
+  // no stream synchronisation: every source above is pageable host memory, which cudaMemcpyAsync has staged when it returns
   h->cem_active = true;
   return VF_OK;
 }
@@ -1243,8 +1382,7 @@ int vf_cem_iter_rollout(vf_engine* h, int32_t it) {
   if (h->nz > 0)                                    // latents of the stochastic predictor: Philox, keyed by the global rollout index
     launch_sample_latents(h->zs, nroll, h->S - 1, h->nz, p.sample_offset * Kf, p.seed, p.plan_index, (uint32_t)it, h->stream);
   h->T = h->cem_T;
-  const char* pc = getenv("VF_PREFIX_CACHE");         // read per call (tests flip it); the mode is part of the graph key
-  const bool cache_env = !(pc && atoi(pc) == 0);
+  const bool cache_env = h->opt.prefix_cache;
   int r = rollout(h, nroll, h->cem_T, !cache_env ? PREFIX_NONE : (it == 0 ? PREFIX_SAVE : PREFIX_RESTORE));
   if (r) return r;
   double* sc = h->cem_scores + (size_t)it * p.global_samples + p.sample_offset;
@@ -1344,7 +1482,8 @@ int vf_topk(vf_engine* h, const double* scores, int32_t n, int32_t k, int32_t* o
   double *ds, *keys;
   int *idx, *oi;
   const int npad = topk_padded(n);
-  DA(ds, n); DA(keys, npad); DA(idx, npad); DA(oi, k);
+  Scratch sc;
+  if (!sc.get(&ds, n) || !sc.get(&keys, npad) || !sc.get(&idx, npad) || !sc.get(&oi, k)) return fail(h, VF_ERR_NOMEM, "topk scratch");
   CU(cudaMemcpyAsync(ds, scores, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
   launch_topk(ds, n, k, oi, keys, idx, h->stream);
   CU(cudaMemcpyAsync(out, oi, sizeof(int) * k, cudaMemcpyDeviceToHost, h->stream));
@@ -1363,7 +1502,9 @@ int vf_refit(vf_engine* h, const double* elites, int32_t K, int32_t nactions, in
     for (int a = 0; a < nactions; ++a)
       for (int d = 0; d < adim; ++d) nr[((size_t)k * nactions + a) * adim + d] = elites[((size_t)k * T + a * repeat + repeat - 1) * adim + d];
   double *dx, *dm, *df, *dc;
-  DA(dx, (size_t)K * D); DA(dm, D); DA(df, (size_t)D * K); DA(dc, (size_t)D * D);
+  Scratch sc;
+  if (!sc.get(&dx, (size_t)K * D) || !sc.get(&dm, D) || !sc.get(&df, (size_t)D * K) || !sc.get(&dc, (size_t)D * D))
+    return fail(h, VF_ERR_NOMEM, "refit scratch");
   CU(cudaMemcpyAsync(dx, nr.data(), sizeof(double) * K * D, cudaMemcpyHostToDevice, h->stream));
   launch_refit(dx, K, D, dm, df, dc, h->stream);
   if (om) CU(cudaMemcpyAsync(om, dm, sizeof(double) * D, cudaMemcpyDeviceToHost, h->stream));
@@ -1380,10 +1521,14 @@ int vf_debug_conv2d(vf_engine* h, int32_t impl, const float* x, const float* w, 
   if (!h || !x || !w || !y || (k != 3 && k != 5)) return fail(h, VF_ERR_INVALID, "bad conv arguments");
   float *dx, *dw, *db = nullptr, *dy;
   const size_t nx = (size_t)B * H * W * Cin, nw = (size_t)k * k * Cin * Cout, ny = (size_t)B * H * W * Cout;
-  DA(dx, nx); DA(dw, nw); DA(dy, ny);
+  Scratch sc;                                                          // every device buffer of this call is released on return
+  if (!sc.get(&dx, nx) || !sc.get(&dw, nw) || !sc.get(&dy, ny)) return fail(h, VF_ERR_NOMEM, "conv scratch");
   CU(cudaMemcpyAsync(dx, x, nx * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(dw, w, nw * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  if (bias) { DA(db, Cout); CU(cudaMemcpyAsync(db, bias, Cout * sizeof(float), cudaMemcpyHostToDevice, h->stream)); }
+  if (bias) {
+    if (!sc.get(&db, Cout)) return fail(h, VF_ERR_NOMEM, "conv scratch");
+    CU(cudaMemcpyAsync(db, bias, Cout * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
   View vx = make_view(dx, (long long)H * W * Cin, Cin, 0, Cin), vy = make_view(dy, (long long)H * W * Cout, Cout, 0, Cout);
   if (impl == VF_PREC_FP32_SIMT) {
     ConvArgs a;
@@ -1395,9 +1540,9 @@ int vf_debug_conv2d(vf_engine* h, int32_t impl, const float* x, const float* w, 
     MmaConvWeights mw;
     std::string e;
     std::vector<float> wh(w, w + nw);
-    if (mma_conv_prepare_weights(wh.data(), k, k, k, Cin, Cout, &mw, &h->allocs, &e)) return fail(h, VF_ERR_CUDA, "mma weight prep: %s", e.c_str());
+    if (mma_conv_prepare_weights(wh.data(), k, k, k, Cin, Cout, &mw, &sc.p, &e)) return fail(h, VF_ERR_CUDA, "mma weight prep: %s", e.c_str());
     float* dxs;                                                        // split-half copy of x (what a producer kernel would write)
-    DA(dxs, nx);
+    if (!sc.get(&dxs, nx)) return fail(h, VF_ERR_NOMEM, "conv scratch");
     View vxs = make_view(dxs, (long long)H * W * Cin, Cin, 0, Cin, (long long)B * H * W * Cin);
     launch_dense_to_view(dx, B, H * W, vxs, h->stream);
     MmaConvCall c;

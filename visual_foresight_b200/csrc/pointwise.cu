@@ -89,8 +89,15 @@ __global__ void k_stats_finalize(const double* __restrict__ partial, int n, int 
 // consumer in its prologue so that no separate finalize launch is needed
 __device__ __forceinline__ float2 stat_of(const StatsRef& r, long long idx) {
   if (r.fin) return __ldg(reinterpret_cast<const float2*>(r.fin) + idx);
+  const double2* p = reinterpret_cast<const double2*>(r.partial) + idx * r.S;
   double ts = 0.0, tq = 0.0;
-  for (int k = 0; k < r.S; ++k) { ts += r.partial[(idx * r.S + k) * 2]; tq += r.partial[(idx * r.S + k) * 2 + 1]; }
+  for (int k0 = 0; k0 < r.S; k0 += 8) {           // 8 independent 16-byte loads in flight, summed in slot order (== k_stats_finalize)
+    double2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = k0 + u < r.S ? __ldg(p + k0 + u) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { ts += v[u].x; tq += v[u].y; }
+  }
   const double mean = ts / r.npix;
   double var = tq / r.npix - mean * mean;
   if (var < 0.0) var = 0.0;
