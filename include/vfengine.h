@@ -199,6 +199,28 @@ VF_API int vf_cem_scores_write(vf_engine* h, int32_t iteration, int32_t offset, 
 /* fetch the action tensor sampled in the last vf_cem_iter_rollout for the local samples: (M,T,adim) f64 */
 VF_API int vf_cem_actions(vf_engine* h, double* out_actions);
 
+/* ---- multi-GPU: score exchange over peer memory (NVLink / NVSwitch), owned by the engine ------------------------------
+ * Replaces the reference's in-graph towers: contiguous action slice per GPU, outputs concatenated in rank order
+ * (video_prediction/setup_predictor.py:34-44,117-123,155-162; ngpu comes from the policy ctor, sim/simulator.py:21).
+ * One handle per GPU (one process per GPU, or several handles in one process).  Every handle owns an exchange WINDOW in its
+ * device memory: the (iterations, global_samples) f64 score matrix plus one arrival counter per rank.
+ *   vf_comm_export : allocate the window, write a 128-byte descriptor (process id, device, cudaIpcMemHandle, pointer)
+ *   <the caller moves the descriptors between ranks: any channel — torch.distributed, MPI, a pipe, a file>
+ *   vf_comm_connect: descs = world x 128 bytes in rank order; maps every peer window (cudaIpcOpenMemHandle across
+ *                    processes, plain peer access inside one process)
+ *   vf_cem_exchange: ONE kernel on the handle's stream: stores the local segment of score row `iteration` into every peer's
+ *                    window (P2P stores), publishes this rank's arrival counter (release, system scope) and waits for the
+ *                    peers' counters (acquire; bounded by VF_COMM_TIMEOUT_MS, default 30000 — a timeout is reported by
+ *                    the next vf_cem_finish, never a hang).  No host synchronisation, no collective library.
+ * Call order per plan on every rank: vf_cem_begin, then per iteration vf_cem_iter_rollout, vf_cem_exchange,
+ * vf_cem_iter_select, then vf_cem_finish.  While connected, vf_cem_begin uses the window as the score matrix. */
+#define VF_PEER_DESC_BYTES 128
+VF_API int vf_comm_export(vf_engine* h, int32_t max_iterations, int32_t max_global_samples, void* out_desc);
+VF_API int vf_comm_connect(vf_engine* h, int32_t rank, int32_t world, const void* descs);
+VF_API int vf_cem_exchange(vf_engine* h, int32_t iteration);
+/* unmap the peers and release the window (also done by vf_destroy) */
+VF_API int vf_comm_close(vf_engine* h);
+
 /* unit-parity hooks: cem_base_controller.py:104 (argsort()[:K], stable, ties -> lower index) */
 VF_API int vf_topk(vf_engine* h, const double* scores, int32_t n, int32_t k, int32_t* out_idx);
 /* samplers/gaussian_sampler.py:96-107 _fit_gaussians on elites (K,T,adim) f64: mean (D), cov (D,D),

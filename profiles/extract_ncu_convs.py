@@ -25,10 +25,13 @@ for r in rows[2:]:
          "inst_M": round((f(r, "smsp__inst_executed.sum") or 0) / 1e6, 2)}
     out.append(e)
 ORDER = ["scratch0", "scratch1", "masks0", "masks1", "enc0", "lstm0", "enc1", "lstm1", "enc2", "lstm2", "dec0", "lstm3", "dec1", "lstm4", "dec2"]
+ORDER2 = ["enc0", "lstm0", "enc1", "lstm1", "enc2", "lstm2", "dec0", "lstm3", "dec1", "lstm4", "dec2", "heads0", "scratch1", "masks1"]
+if "--step-order-r02" in sys.argv:    # round 2: 14 convolutions per cell step, capture starts at enc0 (profiles/r02_call2.sh, skip 624)
+    for i, e in enumerate(out): e["layer"] = ORDER2[i % len(ORDER2)]
 if "--step-order" in sys.argv:        # the capture starts at the first head conv of a cell step (profiles/ncu_full.sh, skip 640)
     for i, e in enumerate(out): e["layer"] = ORDER[i % len(ORDER)]
 json.dump({"capture": sys.argv[1], "launches": out}, open(sys.argv[2], "w"), indent=1)
-gate = [e for e in out if e["time_us"] and e["time_us"] > 150]
+gate = [e for e in out if e["time_us"] and e["time_us"] > 150 and e["kernel"].endswith("<2>")]   # wide-path launches: the conv-LSTM gate convs
 for e in out: print(e)
 if len(sys.argv) > 3 and gate:
     mean = sum((e["dram_read_MB"] + e["dram_write_MB"]) for e in gate) / len(gate) * 1e6

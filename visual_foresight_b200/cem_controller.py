@@ -199,6 +199,10 @@ class PixelCostController(CEMBaseController):
                          state_append=None, finalweight=10., use_predictor_ncam=False, device_cem=True,
                          cem_seed=0, task_weights=None, log_to_stdout=False, model_spec=None, model_seed=0,
                          precision="f16x3",
+                         # ngpu > 1 (one process per GPU): how the per-iteration scores cross ranks ("peer": the engine's
+                         # own NVLink peer-memory kernel; "nccl": torch.distributed all-gather; "host": gloo) and, optionally,
+                         # the CUDA ordinal of every rank (default gpu_id + local rank)
+                         collective="peer", shard_devices=None,
                          # stochastic planning (samplers/gaussian_sampler.py:139-141 repeats every action sequence K times;
                          # variants/ensemble_vidpred.py:56-58 scores mean + lambda * var): futures per action sequence
                          num_futures=1, lambda_variance=0.0).items():

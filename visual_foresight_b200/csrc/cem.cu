@@ -151,7 +151,42 @@ __global__ void k_refit(const double* __restrict__ x, int K, int D, double* mean
     }
 }
 
+// One block.  Peer stores travel over NVLink / NVSwitch (or stay in local HBM when the "peer" is another handle on the same
+// device); the release/acquire pair on the arrival counters orders them against the peers' reads.
+__global__ void __launch_bounds__(256) k_score_exchange(ExchangeArgs a) {
+  const double* mine = a.scores[a.rank] + a.row_off + a.offset;
+  for (int r = 0; r < a.world; ++r) {
+    if (r == a.rank) continue;
+    double* dst = a.scores[r] + a.row_off + a.offset;
+    for (int i = threadIdx.x; i < a.local; i += blockDim.x) dst[i] = mine[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r < a.world && r != a.rank) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[r] + a.rank), "r"(a.epoch) : "memory");
+    const unsigned* f = a.flags[a.rank] + r;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int)(v - a.epoch) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > a.timeout_ns) { *a.status = 1u; break; }          // reported by vf_cem_finish: never hang the GPU
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
 }  // namespace
+
+void launch_score_exchange(const ExchangeArgs& a, cudaStream_t s) {
+  ++g_launch_counter;
+  k_score_exchange<<<1, 256, 0, s>>>(a);
+}
 
 void launch_sample_actions(const SampleArgs& a, int n, cudaStream_t s) {
   ++g_launch_counter;

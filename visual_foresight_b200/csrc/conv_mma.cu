@@ -89,7 +89,11 @@ struct Geometry {
   int ncols_item;   // rg: TMEM columns of one accumulator set (the MMA's N)
   int We;           // row pitch of the epilogue's column -> pixel map (Wp, or W when rg)
   float out_scale;  // 2^-scale_log2
+  // division by kernel-invariant divisors as one multiply-high: x / d == __umulhi(x, ceil(2^32 / d)) for x * d < 2^32 (d > 1)
+  uint32_t m_Wp, m_npass, m_np;
 };
+
+__host__ __device__ inline uint32_t fd_magic(int d) { return d > 1 ? (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d) : 0u; }
 
 struct Params {
   alignas(64) CUtensorMap tmap0;   // activations of source 0: (channel, x, y, sample, plane)
@@ -226,6 +230,8 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+__device__ __forceinline__ int fdiv(int x, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)x, magic) : x; }
+
 // All MMAs of one filter tap (one weight stage): PASSES x KSTEPS x U instructions, straight-line, issued by the single
 // elected thread.  Descriptors only differ in their low word (start address >> 4), advanced by pre-shifted offsets.
 template <int PASSES, int KSTEPS, int U>
@@ -335,8 +341,8 @@ __device__ __forceinline__ void issuer_loop_swap(const Geometry& g, const IssueC
   int s = 0;
   uint32_t ph = 0, job = 0, it = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-    const int a = it % nacc;
-    mbar_wait(&cx.acc_empty[a], ((it / nacc) & 1) ^ 1);
+    const int a = nacc == 2 ? (int)(it & 1u) : 0;
+    mbar_wait(&cx.acc_empty[a], (((nacc == 2 ? it >> 1 : it)) & 1) ^ 1);
     tc_fence_after();
     const uint32_t tacc = cx.tmem_base + (uint32_t)(a * acc_cols);
     const uint64_t item_off16 = (uint64_t)(((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
@@ -379,8 +385,8 @@ __device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const Issue
   int s = 0;
   uint32_t ph = 0, job = 0, it = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-    const int a = it % nacc;
-    mbar_wait(&cx.acc_empty[a], ((it / nacc) & 1) ^ 1);
+    const int a = nacc == 2 ? (int)(it & 1u) : 0;
+    mbar_wait(&cx.acc_empty[a], (((nacc == 2 ? it >> 1 : it)) & 1) ^ 1);
     tc_fence_after();
     const uint32_t tacc = cx.tmem_base + (uint32_t)(a * acc_cols);
     const uint64_t item_off16 = (uint64_t)(((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
@@ -429,20 +435,24 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
   // 16 bytes in each of 32 different lines — the uncoalesced form kept the store queue full (STG operand-release stalls).
   const bool tiled = vec4 && !split && !sigm && (g.Cout & 15) == 0;
   uint32_t par = 0;
-  // work items = (unit, 16-channel block), dealt round-robin to the NG groups of the epilogue (4 warps each)
+  const bool home = row < g.ustride && b < P.B;
+  const long long obase = (long long)b * P.out.sample_stride + P.out.ch_off;      // the item's sample: once per item
+  float* const out_b = P.out.p + obase;
+  // work items = (unit, 16-channel block), dealt round-robin to the NG groups of the epilogue (4 warps each); (u, cb) advance
+  // incrementally (ncb is 1..4: no division)
   const int ncb = g.np >> 4;
-  for (int idx = half; idx < g.units * ncb; idx += NG) {
-    const int u = idx / ncb, c16 = (idx - u * ncb) << 4;
+  int u = 0, cb = half;
+  while (cb >= ncb) { cb -= ncb; ++u; }
+  for (; u < g.units;) {
+    const int c16 = cb << 4;
     const int v = v_lo + u * g.ustride + row;
-    const int oy = v / Wp, ox = v - oy * Wp;
-    const bool valid = row < g.ustride && b < P.B && ox < W && oy < H;
+    const int oy = fdiv(v, g.m_Wp), ox = v - oy * Wp;
+    const bool valid = home && ox < W && oy < H;
     uint32_t sb = tab;                        // this sample's (border class, channel) bias table, staged in shared memory (address)
-    float* op = nullptr;
-    long long oo = 0;
+    int pixo = -1;                            // element offset of the output pixel inside the sample (-1: no output from this lane)
     if (valid) {
       if (P.sabias) sb = tab + (uint32_t)((border_class(oy, H, pad) * g.kcl + border_class(ox, W, pad)) * g.np) * 4u;
-      oo = (long long)b * P.out.sample_stride + (long long)(oy * W + ox) * ps + P.out.ch_off;
-      op = P.out.p + oo;
+      pixo = (oy * W + ox) * ps;
     }
     {
       uint32_t r[KS][16];
@@ -494,16 +504,16 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
                  make_float4(fmaf(acc[j], scale, bb.x), fmaf(acc[j + 1], scale, bb.y), fmaf(acc[j + 2], scale, bb.z), fmaf(acc[j + 3], scale, bb.w)));
         }
         __syncwarp();
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         const int q = lane & 3;
+        float* const out_q = out_b + c16 + 4 * q;
         float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sums / sums of squares of this lane's 4 channels over its 4 pixels
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4) {
           const int pp = 8 * s4 + (lane >> 2);
           const float4 v4 = lds128(stg + (uint32_t)(pp * 64 + (((q ^ (pp >> 1)) & 3) << 4)));
-          const long long oo_p = __shfl_sync(0xffffffffu, oo, pp);
-          if ((vmask >> pp) & 1u) {
-            *reinterpret_cast<float4*>(P.out.p + oo_p + c16 + 4 * q) = v4;
+          const int po = __shfl_sync(0xffffffffu, pixo, pp);
+          if (po >= 0) {
+            *reinterpret_cast<float4*>(out_q + po) = v4;
             sv[0] += v4.x; sv[1] += v4.y; sv[2] += v4.z; sv[3] += v4.w;
             sv[4] = fmaf(v4.x, v4.x, sv[4]); sv[5] = fmaf(v4.y, v4.y, sv[5]);
             sv[6] = fmaf(v4.z, v4.z, sv[6]); sv[7] = fmaf(v4.w, v4.w, sv[7]);
@@ -532,45 +542,46 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
           if constexpr (NG >= 3) {
             stat_acc[0] += tot;                 // NG % (channel blocks) == 0 (host-checked): this group always sees the same block
           } else {
-            const int cb = c16 >> 4;
             stat_acc[0] += cb == 0 ? tot : 0.f; stat_acc[1] += cb == 1 ? tot : 0.f;
             stat_acc[2] += cb == 2 ? tot : 0.f; stat_acc[3] += cb == 3 ? tot : 0.f;
           }
         }
         __syncwarp();
-        continue;
-      }
-      if (!valid) continue;
-      if (vec4) {
+      } else if (valid) {
+        const long long oo = obase + pixo;
+        if (vec4) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          if (c16 + j < g.Cout) {
-            const float4 bb = lds128(sb + (uint32_t)(c16 + j) * 4u);
-            float4 o;
-            o.x = fmaf(acc[j], scale, bb.x);
-            o.y = fmaf(acc[j + 1], scale, bb.y);
-            o.z = fmaf(acc[j + 2], scale, bb.z);
-            o.w = fmaf(acc[j + 3], scale, bb.w);
-            if (sigm) {
-              o.x = __fdividef(1.f, 1.f + __expf(-o.x)); o.y = __fdividef(1.f, 1.f + __expf(-o.y));
-              o.z = __fdividef(1.f, 1.f + __expf(-o.z)); o.w = __fdividef(1.f, 1.f + __expf(-o.w));
+          for (int j = 0; j < 16; j += 4) {
+            if (c16 + j < g.Cout) {
+              const float4 bb = lds128(sb + (uint32_t)(c16 + j) * 4u);
+              float4 o;
+              o.x = fmaf(acc[j], scale, bb.x);
+              o.y = fmaf(acc[j + 1], scale, bb.y);
+              o.z = fmaf(acc[j + 2], scale, bb.z);
+              o.w = fmaf(acc[j + 3], scale, bb.w);
+              if (sigm) {
+                o.x = __fdividef(1.f, 1.f + __expf(-o.x)); o.y = __fdividef(1.f, 1.f + __expf(-o.y));
+                o.z = __fdividef(1.f, 1.f + __expf(-o.z)); o.w = __fdividef(1.f, 1.f + __expf(-o.w));
+              }
+              if (split) vst4(P.out, oo + c16 + j, o);
+              else *reinterpret_cast<float4*>(P.out.p + oo + c16 + j) = o;
             }
-            if (split) vst4(P.out, oo + c16 + j, o);
-            else *reinterpret_cast<float4*>(op + c16 + j) = o;
           }
-        }
-      } else {
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (c16 + j < g.Cout) {
-            float o = fmaf(acc[j], scale, lds32(sb + (uint32_t)(c16 + j) * 4u));
-            if (sigm) o = __fdividef(1.f, 1.f + __expf(-o));
-            if (split) vst1(P.out, oo + c16 + j, o);
-            else op[c16 + j] = o;
+          for (int j = 0; j < 16; ++j) {
+            if (c16 + j < g.Cout) {
+              float o = fmaf(acc[j], scale, lds32(sb + (uint32_t)(c16 + j) * 4u));
+              if (sigm) o = __fdividef(1.f, 1.f + __expf(-o));
+              if (split) vst1(P.out, oo + c16 + j, o);
+              else P.out.p[oo + c16 + j] = o;
+            }
           }
         }
       }
     }
+    cb += NG;
+    while (cb >= ncb) { cb -= ncb; ++u; }
   }
 }
 
@@ -738,13 +749,13 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
     const int tabn = (P.sabias ? g.ntap : 1) * g.np;
     float pre[NPRE];
     auto tab_fetch = [&](int item_) {
-      const int b_ = ((item_ % per_mt) / g.npass) * g.G;
+      const int b_ = fdiv(item_, g.m_npass);       // row-stacked path: one Cout tile, one sample per item -> item = sample * npass + pass
 #pragma unroll
       for (int j = 0; j < NPRE; ++j) {
         const int i = etid + j * NEPI;
         float bv = 0.f;
         if (i < tabn) {
-          const int cls = i / g.np, c = i - cls * g.np;
+          const int cls = fdiv(i, g.m_np), c = i - cls * g.np;
           if (c < g.Cout) bv = P.sabias ? __ldg(P.sabias + ((long long)b_ * g.ntap + cls) * g.Cout + c) : (P.bias ? __ldg(P.bias + c) : 0.f);
         }
         pre[j] = bv;
@@ -769,19 +780,25 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
     float stat_acc[NACC];                       // with NG >= 3 groups a group always handles the same block (NG % blocks == 0)
 #pragma unroll
     for (int i = 0; i < NACC; ++i) stat_acc[i] = 0.f;
+    const bool per_item_tab = stacked && P.sabias != nullptr;   // without the action/state bias the table is the layer's bias: staged once
     for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
-      const int mt = item / per_mt;
-      const int rem = item % per_mt;
-      const int grp = rem / g.npass, ps_ = rem % g.npass;
+      int mt, grp, ps_;
+      if (stacked) {                               // one Cout tile, G = 1: no divisions by runtime values on this path
+        mt = 0; grp = fdiv(item, g.m_npass); ps_ = item - grp * g.npass;
+      } else {
+        mt = item / per_mt;
+        const int rem = item % per_mt;
+        grp = rem / g.npass; ps_ = rem % g.npass;
+      }
       const int b0 = grp * g.G, v_lo = ps_ * g.v_cnt;
       const int n = mt * MT + row;
-      const int a = it % nacc;
+      const int a = nacc == 2 ? (int)(it & 1u) : 0;
       const int next = item + (int)gridDim.x;
-      if (stacked && next < g.nitems) tab_fetch(next);
-      mbar_wait(&acc_full[a], (it / nacc) & 1);
+      if (per_item_tab && next < g.nitems) tab_fetch(next);
+      mbar_wait(&acc_full[a], (nacc == 2 ? it >> 1 : it) & 1);
       tc_fence_after();
       if (stacked) {
-        float* tab = tab0 + (it & 1) * (g.ntap * g.np);
+        float* tab = per_item_tab ? tab0 + (it & 1) * (g.ntap * g.np) : tab0;
         // lane-exchange scratch (the wide path's bias tables live here): 2 parities x 4 quarters x (KS-1)^2 rows x 16 floats
         const uint32_t stg = smem_u32(tail) + STG_OFF + (uint32_t)(warp - EPI_WARP0) * 2048u;   // this warp's output tile
         if constexpr (NG >= 3) {
@@ -806,8 +823,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
             }
           }
         }
-        if (next < g.nitems) tab_store(tab0 + ((it + 1) & 1) * (g.ntap * g.np));   // every reader of the other table finished one item ago
-        if (next < g.nitems || do_stats) named_bar_sync(TAB_BAR, NEPI);
+        if (per_item_tab && next < g.nitems) tab_store(tab0 + ((it + 1) & 1) * (g.ntap * g.np));   // every reader of the other table finished one item ago
+        if ((per_item_tab && next < g.nitems) || do_stats) named_bar_sync(TAB_BAR, NEPI);
         if (do_stats && etid < (g.np >> 4) * 32) {
           // slot = pass: every (sample, channel, pass) is written exactly once; the epilogue warps are combined in a fixed order
           const int cb = etid >> 5, l = etid & 31;
@@ -995,6 +1012,12 @@ bool box_rows(Geometry& g) {
   return g.R <= 256 && g.Wp <= 256;
 }
 
+// VF_THIN_PERTAP=1 (experiment): thin layers run one MMA per filter tap (N = np, lean epilogue) instead of row-stacked
+bool thin_pertap() {
+  static const bool on = getenv("VF_THIN_PERTAP") && atoi(getenv("VF_THIN_PERTAP")) == 1;
+  return on;
+}
+
 bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int Cout, int H, int W, int B, int passes, Geometry* out) {
   Geometry g;
   memset(&g, 0, sizeof(g));
@@ -1010,7 +1033,7 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
   g.nst = k * kw;
   g.ksteps_last = (std::min(g.ch, Cin - (g.nchunk - 1) * g.ch) + 15) / 16;
   const int np_thin = (Cout + 15) / 16 * 16;
-  if (Cout <= 64 && kw == k && k * np_thin <= 256 && 2 * kcl * kcl * np_thin <= 2304) {   // 2 bias tables behind the exchange scratch
+  if (!thin_pertap() && Cout <= 64 && kw == k && k * np_thin <= 256 && 2 * kcl * kcl * np_thin <= 2304) {   // 2 bias tables behind the exchange scratch
     // ---- row-stacked thin path: pixels on M, the k taps of a filter row side by side on N (k*np columns) ----
     g.swap = 2;
     g.np = np_thin; g.ncols = k * g.np; g.ustride = 128 - (k - 1); g.nst = k;
@@ -1256,7 +1279,7 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int kw, int kcl, int cin,
   if (cin % 8) { if (err) *err = "cin % 8"; return -1; }
   const bool swap = cout <= 64;
   const int np = (cout + 15) / 16 * 16;
-  const bool stacked = swap && kw == k && k * np <= 256 && 2 * kcl * kcl * np <= 2304;   // one stage = a filter ROW: rows = (dx, output channel); must agree with plan_geometry
+  const bool stacked = !thin_pertap() && swap && kw == k && k * np <= 256 && 2 * kcl * kcl * np <= 2304;   // one stage = a filter ROW: rows = (dx, output channel); must agree with plan_geometry
   const int rows = stacked ? k * np : (swap ? np : MT);               // operand tile rows
   const int kk = stacked ? k : k * kw;                                // stages per channel chunk
   const int nchunk = (cin + ch - 1) / ch, n_mt = swap ? 1 : (cout + MT - 1) / MT, kc = ch / 8, rb = ch * 2;
@@ -1363,6 +1386,7 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   if (c.src.C + c.src1.C != w.cin) return -5;
   if (!plan_geometry(layout, bo, w.k, w.kw, w.kcl, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
   P.g.out_scale = ldexpf(1.0f, -w.scale_log2);
+  P.g.m_Wp = fd_magic(P.g.Wp); P.g.m_npass = fd_magic(P.g.npass); P.g.m_np = fd_magic(P.g.np > 0 ? P.g.np : 1);
   P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B; P.act = c.act;
   P.stats_partial = nullptr; P.stats_S = 0;
   if (c.stats_partial && !P.g.swap) { P.stats_partial = c.stats_partial; P.stats_S = P.g.npass * 2; }

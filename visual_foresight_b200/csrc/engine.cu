@@ -14,6 +14,7 @@
 // logits), the cell state and the predicted frames stay float32.
 #include <math.h>
 #include <stdarg.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,6 +31,11 @@
 using namespace vf;
 
 namespace {
+
+// exchange window layout: [VF_MAX_WORLD x u32 arrival counters][u32 status] padded to 256 bytes, then the f64 score matrix
+constexpr size_t COMM_HEADER_BYTES = 256;
+inline double* comm_scores(void* window) { return reinterpret_cast<double*>(static_cast<char*>(window) + COMM_HEADER_BYTES); }
+inline unsigned* comm_status_word(void* window) { return reinterpret_cast<unsigned*>(window) + VF_MAX_WORLD; }
 
 struct HostTensor {
   std::vector<int64_t> shape;
@@ -150,6 +156,20 @@ struct vf_engine {
   int cem_Mg_cap = 0;               // capacity (global samples) of the elite buffers
   float* cem_goal_host_copy = nullptr;
 
+  // peer-memory score exchange (vf_comm_*): this handle's window = [VF_MAX_WORLD arrival counters | status | score matrix]
+  struct Comm {
+    void* window = nullptr;           // cudaMalloc'd (IPC-exportable)
+    size_t window_bytes = 0;
+    int cap_iters = 0, cap_global = 0;
+    bool connected = false;
+    int rank = 0, world = 1;
+    void* peer_base[VF_MAX_WORLD] = {nullptr};   // mapped windows in rank order (own entry = window)
+    bool peer_ipc[VF_MAX_WORLD] = {false};       // opened with cudaIpcOpenMemHandle (to be closed)
+    unsigned epoch = 0;
+    unsigned long long timeout_ns = 30000000000ull;
+  } comm;
+  double* cem_scores_final = nullptr;           // while connected: private copy of the rows vf_cem_iter_select consumed
+
   std::map<std::string, DebugEntry> debug[4];
 
   // CUDA graph of one rollout (S-1 cell steps): captured on the second call with a given key, replayed afterwards
@@ -162,7 +182,7 @@ struct vf_engine {
   struct Opts {
     bool shared_prefix = true;   // VF_SHARED_PREFIX [1]: context-only cell steps run once on one sample
     bool prefix_cache = true;    // VF_PREFIX_CACHE [1]: CEM iterations 1.. restore the prefix state saved by iteration 0
-    bool stats_fin = false;      // VF_STATS_FIN [0]: separate k_stats_finalize launches (1) or consumers finalise on the fly (0)
+    bool stats_fin = true;       // VF_STATS_FIN [1]: separate k_stats_finalize launches (1) or consumers finalise on the fly (0; measured 4 % slower)
     bool epi_stats = true;       // VF_EPI_STATS [1]: instance-norm statistics of the thin convolutions come from their epilogue
     bool merge_heads = true;     // VF_MERGE_HEADS [1]: scratch.conv0 + masks.conv0 as one convolution
   } opt;
@@ -1055,7 +1075,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
     auto flag = [](const char* name, bool dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) != 0 : dflt; };
     h->opt.shared_prefix = flag("VF_SHARED_PREFIX", true);
     h->opt.prefix_cache = flag("VF_PREFIX_CACHE", true);
-    h->opt.stats_fin = flag("VF_STATS_FIN", false);
+    h->opt.stats_fin = flag("VF_STATS_FIN", true);
     h->opt.epi_stats = flag("VF_EPI_STATS", true);
     h->opt.merge_heads = flag("VF_MERGE_HEADS", true) && cfg->precision != VF_PREC_FP32_SIMT;
   }
@@ -1112,6 +1132,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
 int vf_destroy(vf_engine* h) {
   if (!h) return VF_OK;
   if (h->stream) cudaStreamSynchronize(h->stream);
+  vf_comm_close(h);
   for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -1295,6 +1316,16 @@ int vf_cem_begin(vf_engine* h, const vf_cem_params* p, const float* goal, const 
     h->cem_scores_cap = need_scores;
   }
   h->cem_scores = h->cem_scores_ext ? h->cem_scores_ext : h->cem_scores_own;
+  h->cem_scores_final = h->cem_scores;
+  if (h->comm.connected && Mg > M) {
+    // sharded plan over the engine's peer exchange: rollouts write into the window, vf_cem_iter_select keeps a private copy of
+    // every row it consumed (a fast peer may already be storing the NEXT plan's scores into the window when vf_cem_finish reads)
+    if (p->iterations > h->comm.cap_iters || (size_t)p->iterations * Mg > (size_t)h->comm.cap_iters * h->comm.cap_global)
+      return fail(h, VF_ERR_INVALID, "plan (%d iterations x %d samples) exceeds the exchange window (%d x %d)", p->iterations, Mg,
+                  h->comm.cap_iters, h->comm.cap_global);
+    h->cem_scores = comm_scores(h->comm.window);
+    h->cem_scores_final = h->cem_scores_own;
+  }
   const size_t npad = (size_t)topk_padded(Mg);
   if (npad > h->topk_cap) {
     CU(cudaStreamSynchronize(h->stream));
@@ -1405,6 +1436,9 @@ int vf_cem_iter_select(vf_engine* h, int32_t it) {
   if (it < 0 || it >= p.iterations) return fail(h, VF_ERR_INVALID, "iteration %d out of range", it);
   const int K = p.num_elites;
   launch_topk(h->cem_scores + (size_t)it * p.global_samples, p.global_samples, K, h->cem_elite_idx, h->topk_keys, h->topk_idx, h->stream);
+  if (h->cem_scores_final != h->cem_scores)
+    CU(cudaMemcpyAsync(h->cem_scores_final + (size_t)it * p.global_samples, h->cem_scores + (size_t)it * p.global_samples,
+                       sizeof(double) * p.global_samples, cudaMemcpyDeviceToDevice, h->stream));
   // regenerate the elites' action rows from their global indices (no exchange of actions between ranks)
   SampleArgs a;
   fill_sample_args(h, a, it);
@@ -1421,8 +1455,118 @@ int vf_cem_finish(vf_engine* h, double* best, int32_t* eidx, double* scores) {
   const vf_cem_params& p = h->cem;
   if (best) CU(cudaMemcpyAsync(best, h->cem_best64, sizeof(double) * (size_t)p.num_elites * h->cem_T * h->adim, cudaMemcpyDeviceToHost, h->stream));
   if (eidx) CU(cudaMemcpyAsync(eidx, h->cem_elite_idx, sizeof(int) * p.num_elites, cudaMemcpyDeviceToHost, h->stream));
-  if (scores) CU(cudaMemcpyAsync(scores, h->cem_scores, sizeof(double) * (size_t)p.iterations * p.global_samples, cudaMemcpyDeviceToHost, h->stream));
+  if (scores) CU(cudaMemcpyAsync(scores, h->cem_scores_final, sizeof(double) * (size_t)p.iterations * p.global_samples, cudaMemcpyDeviceToHost, h->stream));
+  unsigned comm_status = 0;
+  if (h->comm.connected) CU(cudaMemcpyAsync(&comm_status, comm_status_word(h->comm.window), sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  if (comm_status) {
+    cudaMemsetAsync(comm_status_word(h->comm.window), 0, sizeof(unsigned), h->stream);
+    return fail(h, VF_ERR_CUDA, "score exchange timed out after %.1f s waiting for a peer rank (rank %d of %d): the plan's elites are invalid",
+                h->comm.timeout_ns * 1e-9, h->comm.rank, h->comm.world);
+  }
+  return VF_OK;
+}
+
+// ---- peer-memory score exchange --------------------------------------------------------------------
+namespace {
+struct PeerDesc {                      // VF_PEER_DESC_BYTES, plain data
+  uint32_t magic, version;
+  int64_t pid;
+  int32_t device, cap_iters, cap_global, pad;
+  uint64_t ptr, bytes;
+  cudaIpcMemHandle_t ipc;              // 64 bytes
+  unsigned char reserved[VF_PEER_DESC_BYTES - 48 - sizeof(cudaIpcMemHandle_t)];
+};
+static_assert(sizeof(PeerDesc) == VF_PEER_DESC_BYTES, "peer descriptor layout");
+constexpr uint32_t PEER_MAGIC = 0x76665043u;   // 'vfPC'
+}  // namespace
+
+int vf_comm_close(vf_engine* h) {
+  if (!h) return VF_ERR_INVALID;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int r = 0; r < VF_MAX_WORLD; ++r) {
+    if (h->comm.peer_ipc[r] && h->comm.peer_base[r]) cudaIpcCloseMemHandle(h->comm.peer_base[r]);
+    h->comm.peer_base[r] = nullptr;
+    h->comm.peer_ipc[r] = false;
+  }
+  if (h->comm.window) cudaFree(h->comm.window);
+  h->comm = vf_engine::Comm();
+  h->cem_active = false;
+  return VF_OK;
+}
+
+int vf_comm_export(vf_engine* h, int32_t max_iterations, int32_t max_global, void* out_desc) {
+  if (!h || !out_desc || max_iterations < 1 || max_global < 1) return fail(h, VF_ERR_INVALID, "bad exchange window size");
+  vf_comm_close(h);
+  const size_t bytes = COMM_HEADER_BYTES + sizeof(double) * (size_t)max_iterations * max_global;
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMalloc(&h->comm.window, bytes));
+  CU(cudaMemset(h->comm.window, 0, bytes));
+  h->comm.window_bytes = bytes; h->comm.cap_iters = max_iterations; h->comm.cap_global = max_global;
+  { const char* e = getenv("VF_COMM_TIMEOUT_MS"); if (e && atof(e) > 0) h->comm.timeout_ns = (unsigned long long)(atof(e) * 1e6); }
+  PeerDesc d;
+  memset(&d, 0, sizeof(d));
+  d.magic = PEER_MAGIC; d.version = VF_ABI_VERSION; d.pid = (int64_t)getpid(); d.device = h->cfg.device;
+  d.cap_iters = max_iterations; d.cap_global = max_global; d.ptr = (uint64_t)(uintptr_t)h->comm.window; d.bytes = bytes;
+  CU(cudaIpcGetMemHandle(&d.ipc, h->comm.window));
+  memcpy(out_desc, &d, sizeof(d));
+  return VF_OK;
+}
+
+int vf_comm_connect(vf_engine* h, int32_t rank, int32_t world, const void* descs) {
+  if (!h || !descs || world < 1 || world > VF_MAX_WORLD || rank < 0 || rank >= world) return fail(h, VF_ERR_INVALID, "bad rank/world (world <= %d)", VF_MAX_WORLD);
+  if (!h->comm.window) return fail(h, VF_ERR_STATE, "vf_comm_export first");
+  const PeerDesc* d = reinterpret_cast<const PeerDesc*>(descs);
+  CU(cudaSetDevice(h->cfg.device));
+  for (int r = 0; r < world; ++r) {
+    if (d[r].magic != PEER_MAGIC || d[r].version != VF_ABI_VERSION) return fail(h, VF_ERR_INVALID, "descriptor %d is not a vfengine peer descriptor", r);
+    if (d[r].cap_iters != h->comm.cap_iters || d[r].cap_global != h->comm.cap_global)
+      return fail(h, VF_ERR_INVALID, "rank %d exported a %d x %d window, this rank %d x %d", r, d[r].cap_iters, d[r].cap_global, h->comm.cap_iters, h->comm.cap_global);
+    if (r == rank) {
+      if ((uint64_t)(uintptr_t)h->comm.window != d[r].ptr || d[r].pid != (int64_t)getpid()) return fail(h, VF_ERR_INVALID, "descriptor %d is not this handle's", r);
+      h->comm.peer_base[r] = h->comm.window;
+    } else if (d[r].pid == (int64_t)getpid()) {                 // another handle of this process: plain (peer) pointer
+      if (d[r].device != h->cfg.device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, h->cfg.device, d[r].device));
+        if (!can) return fail(h, VF_ERR_UNSUPPORTED, "device %d cannot access device %d", h->cfg.device, d[r].device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(d[r].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(h, VF_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      h->comm.peer_base[r] = (void*)(uintptr_t)d[r].ptr;
+    } else {                                                     // another process: map its window (peer access over NVLink)
+      void* q = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&q, d[r].ipc, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(h, VF_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+      h->comm.peer_base[r] = q;
+      h->comm.peer_ipc[r] = true;
+    }
+  }
+  h->comm.rank = rank; h->comm.world = world; h->comm.connected = world > 1; h->comm.epoch = 0;
+  h->cem_active = false;
+  return VF_OK;
+}
+
+int vf_cem_exchange(vf_engine* h, int32_t it) {
+  if (!h || !h->cem_active) return fail(h, VF_ERR_STATE, "vf_cem_begin first");
+  const vf_cem_params& p = h->cem;
+  if (it < 0 || it >= p.iterations) return fail(h, VF_ERR_INVALID, "iteration %d out of range", it);
+  if (p.global_samples == p.num_samples) return VF_OK;            // nothing to exchange
+  if (!h->comm.connected) return fail(h, VF_ERR_STATE, "vf_comm_connect first");
+  ExchangeArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int r = 0; r < h->comm.world; ++r) {
+    a.scores[r] = comm_scores(h->comm.peer_base[r]);
+    a.flags[r] = reinterpret_cast<unsigned*>(h->comm.peer_base[r]);
+  }
+  a.status = comm_status_word(h->comm.window);
+  a.world = h->comm.world; a.rank = h->comm.rank;
+  a.row_off = (long long)it * p.global_samples; a.offset = p.sample_offset; a.local = p.num_samples;
+  a.epoch = ++h->comm.epoch;
+  a.timeout_ns = h->comm.timeout_ns;
+  launch_score_exchange(a, h->stream);
+  CU(cudaGetLastError());
   return VF_OK;
 }
 

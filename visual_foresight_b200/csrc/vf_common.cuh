@@ -294,6 +294,21 @@ int topk_padded(int n);
 // mean[D], factor[D][K] = Xc^T / sqrt(K-1), cov[D][D] (unbiased)
 void launch_refit(const double* elites_nr, int K, int D, double* mean, double* factor, double* cov, cudaStream_t s);
 
+// score exchange over peer memory (engine.cu: vf_cem_exchange): store my segment of a score row into every peer's window,
+// publish my arrival counter, wait for the peers' counters
+constexpr int VF_MAX_WORLD = 16;
+struct ExchangeArgs {
+  double* scores[VF_MAX_WORLD];      // score matrix of every rank's window (this rank's own included)
+  unsigned* flags[VF_MAX_WORLD];     // arrival counters of every rank's window: flags[r][q] = last epoch rank q published to r
+  unsigned* status;                  // this rank's window status word (set to 1 on timeout)
+  int world, rank;
+  long long row_off;                 // iteration * global_samples
+  int offset, local;
+  unsigned epoch;
+  unsigned long long timeout_ns;
+};
+void launch_score_exchange(const ExchangeArgs& a, cudaStream_t s);
+
 void launch_pack_rgb2(View image, View first, int B, int HW, View out, cudaStream_t s);
 // out[b, (y,x), dx*8 + 0..7] = (image rgb, first rgb, 0, 0) at (y, x + dx - kf/2), zeros outside the image: the kf dx taps of
 // the first encoder conv folded into channels (its tensor-core form is then a kf x 1 convolution over 8*kf channels)

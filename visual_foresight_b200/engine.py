@@ -13,6 +13,7 @@ from .spec import MAX_LAYERS, PredictorSpec
 
 VF_ABI_VERSION = 1
 VF_MAX_TASKS = 16
+VF_PEER_DESC_BYTES = 128
 PREC_FP32_SIMT, PREC_F16X3, PREC_F16X1 = 0, 1, 2
 COST_PIXEL_DISTANCE, COST_GOAL_IMAGE = 0, 1
 PRECISIONS = {"fp32_simt": PREC_FP32_SIMT, "f16x3": PREC_F16X3, "f16x1": PREC_F16X1}
@@ -88,6 +89,10 @@ _SIGS = {
     "vf_cem_bind_scores": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vf_cem_scores_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vf_cem_scores_write": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "vf_comm_export": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "vf_comm_connect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "vf_cem_exchange": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vf_comm_close": (C.c_int, [C.c_void_p]),
     "vf_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "vf_refit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vf_debug_conv2d": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
@@ -328,6 +333,25 @@ class Engine:
     def cem_scores_write(self, it: int, offset: int, values):
         v = np.ascontiguousarray(values, dtype=np.float64)
         self._check(self.lib.vf_cem_scores_write(self._h, it, offset, v.shape[0], _ptr(v)))
+
+    # -- multi-GPU score exchange over peer memory (vf_comm_*) -----------------------------------------
+    def comm_export(self, max_iterations: int, max_global_samples: int) -> bytes:
+        """allocate this handle's exchange window; returns the 128-byte descriptor the other ranks need"""
+        buf = C.create_string_buffer(VF_PEER_DESC_BYTES)
+        self._check(self.lib.vf_comm_export(self._h, int(max_iterations), int(max_global_samples), buf))
+        return bytes(buf.raw)
+
+    def comm_connect(self, rank: int, world: int, descs):
+        """descs: the descriptors of all ranks, in rank order"""
+        blob = b"".join(bytes(d) for d in descs)
+        assert len(blob) == world * VF_PEER_DESC_BYTES, "need one %d-byte descriptor per rank" % VF_PEER_DESC_BYTES
+        self._check(self.lib.vf_comm_connect(self._h, int(rank), int(world), C.c_char_p(blob)))
+
+    def cem_exchange(self, it: int):
+        self._check(self.lib.vf_cem_exchange(self._h, int(it)))
+
+    def comm_close(self):
+        self._check(self.lib.vf_comm_close(self._h))
 
     def cem_actions(self):
         p = self._cem_params

@@ -215,18 +215,35 @@ class B200VPredEvaluation:
         self.sequence_length = self.spec.seq_len
         self.n_cam = self.spec.ncam
         self._precision = pol.get("precision", self._hp.get("precision", "f16x3"))
-        # rollout capacity: every action sequence is rolled num_futures times under stochastic planning
-        self._max_samples = int(pol.get("num_samples", self._hp.get("run_batch_size", 200))) * max(int(pol.get("num_futures", 1) or 1), 1)
+        # rollout capacity: every action sequence is rolled num_futures times under stochastic planning; with ngpu > 1 this
+        # rank holds a contiguous 1/ngpu slice of the samples (setup_predictor.py:34-39; M % ngpu == 0 :70)
+        M = int(pol.get("num_samples", self._hp.get("run_batch_size", 200)))
+        if n_gpus > 1 and M % n_gpus:
+            raise ValueError("num_samples (%d) must be divisible by ngpu (%d)" % (M, n_gpus))
+        self._max_samples = (M // max(n_gpus, 1)) * max(int(pol.get("num_futures", 1) or 1), 1)
         self._state_append = pol.get("state_append")
+        self._collective = pol.get("collective", self._hp.get("collective", "peer")) or "peer"
+        self._shard_devices = pol.get("shard_devices", self._hp.get("shard_devices"))
 
     def restore(self):
+        device, rank = self._first_gpu, 0
         if self._n_gpus > 1:
+            # The reference builds ngpu towers inside ONE TF graph (setup_predictor.py:117-123).  Here: one process per GPU
+            # (torchrun), every process constructs the same policy with the same (gpu_id, ngpu); rank r drives GPU
+            # gpu_id + local_rank and holds samples [r*M/ngpu, (r+1)*M/ngpu).
             import torch.distributed as dist
             if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() == self._n_gpus):
-                raise RuntimeError("ngpu=%d needs one process per GPU under torch.distributed (torchrun); "
-                                   "in-process towers (setup_predictor.py:117-123) are not reproduced" % self._n_gpus)
-        self.backend = EngineBackend(self.spec, self._weights, self._max_samples, device=self._first_gpu,
-                                     precision=self._precision, state_append=self._state_append)
+                raise RuntimeError("ngpu=%d needs one process per GPU under torch.distributed (torchrun) with world size %d; "
+                                   "in-process towers (setup_predictor.py:117-123) are not reproduced" % (self._n_gpus, self._n_gpus))
+            rank = dist.get_rank()
+            local_rank = int(os.environ.get("LOCAL_RANK", rank % self._n_gpus))
+            device = self._first_gpu + local_rank if self._shard_devices is None else int(self._shard_devices[rank])
+        backend = EngineBackend(self.spec, self._weights, self._max_samples, device=device,
+                                precision=self._precision, state_append=self._state_append)
+        if self._n_gpus > 1:
+            from .distributed import ShardedBackend
+            backend = ShardedBackend(backend, rank, self._n_gpus, collective=self._collective)
+        self.backend = backend
         self._weights = None
 
     def __call__(self, context, inputs):
