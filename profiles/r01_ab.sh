@@ -6,7 +6,7 @@ timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${TAG}.log 
 tail -n 25 gpurun_out/pytest_${TAG}.log
 i=0
 for V in "" "$@"; do
-  env $V timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_${TAG}_$i.json 2> gpurun_out/bench_${TAG}_$i.err
+  env $V timeout 600 python bench.py --no-cpu-baseline --no-strong > gpurun_out/bench_${TAG}_$i.json 2> gpurun_out/bench_${TAG}_$i.err
   echo "variant $i [$V]: $(python - <<PY
 import json
 try:

@@ -107,7 +107,26 @@ struct Params {
   int act;
   double* stats_partial;   // optional: per-(sample, channel) sum / sum-of-squares partials of the stored outputs
   int stats_S;             // partial slots per (sample, channel)
+  // optional "last arriver finalises": the warp that completes a (sample, 32- or 16-channel group) — counted with one
+  // atomic per warp per item in stats_cnt[b * VF_STAT_CNT_STRIDE + group] — turns the S partials into (mean, rstd) pairs in
+  // stats_fin[(b * Cout + c) * 2] and resets the counter: no separate finalize launch, consumers read two floats per channel
+  float* stats_fin;
+  int* stats_cnt;
+  int stats_npix;
+  float stats_eps;
 };
+
+// (mean, rstd) of one plane from its S partial slots, combined in slot order (== k_stats_finalize); the slots were written by
+// other SMs: read them from L2 (ld.cg)
+__device__ __forceinline__ void stats_finalize_plane(const double* part, int S, int npix, float eps, float* fin) {
+  double ts = 0.0, tq = 0.0;
+  for (int k = 0; k < S; ++k) { ts += __ldcg(part + 2 * k); tq += __ldcg(part + 2 * k + 1); }
+  const double mean = ts / npix;
+  double var = tq / npix - mean * mean;
+  if (var < 0.0) var = 0.0;
+  fin[0] = (float)mean;
+  fin[1] = (float)(1.0 / sqrt(var + (double)eps));
+}
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -834,6 +853,24 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
           const int ch = cb * 16 + 4 * (l & 3) + 2 * ((l >> 3) & 1) + ((l >> 2) & 1);
           if (ch < g.Cout && b0 < P.B)
             P.stats_partial[(((long long)b0 * g.Cout + ch) * P.stats_S + ps_) * 2 + (l >> 4)] = tot;
+          if (P.stats_fin && b0 < P.B) {        // this warp = channel block cb of the item; the sample's last pass finalises the block
+            __threadfence();
+            __syncwarp();
+            int last = 0;
+            if (l == 0) {
+              int* cnt = P.stats_cnt + (long long)b0 * VF_STAT_CNT_STRIDE + cb;
+              last = atomicAdd(cnt, 1) == g.npass - 1;
+              if (last) *cnt = 0;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+              __threadfence();
+              const int c = cb * 16 + l;
+              if (l < 16 && c < g.Cout)
+                stats_finalize_plane(P.stats_partial + ((long long)b0 * g.Cout + c) * P.stats_S * 2, P.stats_S, P.stats_npix, P.stats_eps,
+                                     P.stats_fin + ((long long)b0 * g.Cout + c) * 2);
+            }
+          }
         }
       } else if constexpr (NG != 2) {
       } else if (g.swap) {
@@ -962,6 +999,23 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
           double* o = P.stats_partial + (((long long)b * g.Cout + n) * P.stats_S + (ps_ * 2 + half)) * 2;
           o[0] = st_s;
           o[1] = st_q;
+        }
+        if (P.stats_fin && b < P.B && mt * MT + q4 * 32 < g.Cout) {   // warp-uniform: this warp holds live channels of sample b
+          __threadfence();
+          __syncwarp();
+          int last = 0;
+          if (lane == 0) {                          // one arrival per (item-image, warp): 2 column-halves x npass per 32-channel group
+            int* cnt = P.stats_cnt + (long long)b * VF_STAT_CNT_STRIDE + (mt * 4 + q4);
+            last = atomicAdd(cnt, 1) == 2 * g.npass - 1;
+            if (last) *cnt = 0;
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last) {
+            __threadfence();
+            if (live)
+              stats_finalize_plane(P.stats_partial + ((long long)b * g.Cout + n) * P.stats_S * 2, P.stats_S, P.stats_npix, P.stats_eps,
+                                   P.stats_fin + ((long long)b * g.Cout + n) * 2);
+          }
         }
       }
       tc_fence_before();
@@ -1389,6 +1443,7 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   P.g.m_Wp = fd_magic(P.g.Wp); P.g.m_npass = fd_magic(P.g.npass); P.g.m_np = fd_magic(P.g.np > 0 ? P.g.np : 1);
   P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B; P.act = c.act;
   P.stats_partial = nullptr; P.stats_S = 0;
+  P.stats_fin = nullptr; P.stats_cnt = nullptr; P.stats_npix = c.H * c.W; P.stats_eps = c.stats_eps;
   if (c.stats_partial && !P.g.swap) { P.stats_partial = c.stats_partial; P.stats_S = P.g.npass * 2; }
 
   if (!P.g.swap && c.out.lo_off) return -6;                           // the wide epilogue writes float32 (pre-norm) outputs
@@ -1423,6 +1478,8 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
     }
   }
   if (c.stats_slots) *c.stats_slots = P.stats_S;
+  if (P.stats_partial && c.stats_fin && c.stats_cnt && (P.g.n_mt * 4 <= VF_STAT_CNT_STRIDE)) { P.stats_fin = c.stats_fin; P.stats_cnt = c.stats_cnt; }
+  if (c.stats_finalized) *c.stats_finalized = P.stats_fin != nullptr;
   ++g_launch_counter;
   if (epi_groups == 4 && P.g.swap == 2 && P.g.k == 3)
     return launch_k(k_conv_mma<4>, dim3(grid), dim3(128 + 128 * 4), smem, s, P) == cudaSuccess ? 0 : -4;

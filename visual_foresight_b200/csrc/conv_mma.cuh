@@ -28,6 +28,10 @@ struct MmaConvCall {
   int act = 0;  // ACT_NONE / ACT_SIGMOID applied in the epilogue
   double* stats_partial = nullptr;   // in: scratch for fused instance-norm partial sums (null = not requested)
   int* stats_slots = nullptr;        // out: partial slots per (sample, channel) written (0 = this launch did not fuse them)
+  float* stats_fin = nullptr;        // in (optional): (mean, rstd) pairs written by the last-arriving warp of every sample
+  int* stats_cnt = nullptr;          // in: zeroed arrival counters [B][VF_STAT_CNT_STRIDE] (left zeroed)
+  float stats_eps = 1e-6f;
+  bool* stats_finalized = nullptr;   // out: the launch also finalised the statistics into stats_fin
 };
 
 bool mma_conv_supported(int k, int cin, int cout, int H, int W);

@@ -108,6 +108,7 @@ struct vf_engine {
   // shared scratch
   float *raw = nullptr, *dec_in = nullptr, *stats = nullptr, *cstats = nullptr;
   double *stats_partial = nullptr, *cstats_partial = nullptr;
+  int* stat_cnt = nullptr;      // [B][VF_STAT_CNT_STRIDE] arrival counters of the fused statistics finalisation (zero between kernels)
   std::vector<float*> act_enc, act_dec;
   float* pack0 = nullptr;    // [B][H][W][8] packed (image, first) input of enc0 (tensor-core path)
   float* heads_h = nullptr;     // [B][H][W][2*ngf] = [scratch hidden | mask hidden] (opt.merge_heads)
@@ -185,6 +186,7 @@ struct vf_engine {
     bool stats_fin = true;       // VF_STATS_FIN [1]: separate k_stats_finalize launches (1) or consumers finalise on the fly (0; measured 4 % slower)
     bool epi_stats = true;       // VF_EPI_STATS [1]: instance-norm statistics of the thin convolutions come from their epilogue
     bool merge_heads = true;     // VF_MERGE_HEADS [1]: scratch.conv0 + masks.conv0 as one convolution
+    bool fuse_fin = true;        // VF_FUSE_FIN [1]: the producer's last-arriving warp/block finalises the statistics (no finalize launch)
   } opt;
   int cur_M = 0;               // samples of the rollout being launched (convs on fewer samples = shared-prefix steps)
 
@@ -517,6 +519,8 @@ int build_net(vf_engine* h) {
   DA(h->stats_partial, std::max(plane_stats_partial_doubles(B, (int)cmax), (size_t)B * stat_max * 2));
   DA(h->cstats_partial, plane_stats_partial_doubles(B, (int)std::max(fmax_, (size_t)1)));
   DA(h->cstats, (size_t)B * std::max(fmax_, (size_t)1) * 2);
+  DA(h->stat_cnt, (size_t)B * VF_STAT_CNT_STRIDE);
+  if (cudaMemset(h->stat_cnt, 0, (size_t)B * VF_STAT_CNT_STRIDE * sizeof(int)) != cudaSuccess) return fail(h, VF_ERR_CUDA, "memset stat_cnt");
   h->act_enc.assign(n, nullptr);
   h->act_dec.assign(n, nullptr);
   {
@@ -625,7 +629,8 @@ int finalize_weights(vf_engine* h) {
 }
 
 // finalise the S partial sums of n planes into (mean, rstd) pairs and hand both to the consumer
-StatsRef fin_stats(vf_engine* h, const double* partial, int S, int n, int npix, float* dst) {
+StatsRef fin_stats(vf_engine* h, const double* partial, int S, int n, int npix, float* dst, bool finalized = false) {
+  if (finalized) return stats_ref(partial, S, npix, h->cfg.norm_eps, dst);               // the producer kernel wrote (mean, rstd) already
   if (!h->opt.stats_fin) return stats_ref(partial, S, npix, h->cfg.norm_eps, nullptr);   // the consumer finalises in its prologue
   launch_stats_finalize(partial, n, S, npix, h->cfg.norm_eps, dst, h->stream);
   return stats_ref(partial, S, npix, h->cfg.norm_eps, dst);
@@ -636,7 +641,8 @@ View cview(const vf_engine* h, float* p, int hw, int ps, int ch_off, int C) {
   return make_view(p, (long long)hw * ps, ps, ch_off, C, h->split ? (long long)h->B * hw * ps : 0);
 }
 
-void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act, double* stats_partial, int* stats_slots);
+void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act, double* stats_partial, int* stats_slots,
+                   bool* finalized);
 
 cudaEvent_t prof_event(vf_engine* h) {
   if (!h->prof_pool.empty()) { cudaEvent_t e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
@@ -645,21 +651,25 @@ cudaEvent_t prof_event(vf_engine* h) {
   return e;
 }
 
+// stats_partial / stats_slots: fused instance-norm partial sums (slots = 0: not fused, run k_plane_stats); finalized: the launch
+// also wrote the (mean, rstd) pairs of its output planes into h->stats
 void run_conv(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act = ACT_NONE, double* stats_partial = nullptr,
-              int* stats_slots = nullptr) {
+              int* stats_slots = nullptr, bool* finalized = nullptr) {
   if (stats_slots) *stats_slots = 0;
-  if (!h->prof_on) { run_conv_impl(h, L, s0, s1, out, B, act, stats_partial, stats_slots); return; }
+  if (finalized) *finalized = false;
+  if (!h->prof_on) { run_conv_impl(h, L, s0, s1, out, B, act, stats_partial, stats_slots, finalized); return; }
   vf_engine::ProfRec r;
   r.a = prof_event(h); r.b = prof_event(h);
   r.cls = (B < h->cur_M) ? 2 : (L.lstm ? 0 : 1);           // class 2: shared-prefix steps (run on one sample)
   r.flops = 2.0 * B * L.H * L.W * L.k * L.k * (double)L.cin_sp * L.cout;
   cudaEventRecord(r.a, h->stream);
-  run_conv_impl(h, L, s0, s1, out, B, act, stats_partial, stats_slots);
+  run_conv_impl(h, L, s0, s1, out, B, act, stats_partial, stats_slots, finalized);
   cudaEventRecord(r.b, h->stream);
   h->prof.push_back(r);
 }
 
-void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act, double* stats_partial, int* stats_slots) {
+void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out, int B, int act, double* stats_partial, int* stats_slots,
+                   bool* finalized) {
   if (h->cfg.precision != VF_PREC_FP32_SIMT && L.mma.ready) {
     MmaConvCall c;
     c.src = s0; c.src1 = s1; c.out = out; c.sabias = L.sabias; c.bias = L.bias;
@@ -668,6 +678,8 @@ void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out,
     c.act = act;
     c.stats_partial = stats_partial;
     c.stats_slots = stats_slots;
+    if (stats_partial && finalized && h->opt.fuse_fin) { c.stats_fin = h->stats; c.stats_cnt = h->stat_cnt; c.stats_finalized = finalized; }
+    c.stats_eps = h->cfg.norm_eps;
     const int rc = mma_conv_launch(L.mma, c, B, h->stream);
     if (rc && !h->conv_error) {
       h->conv_error = rc;
@@ -688,22 +700,39 @@ void run_lstm(vf_engine* h, int v, const ConvLayer& L, RnnState& r, int B, const
   View none = make_view(nullptr, 0, 0, 0, 0);
   const float eps = h->cfg.norm_eps;
   int slots = 0;
-  run_conv(h, L, in, none, gates, B, ACT_NONE, h->stats_partial, &slots);            // gate statistics fused into the epilogue
-  if (slots == 0) slots = launch_plane_stats(gates, B, r.h, r.w, 0, h->stats_partial, h->stream);
-  const StatsRef gsr = fin_stats(h, h->stats_partial, slots, B * 4 * F, hw, h->stats);
+  bool gfin = false, cfin = false;
+  float* ffin = h->opt.fuse_fin ? h->stats : nullptr;
+  float* cffin = h->opt.fuse_fin ? h->cstats : nullptr;
+  run_conv(h, L, in, none, gates, B, ACT_NONE, h->stats_partial, &slots, &gfin);     // gate statistics fused into the epilogue
+  if (slots == 0) {
+    slots = launch_plane_stats(gates, B, r.h, r.w, 0, h->stats_partial, h->stream, ffin, h->stat_cnt, eps);
+    gfin = ffin != nullptr && (4 * F + 31) / 32 <= VF_STAT_CNT_STRIDE;
+  }
+  const StatsRef gsr = fin_stats(h, h->stats_partial, slots, B * 4 * F, hw, h->stats, gfin);
   int cslots;
   if (256 % F == 0) {     // cell-state statistics fused into the pointwise kernel
-    cslots = launch_lstm_gates(gates, B, hw, F, gsr, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->cstats_partial, h->stream);
+    cslots = launch_lstm_gates(gates, B, hw, F, gsr, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->cstats_partial, h->stream, cffin,
+                               h->stat_cnt, eps);
+    cfin = cffin != nullptr;
   } else {
+    if (!gsr.fin) launch_stats_finalize(h->stats_partial, B * 4 * F, slots, hw, eps, h->stats, h->stream);   // the generic kernel reads finalised pairs
     launch_lstm_gates_generic(gates, B, hw, F, h->stats, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->stream);
-    cslots = launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cstats_partial, h->stream);
+    cslots = launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cstats_partial, h->stream, cffin, h->stat_cnt, eps);
+    cfin = cffin != nullptr && (F + 31) / 32 <= VF_STAT_CNT_STRIDE;
   }
   View hv = cview(h, r.lstm_in, hw, 2 * F, F, F);
   View h2 = r.h_s2d ? cview(h, r.h_s2d, hw / 4, 4 * F, 0, 4 * F) : make_view(nullptr, 0, 0, 0, 0);
-  launch_lstm_out(gates, B, hw, F, gsr, L.gamma, L.beta, fin_stats(h, h->cstats_partial, cslots, B * F, hw, h->cstats), L.cgamma,
+  launch_lstm_out(gates, B, hw, F, gsr, L.gamma, L.beta, fin_stats(h, h->cstats_partial, cslots, B * F, hw, h->cstats, cfin), L.cgamma,
                   L.cbeta, r.c, hv, h->stream, h2, r.w);
   h->debug[v][dbg + ".h"] = DebugEntry{hv, r.h, r.w};
   h->debug[v][dbg + ".c"] = DebugEntry{dense_view(r.c, hw, F), r.h, r.w};
+}
+
+// statistics pass over a conv output whose epilogue did not fuse them; *finalized: the pass wrote (mean, rstd) into h->stats too
+int plane_stats_pass(vf_engine* h, View x, int B, int H, int W, int pool, bool* finalized) {
+  float* fin = h->opt.fuse_fin ? h->stats : nullptr;
+  *finalized = fin != nullptr && (x.C + 31) / 32 <= VF_STAT_CNT_STRIDE;
+  return launch_plane_stats(x, B, H, W, pool, h->stats_partial, h->stream, fin, h->stat_cnt, h->cfg.norm_eps);
 }
 
 // one cell step of one view (spec P1-P8)
@@ -760,12 +789,13 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     const int pooled = L.s2d ? 0 : 1;                       // s2d: the conv output is the pooled map already
     View rawv = dense_view(h->raw, L.s2d ? (hh / 2) * (ww / 2) : hh * ww, oc);
     int S_e = 0;                                             // statistics of the POOLED map: only a pool-fused conv can supply them
-    run_conv(h, L, x0, x1, rawv, B, ACT_NONE, (h->opt.epi_stats && !pooled) ? h->stats_partial : nullptr, &S_e);
+    bool f_e = false;
+    run_conv(h, L, x0, x1, rawv, B, ACT_NONE, (h->opt.epi_stats && !pooled) ? h->stats_partial : nullptr, &S_e, &f_e);
     hh /= 2; ww /= 2;
-    if (!S_e) S_e = launch_plane_stats(rawv, B, hh, ww, pooled, h->stats_partial, h->stream);
+    if (!S_e) S_e = plane_stats_pass(h, rawv, B, hh, ww, pooled, &f_e);
     View dst = c.enc_rnn[i] ? cview(h, net.enc_rnn[i].lstm_in, hh * ww, 2 * oc, 0, oc)
                             : cview(h, h->act_enc[i], hh * ww, oc, 0, oc);
-    launch_norm_act(rawv, B, hh, ww, pooled, fin_stats(h, h->stats_partial, S_e, B * oc, hh * ww, h->stats), L.gamma, L.beta, ACT_RELU, dst, h->stream);
+    launch_norm_act(rawv, B, hh, ww, pooled, fin_stats(h, h->stats_partial, S_e, B * oc, hh * ww, h->stats, f_e), L.gamma, L.beta, ACT_RELU, dst, h->stream);
     h->debug[v][L.name] = DebugEntry{dst, hh, ww};
     View out = dst;
     if (c.enc_rnn[i]) {
@@ -787,11 +817,12 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     hh *= 2; ww *= 2;
     View rawv = dense_view(h->raw, hh * ww, oc);
     int S_d = 0;
-    run_conv(h, L, din, none, rawv, B, ACT_NONE, h->opt.epi_stats ? h->stats_partial : nullptr, &S_d);
-    if (!S_d) S_d = launch_plane_stats(rawv, B, hh, ww, 0, h->stats_partial, h->stream);
+    bool f_d = false;
+    run_conv(h, L, din, none, rawv, B, ACT_NONE, h->opt.epi_stats ? h->stats_partial : nullptr, &S_d, &f_d);
+    if (!S_d) S_d = plane_stats_pass(h, rawv, B, hh, ww, 0, &f_d);
     View dst = c.dec_rnn[i] ? cview(h, net.dec_rnn[i].lstm_in, hh * ww, 2 * oc, 0, oc)
                             : cview(h, h->act_dec[i], hh * ww, oc, 0, oc);
-    launch_norm_act(rawv, B, hh, ww, 0, fin_stats(h, h->stats_partial, S_d, B * oc, hh * ww, h->stats), L.gamma, L.beta, ACT_RELU, dst, h->stream);
+    launch_norm_act(rawv, B, hh, ww, 0, fin_stats(h, h->stats_partial, S_d, B * oc, hh * ww, h->stats, f_d), L.gamma, L.beta, ACT_RELU, dst, h->stream);
     h->debug[v][L.name] = DebugEntry{dst, hh, ww};
     x = dst;
     if (c.dec_rnn[i]) {
@@ -816,10 +847,11 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     // one normalise pass; the two hidden maps are the channel halves of heads_h
     View raw2 = dense_view(h->raw, (int)px, 2 * g);
     int S_h = 0;
-    run_conv(h, net.heads0, h_last, none, raw2, B, ACT_NONE, epi_sp, &S_h);
-    if (!S_h) S_h = launch_plane_stats(raw2, B, H, W, 0, h->stats_partial, h->stream);
+    bool f_h = false;
+    run_conv(h, net.heads0, h_last, none, raw2, B, ACT_NONE, epi_sp, &S_h, &f_h);
+    if (!S_h) S_h = plane_stats_pass(h, raw2, B, H, W, 0, &f_h);
     View hh2 = cview(h, h->heads_h, (int)px, 2 * g, 0, 2 * g);
-    launch_norm_act(raw2, B, H, W, 0, fin_stats(h, h->stats_partial, S_h, B * 2 * g, (int)px, h->stats), net.heads0.gamma, net.heads0.beta, ACT_RELU, hh2, h->stream);
+    launch_norm_act(raw2, B, H, W, 0, fin_stats(h, h->stats_partial, S_h, B * 2 * g, (int)px, h->stats, f_h), net.heads0.gamma, net.heads0.beta, ACT_RELU, hh2, h->stream);
     scr = cview(h, h->heads_h, (int)px, 2 * g, 0, g);
     hm = cview(h, h->heads_h, (int)px, 2 * g, g, g);
     run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
@@ -827,17 +859,19 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     // P7 scratch image
     View rawg = dense_view(h->raw, (int)px, g);
     int S_s = 0;
-    run_conv(h, net.scratch0, h_last, none, rawg, B, ACT_NONE, epi_sp, &S_s);
-    if (!S_s) S_s = launch_plane_stats(rawg, B, H, W, 0, h->stats_partial, h->stream);
+    bool f_s = false;
+    run_conv(h, net.scratch0, h_last, none, rawg, B, ACT_NONE, epi_sp, &S_s, &f_s);
+    if (!S_s) S_s = plane_stats_pass(h, rawg, B, H, W, 0, &f_s);
     scr = cview(h, h->scr_h, (int)px, g, 0, g);
-    launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_s, B * g, (int)px, h->stats), net.scratch0.gamma, net.scratch0.beta, ACT_RELU, scr, h->stream);
+    launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_s, B * g, (int)px, h->stats, f_s), net.scratch0.gamma, net.scratch0.beta, ACT_RELU, scr, h->stream);
     run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
     // P8 masks
     int S_m = 0;
-    run_conv(h, net.masks0, h_last, none, rawg, B, ACT_NONE, epi_sp, &S_m);
-    if (!S_m) S_m = launch_plane_stats(rawg, B, H, W, 0, h->stats_partial, h->stream);
+    bool f_m = false;
+    run_conv(h, net.masks0, h_last, none, rawg, B, ACT_NONE, epi_sp, &S_m, &f_m);
+    if (!S_m) S_m = plane_stats_pass(h, rawg, B, H, W, 0, &f_m);
     hm = cview(h, h->mask_h, (int)px, g, 0, g);
-    launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_m, B * g, (int)px, h->stats), net.masks0.gamma, net.masks0.beta, ACT_RELU, hm, h->stream);
+    launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_m, B * g, (int)px, h->stats, f_m), net.masks0.gamma, net.masks0.beta, ACT_RELU, hm, h->stream);
   }
   View lg = dense_view(h->logits, (int)px, nm);
   run_conv(h, net.masks1, hm, layers, lg, B);
@@ -1078,6 +1112,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
     h->opt.stats_fin = flag("VF_STATS_FIN", true);
     h->opt.epi_stats = flag("VF_EPI_STATS", true);
     h->opt.merge_heads = flag("VF_MERGE_HEADS", true) && cfg->precision != VF_PREC_FP32_SIMT;
+    h->opt.fuse_fin = flag("VF_FUSE_FIN", true) && h->opt.stats_fin;
   }
   // programmatic dependent launch: measured SLOWER on B200 inside the replayed graph (131.4 vs 124.7 ms per plan), so opt-in
   { const char* e = getenv("VF_PDL"); g_use_pdl = e && e[0] == '1'; }

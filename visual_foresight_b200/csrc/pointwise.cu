@@ -1,6 +1,8 @@
 // pointwise.cu — instance-norm statistics, normalise+activation, conv-LSTM pointwise, bilinear x2
 // upsample, and the action/state vector with its per-layer border-class bias.  All HBM/L2-bound:
 // threads run along the channel dimension (NHWC innermost) so every warp access is contiguous.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "vf_common.cuh"
@@ -27,7 +29,18 @@ __device__ __forceinline__ float4 pooled4(const View& x, int b, int W, int pool,
   return make_float4(((a0.x + a1.x) + (a2.x + a3.x)) * 0.25f, ((a0.y + a1.y) + (a2.y + a3.y)) * 0.25f,
                      ((a0.z + a1.z) + (a2.z + a3.z)) * 0.25f, ((a0.w + a1.w) + (a2.w + a3.w)) * 0.25f);
 }
-__global__ void __launch_bounds__(256) k_plane_stats(View x, int H, int W, int pool, double* partial) {
+// "last arriver finalises" (see conv_mma.cu): partial slots written by other blocks are read from L2
+struct FinArgs { float* fin; int* cnt; float eps; };
+__device__ __forceinline__ void finalize_plane(const double* part, int S, int npix, float eps, float* fin) {
+  double ts = 0.0, tq = 0.0;
+  for (int k = 0; k < S; ++k) { ts += __ldcg(part + 2 * k); tq += __ldcg(part + 2 * k + 1); }
+  const double mean = ts / npix;
+  double var = tq / npix - mean * mean;
+  if (var < 0.0) var = 0.0;
+  fin[0] = (float)mean;
+  fin[1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+__global__ void __launch_bounds__(256) k_plane_stats(View x, int H, int W, int pool, double* partial, FinArgs fa) {
   pdl_wait();
   pdl_trigger();
   const int b = blockIdx.x;
@@ -68,6 +81,22 @@ __global__ void __launch_bounds__(256) k_plane_stats(View x, int H, int W, int p
     double* o = partial + (((long long)b * x.C + blockIdx.y * 32 + cc) * S + sp) * 2;
     o[0] = ts;
     o[1] = tq;
+  }
+  if (fa.fin && threadIdx.x < 32) {                  // warp 0 wrote this block's slots: the last of the S blocks finalises 32 channels
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (threadIdx.x == 0) {
+      int* cnt = fa.cnt + (long long)b * VF_STAT_CNT_STRIDE + blockIdx.y;
+      last = atomicAdd(cnt, 1) == S - 1;
+      if (last) *cnt = 0;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    if (last && c < x.C) {
+      __threadfence();
+      finalize_plane(partial + ((long long)b * x.C + c) * S * 2, S, npix, fa.eps, fa.fin + ((long long)b * x.C + c) * 2);
+    }
   }
 }
 
@@ -158,7 +187,7 @@ __device__ __forceinline__ float gate_norm(const View& g, int b, long long pix, 
 // are accumulated on the fly (float64 per thread, lanes combined in a fixed order) -> partial[(b*F+f)*S + block].
 __global__ void __launch_bounds__(256) k_lstm_gates(View gates, int HW, int F, StatsRef gsr,
                                                     const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c,
-                                                    double* partial) {
+                                                    double* partial, FinArgs fa) {
   pdl_wait();
   pdl_trigger();
   const int b = blockIdx.y;
@@ -208,6 +237,22 @@ __global__ void __launch_bounds__(256) k_lstm_gates(View gates, int HW, int F, S
     double* o = partial + (((long long)b * F + f) * gridDim.x + blockIdx.x) * 2;
     o[0] = ts;
     o[1] = tq;
+  }
+  if (fa.fin) {                                      // the last of the sample's gridDim.x blocks finalises the cell-state statistics
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int* cnt = fa.cnt + (long long)b * VF_STAT_CNT_STRIDE;
+      const int last = atomicAdd(cnt, 1) == (int)gridDim.x - 1;
+      if (last) *cnt = 0;
+      s_last = last;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < F) {
+      __threadfence();
+      finalize_plane(partial + ((long long)b * F + threadIdx.x) * gridDim.x * 2, gridDim.x, HW, fa.eps, fa.fin + ((long long)b * F + threadIdx.x) * 2);
+    }
   }
 }
 
@@ -317,6 +362,64 @@ __global__ void __launch_bounds__(256) k_upsample2x(View s0, View s1, int H, int
       const float4 v10 = vld4(s, voff(s, b, y1 * W + x0) + cc), v11 = vld4(s, voff(s, b, y1 * W + x1) + cc);
       vst4(out, voff(out, b, pix) + c, bil4(hl0, hl1, wl0, wl1, v00, v01, v10, v11));
     }
+  }
+}
+
+// Same arithmetic, one thread = the 2x2 OUTPUT block of input pixel (i, j) x 8 channels: the block only reads the 3x3 input
+// neighbourhood (9 pixel loads instead of 16 for its 4 outputs) and the index arithmetic is paid once per block.  Horizontal
+// interpolation first, then vertical — the operation order of bil4, so both kernels produce the same bits.
+__device__ __forceinline__ float8 lerp8(float a, const float8& x, float b, const float8& y) {
+  float8 o;
+  o.a = make_float4(a * x.a.x + b * y.a.x, a * x.a.y + b * y.a.y, a * x.a.z + b * y.a.z, a * x.a.w + b * y.a.w);
+  o.b = make_float4(a * x.b.x + b * y.b.x, a * x.b.y + b * y.b.y, a * x.b.z + b * y.b.z, a * x.b.w + b * y.b.w);
+  return o;
+}
+__global__ void __launch_bounds__(256) k_upsample2x_blk(View s0, View s1, int H, int W, View out) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y;
+  const int C = s0.C + s1.C, C8 = C >> 3;
+  const int total = H * W * C8;
+  const int Wo = 2 * W;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = (idx % C8) << 3;
+    const int pix = idx / C8;
+    const int i = pix / W, j = pix - i * W;
+    const View& s = (c < s0.C) ? s0 : s1;
+    const int cc = (c < s0.C) ? c : c - s0.C;
+    const int ra = max(i - 1, 0), rc = min(i + 1, H - 1), ca = max(j - 1, 0), cd = min(j + 1, W - 1);
+    // output rows 2i, 2i+1 (columns 2j, 2j+1): source indices and weights exactly as bil_idx computes them
+    int ye0, ye1, yo0, yo1, xe0, xe1, xo0, xo1;
+    float he0, he1, ho0, ho1, we0, we1, wo0, wo1;
+    bil_idx(2 * i, H, ye0, ye1, he0, he1);
+    bil_idx(2 * i + 1, H, yo0, yo1, ho0, ho1);
+    bil_idx(2 * j, W, xe0, xe1, we0, we1);
+    bil_idx(2 * j + 1, W, xo0, xo1, wo0, wo1);
+    float8 hE[3], hO[3];                           // rows ra, i, rc interpolated to the even / odd output column
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int y = r == 0 ? ra : (r == 1 ? i : rc);
+      const long long rowo = voff(s, b, (long long)y * W) + cc;
+      const float8 vA = vld8(s, rowo + (long long)ca * s.pix_stride), vB = vld8(s, rowo + (long long)j * s.pix_stride);
+      const float8 vC = vld8(s, rowo + (long long)cd * s.pix_stride);
+      // even column: (xe0, xe1) is (j-1, j), or (0, 1) with weights (1, 0) at j == 0; odd column: (j, min(j+1, W-1))
+      const float8& e0 = xe0 == j ? vB : vA;
+      const float8& e1 = xe1 == j ? vB : (xe1 == cd ? vC : vA);
+      hE[r] = lerp8(we0, e0, we1, e1);
+      const float8& o1 = xo1 == j ? vB : vC;
+      hO[r] = lerp8(wo0, vB, wo1, o1);
+    }
+    // vertical: even output row uses (ye0, ye1), odd row (yo0 = i, yo1)
+    const int re0 = ye0 == i ? 1 : 0, re1 = ye1 == i ? 1 : (ye1 == rc ? 2 : 0), ro1 = yo1 == i ? 1 : 2;
+    const long long o00 = voff(out, b, (long long)(2 * i) * Wo + 2 * j) + c;
+    const long long orow = (long long)Wo * out.pix_stride;
+    const float8 E0 = re0 == 1 ? hE[1] : hE[0], E1 = re1 == 1 ? hE[1] : (re1 == 2 ? hE[2] : hE[0]);
+    const float8 F0 = re0 == 1 ? hO[1] : hO[0], F1 = re1 == 1 ? hO[1] : (re1 == 2 ? hO[2] : hO[0]);
+    vst8(out, o00, lerp8(he0, E0, he1, E1));
+    vst8(out, o00 + out.pix_stride, lerp8(he0, F0, he1, F1));
+    const float8 G1 = ro1 == 1 ? hE[1] : hE[2], K1 = ro1 == 1 ? hO[1] : hO[2];
+    vst8(out, o00 + orow, lerp8(ho0, hE[1], ho1, G1));
+    vst8(out, o00 + orow + out.pix_stride, lerp8(ho0, hO[1], ho1, K1));
   }
 }
 
@@ -524,13 +627,16 @@ inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
 
 }  // namespace
 
-int launch_plane_stats(View x, int B, int H, int W, int pool, double* partial, cudaStream_t s) {
+int launch_plane_stats(View x, int B, int H, int W, int pool, double* partial, cudaStream_t s, float* fin, int* cnt, float eps) {
   ++g_launch_counter;
   const int npix = H * W;
   int S = npix >= 2048 ? 8 : (npix >= 512 ? 4 : (npix >= 128 ? 2 : 1));
   while (S < STATS_MAX_SPLIT && (long long)B * ((x.C + 31) / 32) * S < 296 && npix / (2 * S) >= 16) S *= 2;   // fill the 148 SMs
   dim3 grid(B, (x.C + 31) / 32, S);                 // requires C % 4 == 0 and 16-byte aligned pixel rows (all conv outputs)
-  launch_k(k_plane_stats, dim3(grid), dim3(256), 0, s, x, H, W, pool, partial);
+  FinArgs fa;
+  fa.fin = ((x.C + 31) / 32 <= VF_STAT_CNT_STRIDE) ? fin : nullptr; fa.cnt = cnt; fa.eps = eps;
+  if (!cnt) fa.fin = nullptr;
+  launch_k(k_plane_stats, dim3(grid), dim3(256), 0, s, x, H, W, pool, partial, fa);
   return S;
 }
 size_t plane_stats_partial_doubles(int B, int C) { return (size_t)B * C * 16 * 2; }   // up to 16 slots per (sample, channel)
@@ -542,11 +648,13 @@ void launch_norm_act(View x, int B, int H, int W, int pool, StatsRef stats, cons
   launch_k(k_norm_act, dim3(grid), dim3(256), 0, s, x, H, W, pool, stats, gamma, beta, act, y);
 }
 int launch_lstm_gates(View gates, int B, int HW, int F, StatsRef gstats, const float* gg, const float* gb,
-                      float fb, float* c, double* partial, cudaStream_t s) {
+                      float fb, float* c, double* partial, cudaStream_t s, float* fin, int* cnt, float eps) {
   ++g_launch_counter;
   int S = HW >= 1024 ? 8 : (HW >= 256 ? 4 : (HW >= 64 ? 2 : 1));      // pixel blocks per sample = stats partial slots
   dim3 grid(S, B);
-  launch_k(k_lstm_gates, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, fb, c, partial);
+  FinArgs fa;
+  fa.fin = cnt ? fin : nullptr; fa.cnt = cnt; fa.eps = eps;
+  launch_k(k_lstm_gates, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, fb, c, partial, fa);
   return S;
 }
 void launch_lstm_gates_generic(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
@@ -568,7 +676,11 @@ void launch_lstm_out(View gates, int B, int HW, int F, StatsRef gstats, const fl
 void launch_upsample2x(View s0, View s1, int B, int H, int W, View out, cudaStream_t s) {
   ++g_launch_counter;
   auto al8 = [](const View& v) { return v.C == 0 || ((v.C | v.ch_off | v.pix_stride) % 8 == 0 && v.sample_stride % 8 == 0 && v.lo_off % 8 == 0); };
-  if (al8(s0) && al8(s1) && al8(out)) {
+  static const bool blk = !(getenv("VF_UPSAMPLE_BLK") && atoi(getenv("VF_UPSAMPLE_BLK")) == 0);   // A/B switch
+  if (al8(s0) && al8(s1) && al8(out) && blk && H >= 2 && W >= 2) {
+    dim3 grid(grid_for((long long)H * W * ((s0.C + s1.C) >> 3), 256, 64), B);
+    launch_k(k_upsample2x_blk, dim3(grid), dim3(256), 0, s, s0, s1, H, W, out);
+  } else if (al8(s0) && al8(s1) && al8(out)) {
     dim3 grid(grid_for((long long)4 * H * W * ((s0.C + s1.C) >> 3), 256, 64), B);
     launch_k(k_upsample2x<8>, dim3(grid), dim3(256), 0, s, s0, s1, H, W, out);
   } else {

@@ -164,6 +164,7 @@ void launch_conv_simt(const ConvArgs& a, int B, cudaStream_t s);
 // Instance-norm statistics are kept as float64 partial sums partial[((b*C + c)*S + k)*2 + {sum, sumsq}] (k < S slots,
 // written by k_plane_stats, by the tensor-core conv epilogue or by k_lstm_gates); every consumer finalises
 // (mean, rstd) of the planes it needs in its prologue, in a fixed order (bit-reproducible).
+constexpr int VF_STAT_CNT_STRIDE = 32;   // arrival counters per sample of the "last arriver finalises" statistics (channel groups)
 struct StatsRef {
   const float* fin;       // finalised (mean, rstd) pairs (k_stats_finalize), or null: finalise from the partials on the fly
   const double* partial;
@@ -175,7 +176,10 @@ inline StatsRef stats_ref(const double* partial, int S, int npix, float eps, con
   StatsRef r; r.fin = fin; r.partial = partial; r.S = S; r.npix = npix; r.eps = eps; return r;
 }
 // partial sums of the (optionally 2x2 avg-pooled) planes of x; returns the slot count S
-int launch_plane_stats(View x, int B, int H, int W, int pool, double* partial, cudaStream_t s);
+// fin / cnt (optional): the last block of a sample also writes the finalised (mean, rstd) pairs into fin (cnt: zeroed arrival
+// counters [B][VF_STAT_CNT_STRIDE], left zeroed) — no k_stats_finalize launch needed
+int launch_plane_stats(View x, int B, int H, int W, int pool, double* partial, cudaStream_t s, float* fin = nullptr, int* cnt = nullptr,
+                       float eps = 1e-6f);
 size_t plane_stats_partial_doubles(int B, int C);
 // y = act((pool(x) - mean) * rstd * gamma + beta)
 void launch_norm_act(View x, int B, int H, int W, int pool, StatsRef stats, const float* gamma,
@@ -183,7 +187,8 @@ void launch_norm_act(View x, int B, int H, int W, int pool, StatsRef stats, cons
 // conv-LSTM pointwise, part 1: c <- c*sigmoid(f+fb) + sigmoid(i)*tanh(j) with gates instance-normalised
 // also accumulates the instance-norm partial sums of the new cell state; returns the partial slots per (sample, channel)
 int launch_lstm_gates(View gates, int B, int HW, int F, StatsRef gstats, const float* ggamma,
-                      const float* gbeta, float forget_bias, float* c, double* partial, cudaStream_t s);
+                      const float* gbeta, float forget_bias, float* c, double* partial, cudaStream_t s, float* fin = nullptr,
+                      int* cnt = nullptr, float eps = 1e-6f);
 void launch_lstm_gates_generic(View gates, int B, int HW, int F, const float* gstats, const float* ggamma,
                                const float* gbeta, float forget_bias, float* c, cudaStream_t s);
 void launch_stats_finalize(const double* partial, int n, int S, int npix, float eps, float* stats, cudaStream_t s);
