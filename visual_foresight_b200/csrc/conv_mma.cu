@@ -800,6 +800,58 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
 #pragma unroll
     for (int i = 0; i < NACC; ++i) stat_acc[i] = 0.f;
     const bool per_item_tab = stacked && P.sabias != nullptr;   // without the action/state bias the table is the layer's bias: staged once
+    // "Last arriver finalises" (Params::stats_fin).  The arrival of an item is issued at the START of the next item's epilogue
+    // (and after the loop for the last one): a fence right behind the item's output stores would wait for all of them to
+    // drain (measured: thin layers 2x slower), one item later they have long left the SM and the fence is free.
+    int pend_b = -1, pend_mt = 0;
+    auto thin_arrive = [&](int b_) {                 // row-stacked path: warp etid >> 5 combined channel block cb of the item
+      const int cb = etid >> 5, l = etid & 31;
+      __threadfence();
+      __syncwarp();
+      int last = 0;
+      if (l == 0) {
+        int* cnt = P.stats_cnt + (long long)b_ * VF_STAT_CNT_STRIDE + cb;
+        last = atomicAdd(cnt, 1) == g.npass - 1;     // the sample's last pass finalises the block
+        if (last) *cnt = 0;
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence();
+        const int c = cb * 16 + l;
+        if (l < 16 && c < g.Cout)
+          stats_finalize_plane(P.stats_partial + ((long long)b_ * g.Cout + c) * P.stats_S * 2, P.stats_S, P.stats_npix, P.stats_eps,
+                               P.stats_fin + ((long long)b_ * g.Cout + c) * 2);
+      }
+    };
+    auto wide_arrive = [&](int b0_, int mt_) {       // wide path: one arrival per (image of the item, warp): 2 column-halves x npass
+      if (mt_ * MT + q4 * 32 >= g.Cout) return;      //   per 32-channel group (warp-uniform: no live channel in this warp)
+      const int n_ = mt_ * MT + row;
+      __threadfence();
+      __syncwarp();
+      for (int im = 0; im < g.G; ++im) {
+        const int b_ = b0_ + im;
+        if (b_ >= P.B) break;
+        int last = 0;
+        if (lane == 0) {
+          int* cnt = P.stats_cnt + (long long)b_ * VF_STAT_CNT_STRIDE + (mt_ * 4 + q4);
+          last = atomicAdd(cnt, 1) == 2 * g.npass - 1;
+          if (last) *cnt = 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          __threadfence();
+          if (n_ < g.Cout)
+            stats_finalize_plane(P.stats_partial + ((long long)b_ * g.Cout + n_) * P.stats_S * 2, P.stats_S, P.stats_npix, P.stats_eps,
+                                 P.stats_fin + ((long long)b_ * g.Cout + n_) * 2);
+        }
+      }
+    };
+    auto flush_arrival = [&]() {
+      if (pend_b < 0) return;
+      if (stacked) { if (etid < (g.np >> 4) * 32) thin_arrive(pend_b); }
+      else if (!g.swap) wide_arrive(pend_b, pend_mt);
+      pend_b = -1;
+    };
     for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
       int mt, grp, ps_;
       if (stacked) {                               // one Cout tile, G = 1: no divisions by runtime values on this path
@@ -816,6 +868,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
       if (per_item_tab && next < g.nitems) tab_fetch(next);
       mbar_wait(&acc_full[a], (nacc == 2 ? it >> 1 : it) & 1);
       tc_fence_after();
+      flush_arrival();                               // the previous item's statistics (its stores have drained by now)
       if (stacked) {
         float* tab = per_item_tab ? tab0 + (it & 1) * (g.ntap * g.np) : tab0;
         // lane-exchange scratch (the wide path's bias tables live here): 2 parities x 4 quarters x (KS-1)^2 rows x 16 floats
@@ -853,24 +906,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
           const int ch = cb * 16 + 4 * (l & 3) + 2 * ((l >> 3) & 1) + ((l >> 2) & 1);
           if (ch < g.Cout && b0 < P.B)
             P.stats_partial[(((long long)b0 * g.Cout + ch) * P.stats_S + ps_) * 2 + (l >> 4)] = tot;
-          if (P.stats_fin && b0 < P.B) {        // this warp = channel block cb of the item; the sample's last pass finalises the block
-            __threadfence();
-            __syncwarp();
-            int last = 0;
-            if (l == 0) {
-              int* cnt = P.stats_cnt + (long long)b0 * VF_STAT_CNT_STRIDE + cb;
-              last = atomicAdd(cnt, 1) == g.npass - 1;
-              if (last) *cnt = 0;
-            }
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-              __threadfence();
-              const int c = cb * 16 + l;
-              if (l < 16 && c < g.Cout)
-                stats_finalize_plane(P.stats_partial + ((long long)b0 * g.Cout + c) * P.stats_S * 2, P.stats_S, P.stats_npix, P.stats_eps,
-                                     P.stats_fin + ((long long)b0 * g.Cout + c) * 2);
-            }
-          }
+          if (P.stats_fin && b0 < P.B) pend_b = b0;    // arrival deferred to the next item (see thin_arrive)
         }
       } else if constexpr (NG != 2) {
       } else if (g.swap) {
@@ -1000,27 +1036,12 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
           o[0] = st_s;
           o[1] = st_q;
         }
-        if (P.stats_fin && b < P.B && mt * MT + q4 * 32 < g.Cout) {   // warp-uniform: this warp holds live channels of sample b
-          __threadfence();
-          __syncwarp();
-          int last = 0;
-          if (lane == 0) {                          // one arrival per (item-image, warp): 2 column-halves x npass per 32-channel group
-            int* cnt = P.stats_cnt + (long long)b * VF_STAT_CNT_STRIDE + (mt * 4 + q4);
-            last = atomicAdd(cnt, 1) == 2 * g.npass - 1;
-            if (last) *cnt = 0;
-          }
-          last = __shfl_sync(0xffffffffu, last, 0);
-          if (last) {
-            __threadfence();
-            if (live)
-              stats_finalize_plane(P.stats_partial + ((long long)b * g.Cout + n) * P.stats_S * 2, P.stats_S, P.stats_npix, P.stats_eps,
-                                   P.stats_fin + ((long long)b * g.Cout + n) * 2);
-          }
-        }
+        if (P.stats_fin && im == 0) { pend_b = b0; pend_mt = mt; }   // arrivals of the item's images deferred to the next item
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[a]);
     }
+    flush_arrival();
   }
   __syncthreads();
   if (warp == 1) {

@@ -58,7 +58,8 @@ struct ConvLayer {
   float* bias = nullptr;
   float *gamma = nullptr, *beta = nullptr;          // conv norm  (or gates norm for lstm)
   float *cgamma = nullptr, *cbeta = nullptr;        // cell norm (lstm)
-  float* sabias = nullptr;  // [B][k*k][cout]
+  float* sabias = nullptr;  // [B][k*k][cout], or [S-1][B][k*k][cout] when the engine hoists it out of the step loop
+  long long sab_step = 0;   // elements between consecutive cell steps (hoisted form)
   MmaConvWeights mma;       // tensor-core operand copies (precision != SIMT)
 };
 
@@ -111,7 +112,6 @@ struct vf_engine {
   int* stat_cnt = nullptr;      // [B][VF_STAT_CNT_STRIDE] arrival counters of the fused statistics finalisation (zero between kernels)
   std::vector<float*> act_enc, act_dec;
   float* pack0 = nullptr;    // [B][H][W][8] packed (image, first) input of enc0 (tensor-core path)
-  float* heads_h = nullptr;     // [B][H][W][2*ngf] = [scratch hidden | mask hidden] (opt.merge_heads)
   float *scr_h = nullptr, *mask_h = nullptr, *layers = nullptr, *logits = nullptr, *kern = nullptr, *partial = nullptr;
   float* cdna_part = nullptr;   // split-K partial products of the CDNA dense head
   int nblk = 0, cl = 0;
@@ -126,6 +126,7 @@ struct vf_engine {
   int* desig_pix_dev = nullptr;
   float *gen_images = nullptr, *gen_distrib = nullptr, *gen_states = nullptr;
   float *sa = nullptr, *state_cur = nullptr, *zs = nullptr;
+  float* sa_all = nullptr;    // [ncam][S-1][B][A]: every step's tiled action/state vector (opt.hoist_sa)
   float* actions = nullptr;   // [B][Tcap][adim]
   int Tcap = 0, T = 0;
   float* cost = nullptr;      // [B][P][ntask]
@@ -186,8 +187,12 @@ struct vf_engine {
     bool stats_fin = true;       // VF_STATS_FIN [1]: separate k_stats_finalize launches (1) or consumers finalise on the fly (0; measured 4 % slower)
     bool epi_stats = true;       // VF_EPI_STATS [1]: instance-norm statistics of the thin convolutions come from their epilogue
     bool merge_heads = true;     // VF_MERGE_HEADS [1]: scratch.conv0 + masks.conv0 as one convolution
+    bool lstm_fused = true;      // VF_LSTM_FUSED [1]: conv-LSTM pointwise (both instance norms) as one cluster kernel per layer
+    bool hoist_sa = true;        // VF_HOIST_SA [1]: the action/state vectors and border-class biases of ALL cell steps are built
+                                 //   by two launches at the start of a rollout (they do not depend on the predicted frames)
     bool fuse_fin = true;        // VF_FUSE_FIN [1]: the producer's last-arriving warp/block finalises the statistics (no finalize launch)
   } opt;
+  int cur_tau = 0;             // cell step being launched (selects the step's slice of the hoisted sabias tables)
   int cur_M = 0;               // samples of the rollout being launched (convs on fewer samples = shared-prefix steps)
 
   // profiling (vf_profile_*)
@@ -324,7 +329,8 @@ int prepare_conv(vf_engine* h, int view, ConvLayer& L) {
       }
     r = upload(h, &L.wcls, wc);
     if (r) return r;
-    DA(L.sabias, (size_t)h->B * kk * L.cout);
+    L.sab_step = (long long)h->B * kk * L.cout;
+    DA(L.sabias, (size_t)L.sab_step * (h->opt.hoist_sa ? (size_t)(h->S - 1) : 1));
   }
   auto opt = [&](const char* suffix, float** dst, int n) -> int {
     const HostTensor* t = find_w(h, view, L.name + suffix);
@@ -512,6 +518,17 @@ int build_net(vf_engine* h) {
       upd(net.heads0);
     }
   }
+  if (h->opt.hoist_sa) {                                   // all-steps tables: (S-1) x the per-step size (c4 at M = 4096 on one GPU: 8 GiB of 180); cap 12 GiB
+    size_t per_step = 0;
+    for (auto& net : h->views) {
+      auto add = [&](const ConvLayer& L) { if (L.k && L.cin_const > 0) per_step += (size_t)B * L.k * L.k * L.cout * sizeof(float); };
+      for (auto& L : net.enc_conv) add(L);
+      for (auto& L : net.dec_conv) add(L);
+      for (auto& L : net.enc_lstm) add(L);
+      for (auto& L : net.dec_lstm) add(L);
+    }
+    if (per_step * (size_t)(h->S - 1) > ((size_t)12 << 30)) h->opt.hoist_sa = false;
+  }
   // shared scratch (first view's shapes == all views' shapes)
   DA(h->raw, (size_t)B * raw_max);
   DA(h->dec_in, (size_t)B * decin_max);
@@ -535,12 +552,8 @@ int build_net(vf_engine* h) {
     }
   }
   const size_t px = (size_t)h->H * h->W;
-  if (h->opt.merge_heads) {
-    DA(h->heads_h, (size_t)B * px * 2 * h->ngf);
-  } else {
-    DA(h->scr_h, (size_t)B * px * h->ngf);
-    DA(h->mask_h, (size_t)B * px * h->ngf);
-  }
+  DA(h->scr_h, (size_t)B * px * h->ngf);           // two dense buffers even when ONE conv produces both (opt.merge_heads): each
+  DA(h->mask_h, (size_t)B * px * h->ngf);          // consumer's TMA then reads whole 128-byte lines
   if (c.precision != VF_PREC_FP32_SIMT) DA(h->pack0, (size_t)B * px * 8 * 5);   // (image, first) x 5 dx taps, 8 channels each
   DA(h->layers, (size_t)B * px * h->cl);
   if (cudaMemset(h->layers, 0, (size_t)B * px * h->cl * sizeof(float)) != cudaSuccess) return fail(h, VF_ERR_CUDA, "memset layers");
@@ -672,7 +685,8 @@ void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out,
                    bool* finalized) {
   if (h->cfg.precision != VF_PREC_FP32_SIMT && L.mma.ready) {
     MmaConvCall c;
-    c.src = s0; c.src1 = s1; c.out = out; c.sabias = L.sabias; c.bias = L.bias;
+    c.src = s0; c.src1 = s1; c.out = out; c.bias = L.bias;
+    c.sabias = L.sabias ? L.sabias + (h->opt.hoist_sa ? (long long)h->cur_tau * L.sab_step : 0) : nullptr;
     c.H = L.s2d ? L.H / 2 : L.H; c.W = L.s2d ? L.W / 2 : L.W;
     c.passes = (h->cfg.precision == VF_PREC_F16X3) ? 3 : 1;
     c.act = act;
@@ -688,7 +702,8 @@ void run_conv_impl(vf_engine* h, const ConvLayer& L, View s0, View s1, View out,
     return;
   }
   ConvArgs a;
-  a.src0 = s0; a.src1 = s1; a.w = L.w_sp; a.bias = L.bias; a.sabias = L.sabias; a.out = out;
+  a.src0 = s0; a.src1 = s1; a.w = L.w_sp; a.bias = L.bias; a.out = out;
+  a.sabias = L.sabias ? L.sabias + (h->opt.hoist_sa ? (long long)h->cur_tau * L.sab_step : 0) : nullptr;
   a.H = L.H; a.W = L.W; a.Cin = L.cin_sp; a.Cout = L.cout; a.k = L.k; a.act = act;
   launch_conv_simt(a, B, h->stream);
 }
@@ -709,6 +724,13 @@ void run_lstm(vf_engine* h, int v, const ConvLayer& L, RnnState& r, int B, const
     gfin = ffin != nullptr && (4 * F + 31) / 32 <= VF_STAT_CNT_STRIDE;
   }
   const StatsRef gsr = fin_stats(h, h->stats_partial, slots, B * 4 * F, hw, h->stats, gfin);
+  View hv = cview(h, r.lstm_in, hw, 2 * F, F, F);
+  View h2 = r.h_s2d ? cview(h, r.h_s2d, hw / 4, 4 * F, 0, 4 * F) : make_view(nullptr, 0, 0, 0, 0);
+  h->debug[v][dbg + ".h"] = DebugEntry{hv, r.h, r.w};
+  h->debug[v][dbg + ".c"] = DebugEntry{dense_view(r.c, hw, F), r.h, r.w};
+  if (h->opt.lstm_fused && gsr.fin &&
+      launch_lstm_fused(gates, B, hw, F, gsr.fin, L.gamma, L.beta, h->cfg.forget_bias, L.cgamma, L.cbeta, eps, r.c, hv, h->stream, h2, r.w))
+    return;
   int cslots;
   if (256 % F == 0) {     // cell-state statistics fused into the pointwise kernel
     cslots = launch_lstm_gates(gates, B, hw, F, gsr, L.gamma, L.beta, h->cfg.forget_bias, r.c, h->cstats_partial, h->stream, cffin,
@@ -720,12 +742,24 @@ void run_lstm(vf_engine* h, int v, const ConvLayer& L, RnnState& r, int B, const
     cslots = launch_plane_stats(dense_view(r.c, hw, F), B, r.h, r.w, 0, h->cstats_partial, h->stream, cffin, h->stat_cnt, eps);
     cfin = cffin != nullptr && (F + 31) / 32 <= VF_STAT_CNT_STRIDE;
   }
-  View hv = cview(h, r.lstm_in, hw, 2 * F, F, F);
-  View h2 = r.h_s2d ? cview(h, r.h_s2d, hw / 4, 4 * F, 0, 4 * F) : make_view(nullptr, 0, 0, 0, 0);
   launch_lstm_out(gates, B, hw, F, gsr, L.gamma, L.beta, fin_stats(h, h->cstats_partial, cslots, B * F, hw, h->cstats, cfin), L.cgamma,
                   L.cbeta, r.c, hv, h->stream, h2, r.w);
-  h->debug[v][dbg + ".h"] = DebugEntry{hv, r.h, r.w};
-  h->debug[v][dbg + ".c"] = DebugEntry{dense_view(r.c, hw, F), r.h, r.w};
+}
+
+// sabias[b][cls][cout] = bias + sa[b] . wcls[cls] for every layer of view v; nsteps > 1: all cell steps in one launch
+void launch_step_sabias(vf_engine* h, int v, int B, int nsteps, const float* sa, long long sa_step) {
+  ViewNet& net = h->views[v];
+  SabiasBatch sbb;
+  sbb.n = 0; sbb.A = h->A; sbb.B = B; sbb.sa = sa; sbb.nsteps = nsteps; sbb.sa_step = sa_step;
+  auto sab = [&](ConvLayer& L) {
+    if (!(L.k && L.wcls)) return;
+    if (sbb.n == 24) { launch_sabias_batch(sbb, h->stream); sbb.n = 0; }
+    SabiasBatch::Layer& e = sbb.L[sbb.n++];
+    const int kc_ = L.kcls ? L.kcls : L.k;
+    e.wcls = L.wcls; e.bias = L.bias; e.out = L.sabias; e.ncls = kc_ * kc_; e.Cout = L.cout; e.out_step = L.sab_step;
+  };
+  for (int i = 0; i < h->n_enc; ++i) { sab(net.enc_conv[i]); sab(net.enc_lstm[i]); sab(net.dec_conv[i]); sab(net.dec_lstm[i]); }
+  launch_sabias_batch(sbb, h->stream);
 }
 
 // statistics pass over a conv output whose epilogue did not fuse them; *finalized: the pass wrote (mean, rstd) into h->stats too
@@ -755,18 +789,8 @@ void run_step(vf_engine* h, int v, int tau, int B) {
   View first = make_view(h->ctx_frames + (long long)v * px * 3, 0, 3, 0, 3);
   View first_d = make_view(h->ctx_distrib + (long long)v * px * nd, 0, nd, 0, nd);
 
-  // per-layer border-class bias of the tiled action/state vector
-  SabiasBatch sbb;
-  sbb.n = 0; sbb.A = h->A; sbb.B = B; sbb.sa = h->sa;
-  auto sab = [&](ConvLayer& L) {
-    if (!(L.k && L.wcls)) return;
-    if (sbb.n == 24) { launch_sabias_batch(sbb, h->stream); sbb.n = 0; }
-    SabiasBatch::Layer& e = sbb.L[sbb.n++];
-    const int kc_ = L.kcls ? L.kcls : L.k;
-    e.wcls = L.wcls; e.bias = L.bias; e.out = L.sabias; e.ncls = kc_ * kc_; e.Cout = L.cout;
-  };
-  for (int i = 0; i < n; ++i) { sab(net.enc_conv[i]); sab(net.enc_lstm[i]); sab(net.dec_conv[i]); sab(net.dec_lstm[i]); }
-  launch_sabias_batch(sbb, h->stream);
+  // per-layer border-class bias of the tiled action/state vector (hoisted: built for every step at the start of the rollout)
+  if (!h->opt.hoist_sa) launch_step_sabias(h, v, B, 1, h->sa, 0);
 
   // P2 encoder
   std::vector<View> enc_out(n);
@@ -850,10 +874,9 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     bool f_h = false;
     run_conv(h, net.heads0, h_last, none, raw2, B, ACT_NONE, epi_sp, &S_h, &f_h);
     if (!S_h) S_h = plane_stats_pass(h, raw2, B, H, W, 0, &f_h);
-    View hh2 = cview(h, h->heads_h, (int)px, 2 * g, 0, 2 * g);
-    launch_norm_act(raw2, B, H, W, 0, fin_stats(h, h->stats_partial, S_h, B * 2 * g, (int)px, h->stats, f_h), net.heads0.gamma, net.heads0.beta, ACT_RELU, hh2, h->stream);
-    scr = cview(h, h->heads_h, (int)px, 2 * g, 0, g);
-    hm = cview(h, h->heads_h, (int)px, 2 * g, g, g);
+    scr = cview(h, h->scr_h, (int)px, g, 0, g);
+    hm = cview(h, h->mask_h, (int)px, g, 0, g);
+    launch_norm_act(raw2, B, H, W, 0, fin_stats(h, h->stats_partial, S_h, B * 2 * g, (int)px, h->stats, f_h), net.heads0.gamma, net.heads0.beta, ACT_RELU, scr, h->stream, hm);
     run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
   } else {
     // P7 scratch image
@@ -951,8 +974,12 @@ int rollout_body(vf_engine* h, int M, int T, int mode) {
     for (auto& r : h->views[v].dec_rnn) add(r);
     flush();
   };
-  for (int tau = 0; tau < h->S - 1; ++tau) {
+  const int nsteps = h->S - 1;
+  const int first_tau = restore ? n_shared : 0;              // first cell step this rollout actually launches
+  const long long sa_step = (long long)h->B * h->A;          // h->sa holds [S-1][B][A] (one view at a time when hoisted per view below)
+  for (int tau = 0; tau < nsteps; ++tau) {
     const bool shared = tau < n_shared;
+    h->cur_tau = tau;
     if (shared && restore) {                         // prefix cached by iteration 0 of this plan
       if (tau == n_shared - 1)
         for (int v = 0; v < h->ncam; ++v) {
@@ -969,7 +996,14 @@ int rollout_body(vf_engine* h, int M, int T, int mode) {
       sa.w_z = h->views[v].w_z; sa.b_z = h->views[v].b_z; sa.zstate = h->views[v].zstate;
       sa.state_cur = h->sdim ? h->views[v].state_cur : h->state_cur;
       sa.gen_states_all = (h->sdim && v == 0) ? h->gen_states : nullptr;
-      launch_build_sa(sa, M, tau, h->stream);
+      if (!h->opt.hoist_sa) {
+        launch_build_sa(sa, M, tau, h->stream);
+      } else if (tau == first_tau) {
+        // every step's vector and every layer's border-class bias for this view: two launches per rollout instead of two per step
+        sa.sa = h->sa_all + (long long)v * nsteps * sa_step;
+        launch_build_sa_all(sa, M, nsteps, sa_step, h->stream);
+        launch_step_sabias(h, v, M, nsteps, sa.sa, sa_step);
+      }
       run_step(h, v, tau, shared ? 1 : M);
       if (shared && tau == n_shared - 1) {
         BroadcastBatch bb;
@@ -1113,6 +1147,8 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
     h->opt.epi_stats = flag("VF_EPI_STATS", true);
     h->opt.merge_heads = flag("VF_MERGE_HEADS", true) && cfg->precision != VF_PREC_FP32_SIMT;
     h->opt.fuse_fin = flag("VF_FUSE_FIN", true) && h->opt.stats_fin;
+    h->opt.hoist_sa = flag("VF_HOIST_SA", true);
+    h->opt.lstm_fused = flag("VF_LSTM_FUSED", true) && h->opt.stats_fin;
   }
   // programmatic dependent launch: measured SLOWER on B200 inside the replayed graph (131.4 vs 124.7 ms per plan), so opt-in
   { const char* e = getenv("VF_PDL"); g_use_pdl = e && e[0] == '1'; }
@@ -1153,6 +1189,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
   DA(h->gen_distrib, (size_t)h->B * h->P * h->ncam * px * h->nd);
   DA(h->gen_states, (size_t)h->B * h->P * std::max(h->sdim, 1));
   DA(h->sa, (size_t)h->B * h->A);
+  if (h->opt.hoist_sa) DA(h->sa_all, (size_t)h->ncam * (h->S - 1) * h->B * h->A);
   DA(h->state_cur, (size_t)h->B * std::max(h->sdim, 1));
   if (h->nz) DA(h->zs, (size_t)h->B * (h->S - 1) * h->nz);
   DA(h->cost, (size_t)h->B * h->P * h->ncam * h->nd);

@@ -5,6 +5,8 @@
 
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "vf_common.cuh"
 
 namespace vf {
@@ -134,8 +136,10 @@ __device__ __forceinline__ float2 stat_of(const StatsRef& r, long long idx) {
 }
 
 // one thread = 4 consecutive channels of one output pixel; grid.y = sample
+// y2 (optional, y2.C > 0): channels >= y.C go to the second view (the merged scratch/mask head conv feeds two convolutions,
+// each of which should read a dense 32-channel buffer rather than every other 64 bytes of a shared one)
 __global__ void __launch_bounds__(256) k_norm_act(View x, int H, int W, int pool, StatsRef sr,
-                                                  const float* __restrict__ gamma, const float* __restrict__ beta, int act, View y) {
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta, int act, View y, View y2) {
   pdl_wait();
   pdl_trigger();
   const int b = blockIdx.y;
@@ -169,7 +173,8 @@ __global__ void __launch_bounds__(256) k_norm_act(View x, int H, int W, int pool
     o.x = (v.x - s0.x) * s0.y * g4.x + b4.x; o.y = (v.y - s0.z) * s0.w * g4.y + b4.y;
     o.z = (v.z - s1.x) * s1.y * g4.z + b4.z; o.w = (v.w - s1.z) * s1.w * g4.w + b4.w;
     if (act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    vst4(y, voff(y, b, pix) + c, o);
+    if (c < y.C) vst4(y, voff(y, b, pix) + c, o);
+    else vst4(y2, voff(y2, b, pix) + (c - y.C), o);
   }
 }
 
@@ -306,6 +311,113 @@ __global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, Sta
     hv.w = tanhf(cn.w) * sigmoidf_((ov.w - oa[f + 3]) * od[f + 3] * og.w + ob.w);
     vst4(h, voff(h, b, pix) + f, hv);
     if (h2.p) {          // space-to-depth copy for the next encoder conv (2x2 pixel blocks -> channels [sub-position][F])
+      const int y = pix / W, x = pix - y * W;
+      vst4(h2, voff(h2, b, (long long)(y >> 1) * (W >> 1) + (x >> 1)) + ((y & 1) * 2 + (x & 1)) * F + f, hv);
+    }
+  }
+}
+
+// Both halves of the conv-LSTM pointwise (k_lstm_gates + k_lstm_out) in ONE kernel: a thread-block cluster of CL CTAs owns
+// one sample, every thread keeps its NIT float4 slices of the new cell state and of the normalised output gate in registers,
+// the instance-norm statistics of the new cell state are reduced inside the block (fixed order), exchanged between the CTAs
+// of the cluster through distributed shared memory (fixed rank order) and applied without the cell state ever leaving the SM:
+// one read of the gates, one read and one write of c, one write of h; no partial sums in HBM, no finalize launch.
+// Requires finalised gate statistics (gsr.fin), 256 % (F/4) == 0 and HW * F / 4 == CL * NIT * 256.
+template <int NIT>
+__global__ void __launch_bounds__(256) k_lstm_fused(View gates, int HW, int F, const float* __restrict__ gfin,
+                                                    const float* __restrict__ gg, const float* __restrict__ gb, float fb,
+                                                    const float* __restrict__ cg, const float* __restrict__ cb, float eps, float* c,
+                                                    View h, View h2, int W, int CL) {
+  namespace cgp = cooperative_groups;
+  pdl_wait();
+  pdl_trigger();
+  cgp::cluster_group cluster = cgp::this_cluster();
+  const int rank = blockIdx.x;                       // grid.x == cluster size: the CTA's rank in its cluster
+  const int b = blockIdx.y;
+  const int F4 = F >> 2;
+  const int f = (threadIdx.x % F4) << 2;             // this thread's 4 channels (the same for all its items: 256 % F4 == 0)
+  const int per = NIT * 256;
+  float* cb_ = c + (long long)b * HW * F;
+  __shared__ double red[256][8];
+  __shared__ double part[256][2];                    // this CTA's per-channel (sum, sum of squares), F <= 256 channels... F4 <= 64 threads x 4
+  __shared__ float cst[256][2];
+  // gate normalisation of this thread's channels: y = (x - mean) * rstd * gamma + beta
+  float gm[4][4], gr[4][4], ga[4][4], gbt[4][4];    // [gate i,j,f,o][channel]
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 st = __ldg(reinterpret_cast<const float2*>(gfin) + (long long)b * gates.C + g * F + f + j);
+      gm[g][j] = st.x; gr[g][j] = st.y;
+      ga[g][j] = __ldg(gg + g * F + f + j); gbt[g][j] = __ldg(gb + g * F + f + j);
+    }
+  float4 cn[NIT], on[NIT];
+  double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    const int idx = rank * per + k * 256 + threadIdx.x;
+    const int pix = idx / F4;
+    const float* gp = vptr(gates, b, pix) + f;
+    const float4 vi = __ldg(reinterpret_cast<const float4*>(gp)), vj = __ldg(reinterpret_cast<const float4*>(gp + F));
+    const float4 vf = __ldg(reinterpret_cast<const float4*>(gp + 2 * F)), vo = __ldg(reinterpret_cast<const float4*>(gp + 3 * F));
+    const float4 c0 = *reinterpret_cast<const float4*>(cb_ + (long long)pix * F + f);
+    const float xi[4] = {vi.x, vi.y, vi.z, vi.w}, xj[4] = {vj.x, vj.y, vj.z, vj.w}, xf[4] = {vf.x, vf.y, vf.z, vf.w},
+                xo[4] = {vo.x, vo.y, vo.z, vo.w}, cc[4] = {c0.x, c0.y, c0.z, c0.w};
+    float r[4], o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float ni = (xi[j] - gm[0][j]) * gr[0][j] * ga[0][j] + gbt[0][j];
+      const float nj = (xj[j] - gm[1][j]) * gr[1][j] * ga[1][j] + gbt[1][j];
+      const float nf = (xf[j] - gm[2][j]) * gr[2][j] * ga[2][j] + gbt[2][j];
+      o[j] = (xo[j] - gm[3][j]) * gr[3][j] * ga[3][j] + gbt[3][j];
+      r[j] = cc[j] * sigmoidf_(nf + fb) + sigmoidf_(ni) * tanhf(nj);
+      s[j] += (double)r[j];
+      q[j] = fma((double)r[j], (double)r[j], q[j]);
+    }
+    cn[k] = make_float4(r[0], r[1], r[2], r[3]);
+    on[k] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][4 + j] = q[j]; }
+  __syncthreads();
+  if (threadIdx.x < F4) {                            // fixed order over the 256 / F4 threads that share this channel quad
+    double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int l = threadIdx.x; l < 256; l += F4)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] += red[l][j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { part[f + j][0] = t[j]; part[f + j][1] = t[4 + j]; }
+  }
+  cluster.sync();                                    // every CTA's partials are visible cluster-wide
+  if (threadIdx.x < F) {
+    double ts = 0.0, tq = 0.0;
+    for (int rr = 0; rr < CL; ++rr) {                // fixed rank order
+      const double* rp = cluster.map_shared_rank(&part[0][0], rr);
+      ts += rp[2 * threadIdx.x];
+      tq += rp[2 * threadIdx.x + 1];
+    }
+    const double mean = ts / HW;
+    double var = tq / HW - mean * mean;
+    if (var < 0.0) var = 0.0;
+    cst[threadIdx.x][0] = (float)mean;
+    cst[threadIdx.x][1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  cluster.sync();                                    // all remote reads done (a CTA may exit from here on) + cst visible block-wide
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(cg + f)), b4 = __ldg(reinterpret_cast<const float4*>(cb + f));
+  const float m0 = cst[f][0], r0 = cst[f][1], m1 = cst[f + 1][0], r1 = cst[f + 1][1];
+  const float m2 = cst[f + 2][0], r2 = cst[f + 2][1], m3 = cst[f + 3][0], r3 = cst[f + 3][1];
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    const int idx = rank * per + k * 256 + threadIdx.x;
+    const int pix = idx / F4;
+    float4 cv, hv;
+    cv.x = (cn[k].x - m0) * r0 * g4.x + b4.x; cv.y = (cn[k].y - m1) * r1 * g4.y + b4.y;
+    cv.z = (cn[k].z - m2) * r2 * g4.z + b4.z; cv.w = (cn[k].w - m3) * r3 * g4.w + b4.w;
+    *reinterpret_cast<float4*>(cb_ + (long long)pix * F + f) = cv;
+    hv.x = tanhf(cv.x) * sigmoidf_(on[k].x); hv.y = tanhf(cv.y) * sigmoidf_(on[k].y);
+    hv.z = tanhf(cv.z) * sigmoidf_(on[k].z); hv.w = tanhf(cv.w) * sigmoidf_(on[k].w);
+    vst4(h, voff(h, b, pix) + f, hv);
+    if (h2.p) {
       const int y = pix / W, x = pix - y * W;
       vst4(h2, voff(h2, b, (long long)(y >> 1) * (W >> 1) + (x >> 1)) + ((y & 1) * 2 + (x & 1)) * F + f, hv);
     }
@@ -475,6 +587,62 @@ __global__ void k_build_sa(SaArgs a, int M, int tau) {
   }
 }
 
+// All S-1 steps of one rollout at once: the state recurrence (and the latent LSTM) depend on the actions only, never on the
+// predicted frames, so every step's tiled vector is known before the first cell step.  Same arithmetic as k_build_sa, the
+// recurrent values stay in registers.  sa_all[tau][m_stride rows][A].
+__global__ void k_build_sa_all(SaArgs a, int M, int nsteps, long long step_stride) {
+  pdl_wait();
+  pdl_trigger();
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int A = a.adim + a.sdim + a.nz;
+  float st_cur[16], zc[16], zh[16];
+  for (int i = 0; i < 16; ++i) { st_cur[i] = 0.f; zc[i] = 0.f; zh[i] = 0.f; }
+  for (int tau = 0; tau < nsteps; ++tau) {
+    float* sa = a.sa + tau * step_stride + (long long)m * A;
+    float act[8], st[16];
+    for (int i = 0; i < a.adim; ++i) {
+      float v;
+      if (tau < a.n_ctx_actions) v = a.ctx_actions[tau * a.adim + i];
+      else v = a.actions[((long long)m * a.T + (tau - a.n_ctx_actions)) * a.adim + i];
+      act[i] = v;
+      sa[i] = v;
+    }
+    for (int i = 0; i < a.sdim; ++i) {
+      const float v = (tau < a.C) ? a.ctx_states[tau * a.sdim + i] : st_cur[i];
+      st[i] = v;
+      sa[a.adim + i] = v;
+    }
+    if (a.w_z && a.zs && a.nz <= 16) {
+      const int nz = a.nz;
+      float in[32], g[64];
+      for (int i = 0; i < nz; ++i) { in[i] = a.zs[((long long)m * (a.P + a.C - 1) + tau) * nz + i]; in[nz + i] = zh[i]; }
+      for (int j = 0; j < 4 * nz; ++j) {
+        float acc = 0.f;
+        for (int i = 0; i < 2 * nz; ++i) acc = fmaf(in[i], a.w_z[i * 4 * nz + j], acc);
+        g[j] = acc + a.b_z[j];
+      }
+      for (int i = 0; i < nz; ++i) {
+        const float cn = zc[i] * sigmoidf_(g[2 * nz + i] + 1.0f) + sigmoidf_(g[i]) * tanhf(g[nz + i]);
+        const float hn = tanhf(cn) * sigmoidf_(g[3 * nz + i]);
+        zc[i] = cn;
+        zh[i] = hn;
+        sa[a.adim + a.sdim + i] = hn;
+      }
+    } else {
+      for (int i = 0; i < a.nz; ++i) sa[a.adim + a.sdim + i] = a.zs ? a.zs[((long long)m * (a.P + a.C - 1) + tau) * a.nz + i] : 0.f;
+    }
+    for (int j = 0; j < a.sdim; ++j) {
+      float acc = 0.f;
+      for (int i = 0; i < a.adim; ++i) acc = fmaf(act[i], a.w_state[i * a.sdim + j], acc);
+      for (int i = 0; i < a.sdim; ++i) acc = fmaf(st[i], a.w_state[(a.adim + i) * a.sdim + j], acc);
+      acc += a.b_state[j];
+      st_cur[j] = acc;
+      if (a.gen_states_all && tau >= a.C - 1) a.gen_states_all[((long long)m * a.P + (tau - (a.C - 1))) * a.sdim + j] = acc;
+    }
+  }
+}
+
 __global__ void k_sabias(const float* __restrict__ sa, int A, const float* __restrict__ wcls,
                          const float* __restrict__ bias, int ncls, int Cout, int B, float* out) {
   const long long total = (long long)B * ncls * Cout;
@@ -497,9 +665,12 @@ __global__ void __launch_bounds__(256) k_sabias_batch(SabiasBatch a) {
   pdl_trigger();
   const SabiasBatch::Layer L = a.L[blockIdx.y];
   const int per = L.ncls * L.Cout;
-  const int b0 = blockIdx.z * SB_CHUNK, nb = min(SB_CHUNK, a.B - b0);
+  const int nchunk = (a.B + SB_CHUNK - 1) / SB_CHUNK;
+  const int step = blockIdx.z / nchunk;                       // hoisted form: every cell step of the rollout in one launch
+  const int b0 = (blockIdx.z - step * nchunk) * SB_CHUNK, nb = min(SB_CHUNK, a.B - b0);
   __shared__ float ssa[SB_CHUNK][24];
-  for (int i = threadIdx.x; i < nb * a.A; i += blockDim.x) ssa[i / a.A][i % a.A] = a.sa[(long long)b0 * a.A + i];
+  const float* sa_step = a.sa + step * a.sa_step;
+  for (int i = threadIdx.x; i < nb * a.A; i += blockDim.x) ssa[i / a.A][i % a.A] = sa_step[(long long)b0 * a.A + i];
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per) return;
@@ -509,7 +680,7 @@ __global__ void __launch_bounds__(256) k_sabias_batch(SabiasBatch a) {
 #pragma unroll
   for (int k = 0; k < 24; ++k) wr[k] = k < a.A ? __ldg(w + k * L.Cout) : 0.f;
   const float bias = L.bias ? L.bias[n] : 0.f;
-  float* o = L.out + (long long)b0 * per + i;
+  float* o = L.out + step * L.out_step + (long long)b0 * per + i;
   for (int b = 0; b < nb; ++b) {
     float acc = 0.f;
 #pragma unroll
@@ -641,11 +812,11 @@ int launch_plane_stats(View x, int B, int H, int W, int pool, double* partial, c
 }
 size_t plane_stats_partial_doubles(int B, int C) { return (size_t)B * C * 16 * 2; }   // up to 16 slots per (sample, channel)
 void launch_norm_act(View x, int B, int H, int W, int pool, StatsRef stats, const float* gamma,
-                     const float* beta, int act, View y, cudaStream_t s) {
+                     const float* beta, int act, View y, cudaStream_t s, View y2) {
   ++g_launch_counter;
   // few, long-lived blocks per sample: every block stages the sample's statistics in shared memory first
   dim3 grid(grid_for((long long)H * W * (x.C >> 2), 256, B >= 64 ? 16 : 64), B);
-  launch_k(k_norm_act, dim3(grid), dim3(256), 0, s, x, H, W, pool, stats, gamma, beta, act, y);
+  launch_k(k_norm_act, dim3(grid), dim3(256), 0, s, x, H, W, pool, stats, gamma, beta, act, y, y2);
 }
 int launch_lstm_gates(View gates, int B, int HW, int F, StatsRef gstats, const float* gg, const float* gb,
                       float fb, float* c, double* partial, cudaStream_t s, float* fin, int* cnt, float eps) {
@@ -673,10 +844,44 @@ void launch_lstm_out(View gates, int B, int HW, int F, StatsRef gstats, const fl
   dim3 grid(grid_for((long long)HW * F / 4, 256, B >= 64 ? 16 : 64), B);
   launch_k(k_lstm_out, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h, h2, W);
 }
+// returns false when the shape has no fused instance (the caller runs k_lstm_gates / k_lstm_out)
+bool launch_lstm_fused(View gates, int B, int HW, int F, const float* gfin, const float* gg, const float* gb, float fb,
+                       const float* cg, const float* cb, float eps, float* c, View h, cudaStream_t s, View h2, int W) {
+  if ((F & 3) || F > 256 || 256 % (F >> 2) || !gfin) return false;
+  const long long total4 = (long long)HW * (F >> 2);
+  int CL = 0, nit = 0;
+  const int cls[4] = {4, 2, 8, 1};
+  for (int i = 0; i < 4 && !CL; ++i) {
+    const long long per = total4 / cls[i];
+    if (total4 % cls[i] || per % 256) continue;
+    const int n = (int)(per / 256);
+    if (n == 1 || n == 2 || n == 3 || n == 4 || n == 6 || n == 8) { CL = cls[i]; nit = n; }
+  }
+  if (!CL) return false;
+  ++g_launch_counter;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(CL, B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
+#define VF_LF(N) cudaLaunchKernelEx(&cfg, k_lstm_fused<N>, gates, HW, F, gfin, gg, gb, fb, cg, cb, eps, c, h, h2, W, CL)
+  cudaError_t e;
+  switch (nit) {
+    case 1: e = VF_LF(1); break; case 2: e = VF_LF(2); break; case 3: e = VF_LF(3); break;
+    case 4: e = VF_LF(4); break; case 6: e = VF_LF(6); break; default: e = VF_LF(8); break;
+  }
+#undef VF_LF
+  return e == cudaSuccess;
+}
 void launch_upsample2x(View s0, View s1, int B, int H, int W, View out, cudaStream_t s) {
   ++g_launch_counter;
   auto al8 = [](const View& v) { return v.C == 0 || ((v.C | v.ch_off | v.pix_stride) % 8 == 0 && v.sample_stride % 8 == 0 && v.lo_off % 8 == 0); };
-  static const bool blk = !(getenv("VF_UPSAMPLE_BLK") && atoi(getenv("VF_UPSAMPLE_BLK")) == 0);   // A/B switch
+  static const bool blk = getenv("VF_UPSAMPLE_BLK") && atoi(getenv("VF_UPSAMPLE_BLK")) == 1;   // A/B switch; measured no gain -> off
   if (al8(s0) && al8(s1) && al8(out) && blk && H >= 2 && W >= 2) {
     dim3 grid(grid_for((long long)H * W * ((s0.C + s1.C) >> 3), 256, 64), B);
     launch_k(k_upsample2x_blk, dim3(grid), dim3(256), 0, s, s0, s1, H, W, out);
@@ -692,13 +897,17 @@ void launch_build_sa(const SaArgs& a, int M, int tau, cudaStream_t s) {
   ++g_launch_counter;
   launch_k(k_build_sa, dim3((M + 127) / 128), dim3(128), 0, s, a, M, tau);
 }
+void launch_build_sa_all(const SaArgs& a, int M, int nsteps, long long step_stride, cudaStream_t s) {
+  ++g_launch_counter;
+  launch_k(k_build_sa_all, dim3((M + 127) / 128), dim3(128), 0, s, a, M, nsteps, step_stride);
+}
 void launch_sabias_batch(const SabiasBatch& a, cudaStream_t s) {
   if (a.n == 0) return;
   ++g_launch_counter;
   if (a.A > 24) return;                                      // adim + sdim + nz <= 24 (vf_create)
   int mx = 1;
   for (int i = 0; i < a.n; ++i) mx = std::max(mx, a.L[i].ncls * a.L[i].Cout);
-  dim3 grid((mx + 255) / 256, a.n, (a.B + SB_CHUNK - 1) / SB_CHUNK);
+  dim3 grid((mx + 255) / 256, a.n, ((a.B + SB_CHUNK - 1) / SB_CHUNK) * (a.nsteps > 0 ? a.nsteps : 1));
   launch_k(k_sabias_batch, dim3(grid), dim3(256), 0, s, a);
 }
 void launch_sabias(const float* sa, int A, const float* wcls, const float* bias, int ncls, int Cout, int B,

@@ -182,8 +182,9 @@ int launch_plane_stats(View x, int B, int H, int W, int pool, double* partial, c
                        float eps = 1e-6f);
 size_t plane_stats_partial_doubles(int B, int C);
 // y = act((pool(x) - mean) * rstd * gamma + beta)
+// y holds channels [0, y.C); the optional second view y2 the remaining x.C - y.C channels
 void launch_norm_act(View x, int B, int H, int W, int pool, StatsRef stats, const float* gamma,
-                     const float* beta, int act, View y, cudaStream_t s);
+                     const float* beta, int act, View y, cudaStream_t s, View y2 = make_view(nullptr, 0, 0, 0, 0));
 // conv-LSTM pointwise, part 1: c <- c*sigmoid(f+fb) + sigmoid(i)*tanh(j) with gates instance-normalised
 // also accumulates the instance-norm partial sums of the new cell state; returns the partial slots per (sample, channel)
 int launch_lstm_gates(View gates, int B, int HW, int F, StatsRef gstats, const float* ggamma,
@@ -197,6 +198,11 @@ void launch_lstm_out(View gates, int B, int HW, int F, StatsRef gstats, const fl
                      const float* gbeta, StatsRef cstats, const float* cgamma, const float* cbeta,
                      float* c, View h, cudaStream_t s, View h2 = make_view(nullptr, 0, 0, 0, 0), int W = 0);   // h2: optional
                      // space-to-depth copy of h ([B][H/2*W/2][4F]: 2x2 pixel blocks in channels) for a pool-fused encoder conv
+// parts 1 + 2 in one cluster kernel (one cluster of CTAs per sample, cell statistics exchanged through distributed shared
+// memory); gfin: finalised (mean, rstd) pairs of the gates.  false = no instance for this shape (use the two kernels above)
+bool launch_lstm_fused(View gates, int B, int HW, int F, const float* gfin, const float* ggamma, const float* gbeta, float forget_bias,
+                       const float* cgamma, const float* cbeta, float eps, float* c, View h, cudaStream_t s,
+                       View h2 = make_view(nullptr, 0, 0, 0, 0), int W = 0);
 // out[b, 2H, 2W, C0+C1] = bilinear_x2(concat(src0, src1))   (half-pixel centres, edge clamp)
 void launch_upsample2x(View src0, View src1, int B, int H, int W, View out, cudaStream_t s);
 
@@ -219,11 +225,15 @@ struct SaArgs {
 };
 void launch_build_sa(const SaArgs& a, int M, int tau, cudaStream_t s);
 struct SabiasBatch {
-  struct Layer { const float* wcls; const float* bias; float* out; int ncls, Cout; };
+  struct Layer { const float* wcls; const float* bias; float* out; int ncls, Cout; long long out_step; };   // out_step: elements between steps
   Layer L[24];
   int n, A, B;
   const float* sa;
+  int nsteps = 1;            // > 1: all cell steps of a rollout in one launch (sa / out advance by sa_step / out_step per step)
+  long long sa_step = 0;
 };
+// every step's tiled action/state vector at once: sa_all[tau * step_stride + m * A] (the recurrences do not depend on frames)
+void launch_build_sa_all(const SaArgs& a, int M, int nsteps, long long step_stride, cudaStream_t s);
 void launch_sabias_batch(const SabiasBatch& a, cudaStream_t s);
 // rows[m] = rows[0] for m in [1, M): replicates the recurrent state of sample 0 after the shared-prefix cell steps (engine.cu)
 struct BroadcastBatch {
