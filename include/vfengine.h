@@ -29,7 +29,7 @@ extern "C" {
 #define VF_API
 #endif
 
-#define VF_ABI_VERSION 1
+#define VF_ABI_VERSION 2
 #define VF_MAX_LAYERS 8
 #define VF_MAX_TASKS 16 /* ncam * ndesig */
 
@@ -51,6 +51,11 @@ enum vf_precision {
   VF_PREC_FP32_SIMT = 0,   /* fp32 FFMA kernels (checker path for the tensor-core kernels) */
   VF_PREC_F16X3 = 1,       /* tcgen05 kind::f16, fp16 hi/lo split of both operands, 3 MMA passes, fp32 TMEM accumulate (fp32-grade) */
   VF_PREC_F16X1 = 2        /* tcgen05 kind::f16 single pass (fast; ~1e-3 relative per layer) */
+};
+
+enum vf_sampler {
+  VF_SAMPLER_GAUSSIAN = 0,    /* samplers/gaussian_sampler.py: N(mu, Sigma), refit = mean + unbiased covariance of the elites */
+  VF_SAMPLER_CORRELATED = 1   /* samplers/correlated_noise.py:17-66: AR(1)-smoothed noise around a softmax-weighted elite mean */
 };
 
 enum vf_cost_kind {
@@ -120,6 +125,20 @@ typedef struct vf_cem_params {
   int32_t k_futures;
   float lambda_variance;
   int32_t reserved[6];
+  /* ---- ABI 2: sampler family and sampler options on the device path ---- */
+  int32_t sampler;                  /* enum vf_sampler */
+  int32_t n_append;                 /* append_action (cem_base_controller.py:94-96): the LAST n_append action dims of the model are
+                                       constants; the sampler works on adim - n_append dims (initial_std, clip_*, mean0 index those) */
+  uint32_t discrete_mask;           /* bit a: sampled dim a is floor()ed and clipped to [0, 4] before the movement clip
+                                       (discrete_ind, controller_utils.py:107-117; gaussian_sampler.py:87-88) */
+  int32_t pad1;
+  double append_action[8];
+  /* VF_SAMPLER_CORRELATED (repeat must be 1): noise_i = z_i * initial_std + mean_bias; a_i = beta0 * noise_i + beta1 * a_{i-1}
+   * (i = 0 wraps to the un-smoothed LAST step, the reference's quirk); next mean = sum_k S_k elite_k / (sum S + 1e-4),
+   * S_k = exp(kappa * (r_k - max r)), r = -score.  The external noise tensor then supplies nactions*(adim-n_append) normals
+   * per sample in EVERY iteration. */
+  double beta0, beta1, kappa;
+  double mean_bias[8];
 } vf_cem_params;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */

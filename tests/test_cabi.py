@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for name in decl:
         assert hasattr(lib, name), "libvfengine.so does not export %s" % name
     assert sorted(engine.exported_symbols()) == decl, "ctypes binding and header disagree"
-    assert lib.vf_abi_version() == 1
+    assert lib.vf_abi_version() == engine.VF_ABI_VERSION == 2
 
 
 def test_struct_layout_matches_header(tmp_path):

@@ -289,3 +289,95 @@ def test_two_rank_policy_and_planner_one_gpu_two_processes():
                         "127.0.0.1", "--master-port", "29533", os.path.join(here, "multigpu_check.py")],
                        capture_output=True, text=True, timeout=800, env=env)
     assert "MULTIGPU_CHECK_OK world=2" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+# ---- 6. sampler families / options on the device path --------------------------------------------------
+def test_device_correlated_noise_plan_vs_oracle():
+    """CorrelatedNoiseSampler on the device (vf_cem_params.sampler = VF_SAMPLER_CORRELATED): AR(1)-smoothed noise with the
+    reference's index -1 wrap, softmax-weighted elite mean (correlated_noise.py:17-66), a constant appended action dim
+    (cem_base_controller.py:94-96), against OC.cem_plan_correlated on the same standard normals."""
+    from visual_foresight_b200.predictor import EngineBackend
+    sp = S.spec_64(height=32, width=32, seq_len=6, adim=5, sdim=4)           # 4 sampled dims + 1 appended constant
+    w = Hh.make_weights(sp, seed=21)
+    inp = Hh.synth_inputs(sp, seed=22)
+    M, K, iters, nact = 14, 5, 3, 7
+    std = np.array([0.05, 0.05, 0.2, np.pi / 10])
+    bias = np.array([0.01, -0.02, 0.0, 0.05])
+    noise = np.random.default_rng(8).standard_normal((iters, M, nact * 4)).astype(np.float32)
+    onehot = OC.switch_on_pix(inp["desig"], 2, 1, 32, 32, 1)
+    ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"],
+           "context_pixel_distributions": onehot}
+    be = EngineBackend(sp, w, M, precision="f16x3")
+    res = be.plan(ctx, num_samples=M, iterations=iters, num_elites=K, nactions=nact, repeat=1, std=std, clip=None, mean0=None,
+                  reduce_std_scale=1.0, goal_pix=inp["goal"], finalweight=10.0, task_weights=None, seed=0, plan_index=0, noise=noise,
+                  sampler="correlated", beta0=0.6, beta1=0.4, kappa=2.0, mean_bias=bias, append_action=[0.25])
+    last_actions = be.engine.cem_actions()
+    be.engine.close()
+    evaluate = _oracle_eval(sp, w, inp["frames"], inp["states"], onehot, inp["ctx_actions"], inp["goal"])
+    best, idx, scores, all_actions = OC.cem_plan_correlated(evaluate, num_samples=M, iterations=iters, num_elites_k=K, nactions=nact,
+                                                            adim=4, initial_std=std, noise=noise, beta0=0.6, beta1=0.4, kappa=2.0,
+                                                            mean_bias=bias, append_action=[0.25])
+    assert best.shape == (K, nact, 5) and np.all(best[..., 4] == 0.25)
+    np.testing.assert_allclose(res["scores"], scores, rtol=1e-5)
+    np.testing.assert_array_equal(res["elite_idx"], idx)
+    np.testing.assert_allclose(res["best_actions"], best, rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(last_actions, all_actions[-1], rtol=1e-11, atol=1e-14)
+
+
+def test_device_gaussian_discrete_and_appended_dims_vs_oracle():
+    """Gaussian CEM on the device with discrete_ind (floor + clip to [0,4] before truncate_movement, gaussian_sampler.py:87-88,
+    controller_utils.py:107-117) and append_action, against the oracle planner on the same noise."""
+    from visual_foresight_b200.predictor import EngineBackend
+    sp = S.spec_64(height=32, width=32, seq_len=6, adim=5, sdim=4)
+    w = Hh.make_weights(sp, seed=31)
+    inp = Hh.synth_inputs(sp, seed=32)
+    M, K, iters = 12, 4, 3
+    kw = _plan_kwargs(S.spec_64(height=32, width=32, seq_len=6, adim=4, sdim=4), M, K, iters)     # std / clip of the 4 sampled dims
+    kw["std"] = np.array([0.05, 0.05, 1.5, np.pi / 18])            # dim 2 wide enough for several discrete levels
+    lo, hi = kw["clip"]
+    noise = np.random.default_rng(12).standard_normal((iters, M, 20)).astype(np.float32)
+    onehot = OC.switch_on_pix(inp["desig"], 2, 1, 32, 32, 1)
+    ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"],
+           "context_pixel_distributions": onehot}
+    be = EngineBackend(sp, w, M, precision="f16x3")
+    res = be.plan(ctx, goal_pix=inp["goal"], noise=noise, discrete_ind=[2], append_action=[-0.5], **kw)
+    be.engine.close()
+    evaluate = _oracle_eval(sp, w, inp["frames"], inp["states"], onehot, inp["ctx_actions"], inp["goal"])
+    best, idx, scores, all_actions = OC.cem_plan(evaluate, num_samples=M, iterations=iters, num_elites_k=K, nactions=5, repeat=3,
+                                                 adim=4, std=kw["std"], noise=noise, clip=(lo, hi), discrete_ind=[2], append_action=[-0.5])
+    assert set(np.unique(all_actions[0][..., 2])) <= {0.0, 1.0, 2.0, 3.0, 4.0} and len(np.unique(all_actions[0][..., 2])) > 1
+    np.testing.assert_allclose(res["scores"], scores, rtol=1e-5)
+    np.testing.assert_array_equal(res["elite_idx"], idx)
+    np.testing.assert_allclose(res["best_actions"], best, rtol=1e-12, atol=1e-15)
+
+
+def test_controller_takes_the_device_path_for_correlated_noise():
+    """A RoboNet/Franka-style policy (sampler = CorrelatedNoiseSampler, experiments/robonet/franka/franka.py:37-55) plans on the
+    device: _device_path_ok(), no sampler round trip, deterministic in cem_seed."""
+    from visual_foresight_b200.cem_controller import PixelCostController
+    from visual_foresight_b200.policy import get_policy_args
+    from visual_foresight_b200.samplers import CorrelatedNoiseSampler
+    ag = {"adim": 4, "sdim": 4, "image_height": 32, "image_width": 32, "gpu_id": 0}
+    pp = {"sampler": CorrelatedNoiseSampler, "verbose": False, "num_samples": 16, "minimum_selection": 4, "iterations": 2,
+          "model_spec": {"seq_len": 6}, "cem_seed": 3, "nactions": 6}
+    rng = np.random.default_rng(1)
+    images = rng.integers(0, 256, (3, 1, 32, 32, 3), dtype=np.uint8)
+    state = rng.uniform(-.5, .5, (3, 4))
+    runs = []
+    for rep_ in range(2):
+        pol = PixelCostController(ag, dict(pp), 0, 1)
+        pol.reset()
+        assert pol._device_path_ok()
+        called = []
+        pol._sampler.sample_initial_actions = lambda *a, **k: called.append(1)      # the host sampler must not be consulted
+        outs = []
+        for t in range(3):
+            obs = {"images": images[:t + 1], "state": state[:t + 1]}
+            o = pol.act(**get_policy_args(pol, obs, t, 0, {"desig_pix": np.array([[8, 8]]), "goal_pix": np.array([[20, 22]])}))
+            outs.append(o["actions"].copy())
+        assert not called and pol._best_actions.shape == (4, 6, 4)
+        assert sorted(o["plan_stat"]) == ["scores_itr0", "scores_itr1"]
+        runs.append(np.stack(outs))
+        pol.predictor.backend.engine.close()
+    np.testing.assert_array_equal(runs[0], runs[1])
+    assert np.abs(runs[0][1:]).max() > 0

@@ -22,7 +22,7 @@ import numpy as np
 
 from .hparams import HParams
 from .policy import Policy
-from .samplers import GaussianCEMSampler, action_bounds, per_dim_variance
+from .samplers import CorrelatedNoiseSampler, GaussianCEMSampler, action_bounds, per_dim_variance
 
 
 class _Log(object):
@@ -270,33 +270,55 @@ class PixelCostController(CEMBaseController):
 
     # -- device path --------------------------------------------------------------------------------------
     def _device_path_ok(self):
+        """The whole CEM loop runs on the device for the Gaussian sampler (incl. discrete_ind, append_action, warm start) and
+        for the correlated-noise sampler (correlated_noise.py:17-66 without refit_cov / smooth_across_last_action); every
+        other sampler or option takes the host plugin path (sampler on the host, rollouts + cost on the device)."""
         hp = self._hp
-        return (self._backend is not None and hp.device_cem and hp.sampler is GaussianCEMSampler
-                and not hp.rejection_sampling and not hp.cov_blockdiag and not hp.smooth_cov and not hp.reuse_cov
-                and hp.discrete_ind is None and not hp.add_zero_action and not hp.append_action
-                and hasattr(self._backend, "plan"))
+        if self._backend is None or not hp.device_cem or not hasattr(self._backend, "plan"):
+            return False
+        n_app = len(hp.append_action) if hp.append_action else 0
+        if self._backend.spec.adim != self._sampler_adim() + n_app:
+            return False
+        if hp.sampler is GaussianCEMSampler:
+            return (not hp.rejection_sampling and not hp.cov_blockdiag and not hp.smooth_cov and not hp.reuse_cov
+                    and not hp.add_zero_action and not (n_app and hp.reuse_mean))
+        if hp.sampler is CorrelatedNoiseSampler:
+            return not hp.refit_cov and not hp.smooth_across_last_action
+        return False
+
+    def _sampler_adim(self):
+        return len(self._hp.initial_std) if self._hp.sampler is CorrelatedNoiseSampler else self._adim
 
     def perform_CEM(self, state):
         if not self._device_path_ok():
             return super().perform_CEM(state)
         hp = self._hp
         smp = self._sampler
-        warm = self._t >= hp.repeat - 1
-        mean0, shrink = None, False
-        if hp.reuse_mean and warm and smp._best_action_plans and smp._best_action_plans[-1] is not None:
-            mean0 = smp._warm_start_mean(smp._best_action_plans[-1][0])
-            shrink = True
-        M = max(int(hp.num_samples * hp.reuse_factor), 1) if shrink else hp.num_samples
-        lo, hi = action_bounds(hp, self._adim)
         context = {"context_frames": self._images, "context_actions": smp.chosen_actions,
                    "context_pixel_distributions": self._make_input_distrib(0), "context_states": self._state}
-        res = self._backend.plan(
-            context, num_samples=M, iterations=self._n_iter, num_elites=min(self.num_elites(), M),
-            nactions=hp.nactions, repeat=hp.repeat, std=np.sqrt(per_dim_variance(hp, self._adim)),
-            clip=(lo, hi) if hp.action_bound else None, mean0=mean0,
-            reduce_std_scale=(hp.reduce_std_dev if (self._t is not None and self._t >= 2) else 1.0),
-            goal_pix=self._goal_pix, finalweight=hp.finalweight, task_weights=self._task_weights(),
-            seed=hp.cem_seed, plan_index=self._plan_counter, k_futures=hp.num_futures, lambda_variance=hp.lambda_variance)
+        common = dict(iterations=self._n_iter, goal_pix=self._goal_pix, finalweight=hp.finalweight, task_weights=self._task_weights(),
+                      seed=hp.cem_seed, plan_index=self._plan_counter, k_futures=hp.num_futures, lambda_variance=hp.lambda_variance,
+                      append_action=hp.append_action if hp.append_action else None)
+        if hp.sampler is CorrelatedNoiseSampler:
+            M = hp.num_samples
+            res = self._backend.plan(
+                context, num_samples=M, num_elites=min(self.num_elites(), M), nactions=hp.nactions, repeat=1,
+                std=np.asarray(hp.initial_std, np.float64), clip=None, mean0=None, reduce_std_scale=1.0, sampler="correlated",
+                beta0=hp.beta_0, beta1=hp.beta_1, kappa=hp.kappa, mean_bias=hp.mean_bias, **common)
+        else:
+            warm = self._t >= hp.repeat - 1
+            mean0, shrink = None, False
+            if hp.reuse_mean and warm and smp._best_action_plans and smp._best_action_plans[-1] is not None:
+                mean0 = smp._warm_start_mean(smp._best_action_plans[-1][0])
+                shrink = True
+            M = max(int(hp.num_samples * hp.reuse_factor), 1) if shrink else hp.num_samples
+            lo, hi = action_bounds(hp, self._adim)
+            res = self._backend.plan(
+                context, num_samples=M, num_elites=min(self.num_elites(), M),
+                nactions=hp.nactions, repeat=hp.repeat, std=np.sqrt(per_dim_variance(hp, self._adim)),
+                clip=(lo, hi) if hp.action_bound else None, mean0=mean0,
+                reduce_std_scale=(hp.reduce_std_dev if (self._t is not None and self._t >= 2) else 1.0),
+                discrete_ind=hp.discrete_ind, **common)
         self._plan_counter += 1
         self._best_actions, self._best_indices = res["best_actions"], res["elite_idx"]
         for i in range(self._n_iter):

@@ -13,7 +13,16 @@ What is NOT pinned: ``TF_NAMES`` — the variable names of the external ``video_
 SURVEY.md 8c) are written from memory of the public upstream and can be overridden with a JSON table; the layer
 semantics behind each name are spec P.  Shapes are checked tensor by tensor, so a wrong guess fails loudly.
 
-    python -m visual_foresight_b200.checkpoint dump.npz model_hparams.json out_weights.npz [--names table.json] [--view 0]
+Composite-layer ORDER (must be settled before a real checkpoint is loaded; irrelevant for random weights): spec P feeds the
+mask-logit conv ``concat(h_masks, [T_0..T_{n-1}, prev image, first image, scratch])`` and softmaxes the masks in that order.
+Upstream SAVP (from memory) orders the composited layers ``[prev image, first image, scratch, T_0..]``.  If that is what
+the checkpoint was trained with, ``masks.conv1`` needs (a) its INPUT channels [ngf + 0 .. ngf + 3*n_layers) permuted from
+the upstream layer order to spec P's and (b) its OUTPUT channels (one mask per layer) permuted the same way.
+``permute_mask_layers`` does exactly that; pass ``--upstream-layer-order`` to the CLI.  Unverifiable in this environment
+(no TF1, no checkpoint) — hence an explicit switch, not a silent guess.
+
+    python -m visual_foresight_b200.checkpoint dump.npz[,dump_view1.npz] model_hparams.json out_weights.npz
+           [--dataset-hparams dataset_hparams.json] [--conf conf.json] [--names table.json] [--upstream-layer-order]
 """
 from __future__ import annotations
 
@@ -71,8 +80,11 @@ def spec_from_hparams(model_hparams: Mapping, dataset_hparams: Optional[Mapping]
     dh = dict(dataset_hparams or {})
     H, W = conf.get("orig_size", (mh.get("height", 64), mh.get("width", 64)))
     adim = dh["autograsp"] if "autograsp" in dh else conf.get("adim", 4)      # vpred_model_interface.py:28-30
+    # the states are model inputs only when dataset_hparams.json says so (vpred_model_interface.py:61: use_state =
+    # dataset_hparams.get('use_state', False)); conf['sdim'] alone does NOT make the model stateful
+    use_state = bool(dh.get("use_state", False))
     kw = dict(height=int(H), width=int(W), ncam=int(conf.get("ncam", 1)), ndesig=int(conf.get("ndesig", 1)),
-              adim=int(adim), sdim=int(conf.get("sdim", 0)) if mh.get("use_state", conf.get("sdim", 0) > 0) else 0,
+              adim=int(adim), sdim=int(conf.get("sdim", 0)) if use_state else 0,
               seq_len=int(mh.get("sequence_length", conf.get("sequence_length", 15))),
               context_frames=int(mh.get("context_frames", conf.get("context_frames", 2))),
               ngf=int(mh.get("ngf", 32)), num_transformed=int(mh.get("num_transformed_images", 4)),
@@ -146,6 +158,22 @@ def convert_checkpoint(arrays: Mapping[str, np.ndarray], spec: PredictorSpec, na
     return out
 
 
+def permute_mask_layers(weights: Dict[str, np.ndarray], spec: PredictorSpec) -> Dict[str, np.ndarray]:
+    """masks.conv1 trained with the upstream layer order [prev, first, scratch, T_0..T_{n-1}] -> spec P's order
+    [T_0..T_{n-1}, prev, first, scratch]: permutes the layer blocks (3 input channels each, behind the ngf h_masks channels)
+    and the per-layer output channels of ``masks.conv1`` (see the module docstring)."""
+    nt, g = spec.num_transformed, spec.ngf
+    nm = nt + 3
+    src_of = [3 + i for i in range(nt)] + [0, 1, 2]                 # spec-P layer j comes from upstream layer src_of[j]
+    w, b = np.array(weights["masks.conv1.w"]), np.array(weights["masks.conv1.b"])
+    cin = np.concatenate([np.arange(g)] + [g + 3 * s + np.arange(3) for s in src_of])
+    out = dict(weights)
+    out["masks.conv1.w"] = np.ascontiguousarray(w[:, :, cin][..., src_of])
+    out["masks.conv1.b"] = np.ascontiguousarray(b[src_of])
+    assert out["masks.conv1.w"].shape == w.shape and len(src_of) == nm
+    return out
+
+
 def export_as_tf(weights: Mapping[str, np.ndarray], spec: PredictorSpec, scope: str = "generator/rnn/dna_cell",
                  names: Optional[Mapping[str, str]] = None) -> Dict[str, np.ndarray]:
     """inverse of convert_checkpoint (used by the round-trip test and to hand engine weights back to a TF1 graph)."""
@@ -161,14 +189,22 @@ def main(argv: List[str]) -> int:
     ap.add_argument("dump"), ap.add_argument("model_hparams"), ap.add_argument("out")
     ap.add_argument("--dataset-hparams"), ap.add_argument("--conf", help="JSON of the net conf keys (orig_size, ncam, adim, sdim, ndesig)")
     ap.add_argument("--names", help="JSON {engine name: TF suffix} overriding the built-in table")
-    ap.add_argument("--view", type=int, default=0)
+    ap.add_argument("--upstream-layer-order", action="store_true",
+                    help="masks.conv1 was trained with the layer order [prev, first, scratch, T_0..]: permute it to spec P's")
     a = ap.parse_args(argv)
     load = lambda p: json.load(open(p)) if p else None
     spec = spec_from_hparams(load(a.model_hparams), load(a.dataset_hparams), load(a.conf))
-    w = convert_checkpoint(dict(np.load(a.dump)), spec, load(a.names))
+    dumps = a.dump.split(",")                       # one checkpoint dump per view (IndepMultiSAVP: independent weight sets,
+    if len(dumps) != spec.ncam:                     # experiments/sawyer/pixel_cost/conf.py:12-15)
+        raise SystemExit("the net conf has ncam=%d: pass %d comma-separated checkpoint dumps, one per view (got %d)"
+                         % (spec.ncam, spec.ncam, len(dumps)))
+    views = []
+    for d in dumps:
+        w = convert_checkpoint(dict(np.load(d)), spec, load(a.names))
+        views.append(permute_mask_layers(w, spec) if a.upstream_layer_order else w)
     from .predictor import save_weights
-    save_weights(a.out, spec, [w])
-    print("wrote %d tensors for view %d -> %s" % (len(w), a.view, a.out))
+    save_weights(a.out, spec, views)
+    print("wrote %d tensors x %d view(s) -> %s" % (len(views[0]), len(views), a.out))
     return 0
 
 

@@ -81,13 +81,71 @@ __global__ void k_sample_actions(SampleArgs a, int n) {
     }
   }
   const int ad = d % a.adim, na = d / a.adim;
+  if ((a.discrete_mask >> ad) & 1u) x = fmin(fmax(floor(x), 0.0), 4.0);   // discretize (controller_utils.py:107-117), before the clip
   x = fmin(fmax(x, a.clip_lo[ad]), a.clip_hi[ad]);       // truncate_movement
   a.out_nr[(long long)i * a.D + d] = x;
   const int T = a.nactions * a.repeat;
   for (int r = 0; r < a.repeat; ++r) {                     // np.repeat(actions, repeat, axis=1)
-    const long long o = ((long long)i * T + na * a.repeat + r) * a.adim + ad;
+    const long long o = ((long long)i * T + na * a.repeat + r) * a.adim_out + ad;
     if (a.out_actions) a.out_actions[o] = (float)x;
     if (a.out_actions64) a.out_actions64[o] = x;
+    if (ad == 0)                                           // append_action: constant trailing dims of the step
+      for (int e = a.adim; e < a.adim_out; ++e) {
+        if (a.out_actions) a.out_actions[o + e] = (float)a.append[e - a.adim];
+        if (a.out_actions64) a.out_actions64[o + e] = a.append[e - a.adim];
+      }
+  }
+}
+
+// CorrelatedNoiseSampler (samplers/correlated_noise.py:17-35): thread per (row i, action dim ad), sequential over the steps.
+// noise_s = z_s * std + bias; out_s = beta0 * noise_s + beta1 * out_{s-1}, out_{-1} := noise_{last} (the reference's wrap);
+// action_s = mean_s + out_s.  repeat == 1.
+__global__ void k_sample_correlated(SampleArgs a, int n) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n * a.adim) return;
+  const int i = tid / a.adim, ad = tid % a.adim;
+  const int gidx = a.indices ? a.indices[i] : a.offset + i;
+  auto draw = [&](int s) {
+    const int j = s * a.adim + ad;
+    const double z = a.noise ? (double)a.noise[(long long)gidx * a.noise_stride + j]
+                             : philox_normal(a.seed, a.plan_index, a.iteration, (uint32_t)gidx, (uint32_t)j);
+    return z * a.std0[ad] + a.bias[ad];
+  };
+  double prev = draw(a.nactions - 1);
+  for (int s = 0; s < a.nactions; ++s) {
+    const double cur = a.beta0 * draw(s) + a.beta1 * prev;
+    prev = cur;
+    const int d = s * a.adim + ad;
+    const double x = a.mean[d] + cur;
+    a.out_nr[(long long)i * a.D + d] = x;
+    const long long o = ((long long)i * a.nactions + s) * a.adim_out + ad;
+    if (a.out_actions) a.out_actions[o] = (float)x;
+    if (a.out_actions64) a.out_actions64[o] = x;
+    if (ad == 0)
+      for (int e = a.adim; e < a.adim_out; ++e) {
+        if (a.out_actions) a.out_actions[o + e] = (float)a.append[e - a.adim];
+        if (a.out_actions64) a.out_actions64[o + e] = a.append[e - a.adim];
+      }
+  }
+}
+
+// single block: softmax-weighted elite mean (correlated_noise.py:56-60), elites summed in rank order
+__global__ void k_refit_correlated(const double* __restrict__ x, const double* __restrict__ scores, const int* __restrict__ idx, int K,
+                                   int D, double kappa, double* mean) {
+  extern __shared__ double sw[];   // [K] weights
+  __shared__ double s_norm;
+  if (threadIdx.x == 0) {
+    double rmax = -INFINITY;
+    for (int k = 0; k < K; ++k) rmax = fmax(rmax, -scores[idx[k]]);
+    double tot = 0.0;
+    for (int k = 0; k < K; ++k) { sw[k] = exp(kappa * (-scores[idx[k]] - rmax)); tot += sw[k]; }
+    s_norm = tot + 1e-4;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) acc += x[(long long)k * D + d] * sw[k];
+    mean[d] = acc / s_norm;
   }
 }
 
@@ -190,8 +248,18 @@ void launch_score_exchange(const ExchangeArgs& a, cudaStream_t s) {
 
 void launch_sample_actions(const SampleArgs& a, int n, cudaStream_t s) {
   ++g_launch_counter;
+  if (a.kind == 1) {
+    const int total = n * a.adim;
+    k_sample_correlated<<<(total + 127) / 128, 128, 0, s>>>(a, n);
+    return;
+  }
   const int total = n * a.D;
   k_sample_actions<<<(total + 127) / 128, 128, 0, s>>>(a, n);
+}
+void launch_refit_correlated(const double* elites_nr, const double* scores, const int* idx, int K, int D, double kappa, double* mean,
+                             cudaStream_t s) {
+  ++g_launch_counter;
+  k_refit_correlated<<<1, 128, K * sizeof(double), s>>>(elites_nr, scores, idx, K, D, kappa, mean);
 }
 void launch_sample_latents(float* zs, int n, int steps, int nz, int goff, uint64_t seed, uint32_t plan, uint32_t iter,
                            cudaStream_t st) {

@@ -1093,6 +1093,13 @@ bool thin_pertap() {
   return on;
 }
 
+// Largest Cout that still takes the thin (pixels-on-M) tilings.  VF_THIN_MAX_COUT=32 sends the 64-channel layers to the wide
+// tiling (channels on the 128 MMA rows, half of them zero): twice the MMA work, but the wide epilogue has no lane exchange.
+int thin_max_cout() {
+  static const int v = getenv("VF_THIN_MAX_COUT") ? atoi(getenv("VF_THIN_MAX_COUT")) : 64;
+  return v;
+}
+
 bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int Cout, int H, int W, int B, int passes, Geometry* out) {
   Geometry g;
   memset(&g, 0, sizeof(g));
@@ -1108,7 +1115,7 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
   g.nst = k * kw;
   g.ksteps_last = (std::min(g.ch, Cin - (g.nchunk - 1) * g.ch) + 15) / 16;
   const int np_thin = (Cout + 15) / 16 * 16;
-  if (!thin_pertap() && Cout <= 64 && kw == k && k * np_thin <= 256 && 2 * kcl * kcl * np_thin <= 2304) {   // 2 bias tables behind the exchange scratch
+  if (!thin_pertap() && Cout <= thin_max_cout() && kw == k && k * np_thin <= 256 && 2 * kcl * kcl * np_thin <= 2304) {   // 2 bias tables behind the exchange scratch
     // ---- row-stacked thin path: pixels on M, the k taps of a filter row side by side on N (k*np columns) ----
     g.swap = 2;
     g.np = np_thin; g.ncols = k * g.np; g.ustride = 128 - (k - 1); g.nst = k;
@@ -1139,7 +1146,7 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
     *out = g;
     return true;
   }
-  if (Cout <= 64) {
+  if (Cout <= thin_max_cout()) {
     // ---- swapped orientation (thin layers): pixels on M in 128-row units, np = Cout padded to 16 on N ----
     g.swap = 1;
     g.np = (Cout + 15) / 16 * 16; g.ncols = g.np; g.ustride = 128;
@@ -1352,7 +1359,7 @@ int mma_conv_prepare_weights(const float* w_sp, int k, int kw, int kcl, int cin,
   if (layout == 2 && !(cin % 64 == 0 && cout >= 128)) layout = 1;      // SWIZZLE_128B only for the wide gate convolutions
   const int ch = layout == 2 ? 64 : 32;
   if (cin % 8) { if (err) *err = "cin % 8"; return -1; }
-  const bool swap = cout <= 64;
+  const bool swap = cout <= thin_max_cout();
   const int np = (cout + 15) / 16 * 16;
   const bool stacked = !thin_pertap() && swap && kw == k && k * np <= 256 && 2 * kcl * kcl * np <= 2304;   // one stage = a filter ROW: rows = (dx, output channel); must agree with plan_geometry
   const int rows = stacked ? k * np : (swap ? np : MT);               // operand tile rows

@@ -187,10 +187,13 @@ struct vf_engine {
     bool stats_fin = true;       // VF_STATS_FIN [1]: separate k_stats_finalize launches (1) or consumers finalise on the fly (0; measured 4 % slower)
     bool epi_stats = true;       // VF_EPI_STATS [1]: instance-norm statistics of the thin convolutions come from their epilogue
     bool merge_heads = true;     // VF_MERGE_HEADS [1]: scratch.conv0 + masks.conv0 as one convolution
-    bool lstm_fused = true;      // VF_LSTM_FUSED [1]: conv-LSTM pointwise (both instance norms) as one cluster kernel per layer
+    bool lstm_fused = false;     // VF_LSTM_FUSED [0]: conv-LSTM pointwise (both instance norms) as one cluster kernel per layer
+                                 //   (measured SLOWER: 130 us vs 26 + 18 + 4 us at 32x32x32 — one 214-register CTA per SM, phases serialised)
     bool hoist_sa = true;        // VF_HOIST_SA [1]: the action/state vectors and border-class biases of ALL cell steps are built
                                  //   by two launches at the start of a rollout (they do not depend on the predicted frames)
-    bool fuse_fin = true;        // VF_FUSE_FIN [1]: the producer's last-arriving warp/block finalises the statistics (no finalize launch)
+    bool fuse_fin = false;       // VF_FUSE_FIN [0]: the producer's last-arriving warp/block finalises the statistics (no finalize launch);
+                                 //   measured SLOWER (thin convs 80 -> 148 us): the last arriver's serial walk over up to 34 slots sits on
+                                 //   an epilogue warp's critical path, the separate 4.5 us finalize launch is cheaper
   } opt;
   int cur_tau = 0;             // cell step being launched (selects the step's slice of the hoisted sabias tables)
   int cur_M = 0;               // samples of the rollout being launched (convs on fewer samples = shared-prefix steps)
@@ -1146,9 +1149,9 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
     h->opt.stats_fin = flag("VF_STATS_FIN", true);
     h->opt.epi_stats = flag("VF_EPI_STATS", true);
     h->opt.merge_heads = flag("VF_MERGE_HEADS", true) && cfg->precision != VF_PREC_FP32_SIMT;
-    h->opt.fuse_fin = flag("VF_FUSE_FIN", true) && h->opt.stats_fin;
+    h->opt.fuse_fin = flag("VF_FUSE_FIN", false) && h->opt.stats_fin;
     h->opt.hoist_sa = flag("VF_HOIST_SA", true);
-    h->opt.lstm_fused = flag("VF_LSTM_FUSED", true) && h->opt.stats_fin;
+    h->opt.lstm_fused = flag("VF_LSTM_FUSED", false) && h->opt.stats_fin;
   }
   // programmatic dependent launch: measured SLOWER on B200 inside the replayed graph (131.4 vs 124.7 ms per plan), so opt-in
   { const char* e = getenv("VF_PDL"); g_use_pdl = e && e[0] == '1'; }
@@ -1345,8 +1348,12 @@ int vf_fetch(vf_engine* h, const int32_t* idx, int32_t n, float* of, float* od) 
 
 static void fill_sample_args(vf_engine* h, SampleArgs& a, int iteration) {
   const vf_cem_params& p = h->cem;
-  a.D = h->cem_D; a.nactions = p.nactions; a.adim = h->adim; a.repeat = p.repeat;
-  a.K = iteration == 0 ? 0 : p.num_elites;
+  a.D = h->cem_D; a.nactions = p.nactions; a.adim = h->adim - p.n_append; a.repeat = p.repeat;
+  a.adim_out = h->adim;
+  for (int i = 0; i < 8; ++i) { a.append[i] = i < p.n_append ? p.append_action[i] : 0.0; a.bias[i] = p.mean_bias[i]; }
+  a.discrete_mask = p.discrete_mask;
+  a.kind = p.sampler; a.beta0 = p.beta0; a.beta1 = p.beta1;
+  a.K = (iteration == 0 || p.sampler == VF_SAMPLER_CORRELATED) ? 0 : p.num_elites;
   a.mean = h->cem_mean; a.factor = h->cem_factor; a.std0 = h->cem_std0;
   a.noise = h->cem_has_noise ? h->cem_noise + (size_t)iteration * p.global_samples * h->cem_Dmax : nullptr;
   a.noise_stride = h->cem_Dmax;
@@ -1368,11 +1375,16 @@ int vf_cem_begin(vf_engine* h, const vf_cem_params* p, const float* goal, const 
   if (Mg < M || p->sample_offset < 0 || p->sample_offset + M > Mg) return fail(h, VF_ERR_INVALID, "bad shard (offset %d, M %d, global %d)", p->sample_offset, M, Mg);
   if (K < 1 || K > Mg) return fail(h, VF_ERR_INVALID, "num_elites=%d outside [1, %d]", K, Mg);
   if (p->iterations < 1 || p->nactions < 1 || p->repeat < 1) return fail(h, VF_ERR_INVALID, "bad iterations/nactions/repeat");
-  const int D = p->nactions * h->adim;
-  if (D > 128) return fail(h, VF_ERR_INVALID, "nactions*adim=%d > 128", D);
+  if (p->n_append < 0 || p->n_append >= h->adim) return fail(h, VF_ERR_INVALID, "n_append=%d outside [0, adim=%d)", p->n_append, h->adim);
+  if (p->sampler != VF_SAMPLER_GAUSSIAN && p->sampler != VF_SAMPLER_CORRELATED) return fail(h, VF_ERR_INVALID, "unknown sampler %d", p->sampler);
+  if (p->sampler == VF_SAMPLER_CORRELATED && (p->repeat != 1 || p->use_mean0))
+    return fail(h, VF_ERR_INVALID, "the correlated-noise sampler has repeat = 1 and no warm start (correlated_noise.py:37-45)");
+  const int sdims = h->adim - p->n_append;            // dims the sampler draws per step
+  const int D = p->nactions * sdims;
+  if (D > 128) return fail(h, VF_ERR_INVALID, "nactions*(adim - n_append)=%d > 128", D);
   if (p->n_ctx_actions != h->n_ctx_actions) return fail(h, VF_ERR_INVALID, "n_ctx_actions (%d) differs from vf_set_context (%d)", p->n_ctx_actions, h->n_ctx_actions);
   h->cem = *p;
-  h->cem_D = D; h->cem_T = p->nactions * p->repeat; h->cem_Dmax = std::max(D, K);
+  h->cem_D = D; h->cem_T = p->nactions * p->repeat; h->cem_Dmax = p->sampler == VF_SAMPLER_CORRELATED ? D : std::max(D, K);
   int r = ensure_actions(h, h->cem_T);
   if (r) return r;
   if (!h->cem_mean) {
@@ -1445,9 +1457,9 @@ int vf_cem_begin(vf_engine* h, const vf_cem_params* p, const float* goal, const 
   double mean[128], std0[128];
   for (int d = 0; d < D; ++d) {
     mean[d] = p->use_mean0 ? (double)p->mean0[d] : 0.0;
-    double s = (double)p->initial_std[d % h->adim];
+    double s = (double)p->initial_std[d % sdims];
     // construct_initial_sigma scales the VARIANCE of all but the last action block (controller_utils.py:76-81)
-    if (p->reduce_std_scale != 1.0 && d < (p->nactions - 1) * h->adim) s *= sqrt(p->reduce_std_scale);
+    if (p->reduce_std_scale != 1.0 && d < (p->nactions - 1) * sdims) s *= sqrt(p->reduce_std_scale);
     std0[d] = s;
   }
   CU(cudaMemcpyAsync(h->cem_mean, mean, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
@@ -1517,7 +1529,13 @@ int vf_cem_iter_select(vf_engine* h, int32_t it) {
   a.indices = h->cem_elite_idx;
   a.out_nr = h->cem_elites_nr; a.out_actions64 = h->cem_best64;
   launch_sample_actions(a, K, h->stream);
-  if (it < p.iterations - 1) launch_refit(h->cem_elites_nr, K, h->cem_D, h->cem_mean, h->cem_factor, nullptr, h->stream);
+  if (it < p.iterations - 1) {
+    if (p.sampler == VF_SAMPLER_CORRELATED)
+      launch_refit_correlated(h->cem_elites_nr, h->cem_scores + (size_t)it * p.global_samples, h->cem_elite_idx, K, h->cem_D, p.kappa,
+                              h->cem_mean, h->stream);
+    else
+      launch_refit(h->cem_elites_nr, K, h->cem_D, h->cem_mean, h->cem_factor, nullptr, h->stream);
+  }
   CU(cudaGetLastError());
   return VF_OK;
 }

@@ -283,7 +283,12 @@ void launch_goal_image_cost(const float* frames, int M, int P, int ncam, int H, 
 
 // ---- CEM ---------------------------------------------------------------------------------------
 struct SampleArgs {
-  int D, nactions, adim, repeat, K;   // K = columns of the factor (0 -> diagonal, iteration 0)
+  int D, nactions, adim, repeat, K;   // adim = SAMPLED dims per step, D = nactions * adim; K = columns of the factor (0 -> diagonal, iteration 0)
+  int adim_out;                       // dims per step of the action rows (adim + appended constants)
+  double append[8];                   // the adim_out - adim constant dims (append_action)
+  unsigned discrete_mask;             // bit a: floor + clip to [0,4] (discrete_ind)
+  int kind;                           // 0 Gaussian (mean + std0*z | mean + factor z), 1 correlated noise (AR(1) around mean)
+  double beta0, beta1, bias[8];       // correlated noise
   const double* mean;      // [D]
   const double* factor;    // [D][K]  (iteration > 0)
   const double* std0;      // [D]     (iteration 0)
@@ -308,6 +313,9 @@ void launch_topk(const double* scores, int n, int k, int* out_idx, double* work_
 int topk_padded(int n);
 // mean[D], factor[D][K] = Xc^T / sqrt(K-1), cov[D][D] (unbiased)
 void launch_refit(const double* elites_nr, int K, int D, double* mean, double* factor, double* cov, cudaStream_t s);
+// correlated-noise sampler: mean[d] = sum_k S_k x[k][d] / (sum_k S_k + 1e-4), S_k = exp(kappa * (r_k - max r)), r_k = -scores[idx[k]]
+void launch_refit_correlated(const double* elites_nr, const double* scores, const int* idx, int K, int D, double kappa, double* mean,
+                             cudaStream_t s);
 
 // score exchange over peer memory (engine.cu: vf_cem_exchange): store my segment of a score row into every peer's window,
 // publish my arrival counter, wait for the peers' counters

@@ -11,11 +11,12 @@ import numpy as np
 
 from .spec import MAX_LAYERS, PredictorSpec
 
-VF_ABI_VERSION = 1
+VF_ABI_VERSION = 2
 VF_MAX_TASKS = 16
 VF_PEER_DESC_BYTES = 128
 PREC_FP32_SIMT, PREC_F16X3, PREC_F16X1 = 0, 1, 2
 COST_PIXEL_DISTANCE, COST_GOAL_IMAGE = 0, 1
+SAMPLER_GAUSSIAN, SAMPLER_CORRELATED = 0, 1
 PRECISIONS = {"fp32_simt": PREC_FP32_SIMT, "f16x3": PREC_F16X3, "f16x1": PREC_F16X1}
 
 LIB_PATH = os.environ.get("VF_ENGINE_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvfengine.so")
@@ -60,6 +61,9 @@ class VfCemParams(C.Structure):
         ("task_weights", C.c_double * VF_MAX_TASKS),
         ("seed", C.c_uint64), ("plan_index", C.c_uint32),
         ("k_futures", C.c_int32), ("lambda_variance", C.c_float), ("reserved", C.c_int32 * 6),
+        ("sampler", C.c_int32), ("n_append", C.c_int32), ("discrete_mask", C.c_uint32), ("pad1", C.c_int32),
+        ("append_action", C.c_double * 8), ("beta0", C.c_double), ("beta1", C.c_double), ("kappa", C.c_double),
+        ("mean_bias", C.c_double * 8),
     ]
 
 

@@ -22,7 +22,7 @@ from typing import Any, Dict, Optional
 import numpy as np
 
 from . import spec as specmod
-from .engine import (COST_GOAL_IMAGE, COST_PIXEL_DISTANCE, Engine, VfCemParams)
+from .engine import (COST_GOAL_IMAGE, COST_PIXEL_DISTANCE, SAMPLER_CORRELATED, SAMPLER_GAUSSIAN, Engine, VfCemParams)
 from .spec import PredictorSpec
 
 
@@ -53,26 +53,43 @@ def load_weights(path: str):
 def cem_params(spec: PredictorSpec, *, num_samples, iterations, num_elites, nactions, repeat, std, clip=None,
                mean0=None, reduce_std_scale=1.0, cost_kind=COST_PIXEL_DISTANCE, finalweight=10.0, task_weights=None,
                n_ctx_actions=0, seed=0, plan_index=0, global_samples=None, sample_offset=0, k_futures=1,
-               lambda_variance=0.0) -> VfCemParams:
+               lambda_variance=0.0, sampler="gaussian", append_action=None, discrete_ind=None, beta0=0.5, beta1=0.5, kappa=1.0,
+               mean_bias=None) -> VfCemParams:
+    """std / clip / mean0 are indexed by the SAMPLED action dims (adim - len(append_action))."""
     p = VfCemParams()
     p.num_samples = int(num_samples)
     p.global_samples = int(global_samples if global_samples is not None else num_samples)
     p.sample_offset = int(sample_offset)
     p.iterations, p.num_elites, p.nactions, p.repeat = int(iterations), int(num_elites), int(nactions), int(repeat)
+    app = [] if append_action is None else [float(v) for v in np.asarray(append_action, np.float64).reshape(-1)]
+    sdims = spec.adim - len(app)
+    assert sdims >= 1, "append_action leaves no sampled action dimension"
+    p.n_append = len(app)
+    for i, v in enumerate(app):
+        p.append_action[i] = v
     std = np.asarray(std, dtype=np.float64).reshape(-1)
-    assert std.shape[0] >= spec.adim
+    assert std.shape[0] >= sdims
     for i in range(8):
-        p.initial_std[i] = float(std[i]) if i < spec.adim else 0.0
+        p.initial_std[i] = float(std[i]) if i < sdims else 0.0
         p.clip_lo[i], p.clip_hi[i] = -np.inf, np.inf
     p.action_bound = int(clip is not None)
     if clip is not None:
         lo, hi = clip
-        for i in range(spec.adim):
+        for i in range(sdims):
             p.clip_lo[i], p.clip_hi[i] = float(lo[i]), float(hi[i])
+    p.discrete_mask = 0
+    for ind in (discrete_ind or []):
+        assert 0 <= int(ind) < sdims
+        p.discrete_mask |= 1 << int(ind)
+    p.sampler = {"gaussian": SAMPLER_GAUSSIAN, "correlated": SAMPLER_CORRELATED}[sampler] if isinstance(sampler, str) else int(sampler)
+    p.beta0, p.beta1, p.kappa = float(beta0), float(beta1), float(kappa)
+    mb = np.zeros(8) if mean_bias is None else np.asarray(mean_bias, np.float64).reshape(-1)
+    for i in range(min(8, mb.shape[0])):
+        p.mean_bias[i] = float(mb[i])
     p.use_mean0 = int(mean0 is not None)
     if mean0 is not None:
         m = np.asarray(mean0, dtype=np.float64).reshape(-1)
-        assert m.shape[0] == nactions * spec.adim
+        assert m.shape[0] == nactions * sdims
         for i, v in enumerate(m):
             p.mean0[i] = float(v)
     p.reduce_std_scale = float(reduce_std_scale)
@@ -158,13 +175,13 @@ class EngineBackend:
 
     def plan(self, context, *, num_samples, iterations, num_elites, nactions, repeat, std, clip, mean0,
              reduce_std_scale, goal_pix, finalweight, task_weights, seed, plan_index, noise=None,
-             cost_kind=COST_PIXEL_DISTANCE, k_futures=1, lambda_variance=0.0):
+             cost_kind=COST_PIXEL_DISTANCE, k_futures=1, lambda_variance=0.0, **sampler_kw):
         self.set_context(context)
         p = cem_params(self.spec, num_samples=num_samples, iterations=iterations, num_elites=num_elites,
                        nactions=nactions, repeat=repeat, std=std, clip=clip, mean0=mean0,
                        reduce_std_scale=reduce_std_scale, cost_kind=cost_kind, finalweight=finalweight,
                        task_weights=task_weights, n_ctx_actions=self._n_ctx_actions, seed=seed, plan_index=plan_index,
-                       k_futures=k_futures, lambda_variance=lambda_variance)
+                       k_futures=k_futures, lambda_variance=lambda_variance, **sampler_kw)
         best, eidx, scores = self.engine.cem_plan(p, np.asarray(goal_pix, np.float32), noise)
         return {"best_actions": best, "elite_idx": eidx, "scores": scores}
 
