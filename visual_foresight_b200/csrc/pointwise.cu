@@ -178,6 +178,60 @@ __global__ void __launch_bounds__(256) k_norm_act(View x, int H, int W, int pool
   }
 }
 
+// 8 channels per thread: two 16-byte loads of the float32 conv output (x4 when pooling), one 16-byte store per fp16 plane
+template <int POOL>
+__global__ void __launch_bounds__(256) k_norm_act8(View x, int H, int W, StatsRef sr, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, int act, View y, View y2) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y;
+  const int C8 = x.C >> 3;
+  const int total = H * W * C8;
+  __shared__ __align__(16) float sm_[512], sr_[512], sg_[512], sb_[512];     // mean, rstd, gamma, beta per channel
+  for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
+    const float2 v = stat_of(sr, (long long)b * x.C + c);
+    sm_[c] = v.x; sr_[c] = v.y; sg_[c] = __ldg(gamma + c); sb_[c] = __ldg(beta + c);
+  }
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (i % C8) << 3;
+    const int pix = i / C8;
+    float4 v0, v1;
+    if (!POOL) {
+      const float* p = vptr(x, b, pix) + c;
+      v0 = __ldg(reinterpret_cast<const float4*>(p));
+      v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+    } else {
+      const int py = pix / W, px = pix - py * W, Wi = 2 * W;
+      const float* p00 = vptr(x, b, (long long)(2 * py) * Wi + 2 * px) + c;
+      const float* p10 = p00 + (long long)Wi * x.pix_stride;
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(p00)), a1 = __ldg(reinterpret_cast<const float4*>(p00 + x.pix_stride));
+      const float4 a2 = __ldg(reinterpret_cast<const float4*>(p10)), a3 = __ldg(reinterpret_cast<const float4*>(p10 + x.pix_stride));
+      const float4 e0 = __ldg(reinterpret_cast<const float4*>(p00 + 4)), e1 = __ldg(reinterpret_cast<const float4*>(p00 + x.pix_stride + 4));
+      const float4 e2 = __ldg(reinterpret_cast<const float4*>(p10 + 4)), e3 = __ldg(reinterpret_cast<const float4*>(p10 + x.pix_stride + 4));
+      v0 = make_float4(((a0.x + a1.x) + (a2.x + a3.x)) * 0.25f, ((a0.y + a1.y) + (a2.y + a3.y)) * 0.25f,
+                       ((a0.z + a1.z) + (a2.z + a3.z)) * 0.25f, ((a0.w + a1.w) + (a2.w + a3.w)) * 0.25f);
+      v1 = make_float4(((e0.x + e1.x) + (e2.x + e3.x)) * 0.25f, ((e0.y + e1.y) + (e2.y + e3.y)) * 0.25f,
+                       ((e0.z + e1.z) + (e2.z + e3.z)) * 0.25f, ((e0.w + e1.w) + (e2.w + e3.w)) * 0.25f);
+    }
+    const float4 m0 = *reinterpret_cast<const float4*>(sm_ + c), m1 = *reinterpret_cast<const float4*>(sm_ + c + 4);
+    const float4 r0 = *reinterpret_cast<const float4*>(sr_ + c), r1 = *reinterpret_cast<const float4*>(sr_ + c + 4);
+    const float4 g0 = *reinterpret_cast<const float4*>(sg_ + c), g1 = *reinterpret_cast<const float4*>(sg_ + c + 4);
+    const float4 q0 = *reinterpret_cast<const float4*>(sb_ + c), q1 = *reinterpret_cast<const float4*>(sb_ + c + 4);
+    float8 o;                                                    // the arithmetic of k_norm_act, term for term
+    o.a = make_float4((v0.x - m0.x) * r0.x * g0.x + q0.x, (v0.y - m0.y) * r0.y * g0.y + q0.y,
+                      (v0.z - m0.z) * r0.z * g0.z + q0.z, (v0.w - m0.w) * r0.w * g0.w + q0.w);
+    o.b = make_float4((v1.x - m1.x) * r1.x * g1.x + q1.x, (v1.y - m1.y) * r1.y * g1.y + q1.y,
+                      (v1.z - m1.z) * r1.z * g1.z + q1.z, (v1.w - m1.w) * r1.w * g1.w + q1.w);
+    if (act == ACT_RELU) {
+      o.a = make_float4(fmaxf(o.a.x, 0.f), fmaxf(o.a.y, 0.f), fmaxf(o.a.z, 0.f), fmaxf(o.a.w, 0.f));
+      o.b = make_float4(fmaxf(o.b.x, 0.f), fmaxf(o.b.y, 0.f), fmaxf(o.b.z, 0.f), fmaxf(o.b.w, 0.f));
+    }
+    if (c < y.C) vst8(y, voff(y, b, pix) + c, o);
+    else vst8(y2, voff(y2, b, pix) + (c - y.C), o);
+  }
+}
+
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 
 __device__ __forceinline__ float gate_norm(const View& g, int b, long long pix, int ch, const float* gstats,
@@ -815,6 +869,14 @@ void launch_norm_act(View x, int B, int H, int W, int pool, StatsRef stats, cons
                      const float* beta, int act, View y, cudaStream_t s, View y2) {
   ++g_launch_counter;
   // few, long-lived blocks per sample: every block stages the sample's statistics in shared memory first
+  static const bool v8 = getenv("VF_NORM_ACT8") && atoi(getenv("VF_NORM_ACT8")) == 1;   // A/B switch
+  auto al8 = [](const View& v) { return v.C == 0 || ((v.C | v.ch_off | v.pix_stride) % 8 == 0 && v.sample_stride % 8 == 0 && v.lo_off % 8 == 0); };
+  if (v8 && x.C % 8 == 0 && x.C <= 512 && !x.lo_off && (x.pix_stride | x.ch_off) % 4 == 0 && x.sample_stride % 4 == 0 && al8(y) && al8(y2)) {
+    dim3 grid8(grid_for((long long)H * W * (x.C >> 3), 256, B >= 64 ? 16 : 64), B);
+    if (pool) launch_k(k_norm_act8<1>, dim3(grid8), dim3(256), 0, s, x, H, W, stats, gamma, beta, act, y, y2);
+    else launch_k(k_norm_act8<0>, dim3(grid8), dim3(256), 0, s, x, H, W, stats, gamma, beta, act, y, y2);
+    return;
+  }
   dim3 grid(grid_for((long long)H * W * (x.C >> 2), 256, B >= 64 ? 16 : 64), B);
   launch_k(k_norm_act, dim3(grid), dim3(256), 0, s, x, H, W, pool, stats, gamma, beta, act, y, y2);
 }
