@@ -97,6 +97,8 @@ struct vf_engine {
   char err[512];
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t side = nullptr;           // second stream of the CDNA-head branch (opt.side_cdna)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<void*> allocs;
   std::map<std::string, HostTensor> host_w;
   bool weights_ready = false, context_set = false, distrib_set = false, predicted = false;
@@ -187,6 +189,8 @@ struct vf_engine {
     bool stats_fin = true;       // VF_STATS_FIN [1]: separate k_stats_finalize launches (1) or consumers finalise on the fly (0; measured 4 % slower)
     bool epi_stats = true;       // VF_EPI_STATS [1]: instance-norm statistics of the thin convolutions come from their epilogue
     bool merge_heads = true;     // VF_MERGE_HEADS [1]: scratch.conv0 + masks.conv0 as one convolution
+    bool side_cdna = true;       // VF_SIDE_CDNA [1]: the CDNA head (dense -> kernels -> apply) runs on a second stream beside the decoder
+                                 //   (fork after the last encoder conv-LSTM, join before the scratch-image conv; a branch of the graph)
     bool lstm_fused = false;     // VF_LSTM_FUSED [0]: conv-LSTM pointwise (both instance norms) as one cluster kernel per layer
                                  //   (measured SLOWER: 130 us vs 26 + 18 + 4 us at 32x32x32 — one 214-register CTA per SM, phases serialised)
     bool hoist_sa = true;        // VF_HOIST_SA [1]: the action/state vectors and border-class biases of ALL cell steps are built
@@ -833,6 +837,19 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     x0 = out; x1 = none;
     if (i + 1 < n && net.enc_conv[i + 1].s2d) x0 = cview(h, net.enc_rnn[i].h_s2d, (hh / 2) * (ww / 2), 4 * oc, 0, 4 * oc);
   }
+  // P5/P6 on a side branch: the CDNA head only needs the last encoder state and the previous frame, and nothing before the
+  // scratch-image conv needs its outputs — it overlaps the decoder (latency-shaped kernels beside the decoder's streaming ones)
+  const bool emit = tau >= h->C - 1;                      // a warm-up step's prediction is never consumed
+  const bool side = emit && h->opt.side_cdna && h->side;
+  const int featK = enc_h[n - 1] * enc_w[n - 1] * enc_out[n - 1].C;
+  View layers = cview(h, h->layers, (int)px, h->cl, 0, h->cl);
+  if (side) {
+    cudaEventRecord(h->ev_fork, h->stream);
+    cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+    launch_cdna_kernels(enc_out[n - 1], enc_h[n - 1] * enc_w[n - 1], net.cdna_w, h->kc, h->nt, B, h->cdna_part, h->side);
+    launch_cdna_apply(image, first, h->cdna_part, featK, net.cdna_b, h->kern, h->kc, h->nt, B, H, W, layers, h->side);
+    cudaEventRecord(h->ev_join, h->side);
+  }
   // P4 decoder
   View x = enc_out[n - 1];
   for (int i = 0; i < n; ++i) {
@@ -857,15 +874,14 @@ void run_step(vf_engine* h, int v, int tau, int B) {
       x = cview(h, net.dec_rnn[i].lstm_in, hh * ww, 2 * oc, oc, oc);
     }
   }
-  if (tau < h->C - 1) return;   // warm-up step: its prediction is never consumed
+  if (!emit) return;
   const int t_out = tau - (h->C - 1);
   const int g = h->ngf, nm = h->nm, cl = h->cl;
   View h_last = x;
-  // P5/P6
-  const int featK = enc_h[n - 1] * enc_w[n - 1] * enc_out[n - 1].C;
-  launch_cdna_kernels(enc_out[n - 1], enc_h[n - 1] * enc_w[n - 1], net.cdna_w, h->kc, h->nt, B, h->cdna_part, h->stream);
-  View layers = cview(h, h->layers, (int)px, cl, 0, cl);
-  launch_cdna_apply(image, first, h->cdna_part, featK, net.cdna_b, h->kern, h->kc, h->nt, B, H, W, layers, h->stream);
+  if (!side) {                  // P5/P6 in line
+    launch_cdna_kernels(enc_out[n - 1], enc_h[n - 1] * enc_w[n - 1], net.cdna_w, h->kc, h->nt, B, h->cdna_part, h->stream);
+    launch_cdna_apply(image, first, h->cdna_part, featK, net.cdna_b, h->kern, h->kc, h->nt, B, H, W, layers, h->stream);
+  }
   double* epi_sp = h->opt.epi_stats ? h->stats_partial : nullptr;
   View scr, hm;
   View scratch_out = cview(h, h->layers, (int)px, cl, 3 * (h->nt + 2), 3);
@@ -880,6 +896,7 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     scr = cview(h, h->scr_h, (int)px, g, 0, g);
     hm = cview(h, h->mask_h, (int)px, g, 0, g);
     launch_norm_act(raw2, B, H, W, 0, fin_stats(h, h->stats_partial, S_h, B * 2 * g, (int)px, h->stats, f_h), net.heads0.gamma, net.heads0.beta, ACT_RELU, scr, h->stream, hm);
+    if (side) cudaStreamWaitEvent(h->stream, h->ev_join, 0);     // `layers` (written whole by the CDNA apply) before the scratch image lands in it
     run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
   } else {
     // P7 scratch image
@@ -890,6 +907,7 @@ void run_step(vf_engine* h, int v, int tau, int B) {
     if (!S_s) S_s = plane_stats_pass(h, rawg, B, H, W, 0, &f_s);
     scr = cview(h, h->scr_h, (int)px, g, 0, g);
     launch_norm_act(rawg, B, H, W, 0, fin_stats(h, h->stats_partial, S_s, B * g, (int)px, h->stats, f_s), net.scratch0.gamma, net.scratch0.beta, ACT_RELU, scr, h->stream);
+    if (side) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
     run_conv(h, net.scratch1, scr, none, scratch_out, B, ACT_SIGMOID);
     // P8 masks
     int S_m = 0;
@@ -1151,6 +1169,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
     h->opt.merge_heads = flag("VF_MERGE_HEADS", true) && cfg->precision != VF_PREC_FP32_SIMT;
     h->opt.fuse_fin = flag("VF_FUSE_FIN", false) && h->opt.stats_fin;
     h->opt.hoist_sa = flag("VF_HOIST_SA", true);
+    h->opt.side_cdna = flag("VF_SIDE_CDNA", true);
     h->opt.lstm_fused = flag("VF_LSTM_FUSED", false) && h->opt.stats_fin;
   }
   // programmatic dependent launch: measured SLOWER on B200 inside the replayed graph (131.4 vs 124.7 ms per plan), so opt-in
@@ -1179,6 +1198,9 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
   CU(cudaSetDevice(cfg->device));
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
+  CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   int r = build_net(h);
   if (r) return r;
   const size_t px = (size_t)h->H * h->W;
@@ -1211,6 +1233,9 @@ int vf_destroy(vf_engine* h) {
   for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return VF_OK;
 }
