@@ -382,6 +382,122 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------
+# optional lines for the other BASELINE configs (python bench.py --config c3|c5): same timing rules, planner-level calls
+EXTRA = {
+    # Sawyer two-view: M=600 S=13 2x(48x64), registration-weighted cost (ndesig=2, 1/warp-error trade-off), K = 5 % = 30, 13x1 actions
+    "c3": dict(family="64", spec=dict(height=48, width=64, ncam=2, ndesig=2, adim=4, sdim=5, seq_len=13), M=600, K=30, iters=3,
+               nactions=13, repeat=1, futures=1, task_err=[0.8, 2.5, 1.3, 0.4],
+               workload="c3: M=600 S=13 2 views x 48x64, ndesig=2, registration-weighted pixel cost, 3 CEM iters K=30"),
+    # stochastic SAVP predictor: M=200 x K=10 futures, S=15 128x128, nz=8 (recurrent latent); on N GPUs the 200 sequences are sharded,
+    # on ONE GPU this line runs one 1/8 shard (25 sequences x 10 futures = 250 rollouts) of the 8-GPU config
+    "c5": dict(family="128", spec=dict(adim=4, sdim=4, seq_len=15, nz=8, rnn_z=True), M=200, K=10, iters=3, nactions=5, repeat=3,
+               futures=10, task_err=None,
+               workload="c5: M=200 x 10 futures S=15 128x128 nz=8 stochastic predictor, mean + 0.5 var over futures, 3 CEM iters K=10"),
+}
+
+
+def run_extra(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from visual_foresight_b200 import spec as S
+    from visual_foresight_b200.distributed import EngineShard, ShardedCEMPlanner, init_from_env
+    from visual_foresight_b200.hparams import HParams
+    from visual_foresight_b200.predictor import EngineBackend
+    from visual_foresight_b200.samplers import GaussianCEMSampler, action_bounds, per_dim_variance
+    c = EXTRA[args.config]
+    init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    spec = (S.spec_128 if c["family"] == "128" else S.spec_64)(**c["spec"])
+    inp, w = synth(spec)
+    Mg = c["M"]
+    shard_note = ""
+    if args.config == "c5" and world == 1:
+        Mg = c["M"] // 8
+        shard_note = " [ONE 1/8 shard of the 8-GPU config: %d sequences x %d futures]" % (Mg, c["futures"])
+    if Mg % world:
+        raise SystemExit("M=%d not divisible by %d ranks" % (Mg, world))
+    local = Mg // world
+    be = EngineBackend(spec, w, local * c["futures"], device=local_rank, precision=args.precision)
+    stream = torch.cuda.Stream()
+    be.engine.set_stream(stream.cuda_stream)
+    ctx = {"context_frames": inp["frames"], "context_states": inp["states"], "context_actions": inp["ctx_actions"]}
+    desig, goal = inp["desig"].astype(np.float32), inp["goal"].astype(np.float32)
+    hp = HParams(**GaussianCEMSampler.get_default_hparams())
+    lo, hi = action_bounds(hp, spec.adim)
+    tw = None
+    if c["task_err"]:
+        e = np.asarray(c["task_err"], np.float64)
+        tw = (1.0 / e) / (1.0 / e).sum()
+    kw = dict(num_elites=min(c["K"], Mg), nactions=c["nactions"], repeat=c["repeat"], std=np.sqrt(per_dim_variance(hp, spec.adim)), clip=(lo, hi),
+              mean0=None, reduce_std_scale=1.0, finalweight=10.0, task_weights=tw, seed=0, k_futures=c["futures"], lambda_variance=0.5 if c["futures"] > 1 else 0.0)
+    shard = EngineShard(be, collective=args.collective if world > 1 else "host", stream=stream, rank=rank, world=world)
+    planner = ShardedCEMPlanner(shard, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    be.set_context(ctx)
+    be.engine.set_desig(desig)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = be.engine.launch_count()
+    ms = timed_plans(planner, stream, Mg, kw, goal, args.steps, max(args.warmup, 2), barrier, c["iters"])
+    launches = be.engine.launch_count() - l0
+    # e2e: host context in, plan out, per step
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    f0.record(stream)
+    for i in range(args.steps):
+        be.set_context(ctx)
+        be.engine.set_desig(desig)
+        res = planner.plan(Mg, c["iters"], goal=goal, plan_index=200 + i, **kw)
+    f1.record(stream)
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3) / args.steps
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    be.engine.profile_enable(True)
+    planner.plan(Mg, c["iters"], goal=goal, plan_index=300, **kw)
+    prof = be.engine.profile_read()
+    be.engine.profile_enable(False)
+    peak_tf, _, peak_src = measured_peaks()
+    fl = S.flops_per_sample_step(spec)
+    gate_per_step = sum(1 for _, rnn in tuple(spec.encoder) + tuple(spec.decoder) if rnn)
+    nroll = local * c["futures"]
+    full_steps = prof["lstm_conv"]["launches"] // max(gate_per_step * c["iters"] * spec.ncam, 1)
+    alg = fl["conv_lstm"] * full_steps * nroll * c["iters"] * spec.ncam
+    lstm_ms = prof["lstm_conv"]["ms"]
+    ach = alg / (lstm_ms * 1e-3) / 1e12 if lstm_ms > 0 else 0.0
+    if rank == 0:
+        frames = c["iters"] * Mg * c["futures"] * spec.n_pred * spec.ncam
+        line = {"metric": "CEM predicted frames/sec (%s; plans/sec alongside)" % args.config, "value": frames / (ms * 1e-3), "unit": "frames/s",
+                "plans_per_sec": 1e3 / ms, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (fp16 hi/lo split x3 on tcgen05, fp32 accumulate)" if args.precision == "f16x3" else args.precision, "data": "synthetic",
+                "config": {"workload": c["workload"] + shard_note, "parallelism": "sample-parallel dp%d" % world, "precision": args.precision,
+                           "l2": "per-step working set exceeds the 126 MB L2; no flush"},
+                "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "plans_per_sec": 1e3 / ms_e2e,
+                        "h2d_bytes_per_step": int(inp["frames"].nbytes + np.asarray(inp["states"], np.float32).nbytes + desig.nbytes + goal.nbytes),
+                        "d2h_bytes_per_step": int(res["best_actions"].nbytes + res["elite_idx"].nbytes + res["scores"].nbytes),
+                        "call": "EngineBackend.set_context + ShardedCEMPlanner.plan (host buffers)"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "tensor", "kernel": "conv-LSTM gate convolution (%s)" % args.precision, "achieved": ach, "peak": peak_tf,
+                             "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": peak_src + " bf16 sustained", "traffic": None,
+                             "launches": prof["lstm_conv"]["launches"], "ms_per_launch": lstm_ms / max(prof["lstm_conv"]["launches"], 1),
+                             "share_of_step": lstm_ms / ms, "other_conv_ms": prof["other_conv"]["ms"],
+                             "whole_plan_frac": S.flops_per_plan(spec, nroll, c["iters"]) * full_steps / spec.n_steps / (ms * 1e-3) / 1e12 / peak_tf}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -395,10 +511,13 @@ def main():
     ap.add_argument("--ref-samples", type=int, default=200, help="samples per step of the reference arm (one full CEM iteration by default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling legs (c4 M=4096, c2 split)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"], help="c2 = the headline workload (default); c3 / c5 = optional lines for the other BASELINE configs")
     args = ap.parse_args()
     rank, world, local_rank = env_rank()
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.config != "c2":
+        run_extra(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -184,6 +184,21 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Warp-uniform issue: EVERY lane executes the surrounding address arithmetic (so the compiler can keep the warp-uniform
+// descriptors in uniform registers instead of moving them there per MMA), the election happens inside the instruction
+// sequence and only the elected lane's tcgen05 instruction takes effect.  elect.sync picks the same lane every time for the
+// same member mask, so the commits below track the MMAs above.
+__device__ __forceinline__ void tc_mma_f16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
 // 32 lanes x 32 columns of 32-bit: thread (lane) gets 32 consecutive columns of its TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -271,20 +286,32 @@ __device__ __forceinline__ void issue_tap(uint64_t da_st, uint64_t db_tap, uint6
 }
 
 // Swapped orientation: A = activation rows (128 pixels per unit, tap-shifted), B = the weight tile (np output channels).
-template <int PASSES, int U>
-__device__ __forceinline__ void issue_tap_swap(uint64_t da_tap, uint64_t db_st, uint64_t a_plane, uint64_t b_half, uint64_t kstep,
-                                               int ksteps, uint64_t unit_step, uint32_t tmem_acc, uint32_t np, uint32_t idesc,
-                                               uint32_t acc_first) {
+// The thin layers are ISSUE-bound (ncu source view of masks1: 144 MMAs of N = 48 per item, ~14 SASS instructions each on one
+// warp): descriptors are therefore advanced in their LOW word only (start address >> 4 and LBO live there; every offset
+// added is < 2^14, so nothing carries into the constant high word), the K-step count is a template parameter (straight-line
+// code), and the accumulator column / pixel-row offset of every unit come from small precomputed tables.
+__device__ __forceinline__ void tc_mma_f16_elect32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int PASSES, int KSTEPS, int U>
+__device__ __forceinline__ void issue_tap_swap(uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t a_plane, uint32_t b_half,
+                                               uint32_t kstep, const uint32_t (&uoff)[MAX_UNIT_B], const uint32_t (&ucol)[MAX_UNIT_B],
+                                               uint32_t idesc, uint32_t acc_first) {
 #pragma unroll
   for (int pass = 0; pass < PASSES; ++pass) {
-    const uint64_t da_p = da_tap + (pass == 1 ? a_plane : 0);
-    const uint64_t db_p = db_st + (pass == 2 ? b_half : 0);
-#pragma unroll 2
-    for (int j = 0; j < ksteps; ++j) {
-      const uint64_t da = da_p + j * kstep, db = db_p + j * kstep;
+    const uint32_t a_p = a_lo + (pass == 1 ? a_plane : 0u);
+    const uint32_t b_p = b_lo + (pass == 2 ? b_half : 0u);
 #pragma unroll
-      for (int u = 0; u < U; ++u)      // unit u: pixel rows [128u, 128u+128) of the item -> TMEM columns [u*np, (u+1)*np)
-        tc_mma_f16(tmem_acc + u * np, da + (uint64_t)u * unit_step, db, idesc, (pass | j) == 0 ? acc_first : 1u);
+    for (int j = 0; j < KSTEPS; ++j) {
+      const uint32_t a = a_p + j * kstep, b = b_p + j * kstep;
+#pragma unroll
+      for (int u = 0; u < U; ++u)      // unit u: pixel rows [u*ustride, u*ustride + 128) of the item -> its own TMEM columns
+        tc_mma_f16_elect32(ucol[u], a + uoff[u], a_hi, b, b_hi, idesc, (pass | j) == 0 ? acc_first : 1u);
     }
   }
 }
@@ -350,44 +377,49 @@ __device__ __forceinline__ void issuer_loop(const Geometry& g, const IssueCtx& c
 
 template <int PASSES, int U>
 __device__ __forceinline__ void issuer_loop_swap(const Geometry& g, const IssueCtx& cx, int acc_cols) {
-  const uint64_t unit_step = (uint64_t)((128u * cx.pix_b) >> 4);
+  const uint32_t unit_step = (128u * cx.pix_b) >> 4;
   const uint32_t idesc_b = make_idesc(g.np), np = (uint32_t)g.np;
   const int nitems = g.nitems, nchunk = g.nchunk, ntap = g.nst, kk = g.kw, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
   const int ksteps = g.ksteps;
   const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
-  const uint64_t pix16 = (uint64_t)(cx.pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.kw) * cx.pix_b) >> 4);
-  const uint64_t dw_base = cx.da_zero + (uint64_t)(cx.wst_base >> 4), dx_base = cx.db_zero + (uint64_t)(cx.act_base >> 4);
+  const uint32_t pix16 = cx.pix_b >> 4, rowskip16 = ((uint32_t)(g.Wp - g.kw) * cx.pix_b) >> 4;
+  const uint32_t w_hi = (uint32_t)(cx.da_zero >> 32), x_hi = (uint32_t)(cx.db_zero >> 32);
+  const uint32_t dw_base = (uint32_t)cx.da_zero + (cx.wst_base >> 4), dx_base = (uint32_t)cx.db_zero + (cx.act_base >> 4);
+  const uint32_t a_plane = (uint32_t)cx.b_plane, b_half = (uint32_t)cx.a_half, kstep = (uint32_t)cx.kstep_b;
+  uint32_t uoff[MAX_UNIT_B], ucol0[MAX_UNIT_B], ucol[MAX_UNIT_B];
+#pragma unroll
+  for (int u = 0; u < MAX_UNIT_B; ++u) { uoff[u] = (uint32_t)u * unit_step; ucol0[u] = cx.tmem_base + (uint32_t)u * np; }
   int s = 0;
   uint32_t ph = 0, job = 0, it = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
     const int a = nacc == 2 ? (int)(it & 1u) : 0;
     mbar_wait(&cx.acc_empty[a], (((nacc == 2 ? it >> 1 : it)) & 1) ^ 1);
     tc_fence_after();
-    const uint32_t tacc = cx.tmem_base + (uint32_t)(a * acc_cols);
-    const uint64_t item_off16 = (uint64_t)(((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
+#pragma unroll
+    for (int u = 0; u < MAX_UNIT_B; ++u) ucol[u] = ucol0[u] + (uint32_t)(a * acc_cols);
+    const uint32_t item_off16 = ((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4;
     uint32_t acc = 0;
     for (int c = 0; c < nchunk; ++c, ++job) {
       const int buf = job % nbuf;
       mbar_wait(&cx.a_full[buf], (job / nbuf) & 1);
       tc_fence_after();
-      uint64_t da_tap = dx_base + (uint64_t)(buf * buf16) + item_off16;
+      uint32_t da_tap = dx_base + (uint32_t)(buf * buf16) + item_off16;
       int tx = 0;
       for (int tap = 0; tap < ntap; ++tap) {
         mbar_wait(&cx.w_full[s], ph);
         tc_fence_after();
-        if (elect_one()) {
-          issue_tap_swap<PASSES, U>(da_tap, dw_base + (uint64_t)(s * stage16), cx.b_plane, cx.a_half, cx.kstep_b, ksteps, unit_step,
-                                    tacc, np, idesc_b, acc);
-          tc_commit(&cx.w_empty[s]);
-        }
+        if (ksteps == 2) issue_tap_swap<PASSES, 2, U>(da_tap, x_hi, dw_base + (uint32_t)(s * stage16), w_hi, a_plane, b_half, kstep, uoff, ucol, idesc_b, acc);
+        else if (ksteps == 1) issue_tap_swap<PASSES, 1, U>(da_tap, x_hi, dw_base + (uint32_t)(s * stage16), w_hi, a_plane, b_half, kstep, uoff, ucol, idesc_b, acc);
+        else issue_tap_swap<PASSES, 4, U>(da_tap, x_hi, dw_base + (uint32_t)(s * stage16), w_hi, a_plane, b_half, kstep, uoff, ucol, idesc_b, acc);
+        tc_commit_elect(&cx.w_empty[s]);
         acc = 1;
         if (++s == nstage) { s = 0; ph ^= 1; }
         da_tap += pix16;
         if (++tx == kk) { tx = 0; da_tap += rowskip16; }
       }
-      if (elect_one()) tc_commit(&cx.a_empty[buf]);
+      tc_commit_elect(&cx.a_empty[buf]);
     }
-    if (elect_one()) tc_commit(&cx.acc_full[a]);
+    tc_commit_elect(&cx.acc_full[a]);
   }
 }
 
@@ -395,42 +427,47 @@ __device__ __forceinline__ void issuer_loop_swap(const Geometry& g, const IssueC
 // descriptor advances by one padded image row (Wp pixel rows) per stage.  k MMAs-rows instead of k*k taps.
 template <int PASSES, int U>
 __device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const IssueCtx& cx, int acc_cols) {
-  const uint64_t unit_step = (uint64_t)(((uint32_t)g.ustride * cx.pix_b) >> 4);
+  const uint32_t unit_step = ((uint32_t)g.ustride * cx.pix_b) >> 4;
   const uint32_t idesc_b = make_idesc(g.ncols), ncols = (uint32_t)g.ncols;
   const int nitems = g.nitems, nchunk = g.nchunk, kk = g.k, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
   const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
-  const uint64_t row16 = (uint64_t)(((uint32_t)g.Wp * cx.pix_b) >> 4);
-  const uint64_t dw_base = cx.da_zero + (uint64_t)(cx.wst_base >> 4), dx_base = cx.db_zero + (uint64_t)(cx.act_base >> 4);
+  const uint32_t row16 = ((uint32_t)g.Wp * cx.pix_b) >> 4;
+  const uint32_t w_hi = (uint32_t)(cx.da_zero >> 32), x_hi = (uint32_t)(cx.db_zero >> 32);
+  const uint32_t dw_base = (uint32_t)cx.da_zero + (cx.wst_base >> 4), dx_base = (uint32_t)cx.db_zero + (cx.act_base >> 4);
+  const uint32_t a_plane = (uint32_t)cx.b_plane, b_half = (uint32_t)cx.a_half, kstep = (uint32_t)cx.kstep_b;
+  uint32_t uoff[MAX_UNIT_B], ucol0[MAX_UNIT_B], ucol[MAX_UNIT_B];
+#pragma unroll
+  for (int u = 0; u < MAX_UNIT_B; ++u) { uoff[u] = (uint32_t)u * unit_step; ucol0[u] = cx.tmem_base + (uint32_t)u * ncols; }
   int s = 0;
   uint32_t ph = 0, job = 0, it = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
     const int a = nacc == 2 ? (int)(it & 1u) : 0;
     mbar_wait(&cx.acc_empty[a], (((nacc == 2 ? it >> 1 : it)) & 1) ^ 1);
     tc_fence_after();
-    const uint32_t tacc = cx.tmem_base + (uint32_t)(a * acc_cols);
-    const uint64_t item_off16 = (uint64_t)(((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
+#pragma unroll
+    for (int u = 0; u < MAX_UNIT_B; ++u) ucol[u] = ucol0[u] + (uint32_t)(a * acc_cols);
+    const int vlo = (item - fdiv(item, g.m_npass) * g.npass) * g.v_cnt;             // first virtual pixel of the item's pass
+    const uint32_t item_off16 = ((uint32_t)(vlo - fdiv(vlo, g.m_Wp) * g.Wp) * cx.pix_b) >> 4;
     uint32_t acc = 0;
     for (int c = 0; c < nchunk; ++c, ++job) {
       const int buf = job % nbuf;
       const int ksteps = c == nchunk - 1 ? g.ksteps_last : g.ksteps;
       mbar_wait(&cx.a_full[buf], (job / nbuf) & 1);
       tc_fence_after();
-      uint64_t da_row = dx_base + (uint64_t)(buf * buf16) + item_off16;
+      uint32_t da_row = dx_base + (uint32_t)(buf * buf16) + item_off16;
       for (int dy = 0; dy < kk; ++dy) {
         mbar_wait(&cx.w_full[s], ph);
         tc_fence_after();
-        if (elect_one()) {
-          issue_tap_swap<PASSES, U>(da_row, dw_base + (uint64_t)(s * stage16), cx.b_plane, cx.a_half, cx.kstep_b, ksteps, unit_step,
-                                    tacc, ncols, idesc_b, acc);
-          tc_commit(&cx.w_empty[s]);
-        }
+        if (ksteps == 2) issue_tap_swap<PASSES, 2, U>(da_row, x_hi, dw_base + (uint32_t)(s * stage16), w_hi, a_plane, b_half, kstep, uoff, ucol, idesc_b, acc);
+        else issue_tap_swap<PASSES, 1, U>(da_row, x_hi, dw_base + (uint32_t)(s * stage16), w_hi, a_plane, b_half, kstep, uoff, ucol, idesc_b, acc);
+        tc_commit_elect(&cx.w_empty[s]);
         acc = 1;
         if (++s == nstage) { s = 0; ph ^= 1; }
         da_row += row16;
       }
-      if (elect_one()) tc_commit(&cx.a_empty[buf]);
+      tc_commit_elect(&cx.a_empty[buf]);
     }
-    if (elect_one()) tc_commit(&cx.acc_full[a]);
+    tc_commit_elect(&cx.acc_full[a]);
   }
 }
 

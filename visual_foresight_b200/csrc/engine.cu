@@ -189,7 +189,7 @@ struct vf_engine {
     bool stats_fin = true;       // VF_STATS_FIN [1]: separate k_stats_finalize launches (1) or consumers finalise on the fly (0; measured 4 % slower)
     bool epi_stats = true;       // VF_EPI_STATS [1]: instance-norm statistics of the thin convolutions come from their epilogue
     bool merge_heads = true;     // VF_MERGE_HEADS [1]: scratch.conv0 + masks.conv0 as one convolution
-    bool side_cdna = true;       // VF_SIDE_CDNA [1]: the CDNA head (dense -> kernels -> apply) runs on a second stream beside the decoder
+    bool side_cdna = false;      // VF_SIDE_CDNA [0] (measured +1.4 ms: the side kernels delay the decoder's launches more than they hide): the CDNA head (dense -> kernels -> apply) runs on a second stream beside the decoder
                                  //   (fork after the last encoder conv-LSTM, join before the scratch-image conv; a branch of the graph)
     bool lstm_fused = false;     // VF_LSTM_FUSED [0]: conv-LSTM pointwise (both instance norms) as one cluster kernel per layer
                                  //   (measured SLOWER: 130 us vs 26 + 18 + 4 us at 32x32x32 — one 214-register CTA per SM, phases serialised)
@@ -1169,7 +1169,7 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
     h->opt.merge_heads = flag("VF_MERGE_HEADS", true) && cfg->precision != VF_PREC_FP32_SIMT;
     h->opt.fuse_fin = flag("VF_FUSE_FIN", false) && h->opt.stats_fin;
     h->opt.hoist_sa = flag("VF_HOIST_SA", true);
-    h->opt.side_cdna = flag("VF_SIDE_CDNA", true);
+    h->opt.side_cdna = flag("VF_SIDE_CDNA", false);
     h->opt.lstm_fused = flag("VF_LSTM_FUSED", false) && h->opt.stats_fin;
   }
   // programmatic dependent launch: measured SLOWER on B200 inside the replayed graph (131.4 vs 124.7 ms per plan), so opt-in
