@@ -91,6 +91,7 @@ struct Geometry {
   float out_scale;  // 2^-scale_log2
   // division by kernel-invariant divisors as one multiply-high: x / d == __umulhi(x, ceil(2^32 / d)) for x * d < 2^32 (d > 1)
   uint32_t m_Wp, m_npass, m_np;
+  int dual;         // host switch of the two-issuer mode (row-stacked path)
 };
 
 __host__ __device__ inline uint32_t fd_magic(int d) { return d > 1 ? (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d) : 0u; }
@@ -425,8 +426,11 @@ __device__ __forceinline__ void issuer_loop_swap(const Geometry& g, const IssueC
 
 // Row-stacked thin layers: one weight stage = the k taps of filter row dy side by side on N (ncols = k*np); the activation
 // descriptor advances by one padded image row (Wp pixel rows) per stage.  k MMAs-rows instead of k*k taps.
+// u0: first unit this warp issues (the row-stacked thin layers split the units of an item over TWO issuer warps, 1 and 3:
+// their MMAs go to disjoint accumulator columns, and these layers are bound by the ~10 SASS instructions it takes one warp
+// to get an MMA of N = 48..96 out of the door)
 template <int PASSES, int U>
-__device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const IssueCtx& cx, int acc_cols) {
+__device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const IssueCtx& cx, int acc_cols, int u0) {
   const uint32_t unit_step = ((uint32_t)g.ustride * cx.pix_b) >> 4;
   const uint32_t idesc_b = make_idesc(g.ncols), ncols = (uint32_t)g.ncols;
   const int nitems = g.nitems, nchunk = g.nchunk, kk = g.k, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
@@ -437,7 +441,7 @@ __device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const Issue
   const uint32_t a_plane = (uint32_t)cx.b_plane, b_half = (uint32_t)cx.a_half, kstep = (uint32_t)cx.kstep_b;
   uint32_t uoff[MAX_UNIT_B], ucol0[MAX_UNIT_B], ucol[MAX_UNIT_B];
 #pragma unroll
-  for (int u = 0; u < MAX_UNIT_B; ++u) { uoff[u] = (uint32_t)u * unit_step; ucol0[u] = cx.tmem_base + (uint32_t)u * ncols; }
+  for (int u = 0; u < MAX_UNIT_B; ++u) { uoff[u] = (uint32_t)(u0 + u) * unit_step; ucol0[u] = cx.tmem_base + (uint32_t)(u0 + u) * ncols; }
   int s = 0;
   uint32_t ph = 0, job = 0, it = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
@@ -655,6 +659,9 @@ constexpr uint32_t STAT_OFF = STG_OFF + (uint32_t)STG_TILE_BYTES;   // fused ins
 constexpr size_t STAT_BYTES = 2 * 16 * 4 * 32 * 4;
 constexpr size_t STG_BYTES = STG_TILE_BYTES + STAT_BYTES;
 
+// row-stacked thin layers with at least two units per item: warps 1 and 3 both issue (VF_DUAL_ISSUE=0 switches it off)
+__device__ __forceinline__ bool dual_issue(const Geometry& g) { return g.swap == 2 && g.units >= 2 && g.dual; }
+
 template <int NG>
 __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_constant__ Params P) {
   constexpr int NEPI = 128 * NG;
@@ -673,10 +680,11 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    const uint32_t nissue = dual_issue(g) ? 2u : 1u;      // issuer warps committing to the stage / buffer / accumulator barriers
+    for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], nissue); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI);
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], nissue);
+      mbar_init(&acc_full[i], nissue); mbar_init(&acc_empty[i], NEPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -715,7 +723,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (warp == 3 && dual_issue(g))) {
     // ===== MMA issuer: the whole warp walks the loops (warp-uniform), one elected lane issues =====
     const uint32_t sbo_b = (uint32_t)(8 * g.row_bytes);                   // 8-row core-matrix group pitch
     IssueCtx cx;
@@ -727,14 +735,18 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
     cx.act_base = act_base; cx.wst_base = wst_base; cx.tmem_base = tmem_base;
     cx.w_full = w_full; cx.w_empty = w_empty; cx.a_full = a_full; cx.a_empty = a_empty; cx.acc_full = acc_full; cx.acc_empty = acc_empty;
     if (NG >= 3 || g.swap == 2) {
-#define VF_S2(PA, UU) issuer_loop_swap2<PA, UU>(g, cx, acc_cols)
+      // units of this warp: all of them, or with two issuers the first ceil(U/2) (warp 1) / the rest (warp 3)
+      const bool dual = dual_issue(g);
+      const int first = (dual && warp == 3) ? (g.units + 1) / 2 : 0;
+      const int count = dual ? (warp == 3 ? g.units - first : (g.units + 1) / 2) : g.units;
+#define VF_S2(PA, UU) issuer_loop_swap2<PA, UU>(g, cx, acc_cols, first)
       if (g.passes == 3) {
-        switch (g.units) {
+        switch (count) {
           case 1: VF_S2(3, 1); break; case 2: VF_S2(3, 2); break; case 3: VF_S2(3, 3); break; case 4: VF_S2(3, 4); break;
           default: VF_S2(3, 5); break;
         }
       } else {
-        switch (g.units) {
+        switch (count) {
           case 1: VF_S2(1, 1); break; case 2: VF_S2(1, 2); break; case 3: VF_S2(1, 3); break; case 4: VF_S2(1, 4); break;
           default: VF_S2(1, 5); break;
         }
@@ -1506,6 +1518,8 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   if (!plan_geometry(layout, bo, w.k, w.kw, w.kcl, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
   P.g.out_scale = ldexpf(1.0f, -w.scale_log2);
   P.g.m_Wp = fd_magic(P.g.Wp); P.g.m_npass = fd_magic(P.g.npass); P.g.m_np = fd_magic(P.g.np > 0 ? P.g.np : 1);
+  static const int dual_env = getenv("VF_DUAL_ISSUE") ? atoi(getenv("VF_DUAL_ISSUE")) : 1;
+  P.g.dual = dual_env;
   P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B; P.act = c.act;
   P.stats_partial = nullptr; P.stats_S = 0;
   P.stats_fin = nullptr; P.stats_cnt = nullptr; P.stats_npix = c.H * c.W; P.stats_eps = c.stats_eps;
