@@ -1098,6 +1098,268 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
   }
 }
 
+// =====================================================================================================================
+// CTA-PAIR variant (tcgen05 cta_group::2) of the wide tiling for 16x16 maps with Cout % 256 == 0 (the 16x16 conv-LSTM gate
+// convolutions).  Two CTAs of a cluster (one TPC) compute ONE 256-channel x 256-pixel tile: CTA r holds the weight rows
+// [128 r, 128 r + 128) of the tile (its own A half) and the image rows [8 r, 8 r + 8) (+ halo: its half of the B operand);
+// the leader's elected lane issues M = 256 MMAs whose B operand is read half from each SM, so every SM reads HALF the pixel
+// rows per MMA from its shared memory — the single-CTA kernel is bound by exactly that traffic (ncu: L1/shared 69 %, tensor
+// pipe 69 % on these layers).  Accumulators: each CTA's TMEM gets its 128 channels x 256 pixels; epilogue as in the wide tiling.
+//
+// Synchronisation (same barrier offsets in both CTAs):
+//   w_full[s] / a_full[buf]   local TMA arrival.  The PEER's warp 3 relays every completion to the leader's w_peer[s] /
+//                             a_peer[buf] (remote mbarrier arrive, cluster scope); the leader's issuer waits for both.
+//   w_empty / a_empty / acc_full   tcgen05.commit.cta_group::2 with multicast mask 0b11: released in both CTAs at once.
+//   acc_empty[a] (leader)     16 arrivals: the 8 epilogue warps of each CTA (the peer's arrive remotely).
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope (peer-signalled barriers)
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (!done && spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {     // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+constexpr int PAIR_THREADS = 384;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) k_conv_pair(const __grid_constant__ Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  const Geometry& g = P.g;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t act_base = sbase;
+  const uint32_t wst_base = sbase + (uint32_t)(g.nbuf * 2 * g.plane_bytes);
+  uint8_t* tail = smem + g.nbuf * 2 * g.plane_bytes + g.nstage * g.stage_bytes;
+  float* s_sab_all = reinterpret_cast<float*>(tail);                     // [2 halves][25 classes][128 channels]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * 25 * MT * sizeof(float));
+  uint64_t *w_full = bars, *w_empty = bars + MAX_STAGE, *w_peer = bars + 2 * MAX_STAGE;
+  uint64_t *a_full = bars + 3 * MAX_STAGE, *a_empty = a_full + 2, *a_peer = a_empty + 2;
+  uint64_t *acc_full = a_peer + 2, *acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);       // 24 + 10 barriers = 272 bytes < the 512 reserved (PAIR_SLACK)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&w_peer[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_peer[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();                                                    // barriers of both CTAs exist before anyone signals them
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int n_tile = g.Cout / 256;                                        // 256-channel tiles
+  const int nitems = n_tile * P.B;
+  const int Hh = g.H / 2;                                                 // image rows per CTA
+  const uint32_t ltype = 4u;                                              // SWIZZLE_64B
+  const int nplanes = g.passes == 3 ? 2 : 1;
+
+  if (warp == 0) {
+    // ===== weight producer: this CTA's 128 rows of the 256-channel tile =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t bytes = g.passes == 3 ? (uint32_t)g.stage_bytes : (uint32_t)g.half_bytes;
+      for (int item = pair; item < nitems; item += npairs) {
+        const int mt = (item / P.B) * 2 + (int)rank;
+        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.w) + (size_t)mt * g.nchunk * g.nst * g.stage_bytes;
+        for (int ct = 0; ct < g.nchunk * g.nst; ++ct) {
+          mbar_wait(&w_empty[s], ph ^ 1);
+          mbar_expect_tx(&w_full[s], bytes);
+          bulk_g2s(wst_base + s * g.stage_bytes, wbase + (size_t)ct * g.stage_bytes, bytes, &w_full[s]);
+          if (++s == g.nstage) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== activation producer: this CTA's Hh image rows (+ halo) of every channel chunk =====
+    if (lane == 0) {
+      uint32_t job = 0;
+      for (int item = pair; item < nitems; item += npairs) {
+        const int b = item % P.B;
+        for (int c = 0; c < g.nchunk; ++c, ++job) {
+          const int buf = job & 1;
+          mbar_wait(&a_empty[buf], ((job >> 1) & 1) ^ 1);
+          mbar_expect_tx(&a_full[buf], (uint32_t)(nplanes * g.box_bytes));
+          for (int pl = 0; pl < nplanes; ++pl)
+            tma_load_5d(act_base + (uint32_t)((buf * 2 + pl) * g.plane_bytes), &P.tmap0, c * g.ch, -g.padx, (int)rank * Hh - g.pad, b, pl,
+                        &a_full[buf]);
+        }
+      }
+    }
+  } else if (warp == 3 && !leader) {
+    // ===== relay (peer): forward "my half has landed" to the leader's w_peer / a_peer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0, job = 0;
+      for (int item = pair; item < nitems; item += npairs) {
+        for (int c = 0; c < g.nchunk; ++c, ++job) {
+          const int buf = job & 1;
+          mbar_wait(&a_full[buf], (job >> 1) & 1);
+          mbar_arrive_cluster(map_to_cta(smem_u32(&a_peer[buf]), 0));
+          for (int t = 0; t < g.nst; ++t) {
+            mbar_wait(&w_full[s], ph);
+            mbar_arrive_cluster(map_to_cta(smem_u32(&w_peer[s]), 0));
+            if (++s == g.nstage) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===== MMA issuer (leader CTA only): M = 256 over the pair, two N = 128 MMAs (left / right 8-pixel groups) per K step =====
+    const uint32_t pix_b = (uint32_t)g.row_bytes;
+    const uint64_t da_zero = make_desc(0, 16u, 8u * pix_b, ltype, 0);
+    const uint64_t db_zero = make_desc(0, 16u, (uint32_t)g.Wp * pix_b, ltype, 0);     // group pitch = padded image row
+    const uint64_t a_half = (uint64_t)(g.half_bytes >> 4), b_plane = (uint64_t)(g.plane_bytes >> 4);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // D f32, A = B = f16, N = 128, M = 256
+    const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
+    const uint64_t pix16 = (uint64_t)(pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.kw) * pix_b) >> 4);
+    const uint64_t right16 = (uint64_t)((8u * pix_b) >> 4);               // the right 8-pixel group starts 8 pixel rows later
+    const uint64_t da_base = da_zero + (uint64_t)(wst_base >> 4), db_base = db_zero + (uint64_t)(act_base >> 4);
+    int s = 0;
+    uint32_t ph = 0, job = 0, it = 0;
+    for (int item = pair; item < nitems; item += npairs, ++it) {
+      const int a = (int)(it & 1u);
+      mbar_wait_cluster(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(a * 256);
+      uint32_t acc = 0;
+      for (int c = 0; c < g.nchunk; ++c, ++job) {
+        const int buf = job & 1;
+        mbar_wait(&a_full[buf], (job >> 1) & 1);
+        mbar_wait_cluster(&a_peer[buf], (job >> 1) & 1);
+        tc_fence_after();
+        uint64_t db_tap = db_base + (uint64_t)(buf * buf16);
+        int tx = 0;
+        for (int tap = 0; tap < g.nst; ++tap) {
+          mbar_wait(&w_full[s], ph);
+          mbar_wait_cluster(&w_peer[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da_st = da_base + (uint64_t)(s * stage16);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              if (pass < g.passes) {
+                const uint64_t da_p = da_st + (pass == 2 ? a_half : 0), db_p = db_tap + (pass == 1 ? b_plane : 0);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const uint64_t da = da_p + (uint64_t)(j * 2), db = db_p + (uint64_t)(j * 2);
+                  tc_mma_f16_pair(d0, da, db, idesc, (pass | j) == 0 ? acc : 1u);
+                  tc_mma_f16_pair(d0 + 128u, da, db + right16, idesc, (pass | j) == 0 ? acc : 1u);
+                }
+              }
+            }
+            tc_commit_pair(&w_empty[s]);
+          }
+          acc = 1;
+          if (++s == g.nstage) { s = 0; ph ^= 1; }
+          db_tap += pix16;
+          if (++tx == g.kw) { tx = 0; db_tap += rowskip16; }
+        }
+        if (elect_one()) tc_commit_pair(&a_empty[buf]);
+      }
+      if (elect_one()) tc_commit_pair(&acc_full[a]);
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===== epilogue: this CTA's 128 channels x 256 pixels (columns [0,128) = left 8-pixel group of the 16 rows, [128,256) right) =====
+    const int q4 = warp & 3, row = q4 * 32 + lane, half = (warp - EPI_WARP0) >> 2;
+    float* s_sab = s_sab_all + half * 25 * MT;
+    const int ps = P.out.pix_stride, W = g.W, H = g.H, pad = g.padc, kk = g.kcl;
+    const float scale = g.out_scale;
+    const uint32_t acc_empty_leader = map_to_cta(smem_u32(acc_empty), 0);
+    uint32_t it = 0;
+    for (int item = pair; item < nitems; item += npairs, ++it) {
+      const int b = item % P.B;
+      const int n = ((item / P.B) * 2 + (int)rank) * MT + row;
+      const int a = (int)(it & 1u);
+      {                                              // this thread's column of the per-sample class table (private: no sync)
+        if (P.sabias) {
+          const float* sp = P.sabias + (long long)b * g.ntap * g.Cout + n;
+          for (int cls = 0; cls < g.ntap; ++cls) s_sab[cls * MT + row] = __ldg(sp + (long long)cls * g.Cout);
+        } else {
+          const float bv = P.bias ? __ldg(P.bias + n) : 0.f;
+          for (int cls = 0; cls < g.ntap; ++cls) s_sab[cls * MT + row] = bv;
+        }
+      }
+      mbar_wait_cluster(&acc_full[a], (it >> 1) & 1);
+      tc_fence_after();
+      float* op = P.out.p + (long long)b * P.out.sample_stride + P.out.ch_off + n;
+      double st_s = 0.0, st_q = 0.0;
+      for (int cc = half * 32; cc < 256; cc += 64) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * 256 + cc), r);
+        const int xoff = (cc >> 7) * 8;              // second half of the columns = right 8-pixel group
+        const int oy0 = (cc & 127) >> 3;             // 32 columns = 4 image rows x 8 pixels
+        float cs = 0.f, cq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int oy = oy0 + (j >> 3), x = (j & 7) + xoff;
+          const int cx = x < pad ? x : (x >= W - pad ? x - (W - 1 - 2 * pad) : pad);
+          const float bias = s_sab[(border_class(oy, H, pad) * kk + cx) * MT + row];
+          const float val = fmaf(__uint_as_float(r[j]), scale, bias);
+          op[(oy * W + x) * ps] = val;
+          cs += val;
+          cq = fmaf(val, val, cq);
+        }
+        st_s += (double)cs;
+        st_q += (double)cq;
+      }
+      if (P.stats_partial) {                         // slot = column half (2 slots per (sample, channel))
+        double* o = P.stats_partial + (((long long)b * g.Cout + n) * P.stats_S + half) * 2;
+        o[0] = st_s;
+        o[1] = st_q;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty_leader + (uint32_t)(a * 8));   // the leader's acc_empty[a] (8 bytes per barrier)
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                                // nobody frees TMEM / exits while the peer still uses the pair's resources
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 int g_num_sms = 0;
 constexpr size_t SMEM_LIMIT = 227 * 1024;
@@ -1516,6 +1778,21 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   if (layout == 2 && !(w.cin % 64 == 0 && w.cout >= 128)) layout = 1;   // must agree with mma_conv_prepare_weights
   if (c.src.C + c.src1.C != w.cin) return -5;
   if (!plan_geometry(layout, bo, w.k, w.kw, w.kcl, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
+  // CTA-pair kernel (cta_group::2) for the 16x16 wide layers with whole 256-channel tiles: VF_CTA_PAIR=1 (experiment)
+  static const bool pair_env = getenv("VF_CTA_PAIR") && atoi(getenv("VF_CTA_PAIR")) == 1;
+  const bool pair = pair_env && P.g.rg == 2 && P.g.layout == 1 && w.cout % 256 == 0 && c.src1.C == 0 && !c.out.lo_off &&
+                    c.act == ACT_NONE && (P.g.H % 2) == 0;
+  if (pair) {                                             // every CTA stages half of the image rows (+ halo)
+    Geometry& g = P.g;
+    g.R = g.H / 2 + 2 * g.pad;
+    g.box_bytes = g.R * g.Wp * g.row_bytes;
+    g.img_pix = (g.R * g.Wp + 7) / 8 * 8;
+    g.plane_bytes = ((g.img_pix + 16) * g.row_bytes + 1023) / 1024 * 1024;
+    g.nbuf = 2;
+    const size_t fixed = 1024 + 2 * 25 * MT * 4 + 512 + (size_t)2 * 2 * g.plane_bytes;
+    g.nstage = (int)std::min<size_t>(MAX_STAGE, (SMEM_LIMIT - fixed) / g.stage_bytes);
+    if (g.nstage < 2) return -8;
+  }
   P.g.out_scale = ldexpf(1.0f, -w.scale_log2);
   P.g.m_Wp = fd_magic(P.g.Wp); P.g.m_npass = fd_magic(P.g.npass); P.g.m_np = fd_magic(P.g.np > 0 ? P.g.np : 1);
   static const int dual_env = getenv("VF_DUAL_ISSUE") ? atoi(getenv("VF_DUAL_ISSUE")) : 1;
@@ -1557,6 +1834,19 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
     }
   }
   if (c.stats_slots) *c.stats_slots = P.stats_S;
+  if (pair) {
+    static bool pair_attr = false;
+    if (!pair_attr) {
+      if (cudaFuncSetAttribute(k_conv_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) != cudaSuccess) return -3;
+      pair_attr = true;
+    }
+    if (c.stats_finalized) *c.stats_finalized = false;
+    const int nitems_pair = (w.cout / 256) * B;
+    const int pairs = std::min(nitems_pair, (g_num_sms > 0 ? g_num_sms : 148) / 2);
+    const size_t psmem = 1024 + 2 * 25 * MT * 4 + 512 + (size_t)2 * 2 * P.g.plane_bytes + (size_t)P.g.nstage * P.g.stage_bytes;
+    ++g_launch_counter;
+    return launch_k(k_conv_pair, dim3(2 * pairs), dim3(PAIR_THREADS), psmem, s, P) == cudaSuccess ? 0 : -4;
+  }
   if (P.stats_partial && c.stats_fin && c.stats_cnt && (P.g.n_mt * 4 <= VF_STAT_CNT_STRIDE)) { P.stats_fin = c.stats_fin; P.stats_cnt = c.stats_cnt; }
   if (c.stats_finalized) *c.stats_finalized = P.stats_fin != nullptr;
   ++g_launch_counter;
