@@ -1101,14 +1101,18 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
 // =====================================================================================================================
 // CTA-PAIR variant (tcgen05 cta_group::2) of the wide tiling for 16x16 maps with Cout % 256 == 0 (the 16x16 conv-LSTM gate
 // convolutions).  Two CTAs of a cluster (one TPC) compute ONE 256-channel x 256-pixel tile: CTA r holds the weight rows
-// [128 r, 128 r + 128) of the tile (its own A half) and the image rows [8 r, 8 r + 8) (+ halo: its half of the B operand);
-// the leader's elected lane issues M = 256 MMAs whose B operand is read half from each SM, so every SM reads HALF the pixel
-// rows per MMA from its shared memory — the single-CTA kernel is bound by exactly that traffic (ncu: L1/shared 69 %, tensor
-// pipe 69 % on these layers).  Accumulators: each CTA's TMEM gets its 128 channels x 256 pixels; epilogue as in the wide tiling.
+// [128 r, 128 r + 128) of the tile (its own A half) and the 8-pixel COLUMN GROUP r of all 16 image rows (x in [8 r, 8 r + 8)
+// + halo: its half of the B operand, a 12-pixel-wide box); the leader's elected lane issues ONE M = 256 x N = 256 MMA per K
+// step (the single-CTA kernel needs two N = 128 MMAs, one per column group) whose B operand is read half from each SM: per
+// MMA an SM reads 4 KB of weights + 4 KB of pixels for 128 clk of math, against 4 + 4 KB per 64 clk in the single-CTA kernel,
+// which is bound by exactly that shared-memory traffic (ncu: L1/shared 69 %, tensor pipe 69 % on these layers).
+// Accumulators: each CTA's TMEM gets its 128 channels x 256 pixels; epilogue as in the wide tiling.
 //
 // Synchronisation (same barrier offsets in both CTAs):
-//   w_full[s] / a_full[buf]   local TMA arrival.  The PEER's warp 3 relays every completion to the leader's w_peer[s] /
-//                             a_peer[buf] (remote mbarrier arrive, cluster scope); the leader's issuer waits for both.
+//   w_full[s] / a_full[buf]   live in the LEADER: both CTAs' loads are tensor TMA with .cta_group::2, whose completion bytes may
+//                             target the peer's barrier — the leader expects the bytes of both halves (a first version relayed
+//                             the peer's completions through a thread: its release-arrive cost a membar per stage and capped
+//                             the kernel at 201 us).
 //   w_empty / a_empty / acc_full   tcgen05.commit.cta_group::2 with multicast mask 0b11: released in both CTAs at once.
 //   acc_empty[a] (leader)     16 arrivals: the 8 epilogue warps of each CTA (the peer's arrive remotely).
 // =====================================================================================================================
@@ -1136,6 +1140,19 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     if (!done && spins > (1u << 26)) __trap();
   }
 }
+// tensor TMA whose completion is counted on a barrier of EITHER CTA of the pair (mbar: shared::cluster address)
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, int c4, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -1158,18 +1175,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) k_c
   uint8_t* tail = smem + g.nbuf * 2 * g.plane_bytes + g.nstage * g.stage_bytes;
   float* s_sab_all = reinterpret_cast<float*>(tail);                     // [2 halves][25 classes][128 channels]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * 25 * MT * sizeof(float));
-  uint64_t *w_full = bars, *w_empty = bars + MAX_STAGE, *w_peer = bars + 2 * MAX_STAGE;
-  uint64_t *a_full = bars + 3 * MAX_STAGE, *a_empty = a_full + 2, *a_peer = a_empty + 2;
-  uint64_t *acc_full = a_peer + 2, *acc_empty = acc_full + 2;
+  uint64_t *w_full = bars, *w_empty = bars + MAX_STAGE;
+  uint64_t *a_full = bars + 2 * MAX_STAGE, *a_empty = a_full + 2;
+  uint64_t *acc_full = a_empty + 2, *acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);       // 24 + 10 barriers = 272 bytes < the 512 reserved (PAIR_SLACK)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   const bool leader = rank == 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); mbar_init(&w_peer[i], 1); }
+    for (int i = 0; i < MAX_STAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_peer[i], 1);
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
       mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1189,71 +1206,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) k_c
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int n_tile = g.Cout / 256;                                        // 256-channel tiles
   const int nitems = n_tile * P.B;
-  const int Hh = g.H / 2;                                                 // image rows per CTA
   const uint32_t ltype = 4u;                                              // SWIZZLE_64B
   const int nplanes = g.passes == 3 ? 2 : 1;
 
   if (warp == 0) {
     // ===== weight producer: this CTA's 128 rows of the 256-channel tile =====
+    // (P.tmap1 = the packed weights as a 2-D tensor: rows of 512 bytes, one 16 KB stage = 32 rows)
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t bytes = g.passes == 3 ? (uint32_t)g.stage_bytes : (uint32_t)g.half_bytes;
+      const uint32_t w_full_leader = map_to_cta(smem_u32(w_full), 0);
+      const int rows_per_stage = g.stage_bytes / 512;
       for (int item = pair; item < nitems; item += npairs) {
         const int mt = (item / P.B) * 2 + (int)rank;
-        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.w) + (size_t)mt * g.nchunk * g.nst * g.stage_bytes;
+        const int stage0 = mt * g.nchunk * g.nst;
         for (int ct = 0; ct < g.nchunk * g.nst; ++ct) {
           mbar_wait(&w_empty[s], ph ^ 1);
-          mbar_expect_tx(&w_full[s], bytes);
-          bulk_g2s(wst_base + s * g.stage_bytes, wbase + (size_t)ct * g.stage_bytes, bytes, &w_full[s]);
+          if (leader) mbar_expect_tx(&w_full[s], 2u * (uint32_t)g.stage_bytes);      // both CTAs' halves
+          tma_load_2d_pair(wst_base + s * g.stage_bytes, &P.tmap1, 0, (stage0 + ct) * rows_per_stage, w_full_leader + (uint32_t)(s * 8));
           if (++s == g.nstage) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 2) {
-    // ===== activation producer: this CTA's Hh image rows (+ halo) of every channel chunk =====
+    // ===== activation producer: this CTA's 8-pixel column group (+ halo) of every channel chunk =====
     if (lane == 0) {
       uint32_t job = 0;
+      const uint32_t a_full_leader = map_to_cta(smem_u32(a_full), 0);
       for (int item = pair; item < nitems; item += npairs) {
         const int b = item % P.B;
         for (int c = 0; c < g.nchunk; ++c, ++job) {
           const int buf = job & 1;
           mbar_wait(&a_empty[buf], ((job >> 1) & 1) ^ 1);
-          mbar_expect_tx(&a_full[buf], (uint32_t)(nplanes * g.box_bytes));
+          if (leader) mbar_expect_tx(&a_full[buf], 2u * (uint32_t)(nplanes * g.box_bytes));
           for (int pl = 0; pl < nplanes; ++pl)
-            tma_load_5d(act_base + (uint32_t)((buf * 2 + pl) * g.plane_bytes), &P.tmap0, c * g.ch, -g.padx, (int)rank * Hh - g.pad, b, pl,
-                        &a_full[buf]);
-        }
-      }
-    }
-  } else if (warp == 3 && !leader) {
-    // ===== relay (peer): forward "my half has landed" to the leader's w_peer / a_peer =====
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0, job = 0;
-      for (int item = pair; item < nitems; item += npairs) {
-        for (int c = 0; c < g.nchunk; ++c, ++job) {
-          const int buf = job & 1;
-          mbar_wait(&a_full[buf], (job >> 1) & 1);
-          mbar_arrive_cluster(map_to_cta(smem_u32(&a_peer[buf]), 0));
-          for (int t = 0; t < g.nst; ++t) {
-            mbar_wait(&w_full[s], ph);
-            mbar_arrive_cluster(map_to_cta(smem_u32(&w_peer[s]), 0));
-            if (++s == g.nstage) { s = 0; ph ^= 1; }
-          }
+            tma_load_5d_pair(act_base + (uint32_t)((buf * 2 + pl) * g.plane_bytes), &P.tmap0, c * g.ch, (int)rank * 8 - g.padx, -g.pad, b, pl,
+                             a_full_leader + (uint32_t)(buf * 8));
         }
       }
     }
   } else if (warp == 1 && leader) {
-    // ===== MMA issuer (leader CTA only): M = 256 over the pair, two N = 128 MMAs (left / right 8-pixel groups) per K step =====
+    // ===== MMA issuer (leader CTA only): M = 256 x N = 256 over the pair, one MMA per K step =====
     const uint32_t pix_b = (uint32_t)g.row_bytes;
     const uint64_t da_zero = make_desc(0, 16u, 8u * pix_b, ltype, 0);
     const uint64_t db_zero = make_desc(0, 16u, (uint32_t)g.Wp * pix_b, ltype, 0);     // group pitch = padded image row
     const uint64_t a_half = (uint64_t)(g.half_bytes >> 4), b_plane = (uint64_t)(g.plane_bytes >> 4);
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // D f32, A = B = f16, N = 128, M = 256
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // D f32, A = B = f16, N = 256, M = 256
     const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
     const uint64_t pix16 = (uint64_t)(pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.kw) * pix_b) >> 4);
-    const uint64_t right16 = (uint64_t)((8u * pix_b) >> 4);               // the right 8-pixel group starts 8 pixel rows later
     const uint64_t da_base = da_zero + (uint64_t)(wst_base >> 4), db_base = db_zero + (uint64_t)(act_base >> 4);
     int s = 0;
     uint32_t ph = 0, job = 0, it = 0;
@@ -1265,14 +1265,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) k_c
       uint32_t acc = 0;
       for (int c = 0; c < g.nchunk; ++c, ++job) {
         const int buf = job & 1;
-        mbar_wait(&a_full[buf], (job >> 1) & 1);
-        mbar_wait_cluster(&a_peer[buf], (job >> 1) & 1);
+        mbar_wait_cluster(&a_full[buf], (job >> 1) & 1);
         tc_fence_after();
         uint64_t db_tap = db_base + (uint64_t)(buf * buf16);
         int tx = 0;
         for (int tap = 0; tap < g.nst; ++tap) {
-          mbar_wait(&w_full[s], ph);
-          mbar_wait_cluster(&w_peer[s], ph);
+          mbar_wait_cluster(&w_full[s], ph);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da_st = da_base + (uint64_t)(s * stage16);
@@ -1283,8 +1281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) k_c
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                   const uint64_t da = da_p + (uint64_t)(j * 2), db = db_p + (uint64_t)(j * 2);
-                  tc_mma_f16_pair(d0, da, db, idesc, (pass | j) == 0 ? acc : 1u);
-                  tc_mma_f16_pair(d0 + 128u, da, db + right16, idesc, (pass | j) == 0 ? acc : 1u);
+                  tc_mma_f16_pair(d0, da, db, idesc, (pass | j) == 0 ? acc : 1u);   // columns [0,128) from CTA 0's group, [128,256) from CTA 1's
                 }
               }
             }
@@ -1781,10 +1778,11 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   // CTA-pair kernel (cta_group::2) for the 16x16 wide layers with whole 256-channel tiles: VF_CTA_PAIR=1 (experiment)
   static const bool pair_env = getenv("VF_CTA_PAIR") && atoi(getenv("VF_CTA_PAIR")) == 1;
   const bool pair = pair_env && P.g.rg == 2 && P.g.layout == 1 && w.cout % 256 == 0 && c.src1.C == 0 && !c.out.lo_off &&
-                    c.act == ACT_NONE && (P.g.H % 2) == 0;
-  if (pair) {                                             // every CTA stages half of the image rows (+ halo)
+                    c.act == ACT_NONE && c.passes == 3;
+  if (pair) {                                             // every CTA stages ONE 8-pixel column group of all rows (+ halo)
     Geometry& g = P.g;
-    g.R = g.H / 2 + 2 * g.pad;
+    g.Wp = 8 + g.kw - 1;
+    g.R = g.H + 2 * g.pad;
     g.box_bytes = g.R * g.Wp * g.row_bytes;
     g.img_pix = (g.R * g.Wp + 7) / 8 * 8;
     g.plane_bytes = ((g.img_pix + 16) * g.row_bytes + 1023) / 1024 * 1024;
@@ -1835,6 +1833,28 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   }
   if (c.stats_slots) *c.stats_slots = P.stats_S;
   if (pair) {
+    // the packed weights as a 2-D tensor (rows of 512 bytes; one 16 KB stage = 32 rows) for the pair's tensor-TMA weight loads
+    {
+      struct WMap { const void* p; cuuint64_t rows; CUtensorMap m; };
+      static std::vector<WMap> wmaps;                       // keyed by (buffer, extent): a freed buffer's address may be reused
+      const cuuint64_t rows = (cuuint64_t)P.g.n_mt * P.g.nchunk * P.g.nst * (P.g.stage_bytes / 512);
+      bool found = false;
+      for (auto& e : wmaps) if (e.p == (const void*)w.w_hi && e.rows == rows) { P.tmap1 = e.m; found = true; }
+      if (!found) {
+        EncodeTiledFn enc = encode_fn();
+        if (!enc) return -12;
+        const cuuint64_t gdim[2] = {256, rows};
+        const cuuint64_t gstride[1] = {512};
+        const cuuint32_t box[2] = {256, (cuuint32_t)(P.g.stage_bytes / 512)};
+        const cuuint32_t estr[2] = {1, 1};
+        CUtensorMap m;
+        if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(w.w_hi), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -13;
+        if (wmaps.size() > 256) wmaps.clear();
+        wmaps.push_back(WMap{(const void*)w.w_hi, rows, m});
+        P.tmap1 = m;
+      }
+    }
     static bool pair_attr = false;
     if (!pair_attr) {
       if (cudaFuncSetAttribute(k_conv_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) != cudaSuccess) return -3;
