@@ -1775,8 +1775,8 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   if (layout == 2 && !(w.cin % 64 == 0 && w.cout >= 128)) layout = 1;   // must agree with mma_conv_prepare_weights
   if (c.src.C + c.src1.C != w.cin) return -5;
   if (!plan_geometry(layout, bo, w.k, w.kw, w.kcl, w.cin, w.cout, c.H, c.W, B, c.passes == 3 ? 3 : 1, &P.g)) return -1;
-  // CTA-pair kernel (cta_group::2) for the 16x16 wide layers with whole 256-channel tiles: VF_CTA_PAIR=1 (experiment)
-  static const bool pair_env = getenv("VF_CTA_PAIR") && atoi(getenv("VF_CTA_PAIR")) == 1;
+  // CTA-pair kernel (cta_group::2) for the 16x16 wide layers with whole 256-channel tiles (k_conv_pair)
+  static const bool pair_env = !(getenv("VF_CTA_PAIR") && atoi(getenv("VF_CTA_PAIR")) == 0);      // default on; VF_CTA_PAIR=0 = single-CTA kernel
   const bool pair = pair_env && P.g.rg == 2 && P.g.layout == 1 && w.cout % 256 == 0 && c.src1.C == 0 && !c.out.lo_off &&
                     c.act == ACT_NONE && c.passes == 3;
   if (pair) {                                             // every CTA stages ONE 8-pixel column group of all rows (+ halo)
