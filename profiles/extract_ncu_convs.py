@@ -31,7 +31,7 @@ if "--step-order-r02" in sys.argv:    # round 2: 14 convolutions per cell step, 
 if "--step-order" in sys.argv:        # the capture starts at the first head conv of a cell step (profiles/ncu_full.sh, skip 640)
     for i, e in enumerate(out): e["layer"] = ORDER[i % len(ORDER)]
 json.dump({"capture": sys.argv[1], "launches": out}, open(sys.argv[2], "w"), indent=1)
-gate = [e for e in out if e["time_us"] and e["time_us"] > 150 and e["kernel"].endswith("<2>")]   # wide-path launches: the conv-LSTM gate convs
+gate = [e for e in out if e["time_us"] and e["time_us"] > 130 and (e["kernel"].endswith("<2>") or "k_conv_pair" in e["kernel"])]   # wide-path / pair launches: the conv-LSTM gate convs
 for e in out: print(e)
 if len(sys.argv) > 3 and gate:
     mean = sum((e["dram_read_MB"] + e["dram_write_MB"]) for e in gate) / len(gate) * 1e6

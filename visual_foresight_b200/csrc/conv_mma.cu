@@ -23,6 +23,9 @@
 //     + border-class bias, optional sigmoid / instance-norm partial sums -> NHWC stores).  Two TMEM accumulator sets and two
 //     activation buffers: the epilogue of item i and the loads of item i+1 overlap the MMAs.
 //
+//   * k_conv_pair (further down): the 16x16 layers with whole 256-channel tiles run on CTA PAIRS (tcgen05 cta_group::2, M = 256):
+//     each SM of a TPC stages half of both operands, one MMA per K step spans both.
+//
 // Operand layouts (VF_MMA_LAYOUT): 1 = SWIZZLE_64B, 32-channel chunks, pixel rows of 64 B (default);
 //                                  2 = SWIZZLE_128B, 64-channel chunks, pixel rows of 128 B.
 // The swizzle XOR acts on absolute shared-memory address bits for TMA and for the MMA descriptors alike (measured:
