@@ -508,7 +508,9 @@ MMA_SHAPES = [(3, 32, 32, 64, 128, 5), (2, 16, 16, 128, 256, 5), (5, 8, 8, 256, 
               # row-stacked thin path: 5x5 with an 8-channel input (first encoder conv), 48x64 frames, many samples, Cout 64
               (2, 64, 64, 8, 32, 5), (3, 48, 64, 8, 32, 5), (9, 32, 32, 32, 64, 3), (5, 24, 32, 64, 32, 3), (2, 8, 8, 16, 16, 5),
               # thin layer whose k*np exceeds 256 columns: one MMA per tap
-              (2, 16, 16, 32, 64, 5)]
+              (2, 16, 16, 32, 64, 5),
+              # CTA-pair kernel off the 16x16 map: 12x16 / 8x16 (48x64 and 32x64 inputs), two 256-channel tiles, odd sample count
+              (3, 12, 16, 128, 256, 5), (2, 8, 16, 64, 512, 5), (1, 4, 16, 32, 256, 3)]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k", MMA_SHAPES)

@@ -1254,7 +1254,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) k_c
     const uint64_t da_zero = make_desc(0, 16u, 8u * pix_b, ltype, 0);
     const uint64_t db_zero = make_desc(0, 16u, (uint32_t)g.Wp * pix_b, ltype, 0);     // group pitch = padded image row
     const uint64_t a_half = (uint64_t)(g.half_bytes >> 4), b_plane = (uint64_t)(g.plane_bytes >> 4);
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // D f32, A = B = f16, N = 256, M = 256
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(g.v_cnt >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // D f32, A = B = f16, N = 16 * H (256 at 16x16), M = 256
     const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
     const uint64_t pix16 = (uint64_t)(pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.kw) * pix_b) >> 4);
     const uint64_t da_base = da_zero + (uint64_t)(wst_base >> 4), db_base = db_zero + (uint64_t)(act_base >> 4);
@@ -1324,11 +1324,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) k_c
       tc_fence_after();
       float* op = P.out.p + (long long)b * P.out.sample_stride + P.out.ch_off + n;
       double st_s = 0.0, st_q = 0.0;
-      for (int cc = half * 32; cc < 256; cc += 64) {
+      for (int cc = half * 32; cc < g.v_cnt; cc += 64) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * 256 + cc), r);
-        const int xoff = (cc >> 7) * 8;              // second half of the columns = right 8-pixel group
-        const int oy0 = (cc & 127) >> 3;             // 32 columns = 4 image rows x 8 pixels
+        const int grp = cc >= g.half_cols;           // second half of the columns = right 8-pixel group
+        const int xoff = grp * 8;
+        const int oy0 = (cc - grp * g.half_cols) >> 3;   // 32 columns = 4 image rows x 8 pixels
         float cs = 0.f, cq = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -1494,7 +1495,8 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
   // v_cnt is rounded up to 32 columns; the overshoot reads zero-filled staging rows and is masked in the epilogue.
   g.We = g.Wp;
   static const bool rg_env = !(getenv("VF_ROWGROUPS") && atoi(getenv("VF_ROWGROUPS")) == 0);
-  if (rg_env && W == 16 && H == 16 && kw == k && layout == 1) {
+  static const bool rg2_anyh = !(getenv("VF_RG2_ANYH") && atoi(getenv("VF_RG2_ANYH")) == 0);   // [1]: 8x16 / 12x16 maps too (48x64 inputs)
+  if (rg_env && W == 16 && (H == 16 || (rg2_anyh && H >= 4 && H < 16 && H % 4 == 0)) && kw == k && layout == 1) {
     // ---- row-group mode 2 (see Geometry::rg) ----
     g.rg = 2; g.G = 1; g.npass = 1; g.We = 8;
     g.half_cols = H * 8; g.v_cnt = 2 * g.half_cols; g.col_stride = g.v_cnt; g.ncols_item = g.v_cnt;

@@ -187,8 +187,6 @@ struct vf_engine {
     bool shared_prefix = true;   // VF_SHARED_PREFIX [1]: context-only cell steps run once on one sample
     bool prefix_cache = true;    // VF_PREFIX_CACHE [1]: CEM iterations 1.. restore the prefix state saved by iteration 0
     bool stats_fin = true;       // VF_STATS_FIN [1]: separate k_stats_finalize launches (1) or consumers finalise on the fly (0; measured 4 % slower)
-    int fin_otf_slots = 0;       // VF_FIN_OTF_SLOTS [0]: planes with at most this many partial slots are finalised by their consumers
-                                 //   (no k_stats_finalize launch for the whole-image items of the 8x8 / 16x16 layers); same arithmetic
     bool epi_stats = true;       // VF_EPI_STATS [1]: instance-norm statistics of the thin convolutions come from their epilogue
     bool merge_heads = true;     // VF_MERGE_HEADS [1]: scratch.conv0 + masks.conv0 as one convolution
     bool side_cdna = false;      // VF_SIDE_CDNA [0] (measured +1.4 ms: the side kernels delay the decoder's launches more than they hide): the CDNA head (dense -> kernels -> apply) runs on a second stream beside the decoder
@@ -653,7 +651,7 @@ int finalize_weights(vf_engine* h) {
 // finalise the S partial sums of n planes into (mean, rstd) pairs and hand both to the consumer
 StatsRef fin_stats(vf_engine* h, const double* partial, int S, int n, int npix, float* dst, bool finalized = false) {
   if (finalized) return stats_ref(partial, S, npix, h->cfg.norm_eps, dst);               // the producer kernel wrote (mean, rstd) already
-  if (!h->opt.stats_fin || S <= h->opt.fin_otf_slots) return stats_ref(partial, S, npix, h->cfg.norm_eps, nullptr);   // the consumer finalises in its prologue
+  if (!h->opt.stats_fin) return stats_ref(partial, S, npix, h->cfg.norm_eps, nullptr);   // the consumer finalises in its prologue
   launch_stats_finalize(partial, n, S, npix, h->cfg.norm_eps, dst, h->stream);
   return stats_ref(partial, S, npix, h->cfg.norm_eps, dst);
 }
@@ -1168,7 +1166,6 @@ int vf_create(const vf_config* cfg, vf_engine** out) {
     h->opt.prefix_cache = flag("VF_PREFIX_CACHE", true);
     h->opt.stats_fin = flag("VF_STATS_FIN", true);
     h->opt.epi_stats = flag("VF_EPI_STATS", true);
-    { const char* e = getenv("VF_FIN_OTF_SLOTS"); h->opt.fin_otf_slots = e && e[0] ? atoi(e) : 0; }
     h->opt.merge_heads = flag("VF_MERGE_HEADS", true) && cfg->precision != VF_PREC_FP32_SIMT;
     h->opt.fuse_fin = flag("VF_FUSE_FIN", false) && h->opt.stats_fin;
     h->opt.hoist_sa = flag("VF_HOIST_SA", true);

@@ -315,92 +315,6 @@ __global__ void __launch_bounds__(256) k_lstm_gates(View gates, int HW, int F, S
   }
 }
 
-// Same arithmetic, one thread = 4 consecutive channels of a pixel, two pixels per iteration: 16-byte accesses and 128 bytes of
-// loads in flight per thread (the scalar kernel above keeps 32 and stalls on them: long_sb 43 % of its samples).  F % 4 == 0,
-// 256 % (F / 4) == 0.  Per-thread float64 sums, pixel lanes combined in ascending lane order.
-__global__ void __launch_bounds__(256) k_lstm_gates4(View gates, int HW, int F, StatsRef gsr,
-                                                     const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c,
-                                                     double* partial, FinArgs fa) {
-  pdl_wait();
-  pdl_trigger();
-  const int b = blockIdx.y;
-  const int F4 = F >> 2, lanes = 256 / F4;
-  const int f = (threadIdx.x % F4) << 2, pl = threadIdx.x / F4;
-  const int per = (HW + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-  float* cb_ = c + (long long)b * HW * F;
-  __shared__ float4 cst[3 * 256];                      // (mean, rstd, gamma, beta) of gates i, j, f per channel
-  for (int t = threadIdx.x; t < 3 * F; t += 256) {
-    const float2 st = stat_of(gsr, (long long)b * gates.C + t);
-    cst[t] = make_float4(st.x, st.y, gg[t], gb[t]);
-  }
-  __syncthreads();
-  double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
-  auto cell = [&](const float4& ai, const float4& aj, const float4& af, const float4& cv) {
-    const float xi[4] = {ai.x, ai.y, ai.z, ai.w}, xj[4] = {aj.x, aj.y, aj.z, aj.w}, xf[4] = {af.x, af.y, af.z, af.w};
-    const float co[4] = {cv.x, cv.y, cv.z, cv.w};
-    float cn[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 ki = cst[f + j], kj = cst[F + f + j], kf = cst[2 * F + f + j];
-      cn[j] = co[j] * sigmoidf_((xf[j] - kf.x) * kf.y * kf.z + kf.w + fb) +
-              sigmoidf_((xi[j] - ki.x) * ki.y * ki.z + ki.w) * tanhf((xj[j] - kj.x) * kj.y * kj.z + kj.w);
-      s[j] += (double)cn[j];
-      q[j] = fma((double)cn[j], (double)cn[j], q[j]);
-    }
-    return make_float4(cn[0], cn[1], cn[2], cn[3]);
-  };
-  int pix = p0 + pl;
-  for (; pix + lanes < p1; pix += 2 * lanes) {
-    const float* gp = vptr(gates, b, pix) + f;
-    const float* gq = vptr(gates, b, pix + lanes) + f;
-    float4* c0p = reinterpret_cast<float4*>(cb_ + (long long)pix * F + f);
-    float4* c1p = reinterpret_cast<float4*>(cb_ + (long long)(pix + lanes) * F + f);
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(gp)), a1 = __ldg(reinterpret_cast<const float4*>(gp + F));
-    const float4 a2 = __ldg(reinterpret_cast<const float4*>(gp + 2 * F));
-    const float4 e0 = __ldg(reinterpret_cast<const float4*>(gq)), e1 = __ldg(reinterpret_cast<const float4*>(gq + F));
-    const float4 e2 = __ldg(reinterpret_cast<const float4*>(gq + 2 * F));
-    const float4 c0 = *c0p, c1 = *c1p;
-    *c0p = cell(a0, a1, a2, c0);
-    *c1p = cell(e0, e1, e2, c1);
-  }
-  for (; pix < p1; pix += lanes) {
-    const float* gp = vptr(gates, b, pix) + f;
-    float4* c0p = reinterpret_cast<float4*>(cb_ + (long long)pix * F + f);
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(gp)), a1 = __ldg(reinterpret_cast<const float4*>(gp + F));
-    const float4 a2 = __ldg(reinterpret_cast<const float4*>(gp + 2 * F));
-    *c0p = cell(a0, a1, a2, *c0p);
-  }
-  __shared__ double red[2][1024];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { red[0][threadIdx.x * 4 + j] = s[j]; red[1][threadIdx.x * 4 + j] = q[j]; }
-  __syncthreads();
-  if (threadIdx.x < F) {                              // thread t = channel t
-    const int ch = threadIdx.x;
-    double ts = 0.0, tq = 0.0;
-    for (int l = 0; l < lanes; ++l) { ts += red[0][(l * F4 + (ch >> 2)) * 4 + (ch & 3)]; tq += red[1][(l * F4 + (ch >> 2)) * 4 + (ch & 3)]; }
-    double* o = partial + (((long long)b * F + ch) * gridDim.x + blockIdx.x) * 2;
-    o[0] = ts;
-    o[1] = tq;
-  }
-  if (fa.fin) {                                      // the last of the sample's gridDim.x blocks finalises the cell-state statistics
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int* cnt = fa.cnt + (long long)b * VF_STAT_CNT_STRIDE;
-      const int last = atomicAdd(cnt, 1) == (int)gridDim.x - 1;
-      if (last) *cnt = 0;
-      s_last = last;
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x < F) {
-      __threadfence();
-      finalize_plane(partial + ((long long)b * F + threadIdx.x) * gridDim.x * 2, gridDim.x, HW, fa.eps, fa.fin + ((long long)b * F + threadIdx.x) * 2);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(256) k_lstm_gates_generic(View gates, int HW, int F, const float* __restrict__ gstats,
                                                             const float* __restrict__ gg, const float* __restrict__ gb, float fb, float* c) {
   const int b = blockIdx.y;
@@ -415,7 +329,6 @@ __global__ void __launch_bounds__(256) k_lstm_gates_generic(View gates, int HW, 
   }
 }
 
-template <int U>     // U = 2: two items in flight per thread (A/B: U = 1)
 __global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, StatsRef gsr,
                                                   const float* __restrict__ gg, const float* __restrict__ gb,
                                                   StatsRef csr, const float* __restrict__ cg,
@@ -433,17 +346,19 @@ __global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, Sta
     ca[f] = cs.x; cd[f] = cs.y; oa[f] = os.x; od[f] = os.y;
   }
   __syncthreads();
-  // one thread = 4 consecutive channels of one pixel (16-byte accesses), two such items in flight per iteration
-  const int F4 = F >> 2, n4 = total >> 2, stride = gridDim.x * blockDim.x;
-  const float* gbase = vptr(gates, b, 0) + 3 * F;
-  auto item = [&](int i, const float4& cv, const float4& ov) {
+  // one thread = 4 consecutive channels of one pixel (16-byte accesses)
+  const int F4 = F >> 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (total >> 2); i += gridDim.x * blockDim.x) {
     const int f = (i % F4) << 2, pix = i / F4;
+    float4* cp = reinterpret_cast<float4*>(cb_ + (long long)pix * F + f);
+    const float4 cv = *cp;
+    const float4 ov = __ldg(reinterpret_cast<const float4*>(vptr(gates, b, pix) + 3 * F + f));
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(cg + f)), b4 = __ldg(reinterpret_cast<const float4*>(cb + f));
     const float4 og = __ldg(reinterpret_cast<const float4*>(gg + 3 * F + f)), ob = __ldg(reinterpret_cast<const float4*>(gb + 3 * F + f));
     float4 cn, hv;
     cn.x = (cv.x - ca[f]) * cd[f] * g4.x + b4.x;             cn.y = (cv.y - ca[f + 1]) * cd[f + 1] * g4.y + b4.y;
     cn.z = (cv.z - ca[f + 2]) * cd[f + 2] * g4.z + b4.z;     cn.w = (cv.w - ca[f + 3]) * cd[f + 3] * g4.w + b4.w;
-    *reinterpret_cast<float4*>(cb_ + (long long)pix * F + f) = cn;
+    *cp = cn;
     hv.x = tanhf(cn.x) * sigmoidf_((ov.x - oa[f]) * od[f] * og.x + ob.x);
     hv.y = tanhf(cn.y) * sigmoidf_((ov.y - oa[f + 1]) * od[f + 1] * og.y + ob.y);
     hv.z = tanhf(cn.z) * sigmoidf_((ov.z - oa[f + 2]) * od[f + 2] * og.z + ob.z);
@@ -453,18 +368,7 @@ __global__ void __launch_bounds__(256) k_lstm_out(View gates, int HW, int F, Sta
       const int y = pix / W, x = pix - y * W;
       vst4(h2, voff(h2, b, (long long)(y >> 1) * (W >> 1) + (x >> 1)) + ((y & 1) * 2 + (x & 1)) * F + f, hv);
     }
-  };
-  auto gate_o = [&](int i) {
-    return __ldg(reinterpret_cast<const float4*>(gbase + (long long)(i / F4) * gates.pix_stride + ((i % F4) << 2)));
-  };
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  for (; U == 2 && i + stride < n4; i += 2 * stride) {
-    const float4 cv0 = *reinterpret_cast<const float4*>(cb_ + (long long)i * 4), cv1 = *reinterpret_cast<const float4*>(cb_ + (long long)(i + stride) * 4);
-    const float4 ov0 = gate_o(i), ov1 = gate_o(i + stride);
-    item(i, cv0, ov0);
-    item(i + stride, cv1, ov1);
   }
-  for (; i < n4; i += stride) item(i, *reinterpret_cast<const float4*>(cb_ + (long long)i * 4), gate_o(i));
 }
 
 // Both halves of the conv-LSTM pointwise (k_lstm_gates + k_lstm_out) in ONE kernel: a thread-block cluster of CL CTAs owns
@@ -946,12 +850,6 @@ inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
   return (int)g;
 }
 
-// VF_LSTM_PW [3]: bit 0 = 16-byte k_lstm_gates4, bit 1 = two items in flight in k_lstm_out (A/B switch, read once)
-inline int lstm_pw_variant() {
-  static const int v = getenv("VF_LSTM_PW") && getenv("VF_LSTM_PW")[0] ? atoi(getenv("VF_LSTM_PW")) : 3;
-  return v;
-}
-
 }  // namespace
 
 int launch_plane_stats(View x, int B, int H, int W, int pool, double* partial, cudaStream_t s, float* fin, int* cnt, float eps) {
@@ -989,11 +887,7 @@ int launch_lstm_gates(View gates, int B, int HW, int F, StatsRef gstats, const f
   dim3 grid(S, B);
   FinArgs fa;
   fa.fin = cnt ? fin : nullptr; fa.cnt = cnt; fa.eps = eps;
-  const bool v4 = lstm_pw_variant() & 1;
-  if (v4 && F % 4 == 0 && 256 % (F / 4) == 0 && F <= 256 && (gates.pix_stride | gates.ch_off) % 4 == 0 && gates.sample_stride % 4 == 0)
-    launch_k(k_lstm_gates4, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, fb, c, partial, fa);
-  else
-    launch_k(k_lstm_gates, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, fb, c, partial, fa);
+  launch_k(k_lstm_gates, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, fb, c, partial, fa);
   return S;
 }
 void launch_lstm_gates_generic(View gates, int B, int HW, int F, const float* gstats, const float* gg, const float* gb,
@@ -1010,8 +904,7 @@ void launch_lstm_out(View gates, int B, int HW, int F, StatsRef gstats, const fl
                      StatsRef cstats, const float* cg, const float* cb, float* c, View h, cudaStream_t s, View h2, int W) {
   ++g_launch_counter;
   dim3 grid(grid_for((long long)HW * F / 4, 256, B >= 64 ? 16 : 64), B);
-  if (lstm_pw_variant() & 2) launch_k(k_lstm_out<2>, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h, h2, W);
-  else launch_k(k_lstm_out<1>, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h, h2, W);
+  launch_k(k_lstm_out, dim3(grid), dim3(256), 0, s, gates, HW, F, gstats, gg, gb, cstats, cg, cb, c, h, h2, W);
 }
 // returns false when the shape has no fused instance (the caller runs k_lstm_gates / k_lstm_out)
 bool launch_lstm_fused(View gates, int B, int HW, int F, const float* gfin, const float* gg, const float* gb, float fb,
