@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
   // barrier init and the TMEM allocation above overlap the tail of the previous kernel (programmatic dependent launch);
   // nothing before this point touches global memory
   pdl_wait();
-  pdl_trigger();
+  pdl_trigger_conv();
 
   const int per_mt = g.ngroups * g.npass;
   const uint32_t ltype = g.layout == 1 ? 4u : 2u;
@@ -1204,7 +1204,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) k_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
-  pdl_trigger();
+  pdl_trigger_conv();
 
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int n_tile = g.Cout / 256;                                        // 256-channel tiles

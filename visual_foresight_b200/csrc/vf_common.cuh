@@ -35,10 +35,19 @@ __host__ __device__ inline View make_view(float* p, long long ss, int ps, int co
 // completed and flushed) and pdl_trigger() (lets the next kernel's launch + prologue overlap this kernel).  Without the launch
 // attribute both are no-ops, so the kernels behave identically under plain stream ordering.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-#ifdef VF_PDL_LATE   // experiment: no early trigger (dependents are released when the blocks exit)
+// pdl_trigger_conv(): the persistent one-wave convolution kernels (their dependents can only take SMs a finished CTA has left).
+// Experiments (profiles/build_variant.sh): -DVF_PDL_LATE = no early trigger anywhere (dependents are released when the blocks
+// exit); -DVF_PDL_CONV_ONLY = only the convolution kernels trigger early (a waiting 200 KB convolution CTA must not take an SM
+// from the later waves of a multi-wave pointwise kernel).
+#if defined(VF_PDL_LATE)
 __device__ __forceinline__ void pdl_trigger() {}
+__device__ __forceinline__ void pdl_trigger_conv() {}
+#elif defined(VF_PDL_CONV_ONLY)
+__device__ __forceinline__ void pdl_trigger() {}
+__device__ __forceinline__ void pdl_trigger_conv() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #else
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger_conv() { pdl_trigger(); }
 #endif
 extern bool g_use_pdl;
 template <typename... KArgs, typename... Args>
