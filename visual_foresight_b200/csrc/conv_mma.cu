@@ -77,7 +77,10 @@ struct Geometry {
                     //       taps; the dx shifts are undone in the epilogue (lane shuffles).  1 = one MMA per tap (k*np > 256).
   int np;           // swap: output channels padded to a multiple of 16
   int units;        // swap: 128-pixel units per item
-  int ncols;        // swap: TMEM columns per unit (np, or k*np when row-stacked)
+  int ncols;        // swap: weight rows per stage half (np, or k*np when row-stacked) = MMA N of one pass
+  int stk;          // row-stacked, 3 passes: 1 = the hi and lo weight halves of a stage (contiguous rows) are ONE B operand of
+                    //   N = 2*ncols, so X_hi * [W_hi | W_lo] is one MMA (2 MMAs per K step instead of 3; the W_lo products
+                    //   land in their own ncols TMEM columns and are added in the epilogue).  A unit then owns 2*ncols columns.
   int ustride;      // swap: output pixels per unit (128, or 128-(k-1) when row-stacked: units overlap by the dx halo)
   int nst;          // weight stages per channel chunk (k*k taps, or k filter rows when row-stacked)
   int ksteps_last;  // K=16 steps of the last channel chunk (its zero-padded tail is not multiplied)
@@ -235,6 +238,13 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // explicit shared-space accesses on 32-bit shared addresses (generic pointers cost a cvta sequence per access)
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
@@ -302,10 +312,25 @@ __device__ __forceinline__ void tc_mma_f16_elect32(uint32_t tmem_d, uint32_t a_l
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
       ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
-template <int PASSES, int KSTEPS, int U>
+// STK (3 passes only): pass 0 multiplies X_hi by BOTH weight halves (idesc2: N = 2*ncols), pass 1 X_lo by W_hi; no pass 2.
+template <int PASSES, int KSTEPS, int U, int STK = 0>
 __device__ __forceinline__ void issue_tap_swap(uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t a_plane, uint32_t b_half,
                                                uint32_t kstep, const uint32_t (&uoff)[MAX_UNIT_B], const uint32_t (&ucol)[MAX_UNIT_B],
-                                               uint32_t idesc, uint32_t acc_first) {
+                                               uint32_t idesc, uint32_t acc_first, uint32_t idesc2 = 0) {
+  if constexpr (STK == 1) {
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const uint32_t a_p = a_lo + (pass == 1 ? a_plane : 0u);
+#pragma unroll
+      for (int j = 0; j < KSTEPS; ++j) {
+        const uint32_t a = a_p + j * kstep, b = b_lo + j * kstep;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          tc_mma_f16_elect32(ucol[u], a + uoff[u], a_hi, b, b_hi, pass == 0 ? idesc2 : idesc, (pass | j) == 0 ? acc_first : 1u);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int pass = 0; pass < PASSES; ++pass) {
     const uint32_t a_p = a_lo + (pass == 1 ? a_plane : 0u);
@@ -432,10 +457,10 @@ __device__ __forceinline__ void issuer_loop_swap(const Geometry& g, const IssueC
 // u0: first unit this warp issues (the row-stacked thin layers split the units of an item over TWO issuer warps, 1 and 3:
 // their MMAs go to disjoint accumulator columns, and these layers are bound by the ~10 SASS instructions it takes one warp
 // to get an MMA of N = 48..96 out of the door)
-template <int PASSES, int U>
+template <int PASSES, int U, int STK = 0>
 __device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const IssueCtx& cx, int acc_cols, int u0) {
   const uint32_t unit_step = ((uint32_t)g.ustride * cx.pix_b) >> 4;
-  const uint32_t idesc_b = make_idesc(g.ncols), ncols = (uint32_t)g.ncols;
+  const uint32_t idesc_b = make_idesc(g.ncols), idesc_2 = make_idesc(2 * g.ncols), ncols = (uint32_t)(g.ncols * (1 + STK));
   const int nitems = g.nitems, nchunk = g.nchunk, kk = g.k, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
   const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
   const uint32_t row16 = ((uint32_t)g.Wp * cx.pix_b) >> 4;
@@ -465,8 +490,8 @@ __device__ __forceinline__ void issuer_loop_swap2(const Geometry& g, const Issue
       for (int dy = 0; dy < kk; ++dy) {
         mbar_wait(&cx.w_full[s], ph);
         tc_fence_after();
-        if (ksteps == 2) issue_tap_swap<PASSES, 2, U>(da_row, x_hi, dw_base + (uint32_t)(s * stage16), w_hi, a_plane, b_half, kstep, uoff, ucol, idesc_b, acc);
-        else issue_tap_swap<PASSES, 1, U>(da_row, x_hi, dw_base + (uint32_t)(s * stage16), w_hi, a_plane, b_half, kstep, uoff, ucol, idesc_b, acc);
+        if (ksteps == 2) issue_tap_swap<PASSES, 2, U, STK>(da_row, x_hi, dw_base + (uint32_t)(s * stage16), w_hi, a_plane, b_half, kstep, uoff, ucol, idesc_b, acc, idesc_2);
+        else issue_tap_swap<PASSES, 1, U, STK>(da_row, x_hi, dw_base + (uint32_t)(s * stage16), w_hi, a_plane, b_half, kstep, uoff, ucol, idesc_b, acc, idesc_2);
         tc_commit_elect(&cx.w_empty[s]);
         acc = 1;
         if (++s == nstage) { s = 0; ph ^= 1; }
@@ -519,10 +544,23 @@ __device__ __forceinline__ void epilogue_swap2(const Params& P, const Geometry& 
     }
     {
       uint32_t r[KS][16];
-      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + u * g.ncols + c16);
+      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + u * g.ncols * (1 + g.stk) + c16);
 #pragma unroll
       for (int dx = 0; dx < KS; ++dx) tmem_ld16_nowait(t0 + (uint32_t)(dx * g.np), r[dx]);
       tmem_wait_ld();
+      if (NG == 3 && g.stk) {                   // + the X_hi * W_lo products of the stacked pass (their own ncols columns); NG = 3 only:
+                                                // the host launches stacked layers on the 128-register instance (no room at 96 / in the 5x5 epilogue)
+#pragma unroll
+        for (int dx = 0; dx < KS; ++dx) {
+#pragma unroll
+          for (int h8 = 0; h8 < 16; h8 += 8) {        // 8 columns at a time: the 96-register epilogue (NG = 4) has no room for 16
+            uint32_t t[8];
+            tmem_ld8(t0 + (uint32_t)(g.ncols + dx * g.np + h8), t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[dx][h8 + j] = __float_as_uint(__uint_as_float(r[dx][h8 + j]) + __uint_as_float(t[j]));
+          }
+        }
+      }
       const uint32_t xw = xch_half + par * (uint32_t)(4 * (KS - 1) * (KS - 1) * 16 * 4);
       if (lane < KS - 1) {
 #pragma unroll
@@ -706,7 +744,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
 
   const int per_mt = g.ngroups * g.npass;
   const uint32_t ltype = g.layout == 1 ? 4u : 2u;
-  const int acc_cols = g.swap ? g.units * g.ncols : (g.rg ? g.ncols_item : g.G * g.v_cnt);   // TMEM columns of one accumulator set
+  const int acc_cols = g.swap ? g.units * g.ncols * (1 + g.stk) : (g.rg ? g.ncols_item : g.G * g.v_cnt);   // TMEM columns of one accumulator set
   const int nacc = g.nacc;                               // 2 when two sets fit in the 512 columns
 
   if (warp == 0) {
@@ -743,7 +781,10 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
       const int first = (dual && warp == 3) ? (g.units + 1) / 2 : 0;
       const int count = dual ? (warp == 3 ? g.units - first : (g.units + 1) / 2) : g.units;
 #define VF_S2(PA, UU) issuer_loop_swap2<PA, UU>(g, cx, acc_cols, first)
-      if (g.passes == 3) {
+      if (g.passes == 3 && g.stk) {                     // stacked weight halves: <= 2 units per accumulator set
+        if (count == 1) issuer_loop_swap2<3, 1, 1>(g, cx, acc_cols, first);
+        else issuer_loop_swap2<3, 2, 1>(g, cx, acc_cols, first);
+      } else if (g.passes == 3) {
         switch (count) {
           case 1: VF_S2(3, 1); break; case 2: VF_S2(3, 2); break; case 3: VF_S2(3, 3); break; case 4: VF_S2(3, 4); break;
           default: VF_S2(3, 5); break;
@@ -1434,7 +1475,13 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
     g.half_bytes = g.ncols * g.row_bytes; g.stage_bytes = 2 * g.half_bytes;
     g.n_mt = 1; g.G = 1;
     const int Vs = H * g.Wp;
-    const int umax = std::max(1, std::min(4, 256 / g.ncols));            // two accumulator sets in the 512 TMEM columns; <= 4 units
+    static const int stack_np = getenv("VF_STACK_NP") ? atoi(getenv("VF_STACK_NP")) : 16;   // stack the weight halves up to this np (0: never)
+    // 3x3 only (runs on k_conv_mma<3>), and only with >= 2 channel chunks: masks1 (56 -> 7) is bound by MMA issue and gains
+    // (110.7 -> 94.4 us), scratch1 (32 -> 3, one chunk, sigmoid + split-half stores) is bound by its epilogue and loses with the
+    // smaller items / 3 epilogue groups (43.2 -> 56.7 us)
+    g.stk = (passes == 3 && k == 3 && g.np <= stack_np && 2 * g.ncols <= 256 && g.nchunk >= 2) ? 1 : 0;
+    const int ucols = g.ncols * (1 + g.stk);                             // TMEM columns of one unit
+    const int umax = std::max(1, std::min(4, 256 / ucols));              // two accumulator sets in the 512 TMEM columns; <= 4 units
                                                                           // of one channel block = one work item per epilogue group
     bool found = false;
     for (int units = umax; units >= 1 && !found; --units) {
@@ -1452,7 +1499,7 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
       }
     }
     if (!found) return false;
-    g.nacc = (2 * g.units * g.ncols <= 512) ? 2 : 1;
+    g.nacc = (2 * g.units * ucols <= 512) ? 2 : 1;
     g.ngroups = B;
     g.nitems = g.ngroups * g.npass;
     *out = g;
@@ -1645,9 +1692,9 @@ bool mma_conv_describe(int k, int kw, int cin, int cout, int H, int W, int B, in
   if (layout == 2 && !(cin % 64 == 0 && cout >= 128)) layout = 1;
   Geometry g;
   if (!plan_geometry(layout, bo, k, kw, k, cin, cout, H, W, B, passes == 3 ? 3 : 1, &g)) return false;
-  const int acc_cols = g.swap ? g.units * g.ncols : (g.rg ? g.ncols_item : g.G * g.v_cnt);
+  const int acc_cols = g.swap ? g.units * g.ncols * (1 + g.stk) : (g.rg ? g.ncols_item : g.G * g.v_cnt);
   int nmax = 0;                                       // largest MMA N
-  if (g.swap) nmax = g.ncols; else for (int i = 0; i < g.nseg; ++i) nmax = std::max(nmax, g.seg_n[i]);
+  if (g.swap) nmax = g.ncols * (1 + g.stk); else for (int i = 0; i < g.nseg; ++i) nmax = std::max(nmax, g.seg_n[i]);
   // last shared-memory pixel row any MMA of an item reads (relative to the item's plane), and the rows the plane holds
   int last_read, plane_rows = g.plane_bytes / g.row_bytes;
   const int tap_reach = (g.k - 1) * g.Wp + (g.kw - 1);
@@ -1830,7 +1877,7 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   }
   const int grid = std::min(P.g.nitems, g_num_sms > 0 ? g_num_sms : 148);
   {
-    const int ng = (P.g.swap == 2 && P.g.k == 3) ? epi_groups : 2, ncb = P.g.np >> 4;
+    const int ng = P.g.stk ? 3 : ((P.g.swap == 2 && P.g.k == 3) ? epi_groups : 2), ncb = P.g.np >> 4;
     if (c.stats_partial && P.g.swap == 2 && thin_epilogue_tiled(P.g, c.out, c.act) && (ng == 2 || ng % ncb == 0)) {
       P.stats_partial = c.stats_partial;
       P.stats_S = P.g.npass;
@@ -1875,6 +1922,8 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   if (P.stats_partial && c.stats_fin && c.stats_cnt && (P.g.n_mt * 4 <= VF_STAT_CNT_STRIDE)) { P.stats_fin = c.stats_fin; P.stats_cnt = c.stats_cnt; }
   if (c.stats_finalized) *c.stats_finalized = P.stats_fin != nullptr;
   ++g_launch_counter;
+  if (P.g.stk)                                                          // stacked weight halves: the 128-register instance (3 epilogue groups)
+    return launch_k(k_conv_mma<3>, dim3(grid), dim3(128 + 128 * 3), smem, s, P) == cudaSuccess ? 0 : -4;
   if (epi_groups == 4 && P.g.swap == 2 && P.g.k == 3)
     return launch_k(k_conv_mma<4>, dim3(grid), dim3(128 + 128 * 4), smem, s, P) == cudaSuccess ? 0 : -4;
   if (epi_groups == 3 && P.g.swap == 2 && P.g.k == 3)
