@@ -78,17 +78,17 @@ def test_every_layer_has_a_legal_plan(tag, B):
         assert p["R"] <= 256 and p["Wp"] <= 256, where       # TMA box extents
         if k == 5 and cout >= 128:                            # gate convolutions: wide tiling, row groups on narrow maps
             assert p["swap"] == 0, where
-            assert p["rg"] == (1 if W == 8 else (2 if (W == 16 and H in (4, 8, 12, 16)) else 0)), where
+            assert p["rg"] == (1 if W == 8 else (2 if (W == 16 and H in (4, 8, 12, 16)) else (3 if (W > 16 and W % 8 == 0 and H % 4 == 0 and 8 * H <= 256) else 0))), where
             assert p["nacc"] == 2, where                      # the epilogue overlaps the next item's MMAs
         if k == 3 and cout <= 64:
             assert p["swap"] == 2 and p["units"] <= 4, where
 
 
 def test_headline_layer_plans_are_the_documented_ones():
-    """lstm0 (32x32) = 6 passes of N = 192, lstm1 (16x16) = two N = 128 row-group MMAs, lstm2 (8x8) = one N = 224
-    MMA over 3 stacked images; work-item counts at M = 200."""
+    """lstm0 (32x32) = four 8-pixel column strips per image, one N = 256 MMA each (row-group mode 3), lstm1 (16x16)
+    = two N = 128 row-group MMAs, lstm2 (8x8) = one N = 224 MMA over 3 stacked images; work-item counts at M = 200."""
     p0 = plan(5, 5, 64, 128, 32, 32, 200)
-    assert (p0["npass"], p0["v_cnt"], p0["nitems"], p0["rg"]) == (6, 192, 1200, 0)
+    assert (p0["npass"], p0["v_cnt"], p0["nitems"], p0["rg"], p0["Wp"]) == (4, 256, 800, 3, 12)
     p1 = plan(5, 5, 128, 256, 16, 16, 200)
     assert (p1["rg"], p1["nmax"], p1["acc_cols"], p1["nitems"]) == (2, 128, 256, 400)
     p2 = plan(5, 5, 256, 512, 8, 8, 200)

@@ -90,6 +90,9 @@ struct Geometry {
                     //   ONE MMA of N = ((G-1)(H+pad)+H)*8 columns spans all of them.
                     //   rg == 2 (W == 16): one image per item, two MMAs per K step — the left and the right 8-pixel group of every
                     //   row (N = 8*H each, group stride Wp, the right one starting 8 pixels later) -> columns [0, 8H) and [8H, 16H).
+                    //   rg == 3 (W == 32, or any W % 8 == 0 wider than 16 with 8*H <= 256): an item is ONE 8-pixel column group of
+                    //   an image over all rows (npass = W/8 items per image): the staged box is the 8+k-1 pixel wide strip
+                    //   (Wp = strip width), one MMA of N = 8*H per K step, no wrap columns and no row-block halo re-reads.
   int half_cols;    // rg == 2: accumulator columns per 8-pixel column group (8*H)
   int col_stride;   // rg: TMEM columns between consecutive images of an item ((H+pad)*8)
   int ncols_item;   // rg: TMEM columns of one accumulator set (the MMA's N)
@@ -373,7 +376,7 @@ __device__ __forceinline__ void issuer_loop(const Geometry& g, const IssueCtx& c
   for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
     const int a = it % nacc;
     // the box starts at the image row containing the item's first virtual pixel: skip (v_lo mod Wp) pixel rows
-    const uint64_t item_off16 = (uint64_t)(((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
+    const uint64_t item_off16 = g.rg == 3 ? 0ull : (uint64_t)(((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
     mbar_wait(&cx.acc_empty[a], ((it / nacc) & 1) ^ 1);
     tc_fence_after();
 #pragma unroll
@@ -832,7 +835,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
         const int rem = item % per_mt;
         const int grp = rem / g.npass, ps = rem % g.npass;
         const int b0 = grp * g.G;
-        const int qy0 = (ps * g.v_cnt) / g.Wp;                 // first padded-image row the item touches
+        const int qy0 = g.rg == 3 ? 0 : (ps * g.v_cnt) / g.Wp;  // first padded-image row the item touches (rg 3: the whole column strip)
+        const int qx0 = (g.rg == 3 ? ps * 8 : 0) - g.padx;      // rg 3: the item's 8-pixel column group
         const int nimg = min(g.G, P.B - b0);
         for (int c = 0; c < g.nchunk; ++c, ++job) {
           const int buf = job % g.nbuf;
@@ -842,7 +846,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
           mbar_expect_tx(&a_full[buf], (uint32_t)(nimg * nplanes * g.box_bytes));
           for (int im = 0; im < nimg; ++im)
             for (int pl = 0; pl < nplanes; ++pl)
-              tma_load_5d(act_base + (uint32_t)((buf * 2 + pl) * g.plane_bytes + im * g.img_pix * g.row_bytes), tm, c0, -g.padx,
+              tma_load_5d(act_base + (uint32_t)((buf * 2 + pl) * g.plane_bytes + im * g.img_pix * g.row_bytes), tm, c0, qx0,
                           qy0 - g.pad, b0 + im, pl, &a_full[buf]);
         }
       }
@@ -954,7 +958,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
         const int rem = item % per_mt;
         grp = rem / g.npass; ps_ = rem % g.npass;
       }
-      const int b0 = grp * g.G, v_lo = ps_ * g.v_cnt;
+      const int b0 = grp * g.G, v_lo = g.rg == 3 ? 0 : ps_ * g.v_cnt;
       const int n = mt * MT + row;
       const int a = nacc == 2 ? (int)(it & 1u) : 0;
       const int next = item + (int)gridDim.x;
@@ -1093,7 +1097,7 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
           if (!live) continue;
           // Every lane handles the SAME pixel (a different channel).  Branch-free and without loop-carried state so the
           // 32 elements overlap: a 32-column chunk spans at most 4 image rows (Wp >= 10), selected by compare-and-add.
-          const int xoff = g.rg == 2 ? (cc / g.half_cols) * 8 : 0;       // rg 2: second column group of the rows
+          const int xoff = g.rg == 2 ? (cc / g.half_cols) * 8 : (g.rg == 3 ? ps_ * 8 : 0);   // rg 2: second column group of the rows; rg 3: the item's
           const int v = v_lo + (g.rg == 2 ? cc % g.half_cols : cc);
           const int oy0 = v / Wp, ox0 = v - oy0 * Wp;
           int cyk[4], rbase[4];
@@ -1572,6 +1576,34 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
     }
     g.rg = 0; g.We = g.Wp;
   }
+  static const bool rg3_env = !(getenv("VF_RG3") && atoi(getenv("VF_RG3")) == 0);   // [1]: column-strip items for maps wider than 16
+  if (rg_env && rg3_env && W > 16 && W % 8 == 0 && H * 8 <= 256 && H % 4 == 0 && kw == k && layout == 1) {
+    // ---- row-group mode 3 (see Geometry::rg): item = one 8-pixel column group of one image, all rows ----
+    Geometry t = g;
+    t.rg = 3; t.G = 1; t.npass = W / 8; t.We = 8;
+    t.Wp = 8 + kw - 1;                                   // the staged strip: 8 pixels + halo columns
+    t.half_cols = H * 8; t.v_cnt = H * 8; t.col_stride = t.v_cnt; t.ncols_item = t.v_cnt;
+    t.nseg = 1; t.seg_n[0] = t.v_cnt; t.seg_off[0] = 0; t.seg_px[0] = 0;
+    t.R = H + 2 * t.pad;
+    t.img_pix = (t.R * t.Wp + 7) / 8 * 8;
+    t.box_bytes = t.R * t.Wp * t.row_bytes;
+    t.plane_bytes = ((t.img_pix + 16) * t.row_bytes + 1023) / 1024 * 1024;   // + the last tap's reach past the last row
+    bool ok_rg = false;
+    for (t.nbuf = 2; t.nbuf >= 1; --t.nbuf) {
+      const size_t act = (size_t)t.nbuf * 2 * t.plane_bytes;
+      if (act + 2 * (size_t)t.stage_bytes + SMEM_SLACK > SMEM_LIMIT) continue;
+      t.nstage = (int)std::min<size_t>(MAX_STAGE, (SMEM_LIMIT - SMEM_SLACK - act) / t.stage_bytes);
+      ok_rg = true;
+      break;
+    }
+    if (ok_rg && t.R <= 256) {
+      t.nacc = (2 * t.ncols_item <= 512) ? 2 : 1;
+      t.ngroups = B;
+      t.nitems = t.n_mt * t.ngroups * t.npass;
+      *out = t;
+      return true;
+    }
+  }
   if (rg_env && W == 8 && kw == k && layout == 1 && H >= 2 && H * 8 <= 128) {
     // ---- row-group mode (see Geometry::rg) ----
     const int pitch = H + g.pad;
@@ -1704,6 +1736,7 @@ bool mma_conv_describe(int k, int kw, int cin, int cout, int H, int W, int B, in
   else if (g.swap) last_read = off + g.units * 128 - 1 + tap_reach;
   else if (g.rg == 1) last_read = ((g.G - 1) * (g.H + g.pad) + g.H - 1) * g.Wp + 7 + tap_reach;
   else if (g.rg == 2) last_read = (g.H - 1) * g.Wp + 8 + 7 + tap_reach;
+  else if (g.rg == 3) last_read = (g.H - 1) * g.Wp + 7 + tap_reach;
   else last_read = (g.G - 1) * g.img_pix + off + g.v_cnt - 1 + tap_reach;
   const int v[24] = {g.swap, g.rg, g.G, g.npass, g.v_cnt, g.units, g.ncols, nmax, acc_cols, g.nacc, g.nbuf, g.nstage,
                      g.stage_bytes, g.plane_bytes, (int)smem_bytes(g), g.nitems, g.R, g.Wp, g.img_pix, g.box_bytes,
