@@ -78,7 +78,9 @@ def test_every_layer_has_a_legal_plan(tag, B):
         assert p["R"] <= 256 and p["Wp"] <= 256, where       # TMA box extents
         if k == 5 and cout >= 128:                            # gate convolutions: wide tiling, row groups on narrow maps
             assert p["swap"] == 0, where
-            assert p["rg"] == (1 if W == 8 else (2 if (W == 16 and H in (4, 8, 12, 16)) else (3 if (W > 16 and W % 8 == 0 and H % 4 == 0 and 8 * H <= 256) else 0))), where
+            strip = W % 8 == 0 and H % 4 == 0 and 8 * H <= 256            # 8-pixel column strips (row-group mode 3)
+            want = 1 if W == 8 else (0 if not strip else (2 if (W == 16 and cout % 256 == 0) else (3 if W >= 16 else 0)))
+            assert p["rg"] == want, where
             assert p["nacc"] == 2, where                      # the epilogue overlaps the next item's MMAs
         if k == 3 and cout <= 64:
             assert p["swap"] == 2 and p["units"] <= 4, where

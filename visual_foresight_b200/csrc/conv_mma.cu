@@ -1547,7 +1547,12 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
   g.We = g.Wp;
   static const bool rg_env = !(getenv("VF_ROWGROUPS") && atoi(getenv("VF_ROWGROUPS")) == 0);
   static const bool rg2_anyh = !(getenv("VF_RG2_ANYH") && atoi(getenv("VF_RG2_ANYH")) == 0);   // [1]: 8x16 / 12x16 maps too (48x64 inputs)
-  if (rg_env && W == 16 && (H == 16 || (rg2_anyh && H >= 4 && H < 16 && H % 4 == 0)) && kw == k && layout == 1) {
+  static const bool rg3_env = !(getenv("VF_RG3") && atoi(getenv("VF_RG3")) == 0);   // [1]: column-strip items (row-group mode 3)
+  // W == 16: strips only for layers that cannot run on CTA pairs (no whole 256-channel tiles) — twice as many, half as large
+  // items fill the last round of the persistent grid better (enc2: 200 items on 148 CTAs -> 400)
+  static const bool rg3_w16 = !(getenv("VF_RG3_W16") && atoi(getenv("VF_RG3_W16")) == 0);
+  const bool strip16 = rg3_env && rg3_w16 && W == 16 && Cout % 256 != 0;
+  if (rg_env && !strip16 && W == 16 && (H == 16 || (rg2_anyh && H >= 4 && H < 16 && H % 4 == 0)) && kw == k && layout == 1) {
     // ---- row-group mode 2 (see Geometry::rg) ----
     g.rg = 2; g.G = 1; g.npass = 1; g.We = 8;
     g.half_cols = H * 8; g.v_cnt = 2 * g.half_cols; g.col_stride = g.v_cnt; g.ncols_item = g.v_cnt;
@@ -1576,8 +1581,7 @@ bool plan_geometry(int layout, int bo_mode, int k, int kw, int kcl, int Cin, int
     }
     g.rg = 0; g.We = g.Wp;
   }
-  static const bool rg3_env = !(getenv("VF_RG3") && atoi(getenv("VF_RG3")) == 0);   // [1]: column-strip items for maps wider than 16
-  if (rg_env && rg3_env && W > 16 && W % 8 == 0 && H * 8 <= 256 && H % 4 == 0 && kw == k && layout == 1) {
+  if (rg_env && rg3_env && (W > 16 || strip16) && W % 8 == 0 && H * 8 <= 256 && H % 4 == 0 && kw == k && layout == 1) {
     // ---- row-group mode 3 (see Geometry::rg): item = one 8-pixel column group of one image, all rows ----
     Geometry t = g;
     t.rg = 3; t.G = 1; t.npass = W / 8; t.We = 8;
