@@ -9,8 +9,12 @@
 //     register staging, no conversion pass, no im2col.
 //   * The box in shared memory is a FLAT zero-padded image (row pitch Wp = W + k - 1), one operand row per pixel.  Filter
 //     tap (dy,dx) is the SAME buffer read through a matrix descriptor whose start address is advanced by (dy*Wp + dx)
-//     pixel rows: 25 taps = 25 descriptors, zero data movement.  The k-1 wrap-around columns per image row are computed
-//     and discarded (W/Wp efficiency: 89% at 32x32, 80% at 16x16).
+//     pixel rows: 25 taps = 25 descriptors, zero data movement.  In the generic tiling the k-1 wrap-around columns per
+//     image row are computed and discarded (W/Wp efficiency: 89% at 32x32, 80% at 16x16); the "row group" modes
+//     (Geometry::rg) avoid them for maps whose width is a multiple of 8: the descriptor's 8-row group pitch is set to the
+//     padded row, so an MMA's N rows are 8-pixel groups of consecutive IMAGE rows — stacked 8-wide images (rg 1), the two
+//     column groups of a 16-wide image (rg 2), or one 8-pixel column STRIP of a wider image over all its rows (rg 3, the
+//     32x32 gate convs: N = 256 per MMA, staged box = the 12-pixel-wide strip).
 //   * Two orientations.  Cout >= 128: output channels on the MMA M dimension (TMEM lanes), pixels on N; a warp stores 32
 //     consecutive channels of one pixel = one 128-byte NHWC line.  Cout <= 64 ("swap"): pixels on M in 128-row units,
 //     channels on N; one epilogue thread owns one pixel and writes its channels with 16-byte stores.
@@ -25,6 +29,8 @@
 //
 //   * k_conv_pair (further down): the 16x16 layers with whole 256-channel tiles run on CTA PAIRS (tcgen05 cta_group::2, M = 256):
 //     each SM of a TPC stages half of both operands, one MMA per K step spans both.
+//   * Row-stacked thin layers with np <= 16 and >= 2 channel chunks (the mask-logit conv) multiply X_hi by BOTH weight halves
+//     in one MMA of N = 2*k*np (Geometry::stk): 2 MMAs per K step instead of 3, the W_lo products are added in the epilogue.
 //
 // Operand layouts (VF_MMA_LAYOUT): 1 = SWIZZLE_64B, 32-channel chunks, pixel rows of 64 B (default);
 //                                  2 = SWIZZLE_128B, 64-channel chunks, pixel rows of 128 B.
