@@ -97,3 +97,35 @@ def test_headline_layer_plans_are_the_documented_ones():
     assert (p2["rg"], p2["G"], p2["nmax"], p2["nitems"]) == (1, 3, 224, 4 * 67)
     pf = plan(5, 1, 40, 32, 64, 64, 200)                      # the dx-folded first conv (VF_ENC0=fold): per-tap thin tiling
     assert pf is not None and pf["swap"] == 1
+
+
+def test_random_shapes_keep_the_resource_invariants():
+    """Seeded sweep over layer shapes outside the shipped specs (odd heights, wide maps, many channel counts): whatever tiling
+    plan_geometry picks — generic, row groups 1 / 2 / 3, row-stacked, stacked weight halves — stays inside shared memory, TMEM,
+    the legal MMA N and its staged pixel rows; the strip tilings are picked exactly where their preconditions hold."""
+    rng = np.random.default_rng(7)
+    seen = set()
+    for _ in range(400):
+        k = int(rng.choice([3, 5]))
+        cin = int(rng.choice([8, 16, 24, 32, 40, 56, 64, 96, 128, 192, 256]))
+        cout = int(rng.choice([3, 7, 16, 32, 48, 64, 96, 128, 160, 256, 512]))
+        H = int(rng.choice([4, 6, 8, 12, 16, 20, 24, 32, 48, 64]))
+        W = int(rng.choice([8, 12, 16, 24, 32, 40, 64, 96]))
+        B = int(rng.choice([1, 3, 25, 200]))
+        p = plan(k, k, cin, cout, H, W, B)
+        if p is None:
+            continue
+        where = "k%d %d->%d %dx%d B=%d %r" % (k, cin, cout, H, W, B, p)
+        assert p["smem"] <= 227 * 1024, where
+        assert p["acc_cols"] * p["nacc"] <= 512 and p["nacc"] in (1, 2), where
+        assert 16 <= p["nmax"] <= 256 and p["nmax"] % 16 == 0, where
+        assert p["nstage"] >= 2 and p["nbuf"] in (1, 2) and p["nitems"] >= 1, where
+        assert p["last_read"] < p["plane_rows"], where
+        assert p["R"] <= 256 and p["Wp"] <= 256, where
+        if p["rg"] == 3:
+            assert W % 8 == 0 and W >= 16 and H % 4 == 0 and 8 * H <= 256 and p["Wp"] == 8 + k - 1 and p["npass"] == W // 8, where
+            assert p["v_cnt"] == 8 * H and p["nitems"] == p["n_mt"] * B * (W // 8), where
+        if p["rg"] == 2:
+            assert W == 16 and cout % 256 == 0 and p["v_cnt"] == 16 * H, where
+        seen.add((p["swap"], p["rg"]))
+    assert {(0, 0), (0, 1), (0, 2), (0, 3), (2, 0)} <= seen, seen
