@@ -99,6 +99,8 @@ struct Geometry {
                     //   rg == 3 (W == 32, or any W % 8 == 0 wider than 16 with 8*H <= 256): an item is ONE 8-pixel column group of
                     //   an image over all rows (npass = W/8 items per image): the staged box is the 8+k-1 pixel wide strip
                     //   (Wp = strip width), one MMA of N = 8*H per K step, no wrap columns and no row-block halo re-reads.
+  int tsplit;       // rg == 3: 1 = the strips of the LAST, partial round of the persistent grid are split in an upper and a lower
+  int n_full;       //   half (N = 4*H each): work items [0, n_full) are whole strips, the rest half strips (strip_of())
   int half_cols;    // rg == 2: accumulator columns per 8-pixel column group (8*H)
   int col_stride;   // rg: TMEM columns between consecutive images of an item ((H+pad)*8)
   int ncols_item;   // rg: TMEM columns of one accumulator set (the MMA's N)
@@ -360,6 +362,16 @@ struct IssueCtx {
   uint64_t* w_full; uint64_t* w_empty; uint64_t* a_full; uint64_t* a_empty; uint64_t* acc_full; uint64_t* acc_empty;
 };
 
+// work item -> strip (the item index of the unsplit schedule) and part: -1 = whole item, 0 / 1 = upper / lower half of a strip of
+// the split last round (Geometry::tsplit)
+__device__ __forceinline__ int strip_of(const Geometry& g, int item, int& part) {
+  part = -1;
+  if (!g.tsplit || item < g.n_full) return item;
+  const int t = item - g.n_full;
+  part = t & 1;
+  return g.n_full + (t >> 1);
+}
+
 // Whole-kernel MMA issue loop, specialised at compile time on (passes, k-steps, accumulator units): inside the tap loop
 // there is one mbarrier wait, one election, PASSES*KSTEPS*U back-to-back UTCHMMA and one commit.
 template <int PASSES, int KSTEPS, int U>
@@ -373,6 +385,9 @@ __device__ __forceinline__ void issuer_loop(const Geometry& g, const IssueCtx& c
     uoff[u] = (uint64_t)(((uint32_t)(im * g.img_pix + g.seg_px[sg]) * cx.pix_b) >> 4);
     uidesc[u] = make_idesc(g.seg_n[sg]);
   }
+  const uint32_t idesc_half = make_idesc(g.v_cnt >> 1);                  // half strips of the split last round (rg 3: one unit)
+  const uint64_t half_off16 = (uint64_t)(((uint32_t)((g.H >> 1) * g.Wp) * cx.pix_b) >> 4);
+  const uint32_t idesc_full0 = uidesc[0];
   const int nitems = g.nitems, nchunk = g.nchunk, ntap = g.nst, kk = g.kw, nbuf = g.nbuf, nstage = g.nstage, nacc = g.nacc;
   const uint32_t stage16 = (uint32_t)(g.stage_bytes >> 4), buf16 = (uint32_t)((2 * g.plane_bytes) >> 4);
   const uint64_t pix16 = (uint64_t)(cx.pix_b >> 4), rowskip16 = (uint64_t)(((uint32_t)(g.Wp - g.kw) * cx.pix_b) >> 4);
@@ -382,7 +397,11 @@ __device__ __forceinline__ void issuer_loop(const Geometry& g, const IssueCtx& c
   for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
     const int a = it % nacc;
     // the box starts at the image row containing the item's first virtual pixel: skip (v_lo mod Wp) pixel rows
-    const uint64_t item_off16 = g.rg == 3 ? 0ull : (uint64_t)(((uint32_t)(((item % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
+    int part;
+    const int strip = strip_of(g, item, part);
+    const uint64_t item_off16 = g.rg == 3 ? (part > 0 ? half_off16 : 0ull)
+                                          : (uint64_t)(((uint32_t)(((strip % g.npass) * g.v_cnt) % g.Wp) * cx.pix_b) >> 4);
+    uidesc[0] = part >= 0 ? idesc_half : idesc_full0;
     mbar_wait(&cx.acc_empty[a], ((it / nacc) & 1) ^ 1);
     tc_fence_after();
 #pragma unroll
@@ -763,7 +782,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
       uint32_t ph = 0;
       const uint32_t bytes = g.passes == 3 ? (uint32_t)g.stage_bytes : (uint32_t)g.half_bytes;
       for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
-        const int mt = item / per_mt;
+        int part_;
+        const int mt = strip_of(g, item, part_) / per_mt;
         const uint8_t* wbase = reinterpret_cast<const uint8_t*>(P.w) + (size_t)mt * g.nchunk * g.nst * g.stage_bytes;
         for (int ct = 0; ct < g.nchunk * g.nst; ++ct) {
           mbar_wait(&w_empty[s], ph ^ 1);
@@ -838,7 +858,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
       const int nplanes = g.passes == 3 ? 2 : 1;
       uint32_t job = 0;
       for (int item = blockIdx.x; item < g.nitems; item += gridDim.x) {
-        const int rem = item % per_mt;
+        int part_;
+        const int rem = strip_of(g, item, part_) % per_mt;      // a half strip stages the whole strip's box (same tensor map)
         const int grp = rem / g.npass, ps = rem % g.npass;
         const int b0 = grp * g.G;
         const int qy0 = g.rg == 3 ? 0 : (ps * g.v_cnt) / g.Wp;  // first padded-image row the item touches (rg 3: the whole column strip)
@@ -956,15 +977,18 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
       pend_b = -1;
     };
     for (int item = blockIdx.x; item < g.nitems; item += gridDim.x, ++it) {
-      int mt, grp, ps_;
+      int mt, grp, ps_, part = -1;
       if (stacked) {                               // one Cout tile, G = 1: no divisions by runtime values on this path
         mt = 0; grp = fdiv(item, g.m_npass); ps_ = item - grp * g.npass;
       } else {
-        mt = item / per_mt;
-        const int rem = item % per_mt;
+        const int strip = strip_of(g, item, part);
+        mt = strip / per_mt;
+        const int rem = strip % per_mt;
         grp = rem / g.npass; ps_ = rem % g.npass;
       }
-      const int b0 = grp * g.G, v_lo = g.rg == 3 ? 0 : ps_ * g.v_cnt;
+      const int hcols = g.v_cnt >> 1;                 // rg 3: columns of a half strip
+      const int b0 = grp * g.G, v_lo = g.rg == 3 ? (part > 0 ? hcols : 0) : ps_ * g.v_cnt;
+      const int ncols_it = part >= 0 ? hcols : g.v_cnt;
       const int n = mt * MT + row;
       const int a = nacc == 2 ? (int)(it & 1u) : 0;
       const int next = item + (int)gridDim.x;
@@ -1097,7 +1121,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
         const float scale = g.out_scale;
         const bool sigm = P.act == ACT_SIGMOID;
         double st_s = 0.0, st_q = 0.0;              // instance-norm statistics of this thread's channel (fused: no extra pass)
-        for (int cc = half * 32; cc < g.v_cnt; cc += 64) {
+        double st_s1 = 0.0, st_q1 = 0.0;            // rg 3: the lower half of the strip has its own slot (see below)
+        for (int cc = half * 32; cc < ncols_it; cc += 64) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * acc_cols + im * im_cols + cc), r);
           if (!live) continue;
@@ -1131,13 +1156,21 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) k_conv_mma(const __grid_con
               cq = fmaf(val, val, cq);
             }
           }
-          st_s += (double)cs;
-          st_q += (double)cq;
+          if (g.rg == 3 && v >= hcols) { st_s1 += (double)cs; st_q1 += (double)cq; }
+          else { st_s += (double)cs; st_q += (double)cq; }
         }
         if (P.stats_partial && live) {              // slot = (pass, column-half): every slot is written exactly once
-          double* o = P.stats_partial + (((long long)b * g.Cout + n) * P.stats_S + (ps_ * 2 + half)) * 2;
-          o[0] = st_s;
-          o[1] = st_q;
+          if (g.rg == 3) {
+            // (strip, column-half, upper / lower half of the strip): a whole strip writes both of its half slots, a half strip of
+            // the split last round its own — the partial sums and their order never depend on whether the round was split
+            double* o = P.stats_partial + (((long long)b * g.Cout + n) * P.stats_S + (ps_ * 2 + half) * 2) * 2;
+            if (part <= 0) { o[0] = st_s; o[1] = st_q; }
+            if (part != 0) { o[2] = st_s1; o[3] = st_q1; }
+          } else {
+            double* o = P.stats_partial + (((long long)b * g.Cout + n) * P.stats_S + (ps_ * 2 + half)) * 2;
+            o[0] = st_s;
+            o[1] = st_q;
+          }
         }
         if (P.stats_fin && im == 0) { pend_b = b0; pend_mt = mt; }   // arrivals of the item's images deferred to the next item
       }
@@ -1715,6 +1748,20 @@ bool mma_conv_supported(int k, int cin, int cout, int H, int W) {
   return plan_geometry(layout, bo, k, k, k, cin, cout, H, W, 1, 3, &g);
 }
 
+// Row-group mode 3: split the strips of the last, partial round of the persistent grid in two half strips when that lets the
+// round finish in about half the time (800 strips on 148 CTAs: 5 whole rounds + 60 strips -> 120 half strips, 5.6 instead of 6
+// rounds).  Only when a half strip keeps the epilogue's chunk -> warp assignment (4*H % 64 == 0), so that the fused statistics
+// are bit-identical with and without the split; not with producer-side finalisation (its arrival counts assume whole items).
+void apply_tail_split(Geometry& g, int sms, bool fused_finalize) {
+  static const bool on = !(getenv("VF_TAIL_SPLIT") && atoi(getenv("VF_TAIL_SPLIT")) == 0);
+  g.tsplit = 0; g.n_full = g.nitems;
+  if (!on || g.rg != 3 || fused_finalize || ((g.v_cnt >> 1) % 64) != 0 || sms <= 0) return;
+  const int grid = std::min(g.nitems, sms);
+  const int n_full = (g.nitems / grid) * grid, tail = g.nitems - n_full;
+  if (tail <= 0 || 2 * tail > grid) return;
+  g.tsplit = 1; g.n_full = n_full; g.nitems = n_full + 2 * tail;
+}
+
 // partial slots per (sample, channel) the fused instance-norm statistics of this layer shape use (0: not fused); sizes the
 // engine's partial-sum scratch
 int mma_conv_stats_slots(int k, int kw, int cin, int cout, int H, int W) {
@@ -1723,7 +1770,7 @@ int mma_conv_stats_slots(int k, int kw, int cin, int cout, int H, int W) {
   if (layout == 2 && !(cin % 64 == 0 && cout >= 128)) layout = 1;
   Geometry g;
   if (!plan_geometry(layout, bo, k, kw, k, cin, cout, H, W, 1, 3, &g)) return 0;
-  return g.swap == 2 ? g.npass : (g.swap ? 0 : 2 * g.npass);
+  return g.swap == 2 ? g.npass : (g.swap ? 0 : (g.rg == 3 ? 4 : 2) * g.npass);
 }
 
 // Host-only description of the tiling plan_geometry() picks for a layer (no device needed): lets the CPU test suite check the
@@ -1734,6 +1781,7 @@ bool mma_conv_describe(int k, int kw, int cin, int cout, int H, int W, int B, in
   if (layout == 2 && !(cin % 64 == 0 && cout >= 128)) layout = 1;
   Geometry g;
   if (!plan_geometry(layout, bo, k, kw, k, cin, cout, H, W, B, passes == 3 ? 3 : 1, &g)) return false;
+  apply_tail_split(g, 148, false);
   const int acc_cols = g.swap ? g.units * g.ncols * (1 + g.stk) : (g.rg ? g.ncols_item : g.G * g.v_cnt);
   int nmax = 0;                                       // largest MMA N
   if (g.swap) nmax = g.ncols * (1 + g.stk); else for (int i = 0; i < g.nseg; ++i) nmax = std::max(nmax, g.seg_n[i]);
@@ -1893,7 +1941,7 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
   P.out = c.out; P.sabias = c.sabias; P.bias = c.bias; P.w = w.w_hi; P.B = B; P.act = c.act;
   P.stats_partial = nullptr; P.stats_S = 0;
   P.stats_fin = nullptr; P.stats_cnt = nullptr; P.stats_npix = c.H * c.W; P.stats_eps = c.stats_eps;
-  if (c.stats_partial && !P.g.swap) { P.stats_partial = c.stats_partial; P.stats_S = P.g.npass * 2; }
+  if (c.stats_partial && !P.g.swap) { P.stats_partial = c.stats_partial; P.stats_S = P.g.npass * (P.g.rg == 3 ? 4 : 2); }
 
   if (!P.g.swap && c.out.lo_off) return -6;                           // the wide epilogue writes float32 (pre-norm) outputs
   int r = activation_map(c.src, P.g, B, &P.tmap0);
@@ -1918,6 +1966,7 @@ int mma_conv_launch(const MmaConvWeights& w, const MmaConvCall& c, int B, cudaSt
     if (e && atoi(e) >= 2 && atoi(e) <= 4) epi_groups = atoi(e);
     attr_set = true;
   }
+  apply_tail_split(P.g, g_num_sms > 0 ? g_num_sms : 148, c.stats_fin != nullptr && c.stats_cnt != nullptr);
   const int grid = std::min(P.g.nitems, g_num_sms > 0 ? g_num_sms : 148);
   {
     const int ng = P.g.stk ? 3 : ((P.g.swap == 2 && P.g.k == 3) ? epi_groups : 2), ncb = P.g.np >> 4;
